@@ -1,0 +1,216 @@
+// gemm_tc.cuh -- persistent warp-specialised tcgen05 GEMM mainloop for sm_100a (B200).
+//
+//   D[M,N] (fp32, TMEM) = A[M,K] * B[N,K]^T      A, B fp32 containers holding tf32 values, K-major
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, 128 x BLOCK_N x 8)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue functor -> global)
+//
+// Two TMEM accumulator buffers (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile
+// i+1.  The epilogue is a functor so the same mainloop serves the encoder linears (bias / GELU /
+// residual) and the kNN coarse pass (running per-query top-k' over prototype tiles).
+#pragma once
+#include "common.cuh"
+
+namespace ac {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_N = 256;
+constexpr int GEMM_BLOCK_K = 32;                    // fp32 elements = 128 bytes = one swizzle row
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_UMMA_K = 8;                      // tf32: 32 bytes per MMA K-step
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_A_STAGE_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 4;   // 16 KB
+constexpr int GEMM_B_STAGE_BYTES = GEMM_BLOCK_N * GEMM_BLOCK_K * 4;   // 32 KB
+constexpr int GEMM_STAGE_BYTES = GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_TMEM_COLS = 512;
+
+#ifndef AC_MBAR_WATCHDOG
+#define AC_MBAR_WATCHDOG 1
+#endif
+
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity) {
+#if AC_MBAR_WATCHDOG
+    // a broken pipeline must surface as a launch failure, never as a hung GPU box
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("ac: mbarrier watchdog fired (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
+struct GemmTileInfo {
+    int m0, n0;       // tile origin
+    int tile_iter;    // how many tiles this CTA has processed before this one
+};
+
+// Epilogue concept (parameters live in the functor, per-thread running state in Epi::State):
+//   struct Epi { struct State {...};
+//                __device__ void begin_cta(State&, int warp_q, int lane) const;
+//                __device__ void tile(State&, const GemmTileInfo&, int row /*global m*/, int col0 /*global n of v[0]*/,
+//                                     const float (&v)[32]) const;   // called 8x per tile per thread
+//                __device__ void end_cta(State&, int warp_q, int lane) const; };
+//
+// Tile order: kMFastest = false -> n fastest (tiles of the same A row-block run concurrently and share A
+// through L2: encoder linears, A = activations); kMFastest = true -> m fastest (consecutive CTAs share the
+// same B tile: kNN, B = prototype rows streamed once from HBM).
+template <class Epi, bool kMFastest = false>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 int M, int N, int K, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + GEMM_STAGES * GEMM_A_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+    uint64_t *full_bar = bars;                        // [STAGES]
+    uint64_t *empty_bar = bars + GEMM_STAGES;         // [STAGES]
+    uint64_t *tmem_full = bars + 2 * GEMM_STAGES;     // [2]
+    uint64_t *tmem_empty = bars + 2 * GEMM_STAGES + 2;  // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * GEMM_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_m = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    const int tiles_n = (N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < GEMM_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full[0], 1);
+        mbar_init(&tmem_full[1], 1);
+        mbar_init(&tmem_empty[0], 4);
+        mbar_init(&tmem_empty[1], 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (kMFastest ? tile % tiles_m : tile / tiles_n) * GEMM_BLOCK_M;
+                const int n0 = (kMFastest ? tile / tiles_m : tile % tiles_n) * GEMM_BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * GEMM_A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+                    tma_load_2d(smem_b + stage * GEMM_B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (one thread) ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(2 /*tf32*/, GEMM_BLOCK_M, GEMM_BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait_guarded(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * GEMM_BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_guarded(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + stage * GEMM_A_STAGE_BYTES));
+                    const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + stage * GEMM_B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+                        // advance 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
+                        umma_tf32(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full[acc]);         // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ---------------- epilogue warps ----------------
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        typename Epi::State est;
+        epi.begin_cta(est, q, lane);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            GemmTileInfo ti;
+            ti.m0 = (kMFastest ? tile % tiles_m : tile / tiles_n) * GEMM_BLOCK_M;
+            ti.n0 = (kMFastest ? tile / tiles_m : tile % tiles_n) * GEMM_BLOCK_N;
+            ti.tile_iter = it;
+            mbar_wait_guarded(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = ti.m0 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < GEMM_BLOCK_N; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c, r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                epi.tile(est, ti, row, ti.n0 + c, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        epi.end_cta(est, q, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+    }
+}
+
+// host-side launcher
+template <class Epi, bool kMFastest = false>
+int launch_gemm_tf32(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
+                     cudaStream_t stream, int max_ctas = 0) {
+    static bool attr_set = false;   // per instantiation
+    auto kern = gemm_tf32_kernel<Epi, kMFastest>;
+    if (!attr_set) {
+        AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
+    int ctas = sm_count();
+    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+    if (tiles < ctas) ctas = tiles;
+    if (ctas <= 0) return AC_OK;
+    kern<<<ctas, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+}  // namespace ac

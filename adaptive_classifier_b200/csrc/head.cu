@@ -1,0 +1,534 @@
+// head.cu -- stage H: AdaptiveHead forward, one fused-sequence optimizer step (fwd + CE/BCE + bwd +
+// EWC gradient + global-norm clip + AdamW), Fisher accumulation and the EWC penalty.  fp32 SIMT.
+//
+// Replaces (paths relative to /root/reference/src/adaptive_classifier/):
+//   models.py:71-80                 AdaptiveHead.forward (Linear-ReLU-Dropout x2, Linear)
+//   classifier.py:333-351,1489-1505 zero_grad / forward / CrossEntropyLoss / backward /
+//                                   clip_grad_norm_(1.0) / AdamW.step
+//   multilabel.py:41-44,387-397     sigmoid head + BCELoss
+//   ewc.py:67-92, :96-115           Fisher accumulation and penalty
+// The head is ~0.9 M parameters and M = 32 rows per step: latency-bound, so the kernels are small and
+// the step is a fixed launch sequence (graph-capturable: no host sync inside).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace ac {
+
+// ------------------------------------------------------------------------------------------------
+// generic strided SIMT GEMM:  C[m,n] = epi( sum_k A(m,k) * B(k,n) )
+//   A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn]
+// 64x64 tile, 16x16 threads, 4x4 micro-tile, BK = 16.  k is summed in ascending order per thread.
+// ------------------------------------------------------------------------------------------------
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RELU_MASK = 3, EPI_RELUGRAD_MASK = 4 };
+
+struct SgemmEpi {
+    int kind;
+    const float *bias;   // [n]
+    const float *mask;   // [m,n] dropout mask (0 or 1/(1-p)), nullable
+    const float *act;    // [m,n] saved activation for relu-grad
+};
+
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float *__restrict__ A, int64_t sam, int64_t sak, const float *__restrict__ B, int64_t sbk,
+             int64_t sbn, float *__restrict__ C, int64_t ldc, int M, int N, int K, SgemmEpi epi) {
+    __shared__ float sA[SG_BK][SG_BM + 1];
+    __shared__ float sB[SG_BK][SG_BN + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += SG_BK) {
+        for (int e = threadIdx.x; e < SG_BM * SG_BK; e += 256) {
+            // pick the faster-varying index to follow the contiguous stride of the operand
+            int mm, kk;
+            if (sak == 1) { kk = e % SG_BK; mm = e / SG_BK; } else { mm = e % SG_BM; kk = e / SG_BM; }
+            const int m = m0 + mm, k = k0 + kk;
+            sA[kk][mm] = (m < M && k < K) ? A[m * sam + k * sak] : 0.f;
+        }
+        for (int e = threadIdx.x; e < SG_BN * SG_BK; e += 256) {
+            int nn, kk;
+            if (sbk == 1) { kk = e % SG_BK; nn = e / SG_BK; } else { nn = e % SG_BN; kk = e / SG_BN; }
+            const int n = n0 + nn, k = k0 + kk;
+            sB[kk][nn] = (n < N && k < K) ? B[k * sbk + n * sbn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SG_BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            const int64_t off = static_cast<int64_t>(m) * ldc + n;
+            switch (epi.kind) {
+                case EPI_BIAS: v += epi.bias[n]; break;
+                case EPI_BIAS_RELU: v = fmaxf(v + epi.bias[n], 0.f); break;
+                case EPI_BIAS_RELU_MASK:
+                    v = fmaxf(v + epi.bias[n], 0.f);
+                    if (epi.mask) v *= epi.mask[off];
+                    break;
+                case EPI_RELUGRAD_MASK:
+                    // d(pre-activation) = d(out) * mask * [act > 0]   (act = relu(a)*mask; mask = 0 kills it)
+                    if (epi.mask) v *= epi.mask[off];
+                    v = (epi.act[off] > 0.f) ? v : 0.f;
+                    break;
+                default: break;
+            }
+            C[off] = v;
+        }
+    }
+}
+
+static int sgemm(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, float *C,
+                 int64_t ldc, int M, int N, int K, SgemmEpi epi, cudaStream_t s) {
+    if (M <= 0 || N <= 0) return AC_OK;
+    dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
+    sgemm_kernel<<<grid, 256, 0, s>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, epi);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+// y[m,n] = act(X W^T + b):  A = X (sam = K, sak = 1), B(k,n) = W[n*K + k] (sbk = 1, sbn = K)
+static int linear_fwd(const float *X, const float *W, const float *b, float *Y, int M, int N, int K, int kind,
+                      const float *mask, cudaStream_t s) {
+    SgemmEpi e{kind, b, mask, nullptr};
+    return sgemm(X, K, 1, W, 1, K, Y, N, M, N, K, e, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-wise output activations / losses
+// ------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const float *__restrict__ z, int B, int C, float *__restrict__ out, int act) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float *zr = z + static_cast<int64_t>(row) * C;
+    float *orow = out + static_cast<int64_t>(row) * C;
+    if (act == AC_ACT_SIGMOID) {
+        for (int j = lane; j < C; j += 32) orow[j] = 1.f / (1.f + expf(-zr[j]));
+        return;
+    }
+    float mx = -CUDART_INF_F;
+    for (int j = lane; j < C; j += 32) mx = fmaxf(mx, zr[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < C; j += 32) sum += expf(zr[j] - mx);
+    sum = warp_sum(sum);
+    for (int j = lane; j < C; j += 32) orow[j] = expf(zr[j] - mx) / sum;
+}
+
+// loss + dz.  CE: loss_b = -(z_y - lse); dz = (softmax - onehot)/B.
+// BCE on sigmoid: loss = mean over B*C; dz = (s - y)/(B*C).  One warp per row; per-row losses are
+// written to row_loss[B] and reduced in index order by reduce_loss_kernel (deterministic).
+__global__ void loss_grad_kernel(const float *__restrict__ z, const void *__restrict__ targets, int B, int C,
+                                 int loss_kind, float *__restrict__ dz, float *__restrict__ row_loss) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float *zr = z + static_cast<int64_t>(row) * C;
+    float *dr = dz + static_cast<int64_t>(row) * C;
+    if (loss_kind == AC_LOSS_CE) {
+        const int64_t y = static_cast<const int64_t *>(targets)[row];
+        float mx = -CUDART_INF_F;
+        for (int j = lane; j < C; j += 32) mx = fmaxf(mx, zr[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < C; j += 32) sum += expf(zr[j] - mx);
+        sum = warp_sum(sum);
+        const float lse = mx + logf(sum);
+        const float invB = 1.f / static_cast<float>(B);
+        for (int j = lane; j < C; j += 32) {
+            const float p = expf(zr[j] - mx) / sum;
+            dr[j] = (p - (j == y ? 1.f : 0.f)) * invB;
+        }
+        if (lane == 0) row_loss[row] = (y >= 0 && y < C) ? (lse - zr[y]) : 0.f;
+    } else {
+        const float *yr = static_cast<const float *>(targets) + static_cast<int64_t>(row) * C;
+        const float inv = 1.f / (static_cast<float>(B) * static_cast<float>(C));
+        float l = 0.f;
+        for (int j = lane; j < C; j += 32) {
+            const float s = 1.f / (1.f + expf(-zr[j]));
+            const float y = yr[j];
+            // nn.BCELoss clamps log at -100
+            l -= y * fmaxf(logf(s), -100.f) + (1.f - y) * fmaxf(logf(1.f - s), -100.f);
+            // gradient through BCELoss(sigmoid(z)) = (s - y) / (B*C)
+            dr[j] = (s - y) * inv;
+        }
+        l = warp_sum(l);
+        if (lane == 0) row_loss[row] = l / static_cast<float>(C);
+    }
+}
+
+__global__ void reduce_loss_kernel(const float *__restrict__ row_loss, int B, float *__restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < B; ++i) s += row_loss[i];
+        out[0] = s / static_cast<float>(B);
+    }
+}
+
+// column sums of dY[B,N] -> gb[N] (bias gradient), rows added in index order
+__global__ void colsum_kernel(const float *__restrict__ dY, int B, int N, float *__restrict__ gb) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dY[static_cast<int64_t>(b) * N + n];
+    gb[n] = s;
+}
+
+// Philox-free counter hash dropout mask (used only when the caller does not inject masks)
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return static_cast<uint32_t>(x);
+}
+__global__ void dropout_mask_kernel(float *__restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t stream_id) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = mix32(seed * 0x9E3779B97F4A7C15ULL + stream_id * 0xD1B54A32D192ED03ULL + static_cast<uint64_t>(i));
+    const float u = (r >> 8) * (1.0f / 16777216.0f);
+    mask[i] = (u < p) ? 0.f : 1.f / (1.f - p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat parameter views: 6 tensors {W0,b0,W1,b1,W2,b2}
+// ------------------------------------------------------------------------------------------------
+struct Flat6 {
+    float *p[6];
+    int64_t n[6];
+};
+static Flat6 flat_of(const ac_head_params *h) {
+    Flat6 f;
+    f.p[0] = h->W0; f.n[0] = static_cast<int64_t>(h->H0) * h->D;
+    f.p[1] = h->b0; f.n[1] = h->H0;
+    f.p[2] = h->W1; f.n[2] = static_cast<int64_t>(h->H1) * h->H0;
+    f.p[3] = h->b1; f.n[3] = h->H1;
+    f.p[4] = h->W2; f.n[4] = static_cast<int64_t>(h->C) * h->H1;
+    f.p[5] = h->b2; f.n[5] = h->C;
+    return f;
+}
+
+// EWC: g += 2*lam*invB * F * (theta - theta*) over the first `n_lim` elements of each tensor;
+// penalty partial sums (F*(theta-theta*)^2) go to partial[blockIdx] for a deterministic second stage.
+__global__ void ewc_grad_penalty_kernel(Flat6 theta, Flat6 fisher, Flat6 star, Flat6 grad, Flat6 lim, float scale2,
+                                        float *__restrict__ partial, int add_grad) {
+    __shared__ float red[256];
+    float local = 0.f;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int t = 0; t < 6; ++t) {
+        const int64_t n = lim.n[t];
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const float diff = theta.p[t][i] - star.p[t][i];
+            const float f = fisher.p[t][i];
+            local += f * diff * diff;
+            if (add_grad) grad.p[t][i] += scale2 * f * diff;
+        }
+    }
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// sum of squares of all gradients -> partial[blockIdx]
+__global__ void sumsq_kernel(Flat6 g, float *__restrict__ partial) {
+    __shared__ float red[256];
+    float local = 0.f;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int t = 0; t < 6; ++t)
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < g.n[t]; i += stride) {
+            const float v = g.p[t][i];
+            local = fmaf(v, v, local);
+        }
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// finalize: out[0] = scale * sum(partial) (ewc penalty) or sqrt(sum) (grad norm)
+__global__ void finalize_kernel(const float *__restrict__ partial, int n, float scale, int take_sqrt,
+                                float *__restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += partial[i];
+        out[0] = take_sqrt ? sqrtf(s) : scale * s;
+    }
+}
+
+// clip_grad_norm_ + AdamW (decoupled weight decay), one pass over all parameters
+__global__ void adamw_kernel(Flat6 theta, Flat6 grad, Flat6 m, Flat6 v, const float *__restrict__ gnorm, float lr,
+                             float b1, float b2, float eps, float wd, float max_norm, float bc1, float bc2_sqrt) {
+    const float total = gnorm[0];
+    float coef = max_norm / (total + 1e-6f);
+    coef = coef < 1.f ? coef : 1.f;
+    if (!(max_norm > 0.f)) coef = 1.f;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int t = 0; t < 6; ++t)
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < theta.n[t]; i += stride) {
+            const float g = grad.p[t][i] * coef;
+            float p = theta.p[t][i];
+            p = p * (1.f - lr * wd);
+            const float mi = m.p[t][i] * b1 + g * (1.f - b1);
+            const float vi = v.p[t][i] * b2 + g * g * (1.f - b2);
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            p = p - (lr / bc1) * (mi / denom);
+            theta.p[t][i] = p;
+            m.p[t][i] = mi;
+            v.p[t][i] = vi;
+        }
+}
+
+__global__ void fisher_accum_kernel(Flat6 grad, Flat6 fisher, float inv_n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int t = 0; t < 6; ++t)
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < grad.n[t]; i += stride) {
+            const float g = grad.p[t][i];
+            fisher.p[t][i] += g * g * inv_n;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout for a train / grad step
+// ------------------------------------------------------------------------------------------------
+struct TrainWs {
+    float *h0, *h1, *z, *dz, *dh1, *dh0, *mask0, *mask1, *row_loss, *partial, *gnorm;
+    ac_head_params g;   // gradients
+    size_t bytes;
+};
+constexpr int RED_BLOCKS = 64;
+
+static size_t carve(TrainWs &w, void *base, int B, const ac_head_params *p) {
+    uint8_t *ptr = static_cast<uint8_t *>(base);
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float *r = base ? reinterpret_cast<float *>(ptr + off) : nullptr;
+        off += align_up(floats * sizeof(float), 256);
+        return r;
+    };
+    w.h0 = take(static_cast<size_t>(B) * p->H0);
+    w.h1 = take(static_cast<size_t>(B) * p->H1);
+    w.z = take(static_cast<size_t>(B) * p->C);
+    w.dz = take(static_cast<size_t>(B) * p->C);
+    w.dh1 = take(static_cast<size_t>(B) * p->H1);
+    w.dh0 = take(static_cast<size_t>(B) * p->H0);
+    w.mask0 = take(static_cast<size_t>(B) * p->H0);
+    w.mask1 = take(static_cast<size_t>(B) * p->H1);
+    w.row_loss = take(B);
+    w.partial = take(RED_BLOCKS);
+    w.gnorm = take(4);
+    w.g = *p;
+    w.g.W0 = take(static_cast<size_t>(p->H0) * p->D);
+    w.g.b0 = take(p->H0);
+    w.g.W1 = take(static_cast<size_t>(p->H1) * p->H0);
+    w.g.b1 = take(p->H1);
+    w.g.W2 = take(static_cast<size_t>(p->C) * p->H1);
+    w.g.b2 = take(p->C);
+    w.bytes = off;
+    return off;
+}
+
+static int check_params(const ac_head_params *p, const char *who) {
+    AC_REQUIRE(p && p->D > 0 && p->H0 > 0 && p->H1 > 0 && p->C > 0, "%s: bad head dims", who);
+    AC_REQUIRE(p->W0 && p->b0 && p->W1 && p->b1 && p->W2 && p->b2, "%s: null head parameter", who);
+    return AC_OK;
+}
+
+// forward (optionally train mode with masks) + loss + backward into w.g
+static int fwd_bwd(const float *X, const void *targets, int B, const ac_head_params *p, int loss_kind,
+                   const float *mask0, const float *mask1, TrainWs &w, float *out_loss, cudaStream_t s) {
+    int rc;
+    const int D = p->D, H0 = p->H0, H1 = p->H1, C = p->C;
+    if ((rc = linear_fwd(X, p->W0, p->b0, w.h0, B, H0, D, EPI_BIAS_RELU_MASK, mask0, s))) return rc;
+    if ((rc = linear_fwd(w.h0, p->W1, p->b1, w.h1, B, H1, H0, EPI_BIAS_RELU_MASK, mask1, s))) return rc;
+    if ((rc = linear_fwd(w.h1, p->W2, p->b2, w.z, B, C, H1, EPI_BIAS, nullptr, s))) return rc;
+    const int wpb = 4;
+    loss_grad_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(w.z, targets, B, C, loss_kind, w.dz, w.row_loss);
+    AC_LAUNCH_CHECK();
+    reduce_loss_kernel<<<1, 32, 0, s>>>(w.row_loss, B, out_loss);
+    AC_LAUNCH_CHECK();
+    SgemmEpi none{EPI_NONE, nullptr, nullptr, nullptr};
+    // gW2[C,H1] = dz^T h1 : A(m=c,k=b) = dz[b*C+c], B(k=b,n=j) = h1[b*H1+j]
+    if ((rc = sgemm(w.dz, 1, C, w.h1, H1, 1, w.g.W2, H1, C, H1, B, none, s))) return rc;
+    colsum_kernel<<<(C + 127) / 128, 128, 0, s>>>(w.dz, B, C, w.g.b2);
+    AC_LAUNCH_CHECK();
+    // dh1[B,H1] = dz W2, then relu-grad + mask -> da1
+    SgemmEpi rg1{EPI_RELUGRAD_MASK, nullptr, mask1, w.h1};
+    if ((rc = sgemm(w.dz, C, 1, p->W2, H1, 1, w.dh1, H1, B, H1, C, rg1, s))) return rc;
+    if ((rc = sgemm(w.dh1, 1, H1, w.h0, H0, 1, w.g.W1, H0, H1, H0, B, none, s))) return rc;
+    colsum_kernel<<<(H1 + 127) / 128, 128, 0, s>>>(w.dh1, B, H1, w.g.b1);
+    AC_LAUNCH_CHECK();
+    SgemmEpi rg0{EPI_RELUGRAD_MASK, nullptr, mask0, w.h0};
+    if ((rc = sgemm(w.dh1, H1, 1, p->W1, H0, 1, w.dh0, H0, B, H0, H1, rg0, s))) return rc;
+    if ((rc = sgemm(w.dh0, 1, H0, X, D, 1, w.g.W0, D, H0, D, B, none, s))) return rc;
+    colsum_kernel<<<(H0 + 127) / 128, 128, 0, s>>>(w.dh0, B, H0, w.g.b0);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+}  // namespace ac
+
+using namespace ac;
+
+extern "C" int ac_head_forward(const float *X, int B, const ac_head_params *p, int act, float *out, float *scratch,
+                               size_t scratch_floats, ac_stream_t stream) {
+    int rc = check_params(p, "ac_head_forward");
+    if (rc) return rc;
+    AC_REQUIRE(X && out && B >= 0, "ac_head_forward: bad arguments");
+    if (B == 0) return AC_OK;
+    const size_t need = static_cast<size_t>(B) * (p->H0 + p->H1);
+    if (!scratch || scratch_floats < need) {
+        set_error("ac_head_forward: scratch needs %zu floats", need);
+        return AC_E_WORKSPACE;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float *h0 = scratch, *h1 = scratch + static_cast<size_t>(B) * p->H0;
+    if ((rc = linear_fwd(X, p->W0, p->b0, h0, B, p->H0, p->D, EPI_BIAS_RELU, nullptr, s))) return rc;
+    if ((rc = linear_fwd(h0, p->W1, p->b1, h1, B, p->H1, p->H0, EPI_BIAS_RELU, nullptr, s))) return rc;
+    if ((rc = linear_fwd(h1, p->W2, p->b2, out, B, p->C, p->H1, EPI_BIAS, nullptr, s))) return rc;
+    if (act == AC_ACT_SOFTMAX || act == AC_ACT_SIGMOID) {
+        const int wpb = 4;
+        softmax_rows_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(out, B, p->C, out, act);
+        AC_LAUNCH_CHECK();
+    }
+    return AC_OK;
+}
+
+extern "C" int ac_head_train_workspace_bytes(int B, const ac_head_params *p, size_t *bytes) {
+    AC_REQUIRE(p && bytes && B > 0, "ac_head_train_workspace_bytes: bad arguments");
+    TrainWs w;
+    *bytes = carve(w, nullptr, B, p) + 256;
+    return AC_OK;
+}
+
+extern "C" int ac_head_grad(const float *X, const void *targets, int B, const ac_head_params *p, int loss_kind,
+                            ac_head_params *grad_out, ac_head_params *fisher_accum, float inv_n_batches,
+                            float *out_loss, void *workspace, size_t workspace_bytes, ac_stream_t stream) {
+    int rc = check_params(p, "ac_head_grad");
+    if (rc) return rc;
+    AC_REQUIRE(X && targets && B > 0 && out_loss && workspace, "ac_head_grad: bad arguments");
+    TrainWs w;
+    const size_t need = carve(w, workspace, B, p);
+    if (need > workspace_bytes) { set_error("ac_head_grad: workspace needs %zu bytes", need); return AC_E_WORKSPACE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if ((rc = fwd_bwd(X, targets, B, p, loss_kind, nullptr, nullptr, w, out_loss, s))) return rc;
+    Flat6 g = flat_of(&w.g);
+    if (fisher_accum) {
+        Flat6 f = flat_of(fisher_accum);
+        fisher_accum_kernel<<<RED_BLOCKS, 256, 0, s>>>(g, f, inv_n_batches);
+        AC_LAUNCH_CHECK();
+    }
+    if (grad_out) {
+        Flat6 o = flat_of(grad_out);
+        for (int t = 0; t < 6; ++t)
+            AC_CUDA(cudaMemcpyAsync(o.p[t], g.p[t], g.n[t] * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return AC_OK;
+}
+
+static Flat6 ewc_limits(const ac_head_params *p, int C_old) {
+    // the head may have grown since theta* was taken: only the first C_old output rows are penalised
+    ac_head_params q = *p;
+    Flat6 f = flat_of(&q);
+    if (C_old > 0 && C_old < p->C) {
+        f.n[4] = static_cast<int64_t>(C_old) * p->H1;
+        f.n[5] = C_old;
+    }
+    return f;
+}
+
+extern "C" int ac_ewc_penalty(const ac_head_params *p, const ac_head_params *fisher, const ac_head_params *star,
+                              float lambda, float inv_batch, int C_old, float *out, ac_stream_t stream) {
+    int rc = check_params(p, "ac_ewc_penalty");
+    if (rc) return rc;
+    AC_REQUIRE(fisher && star && out, "ac_ewc_penalty: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float *partial = nullptr;
+    AC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&partial), RED_BLOCKS * sizeof(float), s));
+    Flat6 lim = ewc_limits(p, C_old);
+    ewc_grad_penalty_kernel<<<RED_BLOCKS, 256, 0, s>>>(flat_of(p), flat_of(fisher), flat_of(star), flat_of(p), lim, 0.f,
+                                                       partial, 0);
+    AC_LAUNCH_CHECK();
+    finalize_kernel<<<1, 32, 0, s>>>(partial, RED_BLOCKS, lambda * inv_batch, 0, out);
+    AC_LAUNCH_CHECK();
+    AC_CUDA(cudaFreeAsync(partial, s));
+    return AC_OK;
+}
+
+extern "C" int ac_head_train_step(const float *X, const void *targets, int B, ac_head_params *p, ac_head_params *m,
+                                  ac_head_params *v, const ac_train_cfg *cfg, float *out_stats, void *workspace,
+                                  size_t workspace_bytes, ac_stream_t stream) {
+    int rc = check_params(p, "ac_head_train_step");
+    if (rc) return rc;
+    AC_REQUIRE(X && targets && B > 0 && m && v && cfg && out_stats && workspace, "ac_head_train_step: bad arguments");
+    AC_REQUIRE(cfg->step >= 1, "ac_head_train_step: step must be >= 1");
+    TrainWs w;
+    const size_t need = carve(w, workspace, B, p);
+    if (need > workspace_bytes) { set_error("ac_head_train_step: workspace needs %zu bytes", need); return AC_E_WORKSPACE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    const float *mask0 = cfg->mask0, *mask1 = cfg->mask1;
+    if (cfg->dropout_p > 0.f && (!mask0 || !mask1)) {
+        const int64_t n0 = static_cast<int64_t>(B) * p->H0, n1 = static_cast<int64_t>(B) * p->H1;
+        dropout_mask_kernel<<<static_cast<unsigned>((n0 + 255) / 256), 256, 0, s>>>(w.mask0, n0, cfg->dropout_p, cfg->seed,
+                                                                                  2ull * cfg->step);
+        dropout_mask_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, s>>>(w.mask1, n1, cfg->dropout_p, cfg->seed,
+                                                                                  2ull * cfg->step + 1);
+        AC_LAUNCH_CHECK();
+        mask0 = w.mask0;
+        mask1 = w.mask1;
+    } else if (!(cfg->dropout_p > 0.f)) {
+        mask0 = mask1 = nullptr;
+    }
+    if ((rc = fwd_bwd(X, targets, B, p, cfg->loss_kind, mask0, mask1, w, out_stats + 0, s))) return rc;
+
+    Flat6 g = flat_of(&w.g);
+    if (cfg->ewc_fisher && cfg->ewc_star) {
+        Flat6 lim = ewc_limits(p, cfg->ewc_C_old);
+        const float scale = cfg->ewc_lambda / static_cast<float>(B);
+        ewc_grad_penalty_kernel<<<RED_BLOCKS, 256, 0, s>>>(flat_of(p), flat_of(cfg->ewc_fisher), flat_of(cfg->ewc_star), g,
+                                                           lim, 2.f * scale, w.partial, 1);
+        AC_LAUNCH_CHECK();
+        finalize_kernel<<<1, 32, 0, s>>>(w.partial, RED_BLOCKS, scale, 0, out_stats + 1);
+        AC_LAUNCH_CHECK();
+    } else {
+        AC_CUDA(cudaMemsetAsync(out_stats + 1, 0, sizeof(float), s));
+    }
+    sumsq_kernel<<<RED_BLOCKS, 256, 0, s>>>(g, w.partial);
+    AC_LAUNCH_CHECK();
+    finalize_kernel<<<1, 32, 0, s>>>(w.partial, RED_BLOCKS, 1.f, 1, out_stats + 2);
+    AC_LAUNCH_CHECK();
+    const float bc1 = 1.f - powf(cfg->beta1, static_cast<float>(cfg->step));
+    const float bc2 = 1.f - powf(cfg->beta2, static_cast<float>(cfg->step));
+    adamw_kernel<<<RED_BLOCKS * 2, 256, 0, s>>>(flat_of(p), g, flat_of(m), flat_of(v), out_stats + 2, cfg->lr, cfg->beta1,
+                                                cfg->beta2, cfg->eps, cfg->weight_decay, cfg->max_norm, bc1, sqrtf(bc2));
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}

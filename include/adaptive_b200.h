@@ -1,0 +1,209 @@
+/*
+ * adaptive_b200.h -- C ABI of libadaptive_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the predict()/add_examples() hot path of codelion/adaptive-classifier.
+ * The reference has no FFI of its own: the seams are Python object calls into third-party
+ * libraries.  Every entry point below names the reference call site it
+ * replaces (paths relative to /root/reference/).  The ctypes binding a maintainer would add is in
+ * INTEGRATION.md; adaptive_classifier_b200/_cabi.py is that binding.
+ *
+ * Conventions
+ *   - plain C types only; `ac_stream_t` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - unless a name ends in `_host`, every data pointer is a DEVICE pointer owned by the caller.
+ *   - all matrices are row-major, fp32, ids int64 unless stated; no hidden allocation after
+ *     `*_create` / explicit workspaces.
+ *   - return value: 0 = ok, negative = error (AC_E_*); text via ac_last_error() (thread-local).
+ *   - no CPU fallback exists: with no usable sm_100 device every compute call returns AC_E_CUDA.
+ */
+#ifndef ADAPTIVE_B200_H
+#define ADAPTIVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *ac_stream_t;
+
+enum {
+    AC_OK = 0,
+    AC_E_INVALID = -1,   /* bad argument (shape, null pointer, k > limit ...) */
+    AC_E_CUDA = -2,      /* CUDA runtime / launch failure, or no sm_100 device */
+    AC_E_WORKSPACE = -3, /* workspace too small */
+    AC_E_UNSUPPORTED = -4
+};
+
+int ac_version(void);                 /* ABI version, currently 1 */
+const char *ac_last_error(void);      /* thread-local message of the last failing call */
+int ac_device_check(void);            /* 0 when the current device is sm_100 (B200), else AC_E_CUDA */
+
+/* ------------------------------------------------------------------------------------------
+ * Stage K -- prototype kNN.  Replaces faiss.IndexFlatL2.search at
+ *   src/adaptive_classifier/memory.py:110-114 (call sites :34,106,113,114,158,159,164,172,182,190)
+ * ------------------------------------------------------------------------------------------ */
+
+/* algo selector for ac_knn_l2_topk */
+enum {
+    AC_KNN_AUTO = 0,
+    AC_KNN_EXACT = 1,   /* fp32 SIMT exact scan + radix select (any k <= AC_KNN_MAX_K)       */
+    AC_KNN_TENSOR = 2   /* tcgen05 kind::tf32 coarse pass + exact fp32 re-rank, k <= 16,
+                           every query certified against the coarse error bound, uncertified
+                           queries recomputed by the exact scan (indices identical either way) */
+};
+#define AC_KNN_MAX_K 2048
+
+/* bytes of scratch ac_knn_l2_topk needs for these sizes (device memory, 256-byte aligned) */
+int ac_knn_workspace_bytes(int B, int64_t N, int D, int k, int algo, size_t *bytes);
+
+/*
+ * out_d[B,k] ascending squared-L2 distances, out_i[B,k] int64 row ids (+row_offset); ties -> lower id;
+ * when N < k the tail is (+inf, -1)  [IndexFlatL2.search semantics, memory.py:113-114,121].
+ * Distances are the exact fp32 lane-ordered sum restated in oracle/knn_oracle.c (bit-identical).
+ * p_sqnorm[N] (nullable) = cached ||p||^2 for the tensor path; computed into the workspace if NULL.
+ */
+int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqnorm,
+                   int B, int64_t N, int D, int k,
+                   float *out_d, int64_t *out_i, int64_t row_offset,
+                   void *workspace, size_t workspace_bytes, int algo, ac_stream_t stream);
+
+/* ||p||^2 per row (fp32), the cache the tensor path consumes */
+int ac_row_sqnorm(const float *P, int64_t N, int D, float *out, ac_stream_t stream);
+
+/* multi-shard merge (new: row-sharded index over G GPUs); d[G,B,k], i[G,B,k]
+ * -> k smallest by (d, i); entries with i < 0 ignored.  Bit-identical to a single-shard search. */
+int ac_topk_merge(const float *d, const int64_t *i, int G, int B, int k,
+                  float *out_d, int64_t *out_i, ac_stream_t stream);
+
+/* memory.py:117,128-134: scores[b,:] = softmax_k(exp(-d[b,:])); entries with idx < 0 get 0 */
+int ac_proto_scores(const float *d, const int64_t *idx, int B, int k, float *scores, ac_stream_t stream);
+
+/* memory.py:149-150 (prototype = mean of the class's retained examples): rows X[n,D] with class id
+ * cls[n] in [0,C) -> mean[C,D], count[C]; classes with no rows keep mean = 0 */
+int ac_segment_mean(const float *X, const int32_t *cls, int64_t n, int D, int C,
+                    float *mean, int32_t *count, ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage H -- adaptive head.  Replaces nn.Module.__call__ / autograd / AdamW on AdaptiveHead:
+ *   forward  src/adaptive_classifier/models.py:71-80, classifier.py:428-442, :1341-1354
+ *   training classifier.py:333-351, :1489-1505, multilabel.py:387-397
+ * Weights in nn.Linear layout: W0[H0,D], W1[H1,H0], W2[C,H1]  (H0 = D, H1 = D/2 in the reference).
+ * ------------------------------------------------------------------------------------------ */
+enum { AC_ACT_LOGITS = 0, AC_ACT_SOFTMAX = 1, AC_ACT_SIGMOID = 2 };
+enum { AC_LOSS_CE = 0, AC_LOSS_BCE = 1 };
+
+typedef struct {
+    int D, H0, H1, C;
+    float *W0, *b0, *W1, *b1, *W2, *b2;
+} ac_head_params;
+
+/* eval-mode forward (dropout inactive).  out[B,C]; scratch >= B*(H0+H1) floats */
+int ac_head_forward(const float *X, int B, const ac_head_params *p, int act,
+                    float *out, float *scratch, size_t scratch_floats, ac_stream_t stream);
+
+typedef struct {
+    float lr, beta1, beta2, eps, weight_decay, max_norm; /* AdamW + clip_grad_norm_ */
+    int step;                /* 1-based count of this update (bias correction) */
+    int loss_kind;           /* AC_LOSS_CE: targets int64[B]; AC_LOSS_BCE: targets float[B,C] */
+    float dropout_p;         /* 0.1 in the reference; 0 disables */
+    const float *mask0;      /* optional injected dropout masks [B,H0], [B,H1] holding 0 or 1/(1-p);   */
+    const float *mask1;      /*   NULL -> Philox masks from (seed, step)                                */
+    uint64_t seed;
+    /* optional EWC term (ewc.py:96-115): grad += 2*lambda/B * F*(theta-theta*) over the first
+       ewc_rows_out rows of the output layer (the head may have grown), NULL = off */
+    const ac_head_params *ewc_fisher;
+    const ac_head_params *ewc_star;
+    float ewc_lambda;
+    int ewc_C_old;
+} ac_train_cfg;
+
+/* bytes of workspace for one train step at batch B */
+int ac_head_train_workspace_bytes(int B, const ac_head_params *p, size_t *bytes);
+
+/* one optimizer step: fwd(train) + loss + bwd + [EWC grad] + global-norm clip + AdamW.
+ * m, v: AdamW moments (same shapes as p).  out_stats[0] = task loss, [1] = ewc penalty,
+ * [2] = grad norm before clipping (device floats). */
+int ac_head_train_step(const float *X, const void *targets, int B,
+                       ac_head_params *p, ac_head_params *m, ac_head_params *v,
+                       const ac_train_cfg *cfg, float *out_stats,
+                       void *workspace, size_t workspace_bytes, ac_stream_t stream);
+
+/* gradient only (no update) of mean CE/BCE wrt all parameters, eval mode: the building block of
+ * EWC._compute_fisher (ewc.py:67-92).  fisher += grad^2 * inv_n_batches when fisher != NULL */
+int ac_head_grad(const float *X, const void *targets, int B, const ac_head_params *p, int loss_kind,
+                 ac_head_params *grad_out, ac_head_params *fisher_accum, float inv_n_batches,
+                 float *out_loss, void *workspace, size_t workspace_bytes, ac_stream_t stream);
+
+/* ewc.py:105-115: out[0] = lambda/bs * sum F*(theta-theta*)^2 over the parameters (C_old rows of the
+ * output layer) */
+int ac_ewc_penalty(const ac_head_params *p, const ac_head_params *fisher, const ac_head_params *star,
+                   float lambda, float inv_batch, int C_old, float *out, ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage E -- encoder.  Replaces `self.model(**inputs).last_hidden_state[:,0,:]` + F.normalize at
+ *   src/adaptive_classifier/classifier.py:1271-1275 (HF BertModel / RobertaModel forward).
+ * ------------------------------------------------------------------------------------------ */
+enum { AC_ARCH_BERT = 0, AC_ARCH_ROBERTA = 1 };
+enum {
+    AC_PREC_TF32 = 0,   /* tcgen05 kind::tf32, operands rounded to tf32 (RNE), fp32 accumulate */
+    AC_PREC_BF16 = 1    /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (2x rate, ~1.4e-3 distance error) */
+};
+
+typedef struct {
+    int arch;            /* AC_ARCH_* */
+    int layers, hidden, heads, intermediate;
+    int vocab, max_pos, type_vocab;
+    int pad_idx;         /* roberta: position ids start at pad_idx+1 */
+    float ln_eps;
+    int precision;       /* AC_PREC_* */
+    int max_tokens;      /* workspace is sized for B*S <= max_tokens */
+} ac_encoder_config;
+
+/* device pointers to the HF state_dict tensors (fp32, HF layout [out,in]) */
+typedef struct {
+    const float *word_emb, *pos_emb, *type_emb, *emb_ln_w, *emb_ln_b;
+    /* arrays of `layers` device pointers each (host arrays of device pointers) */
+    const float *const *q_w, *const *q_b, *const *k_w, *const *k_b, *const *v_w, *const *v_b;
+    const float *const *ao_w, *const *ao_b, *const *ao_ln_w, *const *ao_ln_b;
+    const float *const *ff1_w, *const *ff1_b, *const *ff2_w, *const *ff2_b;
+    const float *const *out_ln_w, *const *out_ln_b;
+} ac_encoder_weights;
+
+typedef struct ac_encoder ac_encoder;
+
+/* copies + repacks the weights (fused QKV, operand rounding) and allocates the activation workspace */
+int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_weights *w, ac_encoder **out);
+int ac_encoder_destroy(ac_encoder *enc);
+
+/* ids[B,S] int32 token ids, mask[B,S] int32 (1 keep / 0 pad; NULL = all ones), type_ids nullable.
+ * out_unit_cls[B,H] = L2-normalised (eps 1e-12) CLS row of the last hidden state. */
+int ac_encoder_forward_cls(ac_encoder *enc, const int32_t *ids, const int32_t *mask,
+                           const int32_t *type_ids, int B, int S, float *out_unit_cls,
+                           ac_stream_t stream);
+
+/* debugging / parity: copy the full last hidden state [B*S,H] of the previous forward */
+int ac_encoder_last_hidden(ac_encoder *enc, float *out, int64_t n_floats, ac_stream_t stream);
+
+/* generic tensor-core linear (the encoder's GEMM with its fused epilogues), exposed for parity
+ * tests and roofline measurement: Y[M,N] = epi(X[M,K] W[N,K]^T + bias) (+ residual).
+ * epi: 0 bias, 1 bias+GELU(erf), 2 bias+residual.  K % 32 == 0, N % 16 == 0.  precision AC_PREC_*:
+ * operands are used as stored (caller pre-rounds); round_out != 0 rounds Y to tf32 (RNE). */
+int ac_linear_tc(const float *X, const float *W, const float *bias, const float *residual,
+                 float *Y, int M, int N, int K, int epi, int round_out, ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * End-to-end convenience with HOST buffers (the e2e leg of bench.py): ids on (pinned) host memory
+ * -> H2D -> E -> K -> D2H of (d, i) [B,k].  All device buffers live in the handle.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ac_pipeline ac_pipeline;
+int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, int64_t N, int D,
+                       int max_B, int S, int k, int64_t row_offset, ac_pipeline **out);
+int ac_pipeline_destroy(ac_pipeline *pl);
+int ac_pipeline_embed_knn_host(ac_pipeline *pl, const int32_t *ids_host, int B,
+                               float *out_d_host, int64_t *out_i_host, ac_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAPTIVE_B200_H */
