@@ -1,0 +1,257 @@
+"""Host-side mirror of /root/reference/src/adaptive_classifier/memory.py (PrototypeMemory).
+
+Same bookkeeping, attribute names and error behaviour; `self.index` is a FlatL2Index living in B200 HBM
+(csrc/knn_exact.cu, csrc/knn_tc.cu) instead of faiss.IndexFlatL2.  Label aggregation and the
+`exp(-d)` -> softmax post-processing follow memory.py:117-134 exactly (on the device).
+"""
+from __future__ import annotations
+
+import logging
+from collections import defaultdict
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .models import Example, ModelConfig
+
+logger = logging.getLogger(__name__)
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _cabi.AdaptiveB200Error("adaptive_classifier_b200 needs a B200 GPU; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class FlatL2Index:
+    """Device-resident flat squared-L2 index with the faiss.IndexFlatL2 protocol the reference uses
+    (memory.py:34,106,113,114,158,159,164,172,182,190,242): add / search / remove_ids / ntotal."""
+
+    def __init__(self, d: int, capacity: int = 64):
+        self.d = int(d)
+        self._n = 0
+        self._buf: Optional[torch.Tensor] = None
+        self._cap = capacity
+
+    @property
+    def ntotal(self) -> int:
+        return self._n
+
+    def _rows(self) -> torch.Tensor:
+        return self._buf[: self._n]
+
+    def _ensure(self, extra: int):
+        need = self._n + extra
+        if self._buf is None or need > self._buf.shape[0]:
+            cap = max(self._cap, 2 * need)
+            nb = torch.empty((cap, self.d), dtype=torch.float32, device=_device())
+            if self._buf is not None and self._n:
+                nb[: self._n] = self._buf[: self._n]
+            self._buf = nb
+
+    def add(self, x):
+        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float32).reshape(-1, self.d)
+        self._ensure(x.shape[0])
+        self._buf[self._n : self._n + x.shape[0]] = x.to(self._buf.device)
+        self._n += x.shape[0]
+
+    def remove_ids(self, ids) -> int:
+        """faiss semantics: rows after a removed one shift down."""
+        ids = torch.as_tensor(ids).reshape(-1).to(torch.int64)
+        ids = ids[(ids >= 0) & (ids < self._n)].unique()
+        if ids.numel() == 0:
+            return 0
+        keep = torch.ones(self._n, dtype=torch.bool)
+        keep[ids] = False
+        kept = self._rows()[keep.to(self._buf.device)]
+        self._n = kept.shape[0]
+        self._buf[: self._n] = kept
+        return int(ids.numel())
+
+    def search_device(self, q: torch.Tensor, k: int):
+        """q [nq, d] CUDA fp32 -> (D [nq,k] fp32 ascending, I [nq,k] int64; (+inf, -1) padded)."""
+        return _cabi.knn_l2_topk(q, self._rows() if self._n else torch.empty((0, self.d), device=q.device), k)
+
+    def search(self, x, k: int):
+        """numpy in / numpy out like faiss (host convenience; device callers use search_device)."""
+        q = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float32).reshape(-1, self.d)
+        if self._n == 0:
+            nq = q.shape[0]
+            return (np.full((nq, k), np.inf, dtype=np.float32), np.full((nq, k), -1, dtype=np.int64))
+        d, i = self.search_device(q.to(_device()), int(k))
+        return d.cpu().numpy(), i.cpu().numpy()
+
+
+class PrototypeMemory:
+    """Memory system that maintains prototypes for each class (memory.py:11-245)."""
+
+    def __init__(self, embedding_dim: int, config: Optional[ModelConfig] = None):
+        self.embedding_dim = embedding_dim
+        self.config = config or ModelConfig()
+        self.examples = defaultdict(list)   # label -> List[Example]
+        self.prototypes = {}                # label -> tensor
+        self.strategic_prototypes = {}
+        self.index = FlatL2Index(embedding_dim)
+        self.label_to_index = {}
+        self.index_to_label = {}
+        self.updates_since_rebuild = 0
+
+    # ------------------------------------------------------------------ add path (memory.py:41-83)
+    def add_example(self, example: Example, label: str):
+        if example.embedding is None:
+            raise ValueError("Example must have an embedding")
+        if example.embedding.size(-1) != self.embedding_dim:
+            raise ValueError(
+                f"Example embedding dimension {example.embedding.size(-1)} "
+                f"does not match memory dimension {self.embedding_dim}")
+        self.examples[label].append(example)
+        if len(self.examples[label]) > self.config.max_examples_per_class:
+            self._prune_examples(label)
+        self._update_prototype(label)
+        if not getattr(self, "just_rebuilt", False):
+            self.updates_since_rebuild += 1
+        if self.updates_since_rebuild >= self.config.prototype_update_frequency:
+            self._rebuild_index()
+            self.just_rebuilt = True
+        else:
+            self.just_rebuilt = False
+
+    def add_examples_batch(self, examples: List[Example], labels: List[str]):
+        """Batched equivalent of calling add_example for each pair (same final state): when no class crosses
+        max_examples_per_class during the call, prototypes are recomputed once per touched class on the
+        device (ac_segment_mean) instead of once per example."""
+        cap = self.config.max_examples_per_class
+        counts = {}
+        for l in labels:
+            counts[l] = counts.get(l, 0) + 1
+        if any(len(self.examples[l]) + c > cap for l, c in counts.items()):
+            for ex, l in zip(examples, labels):
+                self.add_example(ex, l)
+            return
+        for ex, l in zip(examples, labels):
+            if ex.embedding is None:
+                raise ValueError("Example must have an embedding")
+            if ex.embedding.size(-1) != self.embedding_dim:
+                raise ValueError(
+                    f"Example embedding dimension {ex.embedding.size(-1)} "
+                    f"does not match memory dimension {self.embedding_dim}")
+        for ex, l in zip(examples, labels):
+            self.examples[l].append(ex)
+        touched = list(counts.keys())
+        self._update_prototypes_device(touched)
+        # same counter/rebuild behaviour as the per-example loop
+        for _ in examples:
+            if not getattr(self, "just_rebuilt", False):
+                self.updates_since_rebuild += 1
+            if self.updates_since_rebuild >= self.config.prototype_update_frequency:
+                self._rebuild_index()
+                self.just_rebuilt = True
+            else:
+                self.just_rebuilt = False
+
+    def _update_prototypes_device(self, labels: List[str]):
+        rows, cls = [], []
+        for ci, l in enumerate(labels):
+            for ex in self.examples[l]:
+                rows.append(ex.embedding)
+                cls.append(ci)
+        if not rows:
+            return
+        X = torch.stack([r.reshape(-1).float() for r in rows]).to(_device())
+        mean, _ = _cabi.segment_mean(X, torch.tensor(cls, dtype=torch.int32, device=X.device), len(labels))
+        mean = mean.cpu()
+        for ci, l in enumerate(labels):
+            self.prototypes[l] = mean[ci].clone()
+            if l in self.label_to_index:
+                idx = self.label_to_index[l]
+                self.index.remove_ids(torch.tensor([idx]))
+                self.index.add(self.prototypes[l].unsqueeze(0))
+
+    # ------------------------------------------------------------------ search (memory.py:85-136)
+    def get_nearest_prototypes(self, query_embedding: torch.Tensor, k: int = 5,
+                               min_similarity: Optional[float] = None) -> List[Tuple[str, float]]:
+        if self.updates_since_rebuild >= self.config.prototype_update_frequency:
+            self._rebuild_index()
+        if self.index.ntotal == 0:
+            return []
+        q = query_embedding.reshape(1, -1).to(device=_device(), dtype=torch.float32)
+        out = self.get_nearest_prototypes_batch(q, k)
+        return out[0]
+
+    def get_nearest_prototypes_batch(self, queries: torch.Tensor, k: int) -> List[List[Tuple[str, float]]]:
+        """Batched form (new): queries [B, D] CUDA fp32 -> per query the list memory.py:85-136 returns."""
+        if self.updates_since_rebuild >= self.config.prototype_update_frequency:
+            self._rebuild_index()
+        B = queries.shape[0]
+        if self.index.ntotal == 0:
+            return [[] for _ in range(B)]
+        k = min(k, self.index.ntotal)
+        d, i = self.index.search_device(queries.contiguous(), k)
+        scores = _cabi.proto_scores(d, i)
+        i_h = i.cpu().numpy()
+        s_h = scores.cpu().numpy()
+        res = []
+        for b in range(B):
+            row = []
+            for idx, sc in zip(i_h[b], s_h[b]):
+                if idx >= 0:
+                    row.append((self.index_to_label[int(idx)], float(sc)))
+            res.append(row)
+        return res
+
+    # ------------------------------------------------------------------ prototypes / index maintenance
+    def _update_prototype(self, label: str):
+        """memory.py:138-159: prototype = mean of the class's retained examples (device segment mean)."""
+        examples = self.examples[label]
+        if not examples:
+            return
+        self._update_prototypes_device([label])
+
+    def _rebuild_index(self):
+        """memory.py:161-177: rows in sorted(label) order."""
+        self.index = FlatL2Index(self.embedding_dim)
+        self.label_to_index.clear()
+        self.index_to_label.clear()
+        sorted_labels = sorted(self.prototypes.keys())
+        if sorted_labels:
+            self.index.add(torch.stack([self.prototypes[l].reshape(-1).float().cpu() for l in sorted_labels]))
+        for i, label in enumerate(sorted_labels):
+            self.label_to_index[label] = i
+            self.index_to_label[i] = label
+        self.updates_since_rebuild = 0
+
+    def _restore_from_save(self):
+        """memory.py:179-194."""
+        self._rebuild_index()
+
+    def _prune_examples(self, label: str):
+        """memory.py:196-217: keep the max_examples_per_class examples closest (L2) to the class mean."""
+        examples = self.examples[label]
+        if not examples:
+            return
+        X = torch.stack([ex.embedding.reshape(-1).float() for ex in examples]).to(_device())
+        mean, _ = _cabi.segment_mean(X, torch.zeros(X.shape[0], dtype=torch.int32, device=X.device), 1)
+        dist = torch.linalg.vector_norm(X - mean, dim=1).cpu().numpy()
+        keep = np.argsort(dist, kind="stable")[: self.config.max_examples_per_class]
+        self.examples[label] = [examples[i] for i in keep]
+        assert len(self.examples[label]) <= self.config.max_examples_per_class
+
+    # ------------------------------------------------------------------ stats / clear (memory.py:219-245)
+    def get_stats(self) -> Dict[str, Any]:
+        return {
+            "num_classes": len(self.prototypes),
+            "examples_per_class": {label: len(ex) for label, ex in self.examples.items()},
+            "total_examples": sum(len(ex) for ex in self.examples.values()),
+            "prototype_dimensions": self.embedding_dim,
+            "updates_since_rebuild": self.updates_since_rebuild,
+        }
+
+    def clear(self):
+        self.examples.clear()
+        self.prototypes.clear()
+        self.index = FlatL2Index(self.embedding_dim)
+        self.label_to_index.clear()
+        self.index_to_label.clear()
+        self.updates_since_rebuild = 0
