@@ -30,7 +30,9 @@ EXPORTS = [
     "ac_segment_mean",
     "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
-    "ac_pipeline_create", "ac_pipeline_destroy", "ac_pipeline_embed_knn_host",
+    "ac_proto_class_scores", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
+    "ac_pipeline_create", "ac_pipeline_destroy", "ac_pipeline_predict_device", "ac_pipeline_predict_host",
+    "ac_pipeline_debug_copy", "ac_launch_count", "ac_profile_enable", "ac_profile_read",
 ]
 
 
@@ -108,13 +110,25 @@ def load_library() -> ctypes.CDLL:
     L.ac_encoder_last_hidden.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     L.ac_linear_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]
-    L.ac_pipeline_create.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int64,
-                                     POINTER(c_void_p)]
+    L.ac_proto_class_scores.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.ac_topk_desc_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
+    L.ac_topk_desc.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.ac_blend_topk.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p]
+    L.ac_pipeline_create.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(HeadParams),
+                                     c_int, c_int, c_int, c_int64, POINTER(c_void_p)]
     L.ac_pipeline_destroy.argtypes = [c_void_p]
-    L.ac_pipeline_embed_knn_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.ac_pipeline_predict_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.ac_pipeline_predict_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.ac_pipeline_debug_copy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ac_profile_enable.argtypes = [c_int]
+    L.ac_profile_read.argtypes = [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                                  POINTER(ctypes.c_longlong)]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("ac_last_error",):
+        if name == "ac_launch_count":
+            fn.restype = ctypes.c_longlong
+        elif name not in ("ac_last_error",):
             fn.restype = c_int
     _lib = L
     return L
@@ -404,27 +418,106 @@ class Encoder:
             pass
 
 
-class Pipeline:
-    """Host-buffer end-to-end path (ids on host -> unit CLS -> kNN -> (d, i) on host)."""
+def proto_class_scores(d, idx, row_class=None):
+    L = load_library()
+    d = _f32c(d)
+    idx = idx.contiguous()
+    B, k = d.shape
+    cls = torch.empty((B, k), dtype=torch.int32, device=d.device)
+    sc = torch.empty((B, k), dtype=torch.float32, device=d.device)
+    check(L.ac_proto_class_scores(d.data_ptr(), idx.data_ptr(), ptr(row_class), B, k, cls.data_ptr(), sc.data_ptr(),
+                                  stream_ptr()), "ac_proto_class_scores")
+    return cls, sc
 
-    def __init__(self, enc: Encoder, P: torch.Tensor, max_B: int, S: int, k: int, p_sqnorm=None, row_offset: int = 0):
+
+def topk_desc(values: torch.Tensor, k: int):
+    """-> (vals [B,k] descending, idx [B,k] int64); ties -> lower index."""
+    L = load_library()
+    values = _f32c(values)
+    B, C = values.shape
+    nbytes = c_size_t(0)
+    check(L.ac_topk_desc_workspace_bytes(B, C, k, ctypes.byref(nbytes)), "ac_topk_desc_workspace_bytes")
+    ws = _workspace(nbytes.value, values.device)
+    neg = torch.empty((B, k), dtype=torch.float32, device=values.device)
+    idx = torch.empty((B, k), dtype=torch.int64, device=values.device)
+    check(L.ac_topk_desc(values.data_ptr(), B, C, k, neg.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
+                         stream_ptr()), "ac_topk_desc")
+    return -neg, idx
+
+
+def blend_topk(p_cls, p_score, h_idx, h_val, k: int, w_proto: float = 0.7, w_head: float = 0.3):
+    """h_val: head probabilities (descending) for h_idx, or None for prototype-only."""
+    L = load_library()
+    B = p_cls.shape[0]
+    kh = 0 if h_idx is None else h_idx.shape[1]
+    neg = (-h_val).contiguous() if h_val is not None else None
+    out_cls = torch.empty((B, k), dtype=torch.int32, device=p_cls.device)
+    out_sc = torch.empty((B, k), dtype=torch.float32, device=p_cls.device)
+    check(L.ac_blend_topk(p_cls.data_ptr(), p_score.data_ptr(), ptr(h_idx), ptr(neg), B, k, kh, w_proto, w_head,
+                          out_cls.data_ptr(), out_sc.data_ptr(), stream_ptr()), "ac_blend_topk")
+    return out_cls, out_sc
+
+
+def launch_count() -> int:
+    return int(load_library().ac_launch_count())
+
+
+def profile_enable(on: bool):
+    check(load_library().ac_profile_enable(1 if on else 0), "ac_profile_enable")
+
+
+def profile_read(cls: int):
+    ms, fl, by = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+    n = ctypes.c_longlong(0)
+    check(load_library().ac_profile_read(cls, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by), ctypes.byref(n)),
+          "ac_profile_read")
+    return {"ms": ms.value, "flops": fl.value, "bytes": by.value, "launches": n.value}
+
+
+class Pipeline:
+    """ids -> E -> K -> class scores -> H -> blend, device or host (pinned) buffers at the boundary."""
+
+    def __init__(self, enc: Encoder, P: torch.Tensor, max_B: int, S: int, k: int, *, head: Optional[dict] = None,
+                 row_class: Optional[torch.Tensor] = None, p_sqnorm: Optional[torch.Tensor] = None, row_offset: int = 0):
         L = load_library()
         self._L = L
-        self.enc, self.P, self.p_sqnorm = enc, _f32c(P), p_sqnorm
+        self.enc, self.P, self.p_sqnorm, self.row_class = enc, _f32c(P), p_sqnorm, row_class
+        self.head = head
         self.max_B, self.S, self.k = max_B, S, k
+        hp = head_params_struct(head) if head is not None else None
         h = c_void_p()
-        check(L.ac_pipeline_create(enc.handle, self.P.data_ptr(), ptr(p_sqnorm), self.P.shape[0], self.P.shape[1],
-                                   max_B, S, k, row_offset, ctypes.byref(h)), "ac_pipeline_create")
+        check(L.ac_pipeline_create(enc.handle, self.P.data_ptr(), ptr(p_sqnorm), ptr(row_class), self.P.shape[0],
+                                   self.P.shape[1], ctypes.byref(hp) if hp is not None else None, max_B, S, k,
+                                   row_offset, ctypes.byref(h)), "ac_pipeline_create")
         self.handle = h
-        self.out_d = torch.empty((max_B, k), dtype=torch.float32).pin_memory()
-        self.out_i = torch.empty((max_B, k), dtype=torch.int64).pin_memory()
+        self.out_cls_host = torch.empty((max_B, k), dtype=torch.int32).pin_memory()
+        self.out_score_host = torch.empty((max_B, k), dtype=torch.float32).pin_memory()
+        self.out_cls = torch.empty((max_B, k), dtype=torch.int32, device=self.P.device)
+        self.out_score = torch.empty((max_B, k), dtype=torch.float32, device=self.P.device)
 
-    def run(self, ids_host: torch.Tensor):
+    def predict_device(self, ids_dev: torch.Tensor, mask_dev: Optional[torch.Tensor] = None):
+        B = ids_dev.shape[0]
+        check(self._L.ac_pipeline_predict_device(self.handle, ids_dev.data_ptr(), ptr(mask_dev), B,
+                                                 self.out_cls.data_ptr(), self.out_score.data_ptr(), stream_ptr()),
+              "ac_pipeline_predict_device")
+        return self.out_cls[:B], self.out_score[:B]
+
+    def predict_host(self, ids_host: torch.Tensor):
         assert (not ids_host.is_cuda) and ids_host.dtype == torch.int32 and ids_host.is_contiguous()
         B = ids_host.shape[0]
-        check(self._L.ac_pipeline_embed_knn_host(self.handle, ids_host.data_ptr(), B, self.out_d.data_ptr(),
-                                                 self.out_i.data_ptr(), stream_ptr()), "ac_pipeline_embed_knn_host")
-        return self.out_d[:B], self.out_i[:B]
+        check(self._L.ac_pipeline_predict_host(self.handle, ids_host.data_ptr(), B, self.out_cls_host.data_ptr(),
+                                               self.out_score_host.data_ptr(), stream_ptr()), "ac_pipeline_predict_host")
+        return self.out_cls_host[:B], self.out_score_host[:B]
+
+    def debug_views(self, B: int):
+        """(emb [B,D], knn_d [B,k], knn_i [B,k]) of the last call."""
+        D = self.P.shape[1]
+        emb = torch.empty((B, D), dtype=torch.float32, device=self.P.device)
+        kd = torch.empty((B, self.k), dtype=torch.float32, device=self.P.device)
+        ki = torch.empty((B, self.k), dtype=torch.int64, device=self.P.device)
+        check(self._L.ac_pipeline_debug_copy(self.handle, B, emb.data_ptr(), kd.data_ptr(), ki.data_ptr(), stream_ptr()),
+              "ac_pipeline_debug_copy")
+        return emb, kd, ki
 
     def close(self):
         if getattr(self, "handle", None):

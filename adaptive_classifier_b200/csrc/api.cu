@@ -3,7 +3,9 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cudaTypedefs.h>
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace ac {
 
@@ -20,6 +22,50 @@ int check_cuda(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return AC_OK;
     set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
     return AC_E_CUDA;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfSlot { cudaEvent_t a, b; int cls; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfSlot> g_prof_slots;
+static size_t g_prof_used = 0;
+static double g_prof_ms[PROF_NUM], g_prof_flops[PROF_NUM], g_prof_bytes[PROF_NUM];
+static long long g_prof_n[PROF_NUM];
+
+static void prof_harvest() {
+    cudaDeviceSynchronize();
+    for (size_t i = 0; i < g_prof_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof_slots[i].a, g_prof_slots[i].b) == cudaSuccess) {
+            const int c = g_prof_slots[i].cls;
+            g_prof_ms[c] += ms; g_prof_flops[c] += g_prof_slots[i].flops; g_prof_bytes[c] += g_prof_slots[i].bytes;
+            g_prof_n[c] += 1;
+        }
+    }
+    g_prof_used = 0;
+}
+
+int prof_begin(int cls, double flops, double bytes, cudaStream_t s) {
+    if (!g_prof_on) return -1;
+    if (g_prof_used == g_prof_slots.size()) {
+        if (g_prof_slots.size() >= 8192) {
+            prof_harvest();
+        } else {
+            ProfSlot p{};
+            if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return -1;
+            g_prof_slots.push_back(p);
+        }
+    }
+    ProfSlot &p = g_prof_slots[g_prof_used];
+    p.cls = cls; p.flops = flops; p.bytes = bytes;
+    cudaEventRecord(p.a, s);
+    return static_cast<int>(g_prof_used++);
+}
+void prof_end(int slot, cudaStream_t s) {
+    if (slot < 0) return;
+    cudaEventRecord(g_prof_slots[slot].b, s);
 }
 
 int sm_count() {
@@ -125,6 +171,25 @@ static int resolve_algo(int algo, int B, int64_t N, int D, int k) {
 using namespace ac;
 
 extern "C" int ac_version(void) { return 1; }
+extern "C" long long ac_launch_count(void) { return g_launches.load(); }
+extern "C" int ac_profile_enable(int on) {
+    if (on && !g_prof_on) {
+        for (int c = 0; c < PROF_NUM; ++c) { g_prof_ms[c] = g_prof_flops[c] = g_prof_bytes[c] = 0; g_prof_n[c] = 0; }
+        g_prof_used = 0;
+    }
+    if (!on && g_prof_on) prof_harvest();
+    g_prof_on = on != 0;
+    return AC_OK;
+}
+extern "C" int ac_profile_read(int cls, double *ms, double *flops, double *bytes, long long *launches) {
+    AC_REQUIRE(cls >= 0 && cls < PROF_NUM, "ac_profile_read: bad class");
+    prof_harvest();
+    if (ms) *ms = g_prof_ms[cls];
+    if (flops) *flops = g_prof_flops[cls];
+    if (bytes) *bytes = g_prof_bytes[cls];
+    if (launches) *launches = g_prof_n[cls];
+    return AC_OK;
+}
 extern "C" const char *ac_last_error(void) { return g_err; }
 
 extern "C" int ac_device_check(void) {
@@ -185,59 +250,3 @@ int knn_exact_subset(const float *Q, const float *P, int B, int64_t N, int D, in
 size_t knn_exact_workspace_pub(int B, int64_t N, int k) { return knn_exact_workspace(B, N, k); }
 }  // namespace ac
 
-// ================================================================================================
-// host-buffer pipeline: ids (host) -> E -> K -> (d, i) (host)
-// ================================================================================================
-struct ac_pipeline {
-    ac_encoder *enc;
-    const float *P, *p_sqnorm;
-    int64_t N, row_offset;
-    int D, max_B, S, k;
-    int32_t *ids_dev;
-    float *emb, *out_d;
-    int64_t *out_i;
-    void *ws;
-    size_t ws_bytes;
-};
-
-extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, int64_t N, int D, int max_B,
-                                  int S, int k, int64_t row_offset, ac_pipeline **out) {
-    AC_REQUIRE(enc && P && out && N > 0 && D > 0 && max_B > 0 && S > 0 && k >= 1, "ac_pipeline_create: bad arguments");
-    ac_pipeline *pl = new ac_pipeline();
-    pl->enc = enc; pl->P = P; pl->p_sqnorm = p_sqnorm; pl->N = N; pl->row_offset = row_offset;
-    pl->D = D; pl->max_B = max_B; pl->S = S; pl->k = k;
-    int rc = ac_knn_workspace_bytes(max_B, N, D, k, AC_KNN_AUTO, &pl->ws_bytes);
-    if (rc) { delete pl; return rc; }
-    cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&pl->ids_dev), sizeof(int32_t) * max_B * S);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&pl->emb), sizeof(float) * max_B * D);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&pl->out_d), sizeof(float) * max_B * k);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&pl->out_i), sizeof(int64_t) * max_B * k);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->ws, pl->ws_bytes);
-    if (e != cudaSuccess) { delete pl; return check_cuda(e, "ac_pipeline_create cudaMalloc"); }
-    *out = pl;
-    return AC_OK;
-}
-
-extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
-    if (!pl) return AC_OK;
-    cudaFree(pl->ids_dev); cudaFree(pl->emb); cudaFree(pl->out_d); cudaFree(pl->out_i); cudaFree(pl->ws);
-    delete pl;
-    return AC_OK;
-}
-
-extern "C" int ac_pipeline_embed_knn_host(ac_pipeline *pl, const int32_t *ids_host, int B, float *out_d_host,
-                                          int64_t *out_i_host, ac_stream_t stream) {
-    AC_REQUIRE(pl && ids_host && out_d_host && out_i_host && B > 0 && B <= pl->max_B, "ac_pipeline_embed_knn_host: bad arguments");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    AC_CUDA(cudaMemcpyAsync(pl->ids_dev, ids_host, sizeof(int32_t) * B * pl->S, cudaMemcpyHostToDevice, s));
-    int rc = ac_encoder_forward_cls(pl->enc, pl->ids_dev, nullptr, nullptr, B, pl->S, pl->emb, stream);
-    if (rc) return rc;
-    rc = ac_knn_l2_topk(pl->emb, pl->P, pl->p_sqnorm, B, pl->N, pl->D, pl->k, pl->out_d, pl->out_i, pl->row_offset, pl->ws,
-                        pl->ws_bytes, AC_KNN_AUTO, stream);
-    if (rc) return rc;
-    AC_CUDA(cudaMemcpyAsync(out_d_host, pl->out_d, sizeof(float) * B * pl->k, cudaMemcpyDeviceToHost, s));
-    AC_CUDA(cudaMemcpyAsync(out_i_host, pl->out_i, sizeof(int64_t) * B * pl->k, cudaMemcpyDeviceToHost, s));
-    AC_CUDA(cudaStreamSynchronize(s));
-    return AC_OK;
-}

@@ -31,7 +31,18 @@ int check_cuda(cudaError_t e, const char *what);
         }                                                            \
     } while (0)
 
-#define AC_LAUNCH_CHECK() AC_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here: the counter backs bench.py's `gpu_launches`
+void count_launch();
+#define AC_LAUNCH_CHECK()                                            \
+    do {                                                             \
+        ::ac::count_launch();                                        \
+        AC_CUDA(cudaGetLastError());                                 \
+    } while (0)
+
+// optional CUDA-event timing of individual launches on their own stream (roofline numbers of bench.py)
+enum { PROF_GEMM_LINEAR = 0, PROF_ATTENTION = 1, PROF_KNN_COARSE = 2, PROF_KNN_EXACT = 3, PROF_NUM = 4 };
+int prof_begin(int cls, double flops, double bytes, cudaStream_t s);   // slot id or -1 when disabled
+void prof_end(int slot, cudaStream_t s);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();

@@ -507,7 +507,12 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     for (int l = 0; l < c.layers; ++l) {
         EpiLinear eq{e->bqkv[l], nullptr, e->qkv, M, 3 * H, 0, 1};
         if ((rc = launch_gemm_tf32(e->m_xr, e->m_wqkv[l], M, 3 * H, H, eq, s))) return rc;
-        attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qkv_att, e->qkv, mask, B, S, c.heads, H, e->ctx);
+        {
+            // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
+            const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
+            attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qkv_att, e->qkv, mask, B, S, c.heads, H, e->ctx);
+            prof_end(slot, s);
+        }
         AC_LAUNCH_CHECK();
         EpiLinear eo{e->bo[l], e->x, e->tmp, M, H, 2, 0};
         if ((rc = launch_gemm_tf32(e->m_ctx, e->m_wo[l], M, H, H, eo, s))) return rc;

@@ -196,7 +196,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // host-side launcher
 template <class Epi, bool kMFastest = false>
 int launch_gemm_tf32(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
-                     cudaStream_t stream, int max_ctas = 0) {
+                     cudaStream_t stream, int max_ctas = 0, int prof_cls = PROF_GEMM_LINEAR, double prof_bytes = 0.0) {
     static bool attr_set = false;   // per instantiation
     auto kern = gemm_tf32_kernel<Epi, kMFastest>;
     if (!attr_set) {
@@ -208,7 +208,9 @@ int launch_gemm_tf32(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N,
     if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
     if (tiles < ctas) ctas = tiles;
     if (ctas <= 0) return AC_OK;
+    const int slot = prof_begin(prof_cls, 2.0 * M * static_cast<double>(N) * K, prof_bytes, stream);
     kern<<<ctas, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+    prof_end(slot, stream);
     AC_LAUNCH_CHECK();
     return AC_OK;
 }

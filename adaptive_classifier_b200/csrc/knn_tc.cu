@@ -315,7 +315,9 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, 
     if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
     if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
     EpiKnn epi{pn_use, ckey, cidx, B, N, pl.tiles_m, pl.slots};
-    if ((rc = launch_gemm_tf32<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid))) return rc;
+    // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes)
+    if ((rc = launch_gemm_tf32<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid,
+                                              PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D))) return rc;
 
     // ---- merge per-CTA lists, pick KP candidates + exclusion threshold
     const int64_t nc = static_cast<int64_t>(B) * pl.slots * KNN_KC;

@@ -1,0 +1,261 @@
+// predict.cu -- the glue of predict_batch() on the device and the end-to-end pipeline handle.
+//
+//   ac_proto_class_scores   memory.py:117-134 generalised to many rows per class: the k
+//                           nearest ROWS are mapped to classes, a class keeps its nearest row, scores =
+//                           softmax(exp(-d)) over the distinct classes returned.  With one row per class
+//                           (the reference's own usage) this is exactly memory.py:117-134.
+//   ac_topk_desc            classifier.py:1347-1350 (torch.topk of the head probabilities)
+//   ac_blend_topk           classifier.py:1358-1384: 0.7 * prototype score + 0.3 * head probability per label,
+//                           stable descending sort, normalise by the sum, keep k
+//   ac_pipeline_*           E -> K -> H -> blend with device or host (pinned) buffers at the boundary
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace ac {
+size_t topk_select_workspace(int B, int64_t L, int k);
+int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in_stride, int64_t id_offset, int k,
+                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream);
+
+constexpr int BLEND_MAX_K = 32;
+
+// one thread per query (k <= 32): dedupe by class keeping the first (nearest) row
+__global__ void proto_class_scores_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx,
+                                          const int32_t *__restrict__ row_class, int B, int k,
+                                          int32_t *__restrict__ out_cls, float *__restrict__ out_score) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int32_t cls[BLEND_MAX_K];
+    float sc[BLEND_MAX_K];
+    int n = 0;
+    for (int j = 0; j < k; ++j) {
+        const int64_t id = idx[static_cast<int64_t>(b) * k + j];
+        if (id < 0) continue;
+        const int32_t c = row_class ? row_class[id] : static_cast<int32_t>(id);
+        bool seen = false;
+        for (int t = 0; t < n; ++t) seen |= (cls[t] == c);
+        if (seen) continue;
+        cls[n] = c;
+        sc[n] = expf(-d[static_cast<int64_t>(b) * k + j]);
+        ++n;
+    }
+    float mx = -CUDART_INF_F, sum = 0.f;
+    for (int t = 0; t < n; ++t) mx = fmaxf(mx, sc[t]);
+    for (int t = 0; t < n; ++t) { sc[t] = expf(sc[t] - mx); sum += sc[t]; }
+    for (int j = 0; j < k; ++j) {
+        out_cls[static_cast<int64_t>(b) * k + j] = j < n ? cls[j] : -1;
+        out_score[static_cast<int64_t>(b) * k + j] = j < n ? sc[j] / sum : 0.f;
+    }
+}
+
+__global__ void negate_kernel(const float *__restrict__ in, int64_t n, float *__restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = -in[i];
+}
+
+// classifier.py:1358-1384 with integer labels; insertion order = prototype entries then head-only entries,
+// stable descending sort (Python's sorted(..., reverse=True) keeps insertion order on ties)
+__global__ void blend_topk_kernel(const int32_t *__restrict__ p_cls, const float *__restrict__ p_score,
+                                  const int64_t *__restrict__ h_idx, const float *__restrict__ h_val, int B, int k,
+                                  int kh, float w_proto, float w_head, int32_t *__restrict__ out_cls,
+                                  float *__restrict__ out_score) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int32_t cls[2 * BLEND_MAX_K];
+    float sc[2 * BLEND_MAX_K];
+    int n = 0;
+    for (int j = 0; j < k; ++j) {
+        const int32_t c = p_cls[static_cast<int64_t>(b) * k + j];
+        if (c < 0) continue;
+        cls[n] = c;
+        sc[n] = p_score[static_cast<int64_t>(b) * k + j] * w_proto;
+        ++n;
+    }
+    for (int j = 0; j < kh; ++j) {
+        const int32_t c = static_cast<int32_t>(h_idx[static_cast<int64_t>(b) * kh + j]);
+        if (c < 0) continue;
+        const float v = -h_val[static_cast<int64_t>(b) * kh + j] * w_head;   // h_val holds the NEGATED probabilities
+        int t = 0;
+        for (; t < n; ++t)
+            if (cls[t] == c) break;
+        if (t < n) sc[t] += v;
+        else { cls[n] = c; sc[n] = v; ++n; }
+    }
+    // stable insertion sort, descending
+    for (int i = 1; i < n; ++i) {
+        const int32_t c = cls[i];
+        const float v = sc[i];
+        int j = i - 1;
+        while (j >= 0 && sc[j] < v) { cls[j + 1] = cls[j]; sc[j + 1] = sc[j]; --j; }
+        cls[j + 1] = c; sc[j + 1] = v;
+    }
+    float total = 0.f;
+    for (int t = 0; t < n; ++t) total += sc[t];
+    for (int j = 0; j < k; ++j) {
+        const bool ok = j < n;
+        out_cls[static_cast<int64_t>(b) * k + j] = ok ? cls[j] : -1;
+        out_score[static_cast<int64_t>(b) * k + j] = ok ? (total > 0.f ? sc[j] / total : sc[j]) : 0.f;
+    }
+}
+
+}  // namespace ac
+
+using namespace ac;
+
+extern "C" int ac_proto_class_scores(const float *d, const int64_t *idx, const int32_t *row_class, int B, int k,
+                                     int32_t *out_cls, float *out_score, ac_stream_t stream) {
+    AC_REQUIRE(d && idx && out_cls && out_score && B >= 0, "ac_proto_class_scores: bad arguments");
+    AC_REQUIRE(k >= 1 && k <= BLEND_MAX_K, "ac_proto_class_scores: k=%d outside [1,%d]", k, BLEND_MAX_K);
+    if (B == 0) return AC_OK;
+    proto_class_scores_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d, idx, row_class, B, k,
+                                                                                              out_cls, out_score);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+extern "C" int ac_topk_desc_workspace_bytes(int B, int C, int k, size_t *bytes) {
+    AC_REQUIRE(bytes && B >= 0 && C >= 1 && k >= 1, "ac_topk_desc_workspace_bytes: bad arguments");
+    *bytes = align_up(static_cast<size_t>(B) * C * sizeof(float), 256) + topk_select_workspace(B, C, k) + 512;
+    return AC_OK;
+}
+
+// out_neg_vals[B,k] = NEGATED values in ascending order (i.e. the k largest values, descending, negated);
+// ties -> lower index.  (Negated so that the (d, id) selection kernel is reused unchanged.)
+extern "C" int ac_topk_desc(const float *values, int B, int C, int k, float *out_neg_vals, int64_t *out_idx,
+                            void *workspace, size_t workspace_bytes, ac_stream_t stream) {
+    AC_REQUIRE(values && out_neg_vals && out_idx && workspace && B >= 0 && C >= 1 && k >= 1 && k <= AC_KNN_MAX_K,
+               "ac_topk_desc: bad arguments");
+    if (B == 0) return AC_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t *w = reinterpret_cast<uint8_t *>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+    const size_t slack = w - static_cast<uint8_t *>(workspace);
+    const size_t nb = align_up(static_cast<size_t>(B) * C * sizeof(float), 256);
+    if (slack + nb > workspace_bytes) { set_error("ac_topk_desc: workspace too small"); return AC_E_WORKSPACE; }
+    float *neg = reinterpret_cast<float *>(w);
+    const int64_t n = static_cast<int64_t>(B) * C;
+    negate_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(values, n, neg);
+    AC_LAUNCH_CHECK();
+    return topk_select(neg, nullptr, B, C, C, 0, k, out_neg_vals, out_idx, w + nb, workspace_bytes - slack - nb, s);
+}
+
+extern "C" int ac_blend_topk(const int32_t *proto_cls, const float *proto_score, const int64_t *head_idx,
+                             const float *head_neg_val, int B, int k, int kh, float w_proto, float w_head,
+                             int32_t *out_cls, float *out_score, ac_stream_t stream) {
+    AC_REQUIRE(proto_cls && proto_score && out_cls && out_score && B >= 0, "ac_blend_topk: bad arguments");
+    AC_REQUIRE(k >= 1 && k <= BLEND_MAX_K && kh >= 0 && kh <= BLEND_MAX_K, "ac_blend_topk: k/kh outside [1,%d]", BLEND_MAX_K);
+    AC_REQUIRE(kh == 0 || (head_idx && head_neg_val), "ac_blend_topk: null head inputs");
+    if (B == 0) return AC_OK;
+    blend_topk_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        proto_cls, proto_score, head_idx, head_neg_val, B, k, kh, w_proto, w_head, out_cls, out_score);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+// ================================================================================================
+// pipeline: ids -> E -> K -> class scores -> H -> top-k -> blend
+// ================================================================================================
+struct ac_pipeline {
+    ac_encoder *enc;
+    const float *P, *p_sqnorm;
+    const int32_t *row_class;
+    ac_head_params head;
+    bool has_head;
+    int64_t N, row_offset;
+    int D, max_B, S, k, kh;
+    int32_t *ids_dev, *p_cls, *out_cls;
+    float *emb, *knn_d, *p_score, *probs, *h_val, *out_score, *scratch;
+    int64_t *knn_i, *h_idx;
+    void *ws, *ws_topk;
+    size_t ws_bytes, ws_topk_bytes, scratch_floats;
+};
+
+extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
+    if (!pl) return AC_OK;
+    void *ptrs[] = {pl->ids_dev, pl->p_cls, pl->out_cls, pl->emb, pl->knn_d, pl->p_score, pl->probs, pl->h_val,
+                    pl->out_score, pl->scratch, pl->knn_i, pl->h_idx, pl->ws, pl->ws_topk};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete pl;
+    return AC_OK;
+}
+
+extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const int32_t *row_class,
+                                  int64_t N, int D, const ac_head_params *head, int max_B, int S, int k,
+                                  int64_t row_offset, ac_pipeline **out) {
+    AC_REQUIRE(enc && P && out && N > 0 && D > 0 && max_B > 0 && S > 0, "ac_pipeline_create: bad arguments");
+    AC_REQUIRE(k >= 1 && k <= 16, "ac_pipeline_create: k=%d outside [1,16]", k);
+    ac_pipeline *pl = new ac_pipeline();
+    memset(pl, 0, sizeof(*pl));
+    pl->enc = enc; pl->P = P; pl->p_sqnorm = p_sqnorm; pl->row_class = row_class; pl->N = N; pl->row_offset = row_offset;
+    pl->D = D; pl->max_B = max_B; pl->S = S; pl->k = k;
+    pl->has_head = head != nullptr;
+    if (head) { pl->head = *head; pl->kh = k < head->C ? k : head->C; }
+    int rc = ac_knn_workspace_bytes(max_B, N, D, k, AC_KNN_AUTO, &pl->ws_bytes);
+    if (rc) { delete pl; return rc; }
+    const size_t C = head ? head->C : 1;
+    pl->scratch_floats = head ? static_cast<size_t>(max_B) * (head->H0 + head->H1) : 1;
+    if (head) ac_topk_desc_workspace_bytes(max_B, head->C, pl->kh, &pl->ws_topk_bytes); else pl->ws_topk_bytes = 256;
+    cudaError_t e = cudaSuccess;
+    auto al = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 256); };
+    al(reinterpret_cast<void **>(&pl->ids_dev), sizeof(int32_t) * max_B * S);
+    al(reinterpret_cast<void **>(&pl->emb), sizeof(float) * max_B * D);
+    al(reinterpret_cast<void **>(&pl->knn_d), sizeof(float) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->knn_i), sizeof(int64_t) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->p_cls), sizeof(int32_t) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->p_score), sizeof(float) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->probs), sizeof(float) * max_B * C);
+    al(reinterpret_cast<void **>(&pl->h_val), sizeof(float) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->h_idx), sizeof(int64_t) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->out_cls), sizeof(int32_t) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->out_score), sizeof(float) * max_B * k);
+    al(reinterpret_cast<void **>(&pl->scratch), sizeof(float) * pl->scratch_floats);
+    al(&pl->ws, pl->ws_bytes);
+    al(&pl->ws_topk, pl->ws_topk_bytes);
+    if (e != cudaSuccess) { ac_pipeline_destroy(pl); return check_cuda(e, "ac_pipeline_create cudaMalloc"); }
+    *out = pl;
+    return AC_OK;
+}
+
+// device entry: ids_dev[B,S] int32 (device) -> out_cls_dev[B,k] int32, out_score_dev[B,k] fp32 (device)
+extern "C" int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B,
+                                          int32_t *out_cls_dev, float *out_score_dev, ac_stream_t stream) {
+    AC_REQUIRE(pl && ids_dev && out_cls_dev && out_score_dev && B > 0 && B <= pl->max_B, "ac_pipeline_predict_device: bad arguments");
+    int rc = ac_encoder_forward_cls(pl->enc, ids_dev, mask_dev, nullptr, B, pl->S, pl->emb, stream);
+    if (rc) return rc;
+    rc = ac_knn_l2_topk(pl->emb, pl->P, pl->p_sqnorm, B, pl->N, pl->D, pl->k, pl->knn_d, pl->knn_i, pl->row_offset, pl->ws,
+                        pl->ws_bytes, AC_KNN_AUTO, stream);
+    if (rc) return rc;
+    rc = ac_proto_class_scores(pl->knn_d, pl->knn_i, pl->row_class, B, pl->k, pl->p_cls, pl->p_score, stream);
+    if (rc) return rc;
+    if (pl->has_head) {
+        rc = ac_head_forward(pl->emb, B, &pl->head, AC_ACT_SOFTMAX, pl->probs, pl->scratch, pl->scratch_floats, stream);
+        if (rc) return rc;
+        rc = ac_topk_desc(pl->probs, B, pl->head.C, pl->kh, pl->h_val, pl->h_idx, pl->ws_topk, pl->ws_topk_bytes, stream);
+        if (rc) return rc;
+    }
+    return ac_blend_topk(pl->p_cls, pl->p_score, pl->h_idx, pl->h_val, B, pl->k, pl->has_head ? pl->kh : 0, 0.7f, 0.3f,
+                         out_cls_dev, out_score_dev, stream);
+}
+
+// host entry: ids_host[B,S] (pinned) -> H2D -> predict -> D2H of [B,k] class ids + scores, stream-synchronised
+extern "C" int ac_pipeline_predict_host(ac_pipeline *pl, const int32_t *ids_host, int B, int32_t *out_cls_host,
+                                        float *out_score_host, ac_stream_t stream) {
+    AC_REQUIRE(pl && ids_host && out_cls_host && out_score_host && B > 0 && B <= pl->max_B, "ac_pipeline_predict_host: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AC_CUDA(cudaMemcpyAsync(pl->ids_dev, ids_host, sizeof(int32_t) * B * pl->S, cudaMemcpyHostToDevice, s));
+    int rc = ac_pipeline_predict_device(pl, pl->ids_dev, nullptr, B, pl->out_cls, pl->out_score, stream);
+    if (rc) return rc;
+    AC_CUDA(cudaMemcpyAsync(out_cls_host, pl->out_cls, sizeof(int32_t) * B * pl->k, cudaMemcpyDeviceToHost, s));
+    AC_CUDA(cudaMemcpyAsync(out_score_host, pl->out_score, sizeof(float) * B * pl->k, cudaMemcpyDeviceToHost, s));
+    AC_CUDA(cudaStreamSynchronize(s));
+    return AC_OK;
+}
+
+// intermediate results of the last predict call (parity tests): copied into caller-owned device buffers
+extern "C" int ac_pipeline_debug_copy(ac_pipeline *pl, int B, float *emb_out, float *knn_d_out, int64_t *knn_i_out,
+                                      ac_stream_t stream) {
+    AC_REQUIRE(pl && B > 0 && B <= pl->max_B, "ac_pipeline_debug_copy: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (emb_out) AC_CUDA(cudaMemcpyAsync(emb_out, pl->emb, sizeof(float) * B * pl->D, cudaMemcpyDeviceToDevice, s));
+    if (knn_d_out) AC_CUDA(cudaMemcpyAsync(knn_d_out, pl->knn_d, sizeof(float) * B * pl->k, cudaMemcpyDeviceToDevice, s));
+    if (knn_i_out) AC_CUDA(cudaMemcpyAsync(knn_i_out, pl->knn_i, sizeof(int64_t) * B * pl->k, cudaMemcpyDeviceToDevice, s));
+    return AC_OK;
+}

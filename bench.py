@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of predict() on the BASELINE.json workload (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A step = one predict pass (E encoder -> K prototype kNN -> H head -> blend, top-5 labels) over one batch of
+512 synthetic 128-token queries PER GPU against a 1M x 768 fp32 prototype matrix (1000 classes), the
+configuration BASELINE.json's metric is quoted on (configs[2]); it fits one B200, and at N > 1 the matrix is
+row-sharded while every rank keeps its own 512 queries (weak scaling).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec predict() bert-base 128-tok, 1M x 768 prototypes"
+B_PER_GPU, S, D, N_ROWS, C, K_TOP = 512, 128, 768, 1_000_000, 1000, 5
+WORKLOAD = ("bert-base-uncased architecture (random init seed 1234), S=128, batch 512/GPU, 1M x 768 fp32 prototypes, "
+            "1000 classes, k=5 (predict_batch semantics), prototype rows sharded across GPUs")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's own path (HF BertModel CPU forward -> IndexFlatL2 restatement,
+# nq = 1 per query as in memory.py:110 -> torch head -> blend), on this box's host cores.
+# ------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, n_rows=N_ROWS):
+        import numpy as np
+        import torch
+        from oracle import knn_oracle as ko
+        from oracle import head_oracle as ho
+        from adaptive_classifier_b200 import workload as wl
+        self.torch, self.np, self.ko, self.ho = torch, np, ko, ho
+        self.cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(self.cores)
+        self.model, self.cfg = wl.bert_base_state_dict(1234)
+        self.P = wl.synthetic_rows(0, n_rows, D, C, seed=0, device="cpu").numpy()
+        self.row_class = (np.arange(n_rows) % C).astype(np.int64)
+        self.head = ho.init_head(D, C)
+        ko.lib()
+        self.wl = wl
+
+    def predict(self, ids):
+        """ids int64 [q, S] -> list of top-5 (class, score); returns per-stage seconds too."""
+        torch, np, ko, ho = self.torch, self.np, self.ko, self.ho
+        from concurrent.futures import ThreadPoolExecutor
+        t0 = time.time()
+        with torch.no_grad():
+            h = self.model(input_ids=ids, attention_mask=torch.ones_like(ids)).last_hidden_state[:, 0, :]
+            emb = torch.nn.functional.normalize(h, p=2, dim=1)
+        t1 = time.time()
+        q = emb.numpy()
+
+        def one(b):   # nq = 1 per call like the reference; ctypes releases the GIL
+            return ko.knn_l2(q[b : b + 1], self.P, K_TOP)
+        with ThreadPoolExecutor(max_workers=self.cores) as ex:
+            res = list(ex.map(one, range(q.shape[0])))
+        t2 = time.time()
+        out = []
+        probs = ho.head_forward(emb, self.head, "softmax")
+        for b, (d, i) in enumerate(res):
+            s = ko.proto_scores(d, i)[0]
+            comb = {}
+            for idx, sc in zip(i[0], s):
+                c = int(self.row_class[idx])
+                if c not in comb:
+                    comb[c] = float(sc) * 0.7
+            hv, hi = torch.topk(probs[b], K_TOP)
+            for v, j in zip(hv.tolist(), hi.tolist()):
+                comb[j] = comb.get(j, 0.0) + v * 0.3
+            pr = sorted(comb.items(), key=lambda x: x[1], reverse=True)
+            tot = sum(v for _, v in pr)
+            out.append([(c, v / tot) for c, v in pr][:K_TOP])
+        t3 = time.time()
+        return out, {"encoder_s": t1 - t0, "knn_s": t2 - t1, "head_blend_s": t3 - t2}
+
+
+def cpu_baseline(n_queries=8):
+    import torch
+    cp = CpuPath()
+    ids = cp.wl.synthetic_ids(n_queries, S).to(torch.int64)
+    cp.predict(ids[:1])                                  # warm-up (thread pools, page-in)
+    t0 = time.time()
+    _, stages = cp.predict(ids)
+    dt = time.time() - t0
+    return {"value": n_queries / dt, "unit": "queries/s", "cores": cp.cores, "kind": "port",
+            "sample": (f"{n_queries} queries of the same workload: HF BertModel fp32 CPU forward (all {cp.cores} threads), "
+                       f"IndexFlatL2 restatement nq=1 per query over the full 1M x 768 matrix ({cp.cores} queries in "
+                       f"parallel), torch head + blend; FAISS itself is unavailable offline"),
+            "stages_s": {k: round(v, 3) for k, v in stages.items()}}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    cp = CpuPath()
+    t_probe0 = time.time()
+    cp.predict(cp.wl.synthetic_ids(2, S).to(torch.int64))
+    per_q = (time.time() - t_probe0) / 2
+    budget = 150.0
+    nq = int(max(1, min(16, budget / max(1e-3, per_q * (args.steps + args.warmup)))))
+    ids = cp.wl.synthetic_ids(nq, S).to(torch.int64)
+    for _ in range(args.warmup):
+        cp.predict(ids)
+    t0 = time.time()
+    for _ in range(args.steps):
+        cp.predict(ids)
+    dt = time.time() - t0
+    v = nq * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "queries_per_step": nq},
+            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cp.cores, "kind": "port",
+                             "sample": f"{nq} queries per step, oracle port of the reference path on {cp.cores} host threads "
+                                       "(HF CPU encoder + IndexFlatL2 restatement + torch head)"},
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from adaptive_classifier_b200 import _cabi, workload as wl
+    from adaptive_classifier_b200.models import AdaptiveHead
+    from adaptive_classifier_b200.parallel import ShardedIndex, shard_bounds
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    _cabi.load_library()          # fails loudly if the in-tree .so is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    G = world
+    n_rows = args.rows
+
+    # ---- build the replica: encoder + head (replicated), prototype shard
+    model, cfg = wl.bert_base_state_dict(1234)
+    enc = _cabi.Encoder.from_hf(model, max_tokens=B_PER_GPU * S, device=dev)
+    del model
+    lo, hi = shard_bounds(n_rows, rank, G)
+    P = wl.synthetic_rows(lo, hi, D, C, seed=0, device=dev)
+    p_sqnorm = _cabi.row_sqnorm(P)
+    row_class = (torch.arange(n_rows, device=dev) % C).to(torch.int32)
+    head = AdaptiveHead(D, C, hidden_dims=[D, D // 2]).to(dev).eval()
+    hp = head._param_dict()
+    ids_host = wl.synthetic_ids(B_PER_GPU, S, seed=7 + rank).pin_memory()
+    ids_dev = ids_host.to(dev)
+    torch.cuda.synchronize()
+
+    if G == 1:
+        pipe = _cabi.Pipeline(enc, P, B_PER_GPU, S, K_TOP, head=hp, row_class=row_class, p_sqnorm=p_sqnorm)
+
+        def step_device():
+            return pipe.predict_device(ids_dev)
+
+        def step_host():
+            return pipe.predict_host(ids_host)
+    else:
+        index = ShardedIndex(P, lo)
+        out_cls_host = torch.empty((B_PER_GPU, K_TOP), dtype=torch.int32).pin_memory()
+        out_sc_host = torch.empty((B_PER_GPU, K_TOP), dtype=torch.float32).pin_memory()
+
+        def step_device(ids=None):
+            emb = enc.forward_cls(ids_dev if ids is None else ids)
+            d, i = index.search_local_queries(emb, K_TOP)
+            pc, ps = _cabi.proto_class_scores(d, i, row_class)
+            probs = _cabi.head_forward(emb, hp, _cabi.AC_ACT_SOFTMAX)
+            hv, hi_ = _cabi.topk_desc(probs, K_TOP)
+            return _cabi.blend_topk(pc, ps, hi_, hv, K_TOP)
+
+        def step_host():
+            ids = ids_host.to(dev, non_blocking=True)
+            oc, osc = step_device(ids)
+            out_cls_host.copy_(oc, non_blocking=True)
+            out_sc_host.copy_(osc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_cls_host, out_sc_host
+
+    def barrier():
+        if G > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if G > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    # ---- sanity: the step returns the query's own class nowhere (random encoder), but shapes/ranges must hold
+    for _ in range(args.warmup):
+        oc, osc = step_device()
+    torch.cuda.synchronize()
+    assert oc.shape == (B_PER_GPU, K_TOP) and bool((osc[:, 0] > 0).all()) and bool((oc[:, 0] >= 0).all())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    _cabi.profile_enable(True)
+    l0 = _cabi.launch_count()
+    ms, t0, t1 = timed(step_device, args.steps)
+    launches = _cabi.launch_count() - l0
+    _cabi.profile_enable(False)
+    prof = {c: _cabi.profile_read(c) for c in range(3)}
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    for _ in range(2):
+        step_host()
+    ms_e2e, _, _ = timed(step_host, args.steps)
+
+    if rank != 0:
+        if G > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    total_q = G * B_PER_GPU * args.steps
+    value = total_q / (ms / 1e3)
+    gemm = prof[0]
+    knn = prof[2]
+    att = prof[1]
+    gemm_tflops = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    knn_gbs = knn["bytes"] / (knn["ms"] * 1e-3) / 1e9 if knn["ms"] > 0 else 0.0
+    knn_tflops = knn["flops"] / (knn["ms"] * 1e-3) / 1e12 if knn["ms"] > 0 else 0.0
+    traffic_file = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    traffic = json.load(open(traffic_file)).get("dram_bytes_per_launch") if os.path.exists(traffic_file) else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": G * B_PER_GPU, "seq_len": S, "prototypes": n_rows,
+                   "parallelism": f"dp{G} encoder/head, prototype rows sharded x{G}",
+                   "l2": "inputs larger than L2 every step (3.07 GB prototype matrix / G, ~2 GB activations per step)"},
+        "e2e": {"value": total_q / (ms_e2e / 1e3), "unit": "queries/s",
+                "h2d_bytes_per_step": B_PER_GPU * S * 4 * G, "d2h_bytes_per_step": B_PER_GPU * K_TOP * 8 * G,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel<EpiLinear> (encoder projections, tcgen05 kind::tf32)",
+                     "achieved": gemm_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": traffic,
+                     "peak_source": f"{pk['source']} cuBLAS bf16 sustained; tf32 nominal peak is half of bf16",
+                     "launches": gemm["launches"], "ms_total": gemm["ms"], "share_of_step": gemm["ms"] / ms},
+        "roofline_knn": {"bound": "hbm", "kernel": "gemm_tf32_kernel<EpiKnn> (prototype scan, 4*N*D algorithmic bytes)",
+                         "achieved": knn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": knn_gbs / pk["hbm_gbs"],
+                         "tensor_tflops": knn_tflops, "launches": knn["launches"], "ms_total": knn["ms"],
+                         "share_of_step": knn["ms"] / ms, "peak_source": pk["source"]},
+        "attention": {"tflops_algorithmic": att["flops"] / (att["ms"] * 1e-3) / 1e12 if att["ms"] > 0 else 0.0,
+                      "ms_total": att["ms"], "share_of_step": att["ms"] / ms},
+    }
+    if G == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as ex:           # the CPU arm must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": len(os.sched_getaffinity(0)),
+                                    "kind": "port", "sample": f"failed: {ex!r}"}
+    print(json.dumps(line), flush=True)
+    if G > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

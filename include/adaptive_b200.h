@@ -193,15 +193,52 @@ int ac_linear_tc(const float *X, const float *W, const float *bias, const float 
                  float *Y, int M, int N, int K, int epi, int round_out, ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * End-to-end convenience with HOST buffers (the e2e leg of bench.py): ids on (pinned) host memory
- * -> H2D -> E -> K -> D2H of (d, i) [B,k].  All device buffers live in the handle.
+ * predict_batch() glue on the device (classifier.py:1329-1384) and the end-to-end pipeline.
  * ------------------------------------------------------------------------------------------ */
+
+/* memory.py:117-134 generalised to many rows per class: the k nearest rows (d asc, idx)
+ * are mapped through row_class[global row id] (NULL: class = row id), a class keeps its nearest row,
+ * out_score = softmax(exp(-d)) over the distinct classes; tails padded with (-1, 0).  k <= 32. */
+int ac_proto_class_scores(const float *d, const int64_t *idx, const int32_t *row_class, int B, int k,
+                          int32_t *out_cls, float *out_score, ac_stream_t stream);
+
+/* classifier.py:1347-1350 (torch.topk of the head probabilities): out_neg_vals[B,k] holds the k largest values
+ * NEGATED (ascending), out_idx[B,k] their column ids; ties -> lower id. */
+int ac_topk_desc_workspace_bytes(int B, int C, int k, size_t *bytes);
+int ac_topk_desc(const float *values, int B, int C, int k, float *out_neg_vals, int64_t *out_idx,
+                 void *workspace, size_t workspace_bytes, ac_stream_t stream);
+
+/* classifier.py:1358-1384: combined[label] = w_proto*proto + w_head*head, stable descending sort,
+ * normalised by the sum, top k.  head_neg_val as produced by ac_topk_desc.  k, kh <= 32. */
+int ac_blend_topk(const int32_t *proto_cls, const float *proto_score, const int64_t *head_idx,
+                  const float *head_neg_val, int B, int k, int kh, float w_proto, float w_head,
+                  int32_t *out_cls, float *out_score, ac_stream_t stream);
+
+/* E -> K -> class scores -> H -> top-k -> blend with all intermediate buffers owned by the handle.
+ * head may be NULL (prototype-only prediction).  row_class nullable. */
 typedef struct ac_pipeline ac_pipeline;
-int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, int64_t N, int D,
-                       int max_B, int S, int k, int64_t row_offset, ac_pipeline **out);
+int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const int32_t *row_class,
+                       int64_t N, int D, const ac_head_params *head, int max_B, int S, int k,
+                       int64_t row_offset, ac_pipeline **out);
 int ac_pipeline_destroy(ac_pipeline *pl);
-int ac_pipeline_embed_knn_host(ac_pipeline *pl, const int32_t *ids_host, int B,
-                               float *out_d_host, int64_t *out_i_host, ac_stream_t stream);
+/* device buffers at the boundary (bench.py `value`) */
+int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B,
+                               int32_t *out_cls_dev, float *out_score_dev, ac_stream_t stream);
+/* HOST buffers at the boundary (bench.py `e2e`): H2D of ids and D2H of the [B,k] result inside the call */
+int ac_pipeline_predict_host(ac_pipeline *pl, const int32_t *ids_host, int B, int32_t *out_cls_host,
+                             float *out_score_host, ac_stream_t stream);
+/* parity tests: copy the last call's unit CLS rows [B,D] and kNN result [B,k] into caller device buffers */
+int ac_pipeline_debug_copy(ac_pipeline *pl, int B, float *emb_out, float *knn_d_out, int64_t *knn_i_out,
+                           ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): number of kernels launched by this library so far, and optional
+ * CUDA-event timing of the dominant kernels on their launching stream.
+ * classes: 0 encoder tcgen05 GEMM, 1 attention, 2 kNN coarse pass, 3 kNN exact scan
+ * ------------------------------------------------------------------------------------------ */
+long long ac_launch_count(void);
+int ac_profile_enable(int on);
+int ac_profile_read(int cls, double *ms, double *flops, double *bytes, long long *launches);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,20 @@
+#!/bin/bash
+# smoke + bench + ncu captures (run under gpurun; results land in gpurun_out/)
+mkdir -p gpurun_out
+echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -5
+echo "=== bench"; timeout 900 python bench.py --steps 10 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-1500
+tail -5 gpurun_out/bench.err
+echo "=== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tee gpurun_out/bench_ref.json | cut -c1-600
+echo "=== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rows 200000 > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/ncu_bench.log | cut -c1-300
+echo "=== ncu full: encoder GEMM"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:EpiLinear -s 40 -c 4 -f -o gpurun_out/prof_gemm \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rows 200000 > gpurun_out/ncu_gemm.log 2>&1
+tail -2 gpurun_out/ncu_gemm.log | cut -c1-300
+echo "=== ncu full: kNN coarse + attention"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"EpiKnn|attention_kernel" -s 12 -c 3 -f -o gpurun_out/prof_knn_att \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_knn.log 2>&1
+tail -2 gpurun_out/ncu_knn.log | cut -c1-300
+ls -la gpurun_out

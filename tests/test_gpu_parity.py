@@ -250,16 +250,66 @@ def test_encoder_cls_matches_oracle(cabi, layers, B, S, pad):
     enc.close()
 
 
-def test_pipeline_host_buffers(cabi):
+def test_pipeline_device_and_host_boundaries(cabi):
+    """E -> K -> class scores -> H -> blend through the pipeline handle == the same stages called one by one;
+    device-buffer and host-buffer entry points agree bit for bit."""
     sd, cfg = _small_bert(2)
     B, S, N, D, C, k = 16, 128, 5000, 768, 20, 5
     P, _ = _synthetic_index(N, D, C)
+    Pg = P.cuda()
     enc = _encoder(cabi, sd, cfg, max_tokens=B * S)
     ids = eo.synthetic_ids(B, S).to(torch.int32)
-    pl = cabi.Pipeline(enc, P.cuda(), B, S, k)
-    d, i = pl.run(ids.pin_memory())
-    emb = enc.forward_cls(ids.cuda())
-    d2, i2 = cabi.knn_l2_topk(emb, P.cuda(), k)
-    torch.cuda.synchronize()
-    assert torch.equal(i, i2.cpu()) and torch.equal(d, d2.cpu())
+    p, pg = _head(D, C)
+    row_class = (torch.arange(N) % C).to(torch.int32).cuda()
+    pl = cabi.Pipeline(enc, Pg, B, S, k, head=pg, row_class=row_class)
+    oc, osc = pl.predict_device(ids.cuda())
+    oc, osc = oc.clone(), osc.clone()
+    oc_h, osc_h = pl.predict_host(ids.pin_memory())
+    assert torch.equal(oc.cpu(), oc_h) and torch.equal(osc.cpu(), osc_h)
+    emb, kd, ki = pl.debug_views(B)
+    emb2 = enc.forward_cls(ids.cuda())
+    d2, i2 = cabi.knn_l2_topk(emb2, Pg, k)
+    assert torch.equal(emb, emb2) and torch.equal(ki, i2) and torch.equal(kd, d2)
+    # host restatement of classifier.py:1358-1384 on the device intermediates
+    pc, ps = cabi.proto_class_scores(kd, ki, row_class)
+    probs = cabi.head_forward(emb, pg, cabi.AC_ACT_SOFTMAX)
+    hv, hi = cabi.topk_desc(probs, k)
+    tv, ti = torch.topk(probs, k, dim=1)
+    assert torch.equal(hv, tv)
+    pc, ps, hv, hi = pc.cpu(), ps.cpu(), hv.cpu(), hi.cpu()
+    for b in range(B):
+        comb = {}
+        for c, s_ in zip(pc[b].tolist(), ps[b].tolist()):
+            if c >= 0:
+                comb[c] = s_ * 0.7
+        for v, j in zip(hv[b].tolist(), hi[b].tolist()):
+            comb[j] = comb.get(j, 0) + v * 0.3
+        pr = sorted(comb.items(), key=lambda x: x[1], reverse=True)
+        tot = sum(v for _, v in pr)
+        pr = [(c, v / tot) for c, v in pr][:k]
+        assert [c for c, _ in pr] == oc[b].tolist()[: len(pr)]
+        assert np.allclose([v for _, v in pr], osc[b].tolist()[: len(pr)], atol=1e-6)
     pl.close(); enc.close()
+
+
+def test_proto_class_scores_reduces_to_reference_form(cabi):
+    """one row per class (the reference's usage): ac_proto_class_scores == memory.py:117-134 (ac_proto_scores)"""
+    rng = np.random.default_rng(1)
+    d = np.sort(rng.uniform(0, 4, size=(9, 6)).astype(np.float32), axis=1)
+    idx = np.stack([rng.permutation(50)[:6] for _ in range(9)]).astype(np.int64)
+    dg, ig = torch.from_numpy(d).cuda(), torch.from_numpy(idx).cuda()
+    cls, sc = cabi.proto_class_scores(dg, ig, None)
+    assert torch.equal(cls.cpu().long(), torch.from_numpy(idx))
+    assert np.abs(sc.cpu().numpy() - ko.proto_scores(d, idx)).max() < 1e-6
+    # many rows per class: the nearest row of a class wins, later rows of the same class are dropped
+    rc = torch.tensor([i % 3 for i in range(50)], dtype=torch.int32).cuda()
+    cls2, sc2 = cabi.proto_class_scores(dg, ig, rc)
+    for b in range(9):
+        seen, exp = [], []
+        for j in range(6):
+            c = int(idx[b, j]) % 3
+            if c not in seen:
+                seen.append(c); exp.append(np.exp(-d[b, j]))
+        e = np.exp(np.array(exp, dtype=np.float32) - max(exp)); e /= e.sum()
+        assert cls2[b].tolist()[: len(seen)] == seen and cls2[b].tolist()[len(seen):] == [-1] * (6 - len(seen))
+        assert np.abs(sc2[b].cpu().numpy()[: len(seen)] - e).max() < 1e-6
