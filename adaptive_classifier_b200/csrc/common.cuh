@@ -170,6 +170,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major operand (e.g. V[key][d] used as B[n = d][k = key]) in the 128-byte-swizzled canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: 128 B contiguous along MN per K index, 8 K indices per 1024 B
+// group; LBO = byte distance between consecutive 128-byte MN chunks, SBO = distance between 8-K groups.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
 // instruction descriptor: D fp32, A/B format fmt (0 f16, 1 bf16, 2 tf32), both K-major, shape MxN
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

@@ -186,7 +186,9 @@ __global__ void round_copy_kernel(const float *__restrict__ in, float *__restric
 //   P = exp(scale*(s - max)) masked  thread = query row, tcgen05.ld 32x32b; P -> smem (swizzled, tf32-rounded)
 //   out[128x64] = P V              16 x tcgen05.mma (M128 N64 K8), accumulator TMEM cols [128,192)
 //   ctx[row, h*64 + :] = out / rowsum (rounded to tf32: it is the A operand of the output projection)
-// smem: Q|K tiles (2 x 32 KB, TMA, 128B swizzle) reused for P (64 KB); V^T staged by the threads (32 KB).
+// smem: Q|K tiles (2 x 32 KB, TMA, 128B swizzle) reused for P (64 KB); V tile (32 KB, TMA) consumed as an
+// MN-major B operand: row = key (the MMA K index, 128 B = 32 head dims per row, 8 keys = one 1024 B group),
+// the two 32-dim halves of the head are 16 KB apart (leading byte offset).
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_THREADS = 128;
 constexpr int ATT_SMEM = 64 * 1024 + 32 * 1024 + 1024 /*align*/ + 64;
@@ -200,7 +202,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
     uint8_t *sQ = smem;                    // 2 slabs x [128 rows x 128 B]
     uint8_t *sK = smem + 32 * 1024;        // 2 slabs
     uint8_t *sP = smem;                    // 4 slabs x [128 rows x 128 B]   (after QK^T retired)
-    uint8_t *sVt = smem + 64 * 1024;       // 4 slabs x [64 rows (d) x 128 B (32 keys)]
+    uint8_t *sV = smem + 64 * 1024;        // 2 slabs x [128 rows (keys) x 128 B (32 head dims)]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 96 * 1024);
     uint64_t *bar_load = bars, *bar_s = bars + 1, *bar_o = bars + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
@@ -227,30 +229,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
     const uint32_t tmem_base = *tmem_slot;
 
     if (tid == 0) {
-        mbar_arrive_expect_tx(bar_load, 64 * 1024);
+        mbar_arrive_expect_tx(bar_load, 96 * 1024);
         const int r = static_cast<int>(row0);
         tma_load_2d(sQ, &tmap_qkv, bar_load, h * 64, r);
         tma_load_2d(sQ + 16 * 1024, &tmap_qkv, bar_load, h * 64 + 32, r);
         tma_load_2d(sK, &tmap_qkv, bar_load, H + h * 64, r);
         tma_load_2d(sK + 16 * 1024, &tmap_qkv, bar_load, H + h * 64 + 32, r);
-    }
-
-    // stage V^T (K-major B operand: row = d, contiguous = key) with the 128B swizzle applied by hand
-    {
-        const float *vbase = qkv + row0 * ld + 2 * H + h * 64;
-        for (int e = tid; e < 128 * 16; e += ATT_THREADS) {
-            const int key = e >> 4, d4 = e & 15;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (key < S) v = *reinterpret_cast<const float4 *>(vbase + static_cast<int64_t>(key) * ld + d4 * 4);
-            const int slab = key >> 5, c = (key & 31) >> 2, wi = key & 3;
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int d = d4 * 4 + i;
-                const uint32_t off = slab * 8192 + (d >> 3) * 1024 + (d & 7) * 128 + ((c ^ (d & 7)) << 4) + wi * 4;
-                *reinterpret_cast<float *>(sVt + off) = vv[i];
-            }
-        }
+        tma_load_2d(sV, &tmap_qkv, bar_load, 2 * H + h * 64, r);
+        tma_load_2d(sV + 16 * 1024, &tmap_qkv, bar_load, 2 * H + h * 64 + 32, r);
     }
 
     // ---- S = Q K^T
@@ -312,7 +298,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
             *reinterpret_cast<float4 *>(prow + ((ch ^ (qrow & 7)) << 4)) = o;
         }
     }
-    // generic-proxy smem writes (P, V^T) -> visible to the tensor-core (async) proxy
+    // generic-proxy smem writes (P) -> visible to the tensor-core (async) proxy
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -320,13 +306,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
 
     // ---- O = P V
     if (tid == 0) {
-        constexpr uint32_t idesc_o = umma_idesc(2, 128, 64);
+        // B = V as an MN-major operand (idesc bit 16); one MMA eats 8 keys = one 1024-byte row group of sV
+        constexpr uint32_t idesc_o = umma_idesc(2, 128, 64) | (1u << 16);
 #pragma unroll
         for (int slab = 0; slab < 4; ++slab) {
             const uint64_t a = umma_desc_sw128(smem_u32(sP + slab * 16384));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(sVt + slab * 8192));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base + 128, a + 2 * k, bdesc + 2 * k, idesc_o, (slab | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+                const int kg = slab * 4 + k;   // 8-key group
+                const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sV + kg * 1024), 16 * 1024);
+                umma_tf32(tmem_base + 128, a + 2 * k, bdesc, idesc_o, (slab | k) != 0);
+            }
         }
         tc_commit(bar_o);
     }

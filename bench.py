@@ -135,11 +135,11 @@ class CpuPath:
         return out, {"encoder_s": t1 - t0, "knn_s": t2 - t1, "head_blend_s": t3 - t2}
 
 
-def cpu_baseline(n_queries=8):
+def cpu_baseline(n_queries=32):
     import torch
     cp = CpuPath()
     ids = cp.wl.synthetic_ids(n_queries, S).to(torch.int64)
-    cp.predict(ids[:1])                                  # warm-up (thread pools, page-in)
+    cp.predict(ids)                                      # warm-up at the same shape (oneDNN primitives, page-in)
     t0 = time.time()
     _, stages = cp.predict(ids)
     dt = time.time() - t0
@@ -156,10 +156,12 @@ def run_reference(args, rank, world):
     import torch
     cp = CpuPath()
     t_probe0 = time.time()
-    cp.predict(cp.wl.synthetic_ids(2, S).to(torch.int64))
-    per_q = (time.time() - t_probe0) / 2
+    cp.predict(cp.wl.synthetic_ids(8, S).to(torch.int64))
+    t_probe0 = time.time()
+    cp.predict(cp.wl.synthetic_ids(8, S).to(torch.int64))
+    per_q = (time.time() - t_probe0) / 8
     budget = 150.0
-    nq = int(max(1, min(16, budget / max(1e-3, per_q * (args.steps + args.warmup)))))
+    nq = int(max(1, min(32, budget / max(1e-3, per_q * (args.steps + args.warmup)))))
     ids = cp.wl.synthetic_ids(nq, S).to(torch.int64)
     for _ in range(args.warmup):
         cp.predict(ids)

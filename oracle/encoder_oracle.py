@@ -165,10 +165,10 @@ def make_bert_state_dict(seed: int = 1234, arch: str = "bert", **cfg_over):
 def synthetic_ids(B: int, S: int, vocab: int = 30522, seed: int = 7, arch: str = "bert") -> Tensor:
     """Generator(seed=7), uniform in [1000, vocab), CLS at 0, SEP at S-1."""
     g = torch.Generator().manual_seed(seed)
-    ids = torch.randint(1000, vocab, (B, S), generator=g, dtype=torch.int64)
+    ids = torch.randint(min(1000, vocab // 2), vocab, (B, S), generator=g, dtype=torch.int64)
     if arch == "bert":
-        ids[:, 0] = 101
-        ids[:, -1] = 102
+        ids[:, 0] = min(101, vocab - 1)
+        ids[:, -1] = min(102, vocab - 1)
     else:
         ids[:, 0] = 0
         ids[:, -1] = 2

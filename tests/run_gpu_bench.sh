@@ -10,11 +10,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rows 200000 > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-300
 echo "=== ncu full: encoder GEMM"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:EpiLinear -s 40 -c 4 -f -o gpurun_out/prof_gemm \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32_kernel -s 40 -c 4 -f -o gpurun_out/prof_gemm \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rows 200000 > gpurun_out/ncu_gemm.log 2>&1
 tail -2 gpurun_out/ncu_gemm.log | cut -c1-300
 echo "=== ncu full: kNN coarse + attention"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"EpiKnn|attention_kernel" -s 12 -c 3 -f -o gpurun_out/prof_knn_att \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_kernel|layernorm_kernel" -s 30 -c 2 -f -o gpurun_out/prof_knn_att \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_knn.log 2>&1
 tail -2 gpurun_out/ncu_knn.log | cut -c1-300
 ls -la gpurun_out

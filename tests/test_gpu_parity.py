@@ -190,7 +190,6 @@ def test_head_train_steps_match_oracle(cabi, loss_kind):
             solid = grads[k].abs() > 1e-6 * grads[k].abs().max()
             assert diff[solid].max() < 2e-5, (step, k)
             assert diff.max() <= 2.1e-3 * step, (step, k)
-            assert (~solid).float().mean() < 0.02 or k.startswith("b")
 
 
 def test_ewc_penalty_and_fisher(cabi):

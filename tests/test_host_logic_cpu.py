@@ -1,0 +1,75 @@
+"""CPU tests of the host-side mirror (no kernels): config, examples, seeded head init, label rules, sharding."""
+import os
+
+import numpy as np
+import torch
+
+import adaptive_classifier_b200 as acb
+from adaptive_classifier_b200.parallel import shard_bounds
+from adaptive_classifier_b200.persistence import select_representative_examples
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_public_names_match_reference_init():
+    for n in ["AdaptiveClassifier", "MultiLabelAdaptiveClassifier", "MultiLabelAdaptiveHead", "Example", "AdaptiveHead",
+              "ModelConfig", "PrototypeMemory"]:
+        assert hasattr(acb, n)
+
+
+def test_model_config_defaults_and_roundtrip():
+    c = acb.ModelConfig()
+    assert (c.max_length, c.max_examples_per_class, c.prototype_update_frequency, c.ewc_lambda) == (512, 1000, 100, 100.0)
+    assert (c.prototype_weight, c.neural_weight, c.num_representative_examples) == (0.7, 0.3, 5)
+    d = c.to_dict()
+    assert len(d) == 29 and d["cost_coefficients"] == {}
+    c2 = acb.ModelConfig({"max_length": 64, "b200_max_tokens": 1024})
+    assert c2.max_length == 64 and c2.config["b200_max_tokens"] == 1024
+    c2.update(max_length=32, nonsense=1)
+    assert c2.max_length == 32 and not hasattr(c2, "nonsense")
+
+
+def test_example_roundtrip():
+    e = acb.Example("hello", "greet", torch.tensor([0.5, -1.0]))
+    e2 = acb.Example.from_dict(e.to_dict())
+    assert e2.text == "hello" and e2.label == "greet" and torch.equal(e2.embedding, e.embedding)
+    assert acb.Example.from_dict(acb.Example("x", "y").to_dict()).embedding is None
+
+
+def test_adaptive_head_init_is_the_reference_seeded_init():
+    g = np.load(os.path.join(GOLD, "golden_head.npz"))
+    head = acb.AdaptiveHead(64, 5, hidden_dims=[64, 32])
+    sd = head.state_dict()
+    assert sorted(sd) == ["model.0.bias", "model.0.weight", "model.3.bias", "model.3.weight", "model.6.bias", "model.6.weight"]
+    for k, v in sd.items():
+        assert torch.equal(v, torch.from_numpy(g[k])), k
+    # growth keeps the old rows and re-seeds the new ones (models.py:82-98)
+    w_old = head.model[-1].weight.detach().clone()
+    head.update_num_classes(7)
+    assert head.model[-1].weight.shape == (7, 32) and torch.equal(head.model[-1].weight[:5], w_old)
+    head.update_num_classes(6)
+    assert head.model[-1].weight.shape == (7, 32)
+
+
+def test_multilabel_head_growth_preserves_rows():
+    h = acb.MultiLabelAdaptiveHead(16, 3, hidden_dims=[16, 8])
+    w = h.model[-1].weight.detach().clone()
+    h.update_num_classes(5)
+    assert h.num_classes == 5 and torch.equal(h.model[-1].weight[:3], w)
+
+
+def test_representative_examples_selection():
+    g = torch.Generator().manual_seed(0)
+    exs = [acb.Example(f"t{i}", "a", torch.randn(8, generator=g)) for i in range(20)]
+    sel = select_representative_examples(exs, k=5)
+    assert len(sel) == 5 and all(s in exs for s in sel)
+    assert select_representative_examples(exs[:3], k=5) == exs[:3]
+
+
+def test_shard_bounds_cover_rows_exactly():
+    for N, G in ((1_000_000, 8), (10, 3), (7, 8), (500_000, 4)):
+        spans = [shard_bounds(N, r, G) for r in range(G)]
+        assert spans[0][0] == 0 and spans[-1][1] == N
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
