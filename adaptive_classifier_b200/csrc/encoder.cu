@@ -38,27 +38,53 @@ struct EpiLinear {
         return y;
     }
 
-    __device__ __forceinline__ void tile(State &, const GemmTileInfo &, int row, int col0, const float (&v)[32]) const {
-        if (row >= M || col0 >= N) return;
-        float *y = Y + static_cast<int64_t>(row) * N + col0;
-        const float *r = (mode == 2) ? residual + static_cast<int64_t>(row) * N + col0 : nullptr;
-        if (col0 + 32 <= N) {
+    // v[] = this thread's row (TMEM lane), 32 consecutive columns.  Transposed through the warp's staging tile so
+    // that every global access is a full 128-byte row segment: lane (r4 = lane/8, c4 = lane%8) handles rows
+    // r4 + 4*i and the 16-byte column group c4 -> one warp instruction touches 4 rows x 128 B.
+    __device__ __forceinline__ void tile(State &, const GemmTileInfo &ti, int row, int col0, const float (&v)[32],
+                                         float *stage, int lane) const {
+        (void)row;
+        const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;       // first row of this warp's TMEM quarter
+        if (row_base >= M || col0 >= N) return;                             // warp-uniform
+        float4 *srow = reinterpret_cast<float4 *>(stage + lane * GEMM_EPI_STAGE_STRIDE);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 b4 = bias ? __ldg(reinterpret_cast<const float4 *>(bias + col0 + j)) : make_float4(0, 0, 0, 0);
-                float4 r4 = r ? *reinterpret_cast<const float4 *>(r + j) : make_float4(0, 0, 0, 0);
-                float4 o;
-                o.x = apply(v[j + 0], b4.x, r4.x);
-                o.y = apply(v[j + 1], b4.y, r4.y);
-                o.z = apply(v[j + 2], b4.z, r4.z);
-                o.w = apply(v[j + 3], b4.w, r4.w);
-                *reinterpret_cast<float4 *>(y + j) = o;
+        for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int r4 = lane >> 3, c4 = lane & 7;
+        const int col = col0 + 4 * c4;
+        if (col + 4 <= N) {
+            const float4 b4 = bias ? __ldg(reinterpret_cast<const float4 *>(bias + col)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = r4 + 4 * i;
+                const int grow = row_base + rr;
+                if (grow < M) {
+                    const float4 a = *reinterpret_cast<const float4 *>(stage + rr * GEMM_EPI_STAGE_STRIDE + 4 * c4);
+                    float4 r = make_float4(0, 0, 0, 0);
+                    if (mode == 2) r = *reinterpret_cast<const float4 *>(residual + static_cast<int64_t>(grow) * N + col);
+                    float4 o;
+                    o.x = apply(a.x, b4.x, r.x);
+                    o.y = apply(a.y, b4.y, r.y);
+                    o.z = apply(a.z, b4.z, r.z);
+                    o.w = apply(a.w, b4.w, r.w);
+                    *reinterpret_cast<float4 *>(Y + static_cast<int64_t>(grow) * N + col) = o;
+                }
             }
         } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)   // fully unrolled so v[] stays in registers
-                if (col0 + j < N) y[j] = apply(v[j], bias ? bias[col0 + j] : 0.f, r ? r[j] : 0.f);
+            for (int i = 0; i < 8; ++i) {
+                const int rr = r4 + 4 * i;
+                const int grow = row_base + rr;
+                if (grow >= M) continue;
+                for (int t = 0; t < 4; ++t) {
+                    const int cc = col + t;
+                    if (cc < N)
+                        Y[static_cast<int64_t>(grow) * N + cc] =
+                            apply(stage[rr * GEMM_EPI_STAGE_STRIDE + 4 * c4 + t], bias ? bias[cc] : 0.f,
+                                  mode == 2 ? residual[static_cast<int64_t>(grow) * N + cc] : 0.f);
+                }
+            }
         }
+        __syncwarp();   // staging tile is rewritten by the next chunk
     }
 };
 
@@ -186,9 +212,9 @@ __global__ void round_copy_kernel(const float *__restrict__ in, float *__restric
 //   P = exp(scale*(s - max)) masked  thread = query row, tcgen05.ld 32x32b; P -> smem (swizzled, tf32-rounded)
 //   out[128x64] = P V              16 x tcgen05.mma (M128 N64 K8), accumulator TMEM cols [128,192)
 //   ctx[row, h*64 + :] = out / rowsum (rounded to tf32: it is the A operand of the output projection)
-// smem: Q|K tiles (2 x 32 KB, TMA, 128B swizzle) reused for P (64 KB); V tile (32 KB, TMA) consumed as an
-// MN-major B operand: row = key (the MMA K index, 128 B = 32 head dims per row, 8 keys = one 1024 B group),
-// the two 32-dim halves of the head are 16 KB apart (leading byte offset).
+// smem: Q|K tiles (2 x 32 KB, TMA, 128B swizzle) reused for P (64 KB); V^T (32 KB) staged by the threads into the
+// K-major 128B-swizzled layout (all 16 global loads of a thread are issued before the first shared store).
+// (An MN-major descriptor for V straight from TMA was tried in round 1 and produced wrong results; see DESIGN.md.)
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_THREADS = 128;
 constexpr int ATT_SMEM = 64 * 1024 + 32 * 1024 + 1024 /*align*/ + 64;
@@ -202,7 +228,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
     uint8_t *sQ = smem;                    // 2 slabs x [128 rows x 128 B]
     uint8_t *sK = smem + 32 * 1024;        // 2 slabs
     uint8_t *sP = smem;                    // 4 slabs x [128 rows x 128 B]   (after QK^T retired)
-    uint8_t *sV = smem + 64 * 1024;        // 2 slabs x [128 rows (keys) x 128 B (32 head dims)]
+    uint8_t *sVt = smem + 64 * 1024;       // 4 slabs x [64 rows (d) x 128 B (32 keys)]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 96 * 1024);
     uint64_t *bar_load = bars, *bar_s = bars + 1, *bar_o = bars + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
@@ -229,14 +255,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
     const uint32_t tmem_base = *tmem_slot;
 
     if (tid == 0) {
-        mbar_arrive_expect_tx(bar_load, 96 * 1024);
+        mbar_arrive_expect_tx(bar_load, 64 * 1024);
         const int r = static_cast<int>(row0);
         tma_load_2d(sQ, &tmap_qkv, bar_load, h * 64, r);
         tma_load_2d(sQ + 16 * 1024, &tmap_qkv, bar_load, h * 64 + 32, r);
         tma_load_2d(sK, &tmap_qkv, bar_load, H + h * 64, r);
         tma_load_2d(sK + 16 * 1024, &tmap_qkv, bar_load, H + h * 64 + 32, r);
-        tma_load_2d(sV, &tmap_qkv, bar_load, 2 * H + h * 64, r);
-        tma_load_2d(sV + 16 * 1024, &tmap_qkv, bar_load, 2 * H + h * 64 + 32, r);
+    }
+
+    // stage V^T (K-major B operand: row = d, contiguous = key) with the 128B swizzle applied by hand
+    {
+        const float *vbase = qkv + row0 * ld + 2 * H + h * 64;
+        float4 vreg[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {          // all loads in flight first
+            const int e = tid + it * ATT_THREADS;
+            const int key = e >> 4, d4 = e & 15;
+            vreg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (key < S) vreg[it] = __ldg(reinterpret_cast<const float4 *>(vbase + static_cast<int64_t>(key) * ld + d4 * 4));
+        }
+        const uint32_t sv_base = smem_u32(sVt);
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int e = tid + it * ATT_THREADS;
+            const int key = e >> 4, d4 = e & 15;
+            const int slab = key >> 5, c = (key & 31) >> 2, wi = key & 3;
+            const float vv[4] = {vreg[it].x, vreg[it].y, vreg[it].z, vreg[it].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int d = d4 * 4 + i;
+                const uint32_t off = slab * 8192 + (d >> 3) * 1024 + (d & 7) * 128 + ((c ^ (d & 7)) << 4) + wi * 4;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sv_base + off), "f"(vv[i]) : "memory");
+            }
+        }
     }
 
     // ---- S = Q K^T
@@ -291,14 +342,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
             p[j] = round_tf32(e);
         }
         // slab (c/32), row qrow: 8 x 16-byte chunks at the swizzled positions
-        uint8_t *prow = sP + (c >> 5) * 16384 + (qrow >> 3) * 1024 + (qrow & 7) * 128;
+        const uint32_t prow = smem_u32(sP) + (c >> 5) * 16384 + (qrow >> 3) * 1024 + (qrow & 7) * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-            float4 o = make_float4(p[4 * ch], p[4 * ch + 1], p[4 * ch + 2], p[4 * ch + 3]);
-            *reinterpret_cast<float4 *>(prow + ((ch ^ (qrow & 7)) << 4)) = o;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((ch ^ (qrow & 7)) << 4)), "f"(p[4 * ch]),
+                         "f"(p[4 * ch + 1]), "f"(p[4 * ch + 2]), "f"(p[4 * ch + 3])
+                         : "memory");
         }
     }
-    // generic-proxy smem writes (P) -> visible to the tensor-core (async) proxy
+    // generic-proxy smem writes (P, V^T) -> visible to the tensor-core (async) proxy
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -306,17 +358,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
 
     // ---- O = P V
     if (tid == 0) {
-        // B = V as an MN-major operand (idesc bit 16); one MMA eats 8 keys = one 1024-byte row group of sV
-        constexpr uint32_t idesc_o = umma_idesc(2, 128, 64) | (1u << 16);
+        constexpr uint32_t idesc_o = umma_idesc(2, 128, 64);
 #pragma unroll
         for (int slab = 0; slab < 4; ++slab) {
             const uint64_t a = umma_desc_sw128(smem_u32(sP + slab * 16384));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sVt + slab * 8192));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int kg = slab * 4 + k;   // 8-key group
-                const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sV + kg * 1024), 16 * 1024);
-                umma_tf32(tmem_base + 128, a + 2 * k, bdesc, idesc_o, (slab | k) != 0);
-            }
+            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base + 128, a + 2 * k, bdesc + 2 * k, idesc_o, (slab | k) != 0);
         }
         tc_commit(bar_o);
     }

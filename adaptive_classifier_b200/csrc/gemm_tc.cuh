@@ -23,7 +23,10 @@ constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 4;   // 16 KB
 constexpr int GEMM_B_STAGE_BYTES = GEMM_BLOCK_N * GEMM_BLOCK_K * 4;   // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// per-epilogue-warp staging tile [32 rows][36 floats] for the thread-row -> coalesced-row transpose
+constexpr int GEMM_EPI_STAGE_STRIDE = 36;
+constexpr int GEMM_EPI_STAGE_BYTES = 32 * GEMM_EPI_STAGE_STRIDE * 4;   // 4608 B per warp
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 4 * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_TMEM_COLS = 512;
 
 #ifndef AC_MBAR_WATCHDOG
@@ -54,7 +57,8 @@ struct GemmTileInfo {
 //   struct Epi { struct State {...};
 //                __device__ void begin_cta(State&, int warp_q, int lane) const;
 //                __device__ void tile(State&, const GemmTileInfo&, int row /*global m*/, int col0 /*global n of v[0]*/,
-//                                     const float (&v)[32]) const;   // called 8x per tile per thread
+//                                     const float (&v)[32], float *stage, int lane) const;   // 8x per tile per thread
+//                      (stage = this warp's private [32][36] fp32 smem tile for transposing to coalesced rows)
 //                __device__ void end_cta(State&, int warp_q, int lane) const; };
 //
 // Tile order: kMFastest = false -> n fastest (tiles of the same A row-block run concurrently and share A
@@ -68,7 +72,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + GEMM_STAGES * GEMM_A_STAGE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+    float *epi_stage = reinterpret_cast<float *>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + 4 * GEMM_EPI_STAGE_BYTES);
     uint64_t *full_bar = bars;                        // [STAGES]
     uint64_t *empty_bar = bars + GEMM_STAGES;         // [STAGES]
     uint64_t *tmem_full = bars + 2 * GEMM_STAGES;     // [2]
@@ -175,7 +180,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi.tile(est, ti, row, ti.n0 + c, v);
+                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * (32 * GEMM_EPI_STAGE_STRIDE), lane);
             }
             tc_fence_before();
             __syncwarp();

@@ -52,7 +52,8 @@ struct EpiKnn {
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
     }
 
-    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32]) const {
+    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
+                                         float * /*stage*/, int /*lane*/) const {
         // all lanes walk the same 32 prototype rows; each lane tests them against its own query's threshold
 #pragma unroll
         for (int j = 0; j < 32; ++j) {   // fully unrolled: v[] must stay in registers
