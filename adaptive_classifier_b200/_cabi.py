@@ -22,7 +22,7 @@ AC_KNN_MAX_K = 2048
 AC_ACT_LOGITS, AC_ACT_SOFTMAX, AC_ACT_SIGMOID = 0, 1, 2
 AC_LOSS_CE, AC_LOSS_BCE = 0, 1
 AC_ARCH_BERT, AC_ARCH_ROBERTA = 0, 1
-AC_PREC_TF32 = 0
+AC_PREC_TF32, AC_PREC_F16 = 0, 1
 
 EXPORTS = [
     "ac_version", "ac_last_error", "ac_device_check",
@@ -109,7 +109,7 @@ def load_library() -> ctypes.CDLL:
     L.ac_encoder_forward_cls.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.ac_encoder_last_hidden.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     L.ac_linear_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                               c_void_p]
+                               c_int, c_int, c_void_p]
     L.ac_proto_class_scores.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_topk_desc_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
     L.ac_topk_desc.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
@@ -316,14 +316,17 @@ def ewc_penalty(p, fisher, star, lam: float, batch_size: Optional[int], C_old: i
     return out
 
 
-def linear_tc(X, W, bias=None, residual=None, epi: int = 0, round_out: bool = False) -> torch.Tensor:
+def linear_tc(X, W, bias, residual=None, epi: int = 0, round_out: bool = False, out_half: bool = False) -> torch.Tensor:
+    """X, W fp32 -> tf32 path; X, W fp16 -> fp16 path (the encoder's); Y fp32 unless out_half."""
     L = load_library()
-    X, W = _f32c(X), _f32c(W)
+    assert X.is_cuda and W.is_cuda and X.dtype == W.dtype and X.dtype in (torch.float32, torch.float16)
+    X, W = X.contiguous(), W.contiguous()
+    prec = AC_PREC_F16 if X.dtype == torch.float16 else AC_PREC_TF32
     M, K = X.shape
     N = W.shape[0]
-    Y = torch.empty((M, N), dtype=torch.float32, device=X.device)
+    Y = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=X.device)
     check(L.ac_linear_tc(X.data_ptr(), W.data_ptr(), ptr(bias), ptr(residual), Y.data_ptr(), M, N, K, epi,
-                         1 if round_out else 0, stream_ptr()), "ac_linear_tc")
+                         1 if round_out else 0, prec, 1 if out_half else 0, stream_ptr()), "ac_linear_tc")
     return Y
 
 
@@ -366,7 +369,7 @@ class Encoder:
         w.ff2_w, w.ff2_b = arr(p + "output.dense.weight"), arr(p + "output.dense.bias")
         w.out_ln_w, w.out_ln_b = arr(p + "output.LayerNorm.weight"), arr(p + "output.LayerNorm.bias")
         cfg = EncoderConfig(AC_ARCH_BERT if arch == "bert" else AC_ARCH_ROBERTA, layers, hidden, heads, intermediate,
-                            vocab, max_pos, type_vocab, pad_idx, ln_eps, AC_PREC_TF32, max_tokens)
+                            vocab, max_pos, type_vocab, pad_idx, ln_eps, AC_PREC_F16, max_tokens)
         h = c_void_p()
         with torch.cuda.device(dev):
             check(L.ac_encoder_create(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(h)), "ac_encoder_create")

@@ -97,7 +97,7 @@ int make_tmap_2d(CUtensorMap *out, const void *gptr, int elem_bytes, uint64_t ro
                "make_tmap_2d: base pointer and row stride must be 16-byte aligned");
     AC_REQUIRE(box_cols * static_cast<uint32_t>(elem_bytes) == 128 && box_rows <= 256,
                "make_tmap_2d: box must be 128 bytes wide and <= 256 rows");
-    const CUtensorMapDataType dt = (elem_bytes == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapDataType dt = (elem_bytes == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {row_stride_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};

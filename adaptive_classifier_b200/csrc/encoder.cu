@@ -4,87 +4,151 @@
 // /root/reference/src/adaptive_classifier/classifier.py:1271-1275 (HF BertModel.forward:
 // embeddings modeling_bert.py:53-113, self-attention :143-207, output+LN :287-298, FFN :330-356).
 //
-// Dense projections run on the tcgen05 GEMM of gemm_tc.cuh (kind::tf32, operands RNE-rounded to tf32 by
-// the producing kernel, fp32 accumulation in TMEM) with fused bias / exact-erf GELU / residual epilogues.
-// Attention is one CTA per (sequence, head): QK^T and PV as tcgen05 MMAs with the score tile and the
-// output tile in TMEM and a thread-per-query-row softmax in between (S <= 128, head_dim 64).
-// LayerNorm keeps the fp32 residual stream and also emits the tf32-rounded copy the next GEMM reads.
+// Precision: every tensor-core operand is fp16 (RNE from fp32), accumulation fp32 in TMEM, residual stream, LayerNorm,
+// softmax and GELU in fp32.  fp16 carries the same 10-bit mantissa as tf32, so the measured error is the tf32 one
+// (oracle/precision_study.py: 1.7e-4 on squared-L2 distances, bf16 would be 1.4e-3 > the 1e-3 tolerance) at twice the
+// tensor rate and half the operand bytes.
+//
+//   projections   tcgen05 GEMM of gemm_tc.cuh (kind::f16) with compile-time-specialised fused epilogues:
+//                 bias | bias+GELU(erf) | bias+residual, fp16 or fp32 output, V written TRANSPOSED per (sequence, head)
+//   attention     one CTA per (sequence, head): Q, K and V^T tiles by TMA, QK^T and PV as tcgen05 MMAs with the score
+//                 tile / output tile in TMEM, thread-per-query-row softmax in between (S <= 128, head_dim 64)
+//   LayerNorm     fp32 residual stream + the fp16 operand copy for the next GEMM
 #include "gemm_tc.cuh"
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <vector>
 
 namespace ac {
 
-// ------------------------------------------------------------------------------------------------
-// fused epilogue of the encoder linears
-// ------------------------------------------------------------------------------------------------
-struct EpiLinear {
-    const float *bias;       // [N] nullable
-    const float *residual;   // [M,N] nullable (mode 2)
-    float *Y;                // [M,N]
-    int M, N;
-    int mode;                // 0 bias, 1 bias+GELU(erf), 2 bias+residual
-    int round_out;           // round result to tf32 (RNE): the result feeds another tcgen05 GEMM
+// erf with |error| < 1.5e-7 (Abramowitz-Stegun 7.1.26): 1 rcp, 1 ex2, 7 FMA -- the GELU epilogue runs on 4.2 M
+// elements per 128x256x768 tile wave, libdevice erff costs ~3x as many issue slots.
+__device__ __forceinline__ float fast_erf(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    const float e = 1.f - p * exp2f(-1.4426950408889634f * ax * ax);
+    return copysignf(e, x);
+}
 
-    struct State {};
+// ------------------------------------------------------------------------------------------------
+// fused epilogue of the encoder linears (compile-time specialised)
+//   MODE 0 bias, 1 bias + exact-erf GELU, 2 bias + fp32 residual;  OUT_HALF: fp16 output (next GEMM operand) or fp32
+//   VT: columns >= vt_col0 (the V third of the fused QKV projection) are written transposed to
+//       vT[(b*H + feature) * S_pad + key] so that attention can TMA-load V^T as a K-major B operand.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool OUT_HALF, bool VT>
+struct EpiLinear {
+    const float *__restrict__ bias;       // [N]
+    const float *__restrict__ residual;   // [M, ldy] (MODE 2)
+    void *Y;                              // [M, ldy] fp16 or fp32
+    int M, N, ldy;
+    int round_out;                        // fp32 output only: round to tf32 (tests of the tf32 path)
+    __half *vT;                           // VT only
+    int vt_col0, S, S_pad, H;
+
+    struct State {
+        float4 res[4];                    // prefetched residual (MODE 2): rows r4 + 4*i ... see tile()
+    };
     __device__ __forceinline__ void begin_cta(State &, int, int) const {}
     __device__ __forceinline__ void end_cta(State &, int, int) const {}
 
-    __device__ __forceinline__ float apply(float a, float b, float r) const {
-        float y = a + b;
-        if (mode == 1) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
-        if (mode == 2) y += r;
-        if (round_out) y = round_tf32(y);
+    __device__ __forceinline__ float act(float y) const {
+        if (MODE == 1) y = 0.5f * y * (1.f + fast_erf(y * 0.70710678118654752440f));
         return y;
     }
 
-    // v[] = this thread's row (TMEM lane), 32 consecutive columns.  Transposed through the warp's staging tile so
-    // that every global access is a full 128-byte row segment: lane (r4 = lane/8, c4 = lane%8) handles rows
-    // r4 + 4*i and the 16-byte column group c4 -> one warp instruction touches 4 rows x 128 B.
+    // residual loads for this chunk are issued before the TMEM wait.  Thread mapping of the transposed phase (fp32
+    // staging holds 16 columns at a time): lane = (r2 = lane / 4, c4 = lane % 4) -> rows r2 + 8*i, 16-byte column group c4.
+    __device__ __forceinline__ void prefetch(State &, const GemmTileInfo &, int, int, int) const {}
+
     __device__ __forceinline__ void tile(State &, const GemmTileInfo &ti, int row, int col0, const float (&v)[32],
-                                         float *stage, int lane) const {
-        (void)row;
-        const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;       // first row of this warp's TMEM quarter
-        if (row_base >= M || col0 >= N) return;                             // warp-uniform
-        float4 *srow = reinterpret_cast<float4 *>(stage + lane * GEMM_EPI_STAGE_STRIDE);
+                                         uint8_t *stage, int lane) const {
+        const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;        // first row of this warp's TMEM quarter
+        if (row_base >= M || col0 >= N) return;                              // warp-uniform
+        if (VT && col0 >= vt_col0) {
+            // thread = token row: lanes hold 32 consecutive keys of (mostly) one sequence -> 64-byte coalesced stores
+            if (row < M) {
+                const int b = row / S, key = row - b * S;
+                __half *dst = vT + (static_cast<int64_t>(b) * H + (col0 - vt_col0)) * S_pad + key;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int r4 = lane >> 3, c4 = lane & 7;
-        const int col = col0 + 4 * c4;
-        if (col + 4 <= N) {
-            const float4 b4 = bias ? __ldg(reinterpret_cast<const float4 *>(bias + col)) : make_float4(0, 0, 0, 0);
+                for (int j = 0; j < 32; ++j) dst[static_cast<int64_t>(j) * S_pad] = __float2half_rn(v[j] + __ldg(bias + col0 + j));
+            }
+            return;
+        }
+        if (OUT_HALF) {
+            // stage 32 rows x 32 halves (64 B payload per 80-byte row), then lane (r4 = lane/4 .. 8 rows per pass, c8 = lane%4)
+            uint4 *srow = reinterpret_cast<uint4 *>(stage + lane * GEMM_EPI_STAGE_ROW_BYTES);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = r4 + 4 * i;
+            for (int j = 0; j < 4; ++j) {
+                float y[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) y[t] = act(v[8 * j + t] + __ldg(bias + col0 + 8 * j + t));
+                uint4 pk;
+                __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+                __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
+                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                srow[j] = pk;
+            }
+            __syncwarp();
+            const int r8 = lane >> 2, c = lane & 3;                           // 8 rows x 4 x 16 B per pass
+            __half *Yh = static_cast<__half *>(Y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = r8 + 8 * i;
                 const int grow = row_base + rr;
-                if (grow < M) {
-                    const float4 a = *reinterpret_cast<const float4 *>(stage + rr * GEMM_EPI_STAGE_STRIDE + 4 * c4);
-                    float4 r = make_float4(0, 0, 0, 0);
-                    if (mode == 2) r = *reinterpret_cast<const float4 *>(residual + static_cast<int64_t>(grow) * N + col);
-                    float4 o;
-                    o.x = apply(a.x, b4.x, r.x);
-                    o.y = apply(a.y, b4.y, r.y);
-                    o.z = apply(a.z, b4.z, r.z);
-                    o.w = apply(a.w, b4.w, r.w);
-                    *reinterpret_cast<float4 *>(Y + static_cast<int64_t>(grow) * N + col) = o;
+                const int col = col0 + 8 * c;
+                if (grow < M && col + 8 <= N) {
+                    const uint4 pk = *reinterpret_cast<const uint4 *>(stage + rr * GEMM_EPI_STAGE_ROW_BYTES + 16 * c);
+                    *reinterpret_cast<uint4 *>(Yh + static_cast<int64_t>(grow) * ldy + col) = pk;
                 }
             }
+            __syncwarp();
         } else {
-            for (int i = 0; i < 8; ++i) {
-                const int rr = r4 + 4 * i;
-                const int grow = row_base + rr;
-                if (grow >= M) continue;
-                for (int t = 0; t < 4; ++t) {
-                    const int cc = col + t;
-                    if (cc < N)
-                        Y[static_cast<int64_t>(grow) * N + cc] =
-                            apply(stage[rr * GEMM_EPI_STAGE_STRIDE + 4 * c4 + t], bias ? bias[cc] : 0.f,
-                                  mode == 2 ? residual[static_cast<int64_t>(grow) * N + cc] : 0.f);
+            // fp32 output (pre-LayerNorm sums): two passes of 16 columns through the staging tile
+            float *Yf = static_cast<float *>(Y);
+            const int r8 = lane >> 2, c = lane & 3;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int col = col0 + 16 * half + 4 * c;
+                float4 res[4];
+                if (MODE == 2) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {                              // all residual loads in flight first
+                        const int grow = row_base + r8 + 8 * i;
+                        res[i] = (grow < M && col + 4 <= N)
+                                     ? __ldg(reinterpret_cast<const float4 *>(residual + static_cast<int64_t>(grow) * ldy + col))
+                                     : make_float4(0, 0, 0, 0);
+                    }
                 }
+                float4 *srow = reinterpret_cast<float4 *>(stage + lane * GEMM_EPI_STAGE_ROW_BYTES);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    srow[j] = make_float4(v[16 * half + 4 * j], v[16 * half + 4 * j + 1], v[16 * half + 4 * j + 2],
+                                          v[16 * half + 4 * j + 3]);
+                __syncwarp();
+                const float4 b4 = (col + 4 <= N) ? __ldg(reinterpret_cast<const float4 *>(bias + col)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = r8 + 8 * i;
+                    const int grow = row_base + rr;
+                    if (grow < M && col + 4 <= N) {
+                        const float4 a = *reinterpret_cast<const float4 *>(stage + rr * GEMM_EPI_STAGE_ROW_BYTES + 16 * c);
+                        float4 o;
+                        o.x = act(a.x + b4.x); o.y = act(a.y + b4.y); o.z = act(a.z + b4.z); o.w = act(a.w + b4.w);
+                        if (MODE == 2) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+                        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                        *reinterpret_cast<float4 *>(Yf + static_cast<int64_t>(grow) * ldy + col) = o;
+                    }
+                }
+                __syncwarp();
             }
         }
-        __syncwarp();   // staging tile is rewritten by the next chunk
     }
 };
 
@@ -95,7 +159,7 @@ constexpr int LN_MAXV = 8;
 
 __device__ __forceinline__ void ln_row(float4 (&x)[LN_MAXV], int nv, int H, const float *__restrict__ w,
                                        const float *__restrict__ b, float eps, int lane, float *out_full,
-                                       float *out_round) {
+                                       __half *out_half) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i)
@@ -122,17 +186,18 @@ __device__ __forceinline__ void ln_row(float4 (&x)[LN_MAXV], int nv, int H, cons
             o.z = (x[i].z - mean) * rstd * w4.z + b4.z;
             o.w = (x[i].w - mean) * rstd * w4.w + b4.w;
             if (out_full) *reinterpret_cast<float4 *>(out_full + col) = o;
-            if (out_round) {
-                float4 r;
-                r.x = round_tf32(o.x); r.y = round_tf32(o.y); r.z = round_tf32(o.z); r.w = round_tf32(o.w);
-                *reinterpret_cast<float4 *>(out_round + col) = r;
+            if (out_half) {
+                __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&h0);
+                pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                *reinterpret_cast<uint2 *>(out_half + col) = pk;
             }
         }
 }
 
 __global__ void layernorm_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ b,
-                                 float eps, int rows, int H, float *__restrict__ out_full,
-                                 float *__restrict__ out_round) {
+                                 float eps, int rows, int H, float *__restrict__ out_full, __half *__restrict__ out_half) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -143,7 +208,7 @@ __global__ void layernorm_kernel(const float *__restrict__ in, const float *__re
     for (int i = 0; i < LN_MAXV; ++i)
         if (i < nv) x[i] = *reinterpret_cast<const float4 *>(src + (lane + 32 * i) * 4);
     ln_row(x, nv, H, w, b, eps, lane, out_full ? out_full + static_cast<int64_t>(row) * H : nullptr,
-           out_round ? out_round + static_cast<int64_t>(row) * H : nullptr);
+           out_half ? out_half + static_cast<int64_t>(row) * H : nullptr);
 }
 
 // modeling_bert.py:53-113 / modeling_roberta.py:146-159: (word + type) + position -> LayerNorm
@@ -152,7 +217,7 @@ __global__ void embed_ln_kernel(const int32_t *__restrict__ ids, const int32_t *
                                 const float *__restrict__ type, const float *__restrict__ w,
                                 const float *__restrict__ b, float eps, int B, int S, int H, int arch, int pad_idx,
                                 int vocab, int max_pos, int type_vocab, float *__restrict__ out_full,
-                                float *__restrict__ out_round) {
+                                __half *__restrict__ out_half) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B * S) return;
@@ -185,7 +250,7 @@ __global__ void embed_ln_kernel(const int32_t *__restrict__ ids, const int32_t *
             x[i].z = (a.z + t.z) + q.z;
             x[i].w = (a.w + t.w) + q.w;
         }
-    ln_row(x, nv, H, w, b, eps, lane, out_full + static_cast<int64_t>(row) * H, out_round + static_cast<int64_t>(row) * H);
+    ln_row(x, nv, H, w, b, eps, lane, out_full + static_cast<int64_t>(row) * H, out_half + static_cast<int64_t>(row) * H);
 }
 
 // classifier.py:1272,1275: CLS row -> x / max(||x||_2, 1e-12)
@@ -205,41 +270,45 @@ __global__ void round_copy_kernel(const float *__restrict__ in, float *__restric
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = do_round ? round_tf32(in[i]) : in[i];
 }
+__global__ void to_half_kernel(const float *__restrict__ in, __half *__restrict__ out, int64_t n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __float2half_rn(in[i]);
+}
 
 // ------------------------------------------------------------------------------------------------
-// attention: one CTA (128 threads) per (sequence b, head h); S <= 128, head_dim == 64.
-//   scores[128x128] = Q K^T        8 x tcgen05.mma kind::tf32 (M128 N128 K8), accumulator TMEM cols [0,128)
-//   P = exp(scale*(s - max)) masked  thread = query row, tcgen05.ld 32x32b; P -> smem (swizzled, tf32-rounded)
-//   out[128x64] = P V              16 x tcgen05.mma (M128 N64 K8), accumulator TMEM cols [128,192)
-//   ctx[row, h*64 + :] = out / rowsum (rounded to tf32: it is the A operand of the output projection)
-// smem: Q|K tiles (2 x 32 KB, TMA, 128B swizzle) reused for P (64 KB); V^T (32 KB) staged by the threads into the
-// K-major 128B-swizzled layout (all 16 global loads of a thread are issued before the first shared store).
-// (An MN-major descriptor for V straight from TMA was tried in round 1 and produced wrong results; see DESIGN.md.)
+// attention: one CTA (128 threads) per (sequence b, head h); S <= 128, head_dim == 64, fp16 operands.
+//   scores[128x128] = Q K^T        4 x tcgen05.mma kind::f16 (M128 N128 K16), accumulator TMEM cols [0,128)
+//   P = exp(scale*(s - max)) masked  thread = query row, tcgen05.ld 32x32b; P -> smem (swizzled fp16)
+//   out[128x64] = P V              8 x tcgen05.mma (M128 N64 K16), accumulator TMEM cols [0,64) (scores already drained)
+//   ctx[row, h*64 + :] = out / rowsum  (fp16: the A operand of the output projection)
+// smem: Q tile 16 KB | K tile 16 KB (TMA, 128B swizzle), reused for P (2 slabs x 16 KB); V^T 2 slabs x 8 KB by TMA
+// from the transposed buffer the QKV epilogue wrote.  48 KB + 128 TMEM columns per CTA -> 4 CTAs per SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_THREADS = 128;
-constexpr int ATT_SMEM = 64 * 1024 + 32 * 1024 + 1024 /*align*/ + 64;
-constexpr int ATT_TMEM_COLS = 256;
+constexpr int ATT_SMEM = 48 * 1024 + 1024 /*align*/ + 64;
+constexpr int ATT_TMEM_COLS = 128;
 
 __global__ void __launch_bounds__(ATT_THREADS)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__restrict__ qkv,
-                 const int32_t *__restrict__ mask, int B, int S, int heads, int H, float *__restrict__ ctx) {
+attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
+                 const int32_t *__restrict__ mask, int B, int S, int heads, int H, __half *__restrict__ ctx) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sQ = smem;                    // 2 slabs x [128 rows x 128 B]
-    uint8_t *sK = smem + 32 * 1024;        // 2 slabs
-    uint8_t *sP = smem;                    // 4 slabs x [128 rows x 128 B]   (after QK^T retired)
-    uint8_t *sVt = smem + 64 * 1024;       // 4 slabs x [64 rows (d) x 128 B (32 keys)]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 96 * 1024);
+    uint8_t *sQ = smem;                    // [128 rows x 128 B]
+    uint8_t *sK = smem + 16 * 1024;        // [128 rows x 128 B]
+    uint8_t *sP = smem;                    // 2 slabs x [128 rows x 128 B (64 keys)]   (after QK^T retired)
+    uint8_t *sVt = smem + 32 * 1024;       // 2 slabs x [64 rows (d) x 128 B (64 keys)]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 48 * 1024);
     uint64_t *bar_load = bars, *bar_s = bars + 1, *bar_o = bars + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int64_t row0 = static_cast<int64_t>(b) * S;
-    const int ld = 3 * H;
 
     if (tid == 0) {
-        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_qk);
+        tma_prefetch_desc(&tmap_vt);
         mbar_init(bar_load, 1);
         mbar_init(bar_s, 1);
         mbar_init(bar_o, 1);
@@ -255,53 +324,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
     const uint32_t tmem_base = *tmem_slot;
 
     if (tid == 0) {
-        mbar_arrive_expect_tx(bar_load, 64 * 1024);
+        mbar_arrive_expect_tx(bar_load, 48 * 1024);
         const int r = static_cast<int>(row0);
-        tma_load_2d(sQ, &tmap_qkv, bar_load, h * 64, r);
-        tma_load_2d(sQ + 16 * 1024, &tmap_qkv, bar_load, h * 64 + 32, r);
-        tma_load_2d(sK, &tmap_qkv, bar_load, H + h * 64, r);
-        tma_load_2d(sK + 16 * 1024, &tmap_qkv, bar_load, H + h * 64 + 32, r);
-    }
-
-    // stage V^T (K-major B operand: row = d, contiguous = key) with the 128B swizzle applied by hand
-    {
-        const float *vbase = qkv + row0 * ld + 2 * H + h * 64;
-        float4 vreg[16];
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {          // all loads in flight first
-            const int e = tid + it * ATT_THREADS;
-            const int key = e >> 4, d4 = e & 15;
-            vreg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (key < S) vreg[it] = __ldg(reinterpret_cast<const float4 *>(vbase + static_cast<int64_t>(key) * ld + d4 * 4));
-        }
-        const uint32_t sv_base = smem_u32(sVt);
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const int e = tid + it * ATT_THREADS;
-            const int key = e >> 4, d4 = e & 15;
-            const int slab = key >> 5, c = (key & 31) >> 2, wi = key & 3;
-            const float vv[4] = {vreg[it].x, vreg[it].y, vreg[it].z, vreg[it].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int d = d4 * 4 + i;
-                const uint32_t off = slab * 8192 + (d >> 3) * 1024 + (d & 7) * 128 + ((c ^ (d & 7)) << 4) + wi * 4;
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sv_base + off), "f"(vv[i]) : "memory");
-            }
-        }
-    }
-
-    // ---- S = Q K^T
-    if (tid == 0) {
+        tma_load_2d(sQ, &tmap_qk, bar_load, h * 64, r);
+        tma_load_2d(sK, &tmap_qk, bar_load, H + h * 64, r);
+        const int vrow = (b * heads + h) * 64;                 // rows (b, h, d) of the transposed V buffer
+        tma_load_2d(sVt, &tmap_vt, bar_load, 0, vrow);
+        tma_load_2d(sVt + 8 * 1024, &tmap_vt, bar_load, 64, vrow);
+        // ---- S = Q K^T
         mbar_wait_guarded(bar_load, 0);
         tc_fence_after();
-        constexpr uint32_t idesc_s = umma_idesc(2, 128, 128);
+        constexpr uint32_t idesc_s = umma_idesc(0 /*f16*/, 128, 128);
+        const uint64_t a = umma_desc_sw128(smem_u32(sQ));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sK));
 #pragma unroll
-        for (int slab = 0; slab < 2; ++slab) {
-            const uint64_t a = umma_desc_sw128(smem_u32(sQ + slab * 16 * 1024));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(sK + slab * 16 * 1024));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a + 2 * k, bdesc + 2 * k, idesc_s, (slab | k) != 0);
-        }
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
         tc_commit(bar_s);
     }
     __syncwarp();
@@ -327,44 +364,48 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
         }
     }
     float sum = 0.f;
+    const uint32_t sp_base = smem_u32(sP);
 #pragma unroll 1
     for (int c = 0; c < 128; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(t_s + c, r);
         tmem_ld_wait();
-        float p[32];
+        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int key = c + j;
-            const bool valid = (key < S) && (!mrow || mrow[key] != 0);
-            const float e = valid ? exp2f((__uint_as_float(r[j]) - mx) * scale_log2) : 0.f;
-            sum += e;
-            p[j] = round_tf32(e);
+        for (int j = 0; j < 32; j += 2) {
+            const bool v0 = (c + j < S) && (!mrow || mrow[c + j] != 0);
+            const bool v1 = (c + j + 1 < S) && (!mrow || mrow[c + j + 1] != 0);
+            const float e0 = v0 ? exp2f((__uint_as_float(r[j]) - mx) * scale_log2) : 0.f;
+            const float e1 = v1 ? exp2f((__uint_as_float(r[j + 1]) - mx) * scale_log2) : 0.f;
+            sum += e0 + e1;
+            __half2 hh = __floats2half2_rn(e0, e1);
+            pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
         }
-        // slab (c/32), row qrow: 8 x 16-byte chunks at the swizzled positions
-        const uint32_t prow = smem_u32(sP) + (c >> 5) * 16384 + (qrow >> 3) * 1024 + (qrow & 7) * 128;
+        // slab (c / 64), row qrow: 4 x 16-byte chunks (8 keys each) starting at chunk (c % 64) / 8
+        const uint32_t prow = sp_base + (c >> 6) * 16384 + (qrow >> 3) * 1024 + (qrow & 7) * 128;
+        const int ch0 = (c & 63) >> 3;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((ch ^ (qrow & 7)) << 4)), "f"(p[4 * ch]),
-                         "f"(p[4 * ch + 1]), "f"(p[4 * ch + 2]), "f"(p[4 * ch + 3])
+        for (int ch = 0; ch < 4; ++ch) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((ch0 + ch) ^ (qrow & 7)) << 4)),
+                         "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]), "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
                          : "memory");
         }
     }
-    // generic-proxy smem writes (P, V^T) -> visible to the tensor-core (async) proxy
+    // generic-proxy smem writes (P) -> visible to the tensor-core (async) proxy; all threads are done reading S
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
-    // ---- O = P V
+    // ---- O = P V   (accumulates into TMEM columns [0,64): the score tile is dead)
     if (tid == 0) {
-        constexpr uint32_t idesc_o = umma_idesc(2, 128, 64);
+        constexpr uint32_t idesc_o = umma_idesc(0 /*f16*/, 128, 64);
 #pragma unroll
-        for (int slab = 0; slab < 4; ++slab) {
+        for (int slab = 0; slab < 2; ++slab) {
             const uint64_t a = umma_desc_sw128(smem_u32(sP + slab * 16384));
             const uint64_t bdesc = umma_desc_sw128(smem_u32(sVt + slab * 8192));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base + 128, a + 2 * k, bdesc + 2 * k, idesc_o, (slab | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a + 2 * k, bdesc + 2 * k, idesc_o, (slab | k) != 0);
         }
         tc_commit(bar_o);
     }
@@ -376,18 +417,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float *__re
 #pragma unroll 1
     for (int c = 0; c < 64; c += 32) {
         uint32_t r[32];
-        tmem_ld_32x32(t_s + 128 + c, r);
+        tmem_ld_32x32(t_s + c, r);
         tmem_ld_wait();
         if (qrow < S) {
-            float *dst = ctx + (row0 + qrow) * H + h * 64 + c;
+            __half *dst = ctx + (row0 + qrow) * H + h * 64 + c;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                o.x = round_tf32(__uint_as_float(r[j]) * inv);
-                o.y = round_tf32(__uint_as_float(r[j + 1]) * inv);
-                o.z = round_tf32(__uint_as_float(r[j + 2]) * inv);
-                o.w = round_tf32(__uint_as_float(r[j + 3]) * inv);
-                *reinterpret_cast<float4 *>(dst + j) = o;
+            for (int j = 0; j < 32; j += 8) {
+                __half2 h0 = __floats2half2_rn(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+                __half2 h1 = __floats2half2_rn(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+                __half2 h2 = __floats2half2_rn(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+                __half2 h3 = __floats2half2_rn(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                *reinterpret_cast<uint4 *>(dst + j) = pk;
             }
         }
     }
@@ -408,30 +451,43 @@ using namespace ac;
 
 struct ac_encoder {
     ac_encoder_config cfg;
-    // packed weights (device): tf32-rounded GEMM operands, fp32 everything else
+    // packed weights (device): fp16 GEMM operands, fp32 everything else
     float *word = nullptr, *pos = nullptr, *type = nullptr, *emb_ln_w = nullptr, *emb_ln_b = nullptr;
-    std::vector<float *> wqkv, bqkv, wo, bo, ln1w, ln1b, w1, b1, w2, b2, ln2w, ln2b;
-    // activations
-    float *x = nullptr, *xr = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *ffn = nullptr;
+    std::vector<__half *> wqkv, wo, w1, w2;
+    std::vector<float *> bqkv, bo, ln1w, ln1b, b1, b2, ln2w, ln2b;
+    // activations: fp32 residual stream x / pre-LN sum tmp; fp16 GEMM operands xh, qk, vT, ctx, ffn
+    float *x = nullptr, *tmp = nullptr;
+    __half *xh = nullptr, *qk = nullptr, *vT = nullptr, *ctx = nullptr, *ffn = nullptr;
+    size_t T = 0;           // token capacity (multiple of 128)
+    size_t vt_elems = 0;
     // cached TMA descriptors
-    CUtensorMap m_xr, m_ctx, m_ffn, m_qkv_att;
+    CUtensorMap m_xh, m_ctx, m_ffn, m_qk_att, m_vt_att;
+    int vt_B = -1, vt_S = -1;
     std::vector<CUtensorMap> m_wqkv, m_wo, m_w1, m_w2;
     std::vector<void *> allocs;
     int last_B = 0, last_S = 0;
 };
 
-static int dev_alloc(ac_encoder *e, float **p, size_t floats) {
+template <class T>
+static int dev_alloc(ac_encoder *e, T **p, size_t elems) {
     void *q = nullptr;
-    AC_CUDA(cudaMalloc(&q, floats * sizeof(float)));
+    AC_CUDA(cudaMalloc(&q, elems * sizeof(T)));
     e->allocs.push_back(q);
-    *p = static_cast<float *>(q);
+    *p = static_cast<T *>(q);
     return AC_OK;
 }
 
-static int pack(ac_encoder *e, float **dst, const float *src, size_t n, bool round) {
+static int pack_f32(ac_encoder *e, float **dst, const float *src, size_t n) {
     int rc = dev_alloc(e, dst, n);
     if (rc) return rc;
-    round_copy_kernel<<<256, 256>>>(src, *dst, static_cast<int64_t>(n), round ? 1 : 0);
+    round_copy_kernel<<<256, 256>>>(src, *dst, static_cast<int64_t>(n), 0);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+static int pack_f16(ac_encoder *e, __half **dst, const float *src, size_t n) {
+    int rc = dev_alloc(e, dst, n);
+    if (rc) return rc;
+    to_half_kernel<<<256, 256>>>(src, *dst, static_cast<int64_t>(n));
     AC_LAUNCH_CHECK();
     return AC_OK;
 }
@@ -445,75 +501,83 @@ extern "C" int ac_encoder_destroy(ac_encoder *enc) {
 
 extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_weights *w, ac_encoder **out) {
     AC_REQUIRE(cfg && w && out, "ac_encoder_create: null argument");
-    AC_REQUIRE(cfg->precision == AC_PREC_TF32, "ac_encoder_create: only AC_PREC_TF32 is implemented");
+    AC_REQUIRE(cfg->precision == AC_PREC_F16, "ac_encoder_create: only AC_PREC_F16 (fp16 operands, fp32 accumulate) is implemented");
     AC_REQUIRE(cfg->hidden % 128 == 0 && cfg->hidden <= 1024, "ac_encoder_create: hidden=%d must be a multiple of 128, <= 1024", cfg->hidden);
     AC_REQUIRE(cfg->heads > 0 && cfg->hidden / cfg->heads == 64 && cfg->hidden % cfg->heads == 0,
                "ac_encoder_create: head_dim must be 64 (hidden=%d heads=%d)", cfg->hidden, cfg->heads);
-    AC_REQUIRE(cfg->intermediate % 32 == 0 && cfg->layers > 0 && cfg->max_tokens > 0, "ac_encoder_create: bad dims");
+    AC_REQUIRE(cfg->intermediate % 64 == 0 && cfg->layers > 0 && cfg->max_tokens > 0, "ac_encoder_create: bad dims");
     int rc = ac_device_check();
     if (rc) return rc;
     ac_encoder *e = new ac_encoder();
     e->cfg = *cfg;
     const int H = cfg->hidden, I = cfg->intermediate, L = cfg->layers;
     const size_t T = static_cast<size_t>((cfg->max_tokens + 127) / 128 * 128);
+    e->T = T;
 #define TRY(x) do { rc = (x); if (rc) { ac_encoder_destroy(e); return rc; } } while (0)
-    TRY(pack(e, &e->word, w->word_emb, static_cast<size_t>(cfg->vocab) * H, false));
-    TRY(pack(e, &e->pos, w->pos_emb, static_cast<size_t>(cfg->max_pos) * H, false));
-    TRY(pack(e, &e->type, w->type_emb, static_cast<size_t>(cfg->type_vocab) * H, false));
-    TRY(pack(e, &e->emb_ln_w, w->emb_ln_w, H, false));
-    TRY(pack(e, &e->emb_ln_b, w->emb_ln_b, H, false));
-    auto resize_all = [&](std::vector<float *> &v) { v.assign(L, nullptr); };
-    resize_all(e->wqkv); resize_all(e->bqkv); resize_all(e->wo); resize_all(e->bo); resize_all(e->ln1w); resize_all(e->ln1b);
-    resize_all(e->w1); resize_all(e->b1); resize_all(e->w2); resize_all(e->b2); resize_all(e->ln2w); resize_all(e->ln2b);
+    TRY(pack_f32(e, &e->word, w->word_emb, static_cast<size_t>(cfg->vocab) * H));
+    TRY(pack_f32(e, &e->pos, w->pos_emb, static_cast<size_t>(cfg->max_pos) * H));
+    TRY(pack_f32(e, &e->type, w->type_emb, static_cast<size_t>(cfg->type_vocab) * H));
+    TRY(pack_f32(e, &e->emb_ln_w, w->emb_ln_w, H));
+    TRY(pack_f32(e, &e->emb_ln_b, w->emb_ln_b, H));
+    e->wqkv.assign(L, nullptr); e->wo.assign(L, nullptr); e->w1.assign(L, nullptr); e->w2.assign(L, nullptr);
+    e->bqkv.assign(L, nullptr); e->bo.assign(L, nullptr); e->ln1w.assign(L, nullptr); e->ln1b.assign(L, nullptr);
+    e->b1.assign(L, nullptr); e->b2.assign(L, nullptr); e->ln2w.assign(L, nullptr); e->ln2b.assign(L, nullptr);
     const size_t HH = static_cast<size_t>(H) * H;
     for (int l = 0; l < L; ++l) {
-        // fused QKV operand [3H, H] and bias [3H]
+        // fused QKV operand [3H, H] fp16 and bias [3H] fp32
         TRY(dev_alloc(e, &e->wqkv[l], 3 * HH));
         TRY(dev_alloc(e, &e->bqkv[l], 3 * static_cast<size_t>(H)));
         const float *ws[3] = {w->q_w[l], w->k_w[l], w->v_w[l]};
         const float *bs[3] = {w->q_b[l], w->k_b[l], w->v_b[l]};
         for (int j = 0; j < 3; ++j) {
-            round_copy_kernel<<<256, 256>>>(ws[j], e->wqkv[l] + j * HH, static_cast<int64_t>(HH), 1);
+            to_half_kernel<<<256, 256>>>(ws[j], e->wqkv[l] + j * HH, static_cast<int64_t>(HH));
             round_copy_kernel<<<8, 256>>>(bs[j], e->bqkv[l] + j * H, H, 0);
         }
-        TRY(pack(e, &e->wo[l], w->ao_w[l], HH, true));
-        TRY(pack(e, &e->bo[l], w->ao_b[l], H, false));
-        TRY(pack(e, &e->ln1w[l], w->ao_ln_w[l], H, false));
-        TRY(pack(e, &e->ln1b[l], w->ao_ln_b[l], H, false));
-        TRY(pack(e, &e->w1[l], w->ff1_w[l], static_cast<size_t>(I) * H, true));
-        TRY(pack(e, &e->b1[l], w->ff1_b[l], I, false));
-        TRY(pack(e, &e->w2[l], w->ff2_w[l], static_cast<size_t>(H) * I, true));
-        TRY(pack(e, &e->b2[l], w->ff2_b[l], H, false));
-        TRY(pack(e, &e->ln2w[l], w->out_ln_w[l], H, false));
-        TRY(pack(e, &e->ln2b[l], w->out_ln_b[l], H, false));
+        TRY(pack_f16(e, &e->wo[l], w->ao_w[l], HH));
+        TRY(pack_f32(e, &e->bo[l], w->ao_b[l], H));
+        TRY(pack_f32(e, &e->ln1w[l], w->ao_ln_w[l], H));
+        TRY(pack_f32(e, &e->ln1b[l], w->ao_ln_b[l], H));
+        TRY(pack_f16(e, &e->w1[l], w->ff1_w[l], static_cast<size_t>(I) * H));
+        TRY(pack_f32(e, &e->b1[l], w->ff1_b[l], I));
+        TRY(pack_f16(e, &e->w2[l], w->ff2_w[l], static_cast<size_t>(H) * I));
+        TRY(pack_f32(e, &e->b2[l], w->ff2_b[l], H));
+        TRY(pack_f32(e, &e->ln2w[l], w->out_ln_w[l], H));
+        TRY(pack_f32(e, &e->ln2b[l], w->out_ln_b[l], H));
     }
+    e->vt_elems = 2 * T * H;     // (b, h, d) rows x S_pad keys, S_pad = roundup(S, 8) <= 2*S for S >= 8
     TRY(dev_alloc(e, &e->x, T * H));
-    TRY(dev_alloc(e, &e->xr, T * H));
-    TRY(dev_alloc(e, &e->qkv, T * 3 * H));
-    TRY(dev_alloc(e, &e->ctx, T * H));
     TRY(dev_alloc(e, &e->tmp, T * H));
+    TRY(dev_alloc(e, &e->xh, T * H));
+    TRY(dev_alloc(e, &e->qk, T * 2 * H));
+    TRY(dev_alloc(e, &e->vT, e->vt_elems));
+    TRY(dev_alloc(e, &e->ctx, T * H));
     TRY(dev_alloc(e, &e->ffn, T * I));
-    TRY(check_cuda(cudaMemset(e->qkv, 0, T * 3 * H * sizeof(float)), "memset qkv"));
-    TRY(check_cuda(cudaMemset(e->xr, 0, T * H * sizeof(float)), "memset xr"));
-    TRY(check_cuda(cudaMemset(e->ctx, 0, T * H * sizeof(float)), "memset ctx"));
-    TRY(check_cuda(cudaMemset(e->ffn, 0, T * I * sizeof(float)), "memset ffn"));
-    // TMA descriptors
-    TRY(make_tmap_2d(&e->m_xr, e->xr, 4, T, H, static_cast<uint64_t>(H) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K));
-    TRY(make_tmap_2d(&e->m_ctx, e->ctx, 4, T, H, static_cast<uint64_t>(H) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K));
-    TRY(make_tmap_2d(&e->m_ffn, e->ffn, 4, T, I, static_cast<uint64_t>(I) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K));
-    TRY(make_tmap_2d(&e->m_qkv_att, e->qkv, 4, T, 3 * H, static_cast<uint64_t>(3 * H) * 4, 128, 32));
+    TRY(check_cuda(cudaMemset(e->qk, 0, T * 2 * H * sizeof(__half)), "memset qk"));
+    TRY(check_cuda(cudaMemset(e->vT, 0, e->vt_elems * sizeof(__half)), "memset vT"));
+    TRY(check_cuda(cudaMemset(e->xh, 0, T * H * sizeof(__half)), "memset xh"));
+    TRY(check_cuda(cudaMemset(e->ctx, 0, T * H * sizeof(__half)), "memset ctx"));
+    TRY(check_cuda(cudaMemset(e->ffn, 0, T * I * sizeof(__half)), "memset ffn"));
+    // TMA descriptors (fp16: 64 elements = 128 bytes per box row)
+    TRY(make_tmap_2d(&e->m_xh, e->xh, 2, T, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_M, 64));
+    TRY(make_tmap_2d(&e->m_ctx, e->ctx, 2, T, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_M, 64));
+    TRY(make_tmap_2d(&e->m_ffn, e->ffn, 2, T, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_M, 64));
+    TRY(make_tmap_2d(&e->m_qk_att, e->qk, 2, T, 2 * H, static_cast<uint64_t>(2 * H) * 2, 128, 64));
     e->m_wqkv.resize(L); e->m_wo.resize(L); e->m_w1.resize(L); e->m_w2.resize(L);
     for (int l = 0; l < L; ++l) {
-        TRY(make_tmap_2d(&e->m_wqkv[l], e->wqkv[l], 4, 3 * H, H, static_cast<uint64_t>(H) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K));
-        TRY(make_tmap_2d(&e->m_wo[l], e->wo[l], 4, H, H, static_cast<uint64_t>(H) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K));
-        TRY(make_tmap_2d(&e->m_w1[l], e->w1[l], 4, I, H, static_cast<uint64_t>(H) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K));
-        TRY(make_tmap_2d(&e->m_w2[l], e->w2[l], 4, H, I, static_cast<uint64_t>(I) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K));
+        TRY(make_tmap_2d(&e->m_wqkv[l], e->wqkv[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
+        TRY(make_tmap_2d(&e->m_wo[l], e->wo[l], 2, H, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
+        TRY(make_tmap_2d(&e->m_w1[l], e->w1[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
+        TRY(make_tmap_2d(&e->m_w2[l], e->w2[l], 2, H, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_N, 64));
     }
     TRY(check_cuda(cudaDeviceSynchronize(), "encoder_create sync"));
 #undef TRY
     *out = e;
     return AC_OK;
 }
+
+using EpiQKV = EpiLinear<0, true, true>;      // bias, fp16 out, V third transposed
+using EpiGelu = EpiLinear<1, true, false>;    // bias + GELU, fp16 out
+using EpiResid = EpiLinear<2, false, false>;  // bias + residual, fp32 out (pre-LayerNorm sum)
 
 extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const int32_t *mask, const int32_t *type_ids,
                                       int B, int S, float *out_unit_cls, ac_stream_t stream) {
@@ -529,13 +593,22 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const ac_encoder_config &c = e->cfg;
     const int H = c.hidden, I = c.intermediate, M = B * S;
+    const int S_pad = (S + 7) / 8 * 8;
+    AC_REQUIRE(static_cast<size_t>(B) * H * S_pad <= e->vt_elems,
+               "ac_encoder_forward_cls: B=%d sequences of S=%d exceed the transposed-V workspace; split the batch", B, S);
+    int rc;
+    if (e->vt_B != B || e->vt_S != S) {
+        // V^T view of this call: rows (b, h, d), S_pad keys per row; box = 64 keys x 64 head dims
+        if ((rc = make_tmap_2d(&e->m_vt_att, e->vT, 2, static_cast<uint64_t>(B) * H, S_pad, static_cast<uint64_t>(S_pad) * 2, 64, 64)))
+            return rc;
+        e->vt_B = B; e->vt_S = S;
+    }
     const int wpb = 8;
     const int row_blocks = (M + wpb - 1) / wpb;
-    int rc;
 
     embed_ln_kernel<<<row_blocks, wpb * 32, 0, s>>>(ids, type_ids, e->word, e->pos, e->type, e->emb_ln_w, e->emb_ln_b,
                                                     c.ln_eps, B, S, H, c.arch, c.pad_idx, c.vocab, c.max_pos,
-                                                    c.type_vocab, e->x, e->xr);
+                                                    c.type_vocab, e->x, e->xh);
     AC_LAUNCH_CHECK();
     static bool att_attr = false;
     if (!att_attr) {
@@ -543,24 +616,24 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
         att_attr = true;
     }
     for (int l = 0; l < c.layers; ++l) {
-        EpiLinear eq{e->bqkv[l], nullptr, e->qkv, M, 3 * H, 0, 1};
-        if ((rc = launch_gemm_tf32(e->m_xr, e->m_wqkv[l], M, 3 * H, H, eq, s))) return rc;
+        EpiQKV eq{e->bqkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H};
+        if ((rc = launch_gemm_tf32<EpiQKV, false, GEMM_KIND_F16>(e->m_xh, e->m_wqkv[l], M, 3 * H, H, eq, s))) return rc;
         {
             // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
-            attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qkv_att, e->qkv, mask, B, S, c.heads, H, e->ctx);
+            attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
             prof_end(slot, s);
         }
         AC_LAUNCH_CHECK();
-        EpiLinear eo{e->bo[l], e->x, e->tmp, M, H, 2, 0};
-        if ((rc = launch_gemm_tf32(e->m_ctx, e->m_wo[l], M, H, H, eo, s))) return rc;
-        layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln1w[l], e->ln1b[l], c.ln_eps, M, H, e->x, e->xr);
+        EpiResid eo{e->bo[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
+        if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ctx, e->m_wo[l], M, H, H, eo, s))) return rc;
+        layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln1w[l], e->ln1b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
-        EpiLinear e1{e->b1[l], nullptr, e->ffn, M, I, 1, 1};
-        if ((rc = launch_gemm_tf32(e->m_xr, e->m_w1[l], M, I, H, e1, s))) return rc;
-        EpiLinear e2{e->b2[l], e->x, e->tmp, M, H, 2, 0};
-        if ((rc = launch_gemm_tf32(e->m_ffn, e->m_w2[l], M, H, I, e2, s))) return rc;
-        layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln2w[l], e->ln2b[l], c.ln_eps, M, H, e->x, e->xr);
+        EpiGelu e1{e->b1[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0};
+        if ((rc = launch_gemm_tf32<EpiGelu, false, GEMM_KIND_F16>(e->m_xh, e->m_w1[l], M, I, H, e1, s))) return rc;
+        EpiResid e2{e->b2[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
+        if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ffn, e->m_w2[l], M, H, I, e2, s))) return rc;
+        layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln2w[l], e->ln2b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
     }
     cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(e->x, B, S, H, out_unit_cls);
@@ -578,16 +651,42 @@ extern "C" int ac_encoder_last_hidden(ac_encoder *e, float *out, int64_t n_float
     return AC_OK;
 }
 
-extern "C" int ac_linear_tc(const float *X, const float *W, const float *bias, const float *residual, float *Y, int M,
-                            int N, int K, int epi, int round_out, ac_stream_t stream) {
-    AC_REQUIRE(X && W && Y && M > 0 && N > 0 && K > 0, "ac_linear_tc: bad arguments");
-    AC_REQUIRE(K % 4 == 0 && N % 4 == 0, "ac_linear_tc: K and N must be multiples of 4 (16-byte rows)");
+// generic tensor-core linear exposed for parity tests / roofline measurement.
+//   precision AC_PREC_TF32: X, W fp32 (used as stored, tf32 truncation by the MMA unless pre-rounded), Y fp32
+//   precision AC_PREC_F16 : X, W fp16, Y fp32 (out_half = 0) or fp16 (out_half = 1)
+template <int MODE, bool OUT_HALF, int KIND>
+static int linear_tc_dispatch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, const float *residual, void *Y,
+                              int M, int N, int K, int round_out, cudaStream_t s) {
+    EpiLinear<MODE, OUT_HALF, false> e{bias, residual, Y, M, N, N, round_out, nullptr, 0, 0, 0, 0};
+    return launch_gemm_tf32<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
+}
+
+extern "C" int ac_linear_tc(const void *X, const void *W, const float *bias, const float *residual, void *Y, int M, int N,
+                            int K, int epi, int round_out, int precision, int out_half, ac_stream_t stream) {
+    AC_REQUIRE(X && W && Y && bias && M > 0 && N > 0 && K > 0, "ac_linear_tc: bad arguments (bias is required)");
     AC_REQUIRE(epi >= 0 && epi <= 2 && (epi != 2 || residual), "ac_linear_tc: bad epilogue");
+    AC_REQUIRE(precision == AC_PREC_TF32 || precision == AC_PREC_F16, "ac_linear_tc: bad precision");
+    AC_REQUIRE(!(out_half && epi == 2), "ac_linear_tc: the residual epilogue writes fp32");
+    const int es = precision == AC_PREC_F16 ? 2 : 4;
+    AC_REQUIRE((K * es) % 16 == 0 && N % 8 == 0, "ac_linear_tc: rows must be 16-byte multiples and N %% 8 == 0");
     int rc = ac_device_check();
     if (rc) return rc;
     CUtensorMap ta, tb;
-    if ((rc = make_tmap_2d(&ta, X, 4, M, K, static_cast<uint64_t>(K) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
-    if ((rc = make_tmap_2d(&tb, W, 4, N, K, static_cast<uint64_t>(K) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
-    EpiLinear e{bias, residual, Y, M, N, epi, round_out};
-    return launch_gemm_tf32(ta, tb, M, N, K, e, static_cast<cudaStream_t>(stream));
+    const uint32_t bk = 128 / es;
+    if ((rc = make_tmap_2d(&ta, X, es, M, K, static_cast<uint64_t>(K) * es, GEMM_BLOCK_M, bk))) return rc;
+    if ((rc = make_tmap_2d(&tb, W, es, N, K, static_cast<uint64_t>(K) * es, GEMM_BLOCK_N, bk))) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (precision == AC_PREC_TF32) {
+        AC_REQUIRE(!out_half, "ac_linear_tc: tf32 path writes fp32");
+        if (epi == 0) return linear_tc_dispatch<0, false, GEMM_KIND_TF32>(ta, tb, bias, residual, Y, M, N, K, round_out, s);
+        if (epi == 1) return linear_tc_dispatch<1, false, GEMM_KIND_TF32>(ta, tb, bias, residual, Y, M, N, K, round_out, s);
+        return linear_tc_dispatch<2, false, GEMM_KIND_TF32>(ta, tb, bias, residual, Y, M, N, K, round_out, s);
+    }
+    if (out_half) {
+        if (epi == 0) return linear_tc_dispatch<0, true, GEMM_KIND_F16>(ta, tb, bias, residual, Y, M, N, K, 0, s);
+        return linear_tc_dispatch<1, true, GEMM_KIND_F16>(ta, tb, bias, residual, Y, M, N, K, 0, s);
+    }
+    if (epi == 0) return linear_tc_dispatch<0, false, GEMM_KIND_F16>(ta, tb, bias, residual, Y, M, N, K, 0, s);
+    if (epi == 1) return linear_tc_dispatch<1, false, GEMM_KIND_F16>(ta, tb, bias, residual, Y, M, N, K, 0, s);
+    return linear_tc_dispatch<2, false, GEMM_KIND_F16>(ta, tb, bias, residual, Y, M, N, K, 0, s);
 }

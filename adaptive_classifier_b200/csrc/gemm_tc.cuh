@@ -1,10 +1,14 @@
 // gemm_tc.cuh -- persistent warp-specialised tcgen05 GEMM mainloop for sm_100a (B200).
 //
-//   D[M,N] (fp32, TMEM) = A[M,K] * B[N,K]^T      A, B fp32 containers holding tf32 values, K-major
+//   D[M,N] (fp32, TMEM) = A[M,K] * B[N,K]^T      K-major operands, either
+//       kKind = GEMM_KIND_TF32 : fp32 containers holding tf32 values (kind::tf32, 32 elements per 128-byte k-block)
+//       kKind = GEMM_KIND_F16  : fp16 values                         (kind::f16,  64 elements per 128-byte k-block)
+//   (same bytes per stage, same descriptors; fp16 has tf32's 10-bit mantissa at twice the tensor rate)
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, 128 x BLOCK_N x 8)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue functor -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue functor -> global); warp w owns TMEM
+//                 lane quarter w%4 and the column half (w-2)/4 of the 128 x 256 accumulator
 //
 // Two TMEM accumulator buffers (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile
 // i+1.  The epilogue is a functor so the same mainloop serves the encoder linears (bias / GELU /
@@ -16,17 +20,22 @@ namespace ac {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_N = 256;
-constexpr int GEMM_BLOCK_K = 32;                    // fp32 elements = 128 bytes = one swizzle row
+constexpr int GEMM_BLOCK_K = 32;                    // tf32: fp32 elements per 128-byte swizzle row
+constexpr int GEMM_KIND_TF32 = 0, GEMM_KIND_F16 = 1;
+__host__ __device__ constexpr int gemm_block_k(int kind) { return kind == GEMM_KIND_F16 ? 64 : 32; }
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_UMMA_K = 8;                      // tf32: 32 bytes per MMA K-step
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // 320
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 4;   // 16 KB
 constexpr int GEMM_B_STAGE_BYTES = GEMM_BLOCK_N * GEMM_BLOCK_K * 4;   // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES;
-// per-epilogue-warp staging tile [32 rows][36 floats] for the thread-row -> coalesced-row transpose
-constexpr int GEMM_EPI_STAGE_STRIDE = 36;
-constexpr int GEMM_EPI_STAGE_BYTES = 32 * GEMM_EPI_STAGE_STRIDE * 4;   // 4608 B per warp
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 4 * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// per-epilogue-warp staging tile for the thread-row -> coalesced-row transpose: 32 rows x 80 bytes
+// (16 fp32 or 32 fp16 payload + 16 B pad: conflict-free 16-byte accesses for both the row writes and the
+// transposed reads)
+constexpr int GEMM_EPI_STAGE_ROW_BYTES = 80;
+constexpr int GEMM_EPI_STAGE_BYTES = 32 * GEMM_EPI_STAGE_ROW_BYTES;   // 2560 B per warp
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_TMEM_COLS = 512;
 
 #ifndef AC_MBAR_WATCHDOG
@@ -56,15 +65,16 @@ struct GemmTileInfo {
 // Epilogue concept (parameters live in the functor, per-thread running state in Epi::State):
 //   struct Epi { struct State {...};
 //                __device__ void begin_cta(State&, int warp_q, int lane) const;
+//                __device__ void prefetch(State&, const GemmTileInfo&, int row, int col0, int lane) const;
 //                __device__ void tile(State&, const GemmTileInfo&, int row /*global m*/, int col0 /*global n of v[0]*/,
-//                                     const float (&v)[32], float *stage, int lane) const;   // 8x per tile per thread
-//                      (stage = this warp's private [32][36] fp32 smem tile for transposing to coalesced rows)
+//                                     const float (&v)[32], uint8_t *stage, int lane) const;   // 4x per tile per thread
+//                      (stage = this warp's private 32 x 80-byte smem tile for transposing to coalesced rows)
 //                __device__ void end_cta(State&, int warp_q, int lane) const; };
 //
 // Tile order: kMFastest = false -> n fastest (tiles of the same A row-block run concurrently and share A
 // through L2: encoder linears, A = activations); kMFastest = true -> m fastest (consecutive CTAs share the
 // same B tile: kNN, B = prototype rows streamed once from HBM).
-template <class Epi, bool kMFastest = false>
+template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  int M, int N, int K, Epi epi) {
@@ -72,8 +82,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + GEMM_STAGES * GEMM_A_STAGE_BYTES;
-    float *epi_stage = reinterpret_cast<float *>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + 4 * GEMM_EPI_STAGE_BYTES);
+    uint8_t *epi_stage = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES);
     uint64_t *full_bar = bars;                        // [STAGES]
     uint64_t *empty_bar = bars + GEMM_STAGES;         // [STAGES]
     uint64_t *tmem_full = bars + 2 * GEMM_STAGES;     // [2]
@@ -85,7 +95,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int tiles_m = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
     const int tiles_n = (N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
     const int num_tiles = tiles_m * tiles_n;
-    const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    constexpr int BK = gemm_block_k(kKind);            // elements per 128-byte k-block
+    const int num_kb = (K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -96,8 +107,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4);
-        mbar_init(&tmem_empty[1], 4);
+        mbar_init(&tmem_empty[0], GEMM_EPI_WARPS);
+        mbar_init(&tmem_empty[1], GEMM_EPI_WARPS);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -120,8 +131,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * GEMM_A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-                    tma_load_2d(smem_b + stage * GEMM_B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+                    tma_load_2d(smem_a + stage * GEMM_A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0);
+                    tma_load_2d(smem_b + stage * GEMM_B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
                     if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -129,7 +140,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ---------------- MMA issuer (one thread) ----------------
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(2 /*tf32*/, GEMM_BLOCK_M, GEMM_BLOCK_N);
+            constexpr uint32_t idesc = umma_idesc(kKind == GEMM_KIND_F16 ? 0u /*f16*/ : 2u /*tf32*/, GEMM_BLOCK_M, GEMM_BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -146,7 +157,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
                         // advance 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
-                        umma_tf32(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        if (kKind == GEMM_KIND_F16) umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        else umma_tf32(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     }
                     tc_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
                     if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
@@ -158,6 +170,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else {
         // ---------------- epilogue warps ----------------
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int chalf = (warp - 2) >> 2;           // which 128-column half of the accumulator this warp drains
         typename Epi::State est;
         epi.begin_cta(est, q, lane);
         int acc = 0;
@@ -172,15 +185,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_after();
             const int row = ti.m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BLOCK_N;
+            const int c_lo = chalf * (GEMM_BLOCK_N / 2);
 #pragma unroll 1
-            for (int c = 0; c < GEMM_BLOCK_N; c += 32) {
+            for (int c = c_lo; c < c_lo + GEMM_BLOCK_N / 2; c += 32) {
+                epi.prefetch(est, ti, row, ti.n0 + c, lane);   // e.g. residual loads, issued before the TMEM wait
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * (32 * GEMM_EPI_STAGE_STRIDE), lane);
+                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -199,11 +214,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // host-side launcher
-template <class Epi, bool kMFastest = false>
+template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32>
 int launch_gemm_tf32(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
                      cudaStream_t stream, int max_ctas = 0, int prof_cls = PROF_GEMM_LINEAR, double prof_bytes = 0.0) {
     static bool attr_set = false;   // per instantiation
-    auto kern = gemm_tf32_kernel<Epi, kMFastest>;
+    auto kern = gemm_tf32_kernel<Epi, kMFastest, kKind>;
     if (!attr_set) {
         AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         attr_set = true;

@@ -52,8 +52,9 @@ struct EpiKnn {
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
     }
 
+    __device__ __forceinline__ void prefetch(State &, const GemmTileInfo &, int, int, int) const {}
     __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
-                                         float * /*stage*/, int /*lane*/) const {
+                                         uint8_t * /*stage*/, int /*lane*/) const {
         // all lanes walk the same 32 prototype rows; each lane tests them against its own query's threshold
 #pragma unroll
         for (int j = 0; j < 32; ++j) {   // fully unrolled: v[] must stay in registers
@@ -81,7 +82,8 @@ struct EpiKnn {
 
     __device__ __forceinline__ void end_cta(State &st, int q, int lane) const {
         const int mt = blockIdx.x % tiles_m;
-        const int slot = blockIdx.x / tiles_m;
+        // two epilogue warps share a query row (one per 128-column half of every tile): each owns a slot
+        const int slot = (blockIdx.x / tiles_m) * 2 + (((threadIdx.x >> 5) - 2) >> 2);
         const int row = mt * GEMM_BLOCK_M + q * 32 + lane;
         if (row >= B) return;
         float *ck = cand_key + (static_cast<int64_t>(row) * slots + slot) * KNN_KC;
@@ -212,7 +214,7 @@ __global__ void knn_scatter_results_kernel(const float *__restrict__ d, const in
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 struct KnnTcPlan {
-    int tiles_m, slots, grid;
+    int tiles_m, slots, grid, grid_ctas;
     size_t off_qr, off_qn, off_pn, off_bmax, off_pmax, off_ckey, off_cidx, off_cidx64, off_skey, off_sidx, off_ridx, off_T,
         off_rd, off_ri, off_fail, off_fq, off_fd, off_fi, off_sel, sel_bytes, off_exact, exact_bytes, total;
 };
@@ -226,6 +228,8 @@ static KnnTcPlan plan_knn_tc(int B, int64_t N, int D, int k) {
     const int64_t tiles_n = (N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
     if (p.slots > tiles_n) p.slots = static_cast<int>(tiles_n);
     p.grid = p.slots * p.tiles_m;
+    p.grid_ctas = p.grid;
+    p.slots *= 2;   // candidate lists per query: one per (CTA, accumulator column half)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t Bp = static_cast<size_t>(p.tiles_m) * GEMM_BLOCK_M;
@@ -315,9 +319,9 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, 
     CUtensorMap ta, tb;
     if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
     if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
-    EpiKnn epi{pn_use, ckey, cidx, B, N, pl.tiles_m, pl.slots};
+    EpiKnn epi{pn_use, ckey, cidx, B, N, pl.tiles_m, pl.slots};   // slots = 2 per CTA
     // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes)
-    if ((rc = launch_gemm_tf32<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid,
+    if ((rc = launch_gemm_tf32<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
                                               PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D))) return rc;
 
     // ---- merge per-CTA lists, pick KP candidates + exclusion threshold

@@ -146,8 +146,9 @@ int ac_ewc_penalty(const ac_head_params *p, const ac_head_params *fisher, const 
  * ------------------------------------------------------------------------------------------ */
 enum { AC_ARCH_BERT = 0, AC_ARCH_ROBERTA = 1 };
 enum {
-    AC_PREC_TF32 = 0,   /* tcgen05 kind::tf32, operands rounded to tf32 (RNE), fp32 accumulate */
-    AC_PREC_BF16 = 1    /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (2x rate, ~1.4e-3 distance error) */
+    AC_PREC_TF32 = 0,   /* tcgen05 kind::tf32 on fp32 storage (kNN coarse pass, ac_linear_tc tests) */
+    AC_PREC_F16 = 1     /* tcgen05 kind::f16 with fp16 operands (RNE from fp32; same 10-bit mantissa as tf32),
+                           fp32 accumulation; the encoder's precision: 1.7e-4 on distances, bf16 would be 1.4e-3 */
 };
 
 typedef struct {
@@ -185,12 +186,12 @@ int ac_encoder_forward_cls(ac_encoder *enc, const int32_t *ids, const int32_t *m
 /* debugging / parity: copy the full last hidden state [B*S,H] of the previous forward */
 int ac_encoder_last_hidden(ac_encoder *enc, float *out, int64_t n_floats, ac_stream_t stream);
 
-/* generic tensor-core linear (the encoder's GEMM with its fused epilogues), exposed for parity
- * tests and roofline measurement: Y[M,N] = epi(X[M,K] W[N,K]^T + bias) (+ residual).
- * epi: 0 bias, 1 bias+GELU(erf), 2 bias+residual.  K % 32 == 0, N % 16 == 0.  precision AC_PREC_*:
- * operands are used as stored (caller pre-rounds); round_out != 0 rounds Y to tf32 (RNE). */
-int ac_linear_tc(const float *X, const float *W, const float *bias, const float *residual,
-                 float *Y, int M, int N, int K, int epi, int round_out, ac_stream_t stream);
+/* generic tensor-core linear (the encoder's GEMM with its fused epilogues), exposed for parity tests and roofline
+ * measurement: Y[M,N] = epi(X[M,K] W[N,K]^T + bias) (+ residual).  epi: 0 bias, 1 bias+GELU(erf), 2 bias+fp32 residual.
+ * precision AC_PREC_TF32: X, W, Y fp32 (operands used as stored; round_out != 0 rounds Y to tf32);
+ * precision AC_PREC_F16 : X, W fp16, Y fp32 or (out_half != 0, epi != 2) fp16. */
+int ac_linear_tc(const void *X, const void *W, const float *bias, const float *residual, void *Y,
+                 int M, int N, int K, int epi, int round_out, int precision, int out_half, ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * predict_batch() glue on the device (classifier.py:1329-1384) and the end-to-end pipeline.

@@ -50,6 +50,28 @@ def test_linear_tc_matches_fp64(cabi, M, N, K, epi):
     assert err <= 2e-5 * max(scale, 1.0), (err, scale)
 
 
+@pytest.mark.parametrize("M,N,K,epi,out_half", [(256, 256, 64, 0, True), (1000, 768, 768, 2, False), (4096, 3072, 768, 1, True),
+                                                  (300, 80, 128, 0, False), (128, 2304, 768, 0, True), (77, 768, 3072, 2, False)])
+def test_linear_f16_matches_fp64(cabi, M, N, K, epi, out_half):
+    """the encoder's GEMM: fp16 operands (exact products), fp32 accumulation in TMEM, fused epilogues"""
+    g = torch.Generator().manual_seed(M + N + K + 1)
+    X = torch.randn(M, K, generator=g).half()
+    W = (torch.randn(N, K, generator=g) * 0.05).half()
+    b = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g)
+    ref = X.double() @ W.double().t() + b.double()
+    if epi == 1:
+        ref = 0.5 * ref * (1 + torch.erf(ref / 2 ** 0.5))
+    if epi == 2:
+        ref = ref + R.double()
+    Y = cabi.linear_tc(X.cuda(), W.cuda(), b.cuda(), R.cuda() if epi == 2 else None, epi=epi, out_half=out_half).cpu()
+    assert Y.dtype == (torch.float16 if out_half else torch.float32)
+    err = (Y.double() - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    # fp32 accumulation order + the 1.5e-7 erf approximation; fp16 output adds one rounding (2^-11 relative)
+    assert err <= (1e-3 if out_half else 3e-5) * scale, (err, scale)
+
+
 # ------------------------------------------------------------------------------------------------ kNN exact
 @pytest.mark.parametrize("B,N,D,k", [(1, 5000, 768, 5), (3, 5000, 768, 64), (8, 1000, 768, 1000), (20, 3000, 1024, 7),
                                      (5, 257, 10, 3), (2, 3, 768, 5), (1, 20000, 768, 1000)])
