@@ -26,7 +26,7 @@ AC_PREC_TF32, AC_PREC_F16 = 0, 1
 
 EXPORTS = [
     "ac_version", "ac_last_error", "ac_device_check",
-    "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
+    "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
     "ac_segment_mean",
     "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
@@ -58,7 +58,7 @@ class TrainCfg(Structure):
 class EncoderConfig(Structure):
     _fields_ = [("arch", c_int), ("layers", c_int), ("hidden", c_int), ("heads", c_int), ("intermediate", c_int),
                 ("vocab", c_int), ("max_pos", c_int), ("type_vocab", c_int), ("pad_idx", c_int),
-                ("ln_eps", c_float), ("precision", c_int), ("max_tokens", c_int)]
+                ("ln_eps", c_float), ("precision", c_int), ("max_tokens", c_int), ("cls_only", c_int)]
 
 
 _PP = POINTER(c_void_p)
@@ -90,8 +90,9 @@ def load_library() -> ctypes.CDLL:
     L.ac_last_error.restype = c_char_p
     L.ac_device_check.restype = c_int
     L.ac_knn_workspace_bytes.argtypes = [c_int, c_int64, c_int, c_int, c_int, POINTER(c_size_t)]
-    L.ac_knn_l2_topk.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
+    L.ac_knn_l2_topk.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_size_t, c_int, c_void_p]
+    L.ac_knn_make_shadow.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
     L.ac_row_sqnorm.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
     L.ac_topk_merge.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_proto_scores.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
@@ -115,7 +116,7 @@ def load_library() -> ctypes.CDLL:
     L.ac_topk_desc.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_blend_topk.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]
-    L.ac_pipeline_create.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(HeadParams),
+    L.ac_pipeline_create.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(HeadParams),
                                      c_int, c_int, c_int, c_int64, POINTER(c_void_p)]
     L.ac_pipeline_destroy.argtypes = [c_void_p]
     L.ac_pipeline_predict_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
@@ -168,8 +169,17 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+def knn_make_shadow(P: torch.Tensor) -> torch.Tensor:
+    """fp16 (RNE) shadow of the prototype matrix for the tensor path's coarse pass"""
+    L = load_library()
+    P = _f32c(P)
+    out = torch.empty(P.shape, dtype=torch.float16, device=P.device)
+    check(L.ac_knn_make_shadow(P.data_ptr(), P.shape[0], P.shape[1], out.data_ptr(), stream_ptr()), "ac_knn_make_shadow")
+    return out
+
+
 def knn_l2_topk(Q: torch.Tensor, P: torch.Tensor, k: int, *, p_sqnorm: Optional[torch.Tensor] = None,
-                row_offset: int = 0, algo: int = AC_KNN_AUTO):
+                p_half: Optional[torch.Tensor] = None, row_offset: int = 0, algo: int = AC_KNN_AUTO):
     L = load_library()
     Q = _f32c(Q)
     P = _f32c(P)
@@ -181,8 +191,8 @@ def knn_l2_topk(Q: torch.Tensor, P: torch.Tensor, k: int, *, p_sqnorm: Optional[
     ws = _workspace(nbytes.value, Q.device)
     out_d = torch.empty((B, k), dtype=torch.float32, device=Q.device)
     out_i = torch.empty((B, k), dtype=torch.int64, device=Q.device)
-    check(L.ac_knn_l2_topk(Q.data_ptr(), P.data_ptr(), ptr(p_sqnorm), B, N, D, k, out_d.data_ptr(), out_i.data_ptr(),
-                           row_offset, ws.data_ptr(), ws.numel(), algo, stream_ptr()), "ac_knn_l2_topk")
+    check(L.ac_knn_l2_topk(Q.data_ptr(), P.data_ptr(), ptr(p_sqnorm), ptr(p_half), B, N, D, k, out_d.data_ptr(),
+                           out_i.data_ptr(), row_offset, ws.data_ptr(), ws.numel(), algo, stream_ptr()), "ac_knn_l2_topk")
     return out_d, out_i
 
 
@@ -335,7 +345,7 @@ class Encoder:
 
     def __init__(self, sd: dict, *, arch: str, layers: int, hidden: int, heads: int, intermediate: int, vocab: int,
                  max_pos: int, type_vocab: int, ln_eps: float, pad_idx: int = 0, max_tokens: int = 65536,
-                 device="cuda"):
+                 device="cuda", cls_only: bool = True):
         L = load_library()
         self._L = L
         self.hidden = hidden
@@ -369,7 +379,7 @@ class Encoder:
         w.ff2_w, w.ff2_b = arr(p + "output.dense.weight"), arr(p + "output.dense.bias")
         w.out_ln_w, w.out_ln_b = arr(p + "output.LayerNorm.weight"), arr(p + "output.LayerNorm.bias")
         cfg = EncoderConfig(AC_ARCH_BERT if arch == "bert" else AC_ARCH_ROBERTA, layers, hidden, heads, intermediate,
-                            vocab, max_pos, type_vocab, pad_idx, ln_eps, AC_PREC_F16, max_tokens)
+                            vocab, max_pos, type_vocab, pad_idx, ln_eps, AC_PREC_F16, max_tokens, 1 if cls_only else 0)
         h = c_void_p()
         with torch.cuda.device(dev):
             check(L.ac_encoder_create(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(h)), "ac_encoder_create")
@@ -481,15 +491,16 @@ class Pipeline:
     """ids -> E -> K -> class scores -> H -> blend, device or host (pinned) buffers at the boundary."""
 
     def __init__(self, enc: Encoder, P: torch.Tensor, max_B: int, S: int, k: int, *, head: Optional[dict] = None,
-                 row_class: Optional[torch.Tensor] = None, p_sqnorm: Optional[torch.Tensor] = None, row_offset: int = 0):
+                 row_class: Optional[torch.Tensor] = None, p_sqnorm: Optional[torch.Tensor] = None,
+                 p_half: Optional[torch.Tensor] = None, row_offset: int = 0):
         L = load_library()
         self._L = L
-        self.enc, self.P, self.p_sqnorm, self.row_class = enc, _f32c(P), p_sqnorm, row_class
+        self.enc, self.P, self.p_sqnorm, self.row_class, self.p_half = enc, _f32c(P), p_sqnorm, row_class, p_half
         self.head = head
         self.max_B, self.S, self.k = max_B, S, k
         hp = head_params_struct(head) if head is not None else None
         h = c_void_p()
-        check(L.ac_pipeline_create(enc.handle, self.P.data_ptr(), ptr(p_sqnorm), ptr(row_class), self.P.shape[0],
+        check(L.ac_pipeline_create(enc.handle, self.P.data_ptr(), ptr(p_sqnorm), ptr(p_half), ptr(row_class), self.P.shape[0],
                                    self.P.shape[1], ctypes.byref(hp) if hp is not None else None, max_B, S, k,
                                    row_offset, ctypes.byref(h)), "ac_pipeline_create")
         self.handle = h

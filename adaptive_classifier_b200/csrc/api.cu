@@ -122,8 +122,8 @@ int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in
                 float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream);
 // from knn_tc.cu
 size_t knn_tc_workspace(int B, int64_t N, int D, int k);
-int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, int64_t N, int D, int k, float *out_d,
-                  int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, cudaStream_t stream);
+int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N, int D, int k,
+                  float *out_d, int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, cudaStream_t stream);
 
 // exact path processes the queries in blocks so the [qb, N] distance slab stays bounded
 static int exact_query_block(int B, int64_t N) {
@@ -219,8 +219,8 @@ extern "C" int ac_knn_workspace_bytes(int B, int64_t N, int D, int k, int algo, 
     return AC_OK;
 }
 
-extern "C" int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqnorm, int B, int64_t N, int D, int k,
-                              float *out_d, int64_t *out_i, int64_t row_offset, void *workspace,
+extern "C" int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N,
+                              int D, int k, float *out_d, int64_t *out_i, int64_t row_offset, void *workspace,
                               size_t workspace_bytes, int algo, ac_stream_t stream) {
     AC_REQUIRE(Q && out_d && out_i && B >= 0 && N >= 0 && D > 0, "ac_knn_l2_topk: bad arguments");
     AC_REQUIRE(k >= 1 && k <= AC_KNN_MAX_K, "ac_knn_l2_topk: k=%d outside [1,%d]", k, AC_KNN_MAX_K);
@@ -236,7 +236,8 @@ extern "C" int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqn
     const size_t avail = workspace_bytes - slack;
     if (a == AC_KNN_TENSOR) {
         AC_REQUIRE(k <= 16 && D % 32 == 0, "ac_knn_l2_topk: tensor path needs k <= 16 and D %% 32 == 0");
-        return knn_tc_search(Q, P, p_sqnorm, B, N, D, k, out_d, out_i, row_offset, ws, avail, s);
+        AC_REQUIRE(!p_half || D % 64 == 0, "ac_knn_l2_topk: the fp16 shadow path needs D %% 64 == 0");
+        return knn_tc_search(Q, P, p_sqnorm, p_half, B, N, D, k, out_d, out_i, row_offset, ws, avail, s);
     }
     return knn_exact(Q, P, B, N, D, k, out_d, out_i, row_offset, ws, avail, s);
 }

@@ -300,6 +300,20 @@ __global__ void cls_normalize_kernel(const float *__restrict__ x, int B, int S, 
     for (int i = lane; i < H; i += 32) out[static_cast<int64_t>(bq) * H + i] = src[i] / nrm;
 }
 
+// last layer: only the CLS row of every sequence is needed downstream of attention (classifier.py:1272), so the
+// output projection, both LayerNorms and the FFN of the last layer run on B rows instead of B*S
+__global__ void gather_cls_kernel(const __half *__restrict__ ctx, const float *__restrict__ x, int B, int S, int H,
+                                  __half *__restrict__ ctx_cls, float *__restrict__ x_cls) {
+    const int bq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (bq >= B) return;
+    const int64_t src = static_cast<int64_t>(bq) * S * H, dst = static_cast<int64_t>(bq) * H;
+    for (int i = lane; i < H / 8; i += 32)
+        reinterpret_cast<uint4 *>(ctx_cls + dst)[i] = reinterpret_cast<const uint4 *>(ctx + src)[i];
+    for (int i = lane; i < H / 4; i += 32)
+        reinterpret_cast<float4 *>(x_cls + dst)[i] = reinterpret_cast<const float4 *>(x + src)[i];
+}
+
 __global__ void round_copy_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t n, int do_round) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -501,12 +515,18 @@ struct ac_encoder {
     __half *xh = nullptr, *qk = nullptr, *vT = nullptr, *ctx = nullptr, *ffn = nullptr;
     size_t T = 0;           // token capacity (multiple of 128)
     size_t vt_elems = 0;
+    // compact CLS-row buffers of the last layer (Bc rows)
+    size_t Bc = 0;
+    float *x_cls = nullptr, *tmp_cls = nullptr;
+    __half *xh_cls = nullptr, *ctx_cls = nullptr, *ffn_cls = nullptr;
+    CUtensorMap m_xh_cls, m_ctx_cls, m_ffn_cls;
     // cached TMA descriptors
     CUtensorMap m_xh, m_ctx, m_ffn, m_qk_att, m_vt_att;
     int vt_B = -1, vt_S = -1;
     std::vector<CUtensorMap> m_wqkv, m_wo, m_w1, m_w2;
     std::vector<void *> allocs;
     int last_B = 0, last_S = 0;
+    bool last_cls_only = false;
 };
 
 template <class T>
@@ -593,6 +613,15 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
     TRY(dev_alloc(e, &e->vT, e->vt_elems));
     TRY(dev_alloc(e, &e->ctx, T * H));
     TRY(dev_alloc(e, &e->ffn, T * I));
+    e->Bc = T < 16384 ? T : 16384;
+    TRY(dev_alloc(e, &e->x_cls, e->Bc * H));
+    TRY(dev_alloc(e, &e->tmp_cls, e->Bc * H));
+    TRY(dev_alloc(e, &e->xh_cls, e->Bc * H));
+    TRY(dev_alloc(e, &e->ctx_cls, e->Bc * H));
+    TRY(dev_alloc(e, &e->ffn_cls, e->Bc * I));
+    TRY(check_cuda(cudaMemset(e->xh_cls, 0, e->Bc * H * sizeof(__half)), "memset xh_cls"));
+    TRY(check_cuda(cudaMemset(e->ctx_cls, 0, e->Bc * H * sizeof(__half)), "memset ctx_cls"));
+    TRY(check_cuda(cudaMemset(e->ffn_cls, 0, e->Bc * I * sizeof(__half)), "memset ffn_cls"));
     TRY(check_cuda(cudaMemset(e->qk, 0, T * 2 * H * sizeof(__half)), "memset qk"));
     TRY(check_cuda(cudaMemset(e->vT, 0, e->vt_elems * sizeof(__half)), "memset vT"));
     TRY(check_cuda(cudaMemset(e->xh, 0, T * H * sizeof(__half)), "memset xh"));
@@ -603,6 +632,9 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
     TRY(make_tmap_2d(&e->m_ctx, e->ctx, 2, T, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_M, 64));
     TRY(make_tmap_2d(&e->m_ffn, e->ffn, 2, T, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_M, 64));
     TRY(make_tmap_2d(&e->m_qk_att, e->qk, 2, T, 2 * H, static_cast<uint64_t>(2 * H) * 2, 128, 64));
+    TRY(make_tmap_2d(&e->m_xh_cls, e->xh_cls, 2, e->Bc, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_M, 64));
+    TRY(make_tmap_2d(&e->m_ctx_cls, e->ctx_cls, 2, e->Bc, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_M, 64));
+    TRY(make_tmap_2d(&e->m_ffn_cls, e->ffn_cls, 2, e->Bc, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_M, 64));
     e->m_wqkv.resize(L); e->m_wo.resize(L); e->m_w1.resize(L); e->m_w2.resize(L);
     for (int l = 0; l < L; ++l) {
         TRY(make_tmap_2d(&e->m_wqkv[l], e->wqkv[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
@@ -666,6 +698,28 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             prof_end(slot, s);
         }
         AC_LAUNCH_CHECK();
+        if (l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc) {
+            // ---- CLS-only tail of the last layer: M = B rows
+            const int cb = (B + wpb - 1) / wpb;
+            gather_cls_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, e->ctx_cls, e->x_cls);
+            AC_LAUNCH_CHECK();
+            EpiResid eo{e->bo[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
+            if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ctx_cls, e->m_wo[l], B, H, H, eo, s))) return rc;
+            layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln1w[l], e->ln1b[l], c.ln_eps, B, H, e->x_cls, e->xh_cls);
+            AC_LAUNCH_CHECK();
+            EpiGelu e1{e->b1[l], nullptr, e->ffn_cls, B, I, I, 0, nullptr, 0, 0, 0, 0};
+            if ((rc = launch_gemm_tf32<EpiGelu, false, GEMM_KIND_F16>(e->m_xh_cls, e->m_w1[l], B, I, H, e1, s))) return rc;
+            EpiResid e2{e->b2[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
+            if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ffn_cls, e->m_w2[l], B, H, I, e2, s))) return rc;
+            layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
+            AC_LAUNCH_CHECK();
+            cls_normalize_kernel<<<cb, wpb * 32, 0, s>>>(e->x_cls, B, 1, H, out_unit_cls);
+            AC_LAUNCH_CHECK();
+            e->last_B = B;
+            e->last_S = S;
+            e->last_cls_only = true;
+            return AC_OK;
+        }
         EpiResid eo{e->bo[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
         if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ctx, e->m_wo[l], M, H, H, eo, s))) return rc;
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln1w[l], e->ln1b[l], c.ln_eps, M, H, e->x, e->xh);
@@ -681,11 +735,14 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     AC_LAUNCH_CHECK();
     e->last_B = B;
     e->last_S = S;
+    e->last_cls_only = false;
     return AC_OK;
 }
 
 extern "C" int ac_encoder_last_hidden(ac_encoder *e, float *out, int64_t n_floats, ac_stream_t stream) {
     AC_REQUIRE(e && out, "ac_encoder_last_hidden: null argument");
+    AC_REQUIRE(!e->last_cls_only, "ac_encoder_last_hidden: the previous forward computed only the CLS rows of the last layer "
+                                  "(create the encoder with cls_only = 0 to keep the full hidden state)");
     const int64_t have = static_cast<int64_t>(e->last_B) * e->last_S * e->cfg.hidden;
     AC_REQUIRE(n_floats <= have, "ac_encoder_last_hidden: asked %lld floats, have %lld", (long long)n_floats, (long long)have);
     AC_CUDA(cudaMemcpyAsync(out, e->x, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));

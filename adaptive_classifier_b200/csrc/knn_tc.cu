@@ -15,6 +15,7 @@
 // Replaces faiss.IndexFlatL2.search (/root/reference/src/adaptive_classifier/memory.py:110-114) for the
 // batched, large-N configuration of BASELINE.json (configs[1], configs[2]).
 #include "gemm_tc.cuh"
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 namespace ac {
@@ -102,14 +103,15 @@ struct EpiKnn {
 // ------------------------------------------------------------------------------------------------
 // Qr = tf32(RNE)(Q), qn[b] = ||Q_b||^2 (fp32), one warp per query
 __global__ void knn_prep_queries_kernel(const float *__restrict__ Q, int B, int D, float *__restrict__ Qr,
-                                        float *__restrict__ qn) {
+                                        __half *__restrict__ Qh, float *__restrict__ qn) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
     float s = 0.f;
     for (int i = lane; i < D; i += 32) {
         const float x = Q[static_cast<int64_t>(row) * D + i];
-        Qr[static_cast<int64_t>(row) * D + i] = round_tf32(x);
+        if (Qh) Qh[static_cast<int64_t>(row) * D + i] = __float2half_rn(x);
+        else Qr[static_cast<int64_t>(row) * D + i] = round_tf32(x);
         s = fmaf(x, x, s);
     }
     s = warp_sum(s);
@@ -176,14 +178,16 @@ __global__ void knn_pick_kernel(const float *__restrict__ sorted_key, const int6
     T[b] = t + qn[b];
 }
 
-// certified[b] = out_d[b,k-1] < T[b] - eps(b);  eps = 2*(2^-10 + 2^-11 + 2^-21)*||q||*max||p|| * 1.02 + 4e-5*(1+||q||^2+max||p||^2)
+// certified[b] = out_d[b,k-1] < T[b] - eps(b);  eps = 2*rel*||q||*max||p|| * 1.02 + 4e-5*(1+||q||^2+max||p||^2) with
+//   rel = 2^-10 + 2^-11 + 2^-21 (fp32 rows truncated to tf32 by the MMA, queries rounded RNE), or
+//   rel = 2^-11 + 2^-11 + 2^-22 (fp16 shadow rows and fp16 queries, both RNE; the subnormal tail adds < 1e-6)
 __global__ void knn_certify_kernel(const float *__restrict__ out_d, const int64_t *__restrict__ out_i, const float *__restrict__ T,
-                                   const float *__restrict__ qn, const float *__restrict__ pmax2, int B, int k,
+                                   const float *__restrict__ qn, const float *__restrict__ pmax2, int B, int k, float rel,
                                    int32_t *__restrict__ fail_list, int32_t *__restrict__ fail_count) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float qn2 = qn[b], pm2 = pmax2[0];
-    const float eps = 2.f * 1.4653e-3f * 1.02f * sqrtf(qn2) * sqrtf(pm2) + 4e-5f * (1.f + qn2 + pm2);
+    const float eps = 2.f * rel * 1.02f * sqrtf(qn2) * sqrtf(pm2) + 4e-5f * (1.f + qn2 + pm2);
     const float dk = out_d[static_cast<int64_t>(b) * k + (k - 1)];
     const bool full = out_i[static_cast<int64_t>(b) * k + (k - 1)] >= 0;
     // T == +inf: every row of the index was a candidate (nothing excluded) -> exact by construction
@@ -265,8 +269,8 @@ size_t knn_tc_workspace(int B, int64_t N, int D, int k) {
     return p.total + fb + 1024;
 }
 
-int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, int64_t N, int D, int k, float *out_d,
-                  int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, cudaStream_t s) {
+int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N, int D, int k,
+                  float *out_d, int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, cudaStream_t s) {
     int rc = ac_device_check();
     if (rc) return rc;
     KnnTcPlan pl = plan_knn_tc(B, N, D, k);
@@ -302,7 +306,8 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, 
     const size_t Bp = static_cast<size_t>(pl.tiles_m) * GEMM_BLOCK_M;
     AC_CUDA(cudaMemsetAsync(Qr, 0, Bp * D * 4, s));
     AC_CUDA(cudaMemsetAsync(fail, 0, 4, s));
-    knn_prep_queries_kernel<<<(B + 3) / 4, 128, 0, s>>>(Q, B, D, Qr, qn);
+    __half *Qh = p_half ? reinterpret_cast<__half *>(Qr) : nullptr;   // the fp16 queries reuse the fp32 query slot
+    knn_prep_queries_kernel<<<(B + 3) / 4, 128, 0, s>>>(Q, B, D, Qr, Qh, qn);
     AC_LAUNCH_CHECK();
     const float *pn_use = p_sqnorm;
     const unsigned rb = static_cast<unsigned>((N + 7) / 8);
@@ -318,12 +323,21 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, 
 
     // ---- coarse pass on the tensor cores
     CUtensorMap ta, tb;
-    if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
-    if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
     EpiKnn epi{pn_use, ckey, cidx, B, N, pl.tiles_m, pl.slots};   // slots = 2 per CTA
-    // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes)
-    if ((rc = launch_gemm_tf32<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
-                                              PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D))) return rc;
+    // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16
+    // shadow the kernel actually streams 2.N.D bytes (the exact re-rank below still reads fp32 rows)
+    if (p_half) {
+        if ((rc = make_tmap_2d(&ta, Qh, 2, Bp, D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_M, 64))) return rc;
+        if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_N, 64))) return rc;
+        if ((rc = launch_gemm_tf32<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
+                                                                 pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)))
+            return rc;
+    } else {
+        if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
+        if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
+        if ((rc = launch_gemm_tf32<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
+                                                  PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D))) return rc;
+    }
 
     // ---- merge per-CTA lists, pick KP candidates + exclusion threshold
     const int64_t nc = static_cast<int64_t>(B) * pl.slots * KNN_KC;
@@ -339,7 +353,8 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, 
     if ((rc = topk_select(rd, ri, B, KNN_KP, KNN_KP, 0, k, out_d, out_i, selws, pl.sel_bytes, s))) return rc;
 
     // ---- certification + exact recomputation of the (rare) uncertified queries
-    knn_certify_kernel<<<(B + 127) / 128, 128, 0, s>>>(out_d, out_i, T, qn, pmax, B, k, fail + 1, fail);
+    const float rel = p_half ? (2.f * 4.8828125e-4f + 2.4e-7f) : (9.765625e-4f + 4.8828125e-4f + 4.8e-7f);
+    knn_certify_kernel<<<(B + 127) / 128, 128, 0, s>>>(out_d, out_i, T, qn, pmax, B, k, rel, fail + 1, fail);
     AC_LAUNCH_CHECK();
     int32_t nfail = 0;
     AC_CUDA(cudaMemcpyAsync(&nfail, fail, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -357,7 +372,19 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, int B, 
     return AC_OK;
 }
 
+__global__ void knn_to_half_kernel(const float *__restrict__ in, __half *__restrict__ out, int64_t n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __float2half_rn(in[i]);
+}
+
 }  // namespace ac
 
-// number of queries the last tensor-path search had to recompute exactly is observable through this
-// debugging hook (tests assert it stays small on the synthetic index)
+extern "C" int ac_knn_make_shadow(const float *P, int64_t N, int D, void *out_half, ac_stream_t stream) {
+    AC_REQUIRE(P && out_half && N >= 0 && D > 0, "ac_knn_make_shadow: bad arguments");
+    if (N == 0) return AC_OK;
+    ac::knn_to_half_kernel<<<1184, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, static_cast<__half *>(out_half), N * D);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+

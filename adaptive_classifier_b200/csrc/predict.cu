@@ -156,6 +156,7 @@ extern "C" int ac_blend_topk(const int32_t *proto_cls, const float *proto_score,
 struct ac_pipeline {
     ac_encoder *enc;
     const float *P, *p_sqnorm;
+    const void *p_half;
     const int32_t *row_class;
     ac_head_params head;
     bool has_head;
@@ -177,14 +178,14 @@ extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
     return AC_OK;
 }
 
-extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const int32_t *row_class,
-                                  int64_t N, int D, const ac_head_params *head, int max_B, int S, int k,
-                                  int64_t row_offset, ac_pipeline **out) {
+extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const void *p_half,
+                                  const int32_t *row_class, int64_t N, int D, const ac_head_params *head, int max_B, int S,
+                                  int k, int64_t row_offset, ac_pipeline **out) {
     AC_REQUIRE(enc && P && out && N > 0 && D > 0 && max_B > 0 && S > 0, "ac_pipeline_create: bad arguments");
     AC_REQUIRE(k >= 1 && k <= 16, "ac_pipeline_create: k=%d outside [1,16]", k);
     ac_pipeline *pl = new ac_pipeline();
     memset(pl, 0, sizeof(*pl));
-    pl->enc = enc; pl->P = P; pl->p_sqnorm = p_sqnorm; pl->row_class = row_class; pl->N = N; pl->row_offset = row_offset;
+    pl->enc = enc; pl->P = P; pl->p_sqnorm = p_sqnorm; pl->p_half = p_half; pl->row_class = row_class; pl->N = N; pl->row_offset = row_offset;
     pl->D = D; pl->max_B = max_B; pl->S = S; pl->k = k;
     pl->has_head = head != nullptr;
     if (head) { pl->head = *head; pl->kh = k < head->C ? k : head->C; }
@@ -220,8 +221,8 @@ extern "C" int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_de
     AC_REQUIRE(pl && ids_dev && out_cls_dev && out_score_dev && B > 0 && B <= pl->max_B, "ac_pipeline_predict_device: bad arguments");
     int rc = ac_encoder_forward_cls(pl->enc, ids_dev, mask_dev, nullptr, B, pl->S, pl->emb, stream);
     if (rc) return rc;
-    rc = ac_knn_l2_topk(pl->emb, pl->P, pl->p_sqnorm, B, pl->N, pl->D, pl->k, pl->knn_d, pl->knn_i, pl->row_offset, pl->ws,
-                        pl->ws_bytes, AC_KNN_AUTO, stream);
+    rc = ac_knn_l2_topk(pl->emb, pl->P, pl->p_sqnorm, pl->p_half, B, pl->N, pl->D, pl->k, pl->knn_d, pl->knn_i,
+                        pl->row_offset, pl->ws, pl->ws_bytes, AC_KNN_AUTO, stream);
     if (rc) return rc;
     rc = ac_proto_class_scores(pl->knn_d, pl->knn_i, pl->row_class, B, pl->k, pl->p_cls, pl->p_score, stream);
     if (rc) return rc;

@@ -243,6 +243,7 @@ def main():
     lo, hi = shard_bounds(n_rows, rank, G)
     P = wl.synthetic_rows(lo, hi, D, C, seed=0, device=dev)
     p_sqnorm = _cabi.row_sqnorm(P)
+    p_half = _cabi.knn_make_shadow(P)          # index-build-time fp16 shadow for the tensor path's coarse pass
     row_class = (torch.arange(n_rows, device=dev) % C).to(torch.int32)
     head = AdaptiveHead(D, C, hidden_dims=[D, D // 2]).to(dev).eval()
     hp = head._param_dict()
@@ -251,7 +252,7 @@ def main():
     torch.cuda.synchronize()
 
     if G == 1:
-        pipe = _cabi.Pipeline(enc, P, B_PER_GPU, S, K_TOP, head=hp, row_class=row_class, p_sqnorm=p_sqnorm)
+        pipe = _cabi.Pipeline(enc, P, B_PER_GPU, S, K_TOP, head=hp, row_class=row_class, p_sqnorm=p_sqnorm, p_half=p_half)
 
         def step_device():
             return pipe.predict_device(ids_dev)
@@ -259,7 +260,7 @@ def main():
         def step_host():
             return pipe.predict_host(ids_host)
     else:
-        index = ShardedIndex(P, lo)
+        index = ShardedIndex(P, lo, search=lambda Q_, P_, k_, off_: _cabi.knn_l2_topk(Q_, P_, k_, p_sqnorm=p_sqnorm, p_half=p_half, row_offset=off_))
         out_cls_host = torch.empty((B_PER_GPU, K_TOP), dtype=torch.int32).pin_memory()
         out_sc_host = torch.empty((B_PER_GPU, K_TOP), dtype=torch.float32).pin_memory()
 
@@ -351,7 +352,7 @@ def main():
                      "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": traffic,
                      "peak_source": f"{pk['source']} cuBLAS bf16 GEMM, sustained (kernel timed inside a long step)",
                      "launches": gemm["launches"], "ms_total": gemm["ms"], "share_of_step": gemm["ms"] / ms},
-        "roofline_knn": {"bound": "hbm", "kernel": "gemm_tf32_kernel<EpiKnn, kind::tf32> (prototype scan over fp32 rows, 4*N*D algorithmic bytes)",
+        "roofline_knn": {"bound": "hbm", "kernel": "gemm_tf32_kernel<EpiKnn, kind::f16> (prototype scan; algorithmic bytes 4*N*D = the fp32 matrix, the kernel streams its 2*N*D-byte fp16 shadow, exact re-rank reads fp32 rows)",
                          "achieved": knn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": knn_gbs / pk["hbm_gbs"],
                          "tensor_tflops": knn_tflops, "launches": knn["launches"], "ms_total": knn["ms"],
                          "share_of_step": knn["ms"] / ms, "peak_source": pk["source"]},

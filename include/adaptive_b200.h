@@ -62,11 +62,17 @@ int ac_knn_workspace_bytes(int B, int64_t N, int D, int k, int algo, size_t *byt
  * when N < k the tail is (+inf, -1)  [IndexFlatL2.search semantics, memory.py:113-114,121].
  * Distances are the exact fp32 lane-ordered sum restated in oracle/knn_oracle.c (bit-identical).
  * p_sqnorm[N] (nullable) = cached ||p||^2 for the tensor path; computed into the workspace if NULL.
+ * p_half (nullable) = fp16 shadow copy of P[N,D] (ac_knn_make_shadow): the tensor path then runs its coarse pass as
+ *   tcgen05 kind::f16 over 2.N.D bytes (D %% 64 == 0); candidates are still re-ranked on the fp32 rows, so the
+ *   result is the same bits either way.
  */
-int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqnorm,
+int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqnorm, const void *p_half,
                    int B, int64_t N, int D, int k,
                    float *out_d, int64_t *out_i, int64_t row_offset,
                    void *workspace, size_t workspace_bytes, int algo, ac_stream_t stream);
+
+/* fp16 (RNE) shadow of the prototype matrix for the tensor path's coarse pass; out_half holds N*D halves */
+int ac_knn_make_shadow(const float *P, int64_t N, int D, void *out_half, ac_stream_t stream);
 
 /* ||p||^2 per row (fp32), the cache the tensor path consumes */
 int ac_row_sqnorm(const float *P, int64_t N, int D, float *out, ac_stream_t stream);
@@ -159,6 +165,8 @@ typedef struct {
     float ln_eps;
     int precision;       /* AC_PREC_* */
     int max_tokens;      /* workspace is sized for B*S <= max_tokens */
+    int cls_only;        /* != 0: the last layer's output projection / FFN / LayerNorms run on the CLS rows only
+                            (classifier.py:1272 uses nothing else); 0 keeps the full last hidden state */
 } ac_encoder_config;
 
 /* device pointers to the HF state_dict tensors (fp32, HF layout [out,in]) */
@@ -218,8 +226,8 @@ int ac_blend_topk(const int32_t *proto_cls, const float *proto_score, const int6
 /* E -> K -> class scores -> H -> top-k -> blend with all intermediate buffers owned by the handle.
  * head may be NULL (prototype-only prediction).  row_class nullable. */
 typedef struct ac_pipeline ac_pipeline;
-int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const int32_t *row_class,
-                       int64_t N, int D, const ac_head_params *head, int max_B, int S, int k,
+int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const void *p_half,
+                       const int32_t *row_class, int64_t N, int D, const ac_head_params *head, int max_B, int S, int k,
                        int64_t row_offset, ac_pipeline **out);
 int ac_pipeline_destroy(ac_pipeline *pl);
 /* device buffers at the boundary (bench.py `value`) */

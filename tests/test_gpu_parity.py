@@ -118,6 +118,24 @@ def test_knn_tensor_equals_exact_scan_large(cabi, B, N, C, k):
     assert bool((d1[:, 1:] >= d1[:, :-1]).all())
 
 
+@pytest.mark.parametrize("B,N,C,k", [(512, 200_000, 1000, 5), (96, 50_000, 20, 16)])
+def test_knn_tensor_fp16_shadow_equals_exact_scan(cabi, B, N, C, k):
+    """coarse pass over the fp16 shadow (kind::f16, 2.N.D bytes) + exact fp32 re-rank + certification == exact scan"""
+    D = 768
+    P, _ = _synthetic_index(N, D, C, seed=0)
+    Q, _ = _synthetic_index(B, D, C, seed=1)
+    Pg, Qg = P.cuda(), Q.cuda()
+    Ph = cabi.knn_make_shadow(Pg)
+    assert Ph.dtype == torch.float16 and torch.equal(Ph, Pg.half())
+    d1, i1 = cabi.knn_l2_topk(Qg, Pg, k, p_half=Ph, algo=cabi.AC_KNN_TENSOR)
+    d2, i2 = cabi.knn_l2_topk(Qg, Pg, k, algo=cabi.AC_KNN_TENSOR)           # tf32 coarse pass on the fp32 rows
+    d0, i0 = cabi.knn_l2_topk(Qg[:48], Pg, k, algo=cabi.AC_KNN_EXACT)
+    torch.cuda.synchronize()
+    assert torch.equal(i1, i2) and torch.equal(d1, d2)
+    assert torch.equal(i1[:48], i0) and torch.equal(d1[:48], d0)
+    assert torch.equal(i1[:, 0].cpu() % C, torch.arange(B) % C)
+
+
 def test_proto_scores_and_merge(cabi):
     rng = np.random.default_rng(3)
     d = np.sort(rng.uniform(0, 4, size=(7, 9)).astype(np.float32), axis=1)
@@ -184,6 +202,10 @@ def test_head_forward(cabi, B, D, C):
 
 @pytest.mark.parametrize("loss_kind", ["ce", "bce"])
 def test_head_train_steps_match_oracle(cabi, loss_kind):
+    """3 optimizer steps (fwd with injected dropout masks, loss, bwd, clip, AdamW) vs the torch-CPU restatement.
+    ReLU'(a) is discontinuous at a = 0: a batch with a pre-activation within fp32 summation noise of zero (seed 9 of an
+    earlier version of this test had a1[19,33] = -9e-9) makes GPU and CPU legitimately disagree on a whole gradient
+    row, so batches are drawn until every |pre-activation| > 1e-6."""
     B, D, C = 32, 768, 20
     g = torch.Generator().manual_seed(9)
     p, pg = _head(D, C)
@@ -192,12 +214,17 @@ def test_head_train_steps_match_oracle(cabi, loss_kind):
     mg = {k: torch.zeros_like(t) for k, t in pg.items()}
     vg = {k: torch.zeros_like(t) for k, t in pg.items()}
     for step in range(1, 4):
-        X = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1)
+        while True:
+            X = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1)
+            masks = tuple(((torch.rand(B, n, generator=g) >= 0.1).float() / 0.9) for n in (D, D // 2))
+            a0 = X @ p["W0"].t() + p["b0"]
+            a1 = (torch.relu(a0) * masks[0]) @ p["W1"].t() + p["b1"]
+            if min(a0.abs().min().item(), a1.abs().min().item()) > 1e-6:
+                break
         if loss_kind == "ce":
             y = torch.randint(0, C, (B,), generator=g)
         else:
             y = (torch.rand(B, C, generator=g) < 0.2).float()
-        masks = tuple(((torch.rand(B, n, generator=g) >= 0.1).float() / 0.9) for n in (D, D // 2))
         loss_ref, grads, _ = ho.head_grads(X, y, p, masks, loss_kind)
         norm_ref = ho.clip_and_adamw(p, grads, m, v, step)
         stats = cabi.head_train_step(X.cuda(), y.cuda(), pg, mg, vg, step=step,
@@ -210,11 +237,9 @@ def test_head_train_steps_match_oracle(cabi, loss_kind):
             # Adam's first steps move a weight by lr*sign(g): where |g| is at rounding level the sign is
             # ill-conditioned, so those (rare) elements may differ by up to 2*lr; everything else is tight
             solid = grads[k].abs() > 1e-6 * grads[k].abs().max()
-            j = int((diff * solid).flatten().argmax())
-            info = (step, k, j, float(diff.flatten()[j]), float(grads[k].flatten()[j]), float(grads[k].abs().max()),
-                    float(pg[k].cpu().flatten()[j]), float(p[k].flatten()[j]), float(mg[k].cpu().flatten()[j]), float(m[k].flatten()[j]))
-            assert diff[solid].max() < 2e-5, info
+            assert diff[solid].max() < 2e-5, (step, k, float(diff[solid].max()))
             assert diff.max() <= 2.1e-3 * step, (step, k)
+            assert (mg[k].cpu() - m[k]).abs().max() <= 1e-6 + 1e-4 * m[k].abs().max(), (step, k)
 
 
 def test_ewc_penalty_and_fisher(cabi):
@@ -245,11 +270,47 @@ def _small_bert(layers=2):
     return sd, cfg
 
 
-def _encoder(cabi, sd, cfg, max_tokens):
-    return cabi.Encoder(sd, arch="bert", layers=cfg.num_hidden_layers, hidden=cfg.hidden_size,
+def _encoder(cabi, sd, cfg, max_tokens, cls_only=True, arch="bert"):
+    return cabi.Encoder(sd, arch=arch, layers=cfg.num_hidden_layers, hidden=cfg.hidden_size,
                         heads=cfg.num_attention_heads, intermediate=cfg.intermediate_size, vocab=cfg.vocab_size,
                         max_pos=cfg.max_position_embeddings, type_vocab=cfg.type_vocab_size,
-                        ln_eps=cfg.layer_norm_eps, max_tokens=max_tokens)
+                        ln_eps=cfg.layer_norm_eps, pad_idx=(cfg.pad_token_id or 0), max_tokens=max_tokens,
+                        cls_only=cls_only)
+
+
+def test_encoder_full_last_layer_and_hidden_state(cabi):
+    """cls_only = 0 keeps the whole last hidden state (HF last_hidden_state) and gives the same CLS rows"""
+    sd, cfg = _small_bert(2)
+    B, S = 3, 64
+    ids = eo.synthetic_ids(B, S)
+    ref_cls, ref_hidden = eo.encoder_forward_cls(sd, ids, None, return_hidden=True)
+    enc_full = _encoder(cabi, sd, cfg, B * S, cls_only=False)
+    enc_cls = _encoder(cabi, sd, cfg, B * S, cls_only=True)
+    a = enc_full.forward_cls(ids.to(torch.int32).cuda()).cpu()
+    hid = enc_full.last_hidden(B, S).cpu().view(B, S, -1)
+    b = enc_cls.forward_cls(ids.to(torch.int32).cuda()).cpu()
+    assert (a - ref_cls).norm(dim=1).max() < 1e-3 and (b - ref_cls).norm(dim=1).max() < 1e-3
+    assert (a - b).abs().max() < 1e-6            # same arithmetic on the CLS rows, different tile shapes only
+    assert (hid - ref_hidden).abs().max() < 2e-2 * ref_hidden.abs().max()
+    with pytest.raises(cabi.AdaptiveB200Error):
+        enc_cls.last_hidden(B, S)
+    enc_full.close(); enc_cls.close()
+
+
+def test_encoder_roberta_positions_and_padding(cabi):
+    """RoBERTa position ids (cumsum of non-pad + pad_idx, HF modeling_roberta.py:146-159), hidden 128 / 2 heads"""
+    sd, cfg, _ = eo.make_bert_state_dict(5, arch="roberta", num_hidden_layers=2, hidden_size=128, num_attention_heads=2,
+                                         intermediate_size=256, vocab_size=300, max_position_embeddings=130)
+    B, S = 4, 40
+    ids = eo.synthetic_ids(B, S, vocab=300, arch="roberta")
+    for b in range(B):
+        ids[b, S - 3 * b:] = 1
+    mask = (ids != 1).long()
+    ref = eo.encoder_forward_cls(sd, ids, mask, arch="roberta", num_heads=2, ln_eps=cfg.layer_norm_eps, pad_idx=1)
+    enc = _encoder(cabi, sd, cfg, B * S, arch="roberta")
+    out = enc.forward_cls(ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()).cpu()
+    assert (out - ref).norm(dim=1).max() < 1e-3
+    enc.close()
 
 
 @pytest.mark.parametrize("layers,B,S,pad", [(1, 2, 128, False), (2, 3, 16, True), (12, 8, 128, False), (2, 5, 77, True)])
