@@ -162,6 +162,7 @@ def gen_classifier():
     pred = [clf.predict(t, k=3) for t in test_texts]
     pred_k1 = [clf.predict(t, k=1) for t in test_texts]
     pred_b = clf.predict_batch(test_texts, k=2)
+    train_top1 = [p[0][0] for p in clf.predict_batch(texts, k=1)]     # end metric of the reference's own training
 
     def pack(preds, k):
         L = np.full((len(preds), k), -1, dtype=np.int64)
@@ -185,6 +186,7 @@ def gen_classifier():
         emb_train=emb_train, emb_test=emb_test, prototypes=protos, proto_labels=np.array(sorted(clf.memory.prototypes)),
         training_history=json.dumps(clf.training_history), train_steps=clf.train_steps,
         pred_labels=pl, pred_scores=ps, pred_k1_labels=p1l, pred_k1_scores=p1s, predb_labels=pbl, predb_scores=pbs,
+        train_top1=np.array([label_names.index(l) for l in train_top1]),
         bert_config=json.dumps(cfg.to_dict()), **head_sd, **model_sd)
     print("golden_classifier ok; labels", label_names, "pred[0]", pred[0])
 
