@@ -497,6 +497,192 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// attention for 128 < S <= 512: one CTA per (sequence, head, 128-query block), key blocks of 128 streamed twice.
+//   pass A  row max over all key blocks        (QK^T only)
+//   pass B  P = exp(scale*(s - max)) per block, O += P V_block accumulated in TMEM, row sums in registers
+// Using the final max in pass B means the TMEM accumulator never has to be rescaled; the price is computing QK^T
+// twice (QK^T is half of the attention flops, attention is ~3 % of the encoder).  Serial per block (TMA -> MMA ->
+// softmax -> MMA); the S <= 128 kernel above is the tuned path of the benchmark configurations.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTL_SMEM = 80 * 1024 + 1024 + 64;
+constexpr int ATTL_TMEM_COLS = 256;
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_long_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
+                      const int32_t *__restrict__ mask, int B, int S, int heads, int H, __half *__restrict__ ctx) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem;                    // [128 x 128 B]
+    uint8_t *sK = smem + 16 * 1024;        // [128 x 128 B] current key block
+    uint8_t *sVt = smem + 32 * 1024;       // 2 slabs x [64 (d) x 128 B (64 keys)]
+    uint8_t *sP = smem + 48 * 1024;        // 2 slabs x [128 x 128 B (64 keys)]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 80 * 1024);
+    uint64_t *bar_load = bars, *bar_s = bars + 1, *bar_o = bars + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int qb = blockIdx.y;                                   // query block
+    const int nkb = (S + 127) / 128;
+    const int64_t row0 = static_cast<int64_t>(b) * S;
+    const int vrow = (b * heads + h) * 64;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap_qk);
+        tma_prefetch_desc(&tmap_vt);
+        mbar_init(bar_load, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_o, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, ATTL_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int qrow = warp * 32 + lane;                            // row inside the query block
+    const int qglob = qb * 128 + qrow;                            // position inside the sequence
+    const float scale_log2 = rsqrtf(64.f) * 1.44269504088896340736f;
+    constexpr uint32_t idesc_s = umma_idesc(0, 128, 128);
+    constexpr uint32_t idesc_o = umma_idesc(0, 128, 64);
+
+    uint32_t ph_load = 0, ph_s = 0, ph_o = 0;
+    float mx = -CUDART_INF_F, sum = 0.f;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < nkb; ++j) {
+            const int key0 = j * 128;
+            if (tid == 0) {
+                const bool first = (pass == 0 && j == 0);
+                const uint32_t bytes = (first ? 16 * 1024 : 0) + 16 * 1024 + (pass == 1 ? 16 * 1024 : 0);
+                mbar_arrive_expect_tx(bar_load, bytes);
+                if (first) tma_load_2d(sQ, &tmap_qk, bar_load, h * 64, static_cast<int>(row0) + qb * 128);
+                tma_load_2d(sK, &tmap_qk, bar_load, H + h * 64, static_cast<int>(row0) + key0);
+                if (pass == 1) {
+                    tma_load_2d(sVt, &tmap_vt, bar_load, key0, vrow);
+                    tma_load_2d(sVt + 8 * 1024, &tmap_vt, bar_load, key0 + 64, vrow);
+                }
+                mbar_wait_guarded(bar_load, ph_load);
+                tc_fence_after();
+                const uint64_t a = umma_desc_sw128(smem_u32(sQ));
+                const uint64_t bd = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a + 2 * k, bd + 2 * k, idesc_s, k != 0);
+                tc_commit(bar_s);
+            }
+            ph_load ^= 1;
+            __syncwarp();
+            mbar_wait_guarded(bar_s, ph_s);
+            ph_s ^= 1;
+            tc_fence_after();
+
+            // key validity bits of this block
+            uint32_t kmask[4];
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+                const int key = key0 + 32 * w4 + lane;
+                const bool ok = (key < S) && (!mask || mask[row0 + key] != 0);
+                kmask[w4] = __ballot_sync(0xffffffffu, ok);
+            }
+            if (pass == 0) {
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_s + 32 * ci, r);
+                    tmem_ld_wait();
+                    const uint32_t km = kmask[ci];
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj)
+                        if ((km >> jj) & 1u) mx = fmaxf(mx, __uint_as_float(r[jj]));
+                }
+                tc_fence_before();
+                __syncthreads();                                  // S columns and sK may be overwritten now
+                tc_fence_after();
+            } else {
+                const uint32_t sp_base = smem_u32(sP);
+                const float mxs = mx * scale_log2;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int c = 32 * ci;
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_s + c, r);
+                    tmem_ld_wait();
+                    const uint32_t km = kmask[ci];
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj += 2) {
+                        const float e0 = ((km >> jj) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[jj]), scale_log2, -mxs)) : 0.f;
+                        const float e1 = ((km >> (jj + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[jj + 1]), scale_log2, -mxs)) : 0.f;
+                        sum += e0 + e1;
+                        __half2 hh = __floats2half2_rn(e0, e1);
+                        pk[jj >> 1] = *reinterpret_cast<uint32_t *>(&hh);
+                    }
+                    const uint32_t prow = sp_base + (c >> 6) * 16384 + (qrow >> 3) * 1024 + (qrow & 7) * 128;
+                    const int ch0 = (c & 63) >> 3;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((ch0 + ch) ^ (qrow & 7)) << 4)),
+                                     "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]), "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
+                                     : "memory");
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
+                if (tid == 0) {
+#pragma unroll
+                    for (int slab = 0; slab < 2; ++slab) {
+                        const uint64_t a = umma_desc_sw128(smem_u32(sP + slab * 16384));
+                        const uint64_t bd = umma_desc_sw128(smem_u32(sVt + slab * 8192));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem_base + 128, a + 2 * k, bd + 2 * k, idesc_o, (j | slab | k) != 0);
+                    }
+                    tc_commit(bar_o);
+                }
+                __syncwarp();
+                mbar_wait_guarded(bar_o, ph_o);                   // sK / sVt / sP / S columns are free again
+                ph_o ^= 1;
+                tc_fence_after();
+            }
+        }
+    }
+
+    const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + 128 + c, r);
+        tmem_ld_wait();
+        if (qglob < S) {
+            __half *dst = ctx + (row0 + qglob) * H + h * 64 + c;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 8) {
+                __half2 h0 = __floats2half2_rn(__uint_as_float(r[jj]) * inv, __uint_as_float(r[jj + 1]) * inv);
+                __half2 h1 = __floats2half2_rn(__uint_as_float(r[jj + 2]) * inv, __uint_as_float(r[jj + 3]) * inv);
+                __half2 h2 = __floats2half2_rn(__uint_as_float(r[jj + 4]) * inv, __uint_as_float(r[jj + 5]) * inv);
+                __half2 h3 = __floats2half2_rn(__uint_as_float(r[jj + 6]) * inv, __uint_as_float(r[jj + 7]) * inv);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                *reinterpret_cast<uint4 *>(dst + jj) = pk;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ATTL_TMEM_COLS);
+    }
+}
+
 }  // namespace ac
 
 // ================================================================================================
@@ -656,8 +842,8 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
                                       int B, int S, float *out_unit_cls, ac_stream_t stream) {
     AC_REQUIRE(e && ids && out_unit_cls, "ac_encoder_forward_cls: null argument");
     AC_REQUIRE(B > 0 && S > 0, "ac_encoder_forward_cls: B=%d S=%d", B, S);
-    if (S > 128) {
-        set_error("ac_encoder_forward_cls: S=%d > 128 is not implemented yet (attention tile)", S);
+    if (S > 512) {
+        set_error("ac_encoder_forward_cls: S=%d > 512 is not supported (the reference truncates at max_length = 512)", S);
         return AC_E_UNSUPPORTED;
     }
     AC_REQUIRE(static_cast<int64_t>(B) * S <= e->cfg.max_tokens, "ac_encoder_forward_cls: B*S=%lld exceeds max_tokens=%d",
@@ -686,6 +872,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     static bool att_attr = false;
     if (!att_attr) {
         AC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        AC_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTL_SMEM));
         att_attr = true;
     }
     for (int l = 0; l < c.layers; ++l) {
@@ -694,7 +881,11 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
         {
             // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
-            attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+            if (S <= 128)
+                attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+            else
+                attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(
+                    e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
             prof_end(slot, s);
         }
         AC_LAUNCH_CHECK();

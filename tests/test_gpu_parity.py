@@ -278,6 +278,24 @@ def _encoder(cabi, sd, cfg, max_tokens, cls_only=True, arch="bert"):
                         cls_only=cls_only)
 
 
+@pytest.mark.parametrize("B,S,pad", [(2, 300, True), (3, 129, False), (1, 512, False), (2, 384, True)])
+def test_encoder_long_sequences(cabi, B, S, pad):
+    """128 < S <= 512 (the reference truncates at max_length = 512, classifier.py:1261): two-pass key-block attention"""
+    sd, cfg = _small_bert(2)
+    ids = eo.synthetic_ids(B, S)
+    mask = torch.ones_like(ids)
+    if pad:
+        for b in range(B):
+            n = S - 37 * (b + 1)
+            mask[b, n:] = 0
+            ids[b, n:] = 0
+    ref = eo.encoder_forward_cls(sd, ids, mask)
+    enc = _encoder(cabi, sd, cfg, max_tokens=B * S)
+    out = enc.forward_cls(ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()).cpu()
+    assert (out - ref).norm(dim=1).max() < 1e-3, (out - ref).norm(dim=1).max()
+    enc.close()
+
+
 def test_encoder_full_last_layer_and_hidden_state(cabi):
     """cls_only = 0 keeps the whole last hidden state (HF last_hidden_state) and gives the same CLS rows"""
     sd, cfg = _small_bert(2)
