@@ -47,21 +47,29 @@ struct EpiKnn {
     struct State {
         float key[KNN_KC];
         int32_t idx[KNN_KC];
+        float pn[2];          // ||p||^2 of the 32 rows of a chunk, one per lane, requested one chunk ahead
     };
 
     __device__ __forceinline__ void begin_cta(State &st, int, int) const {
 #pragma unroll
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
+        st.pn[0] = st.pn[1] = CUDART_INF_F;
     }
 
-    __device__ __forceinline__ void prefetch(State &, const GemmTileInfo &, int, int, int, int) const {}
+    // one coalesced 128-byte load per warp and chunk (lane l fetches the norm of row col0 + l), off the critical path
+    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &, int, int col0, int lane, int buf) const {
+        const int64_t n = static_cast<int64_t>(col0) + lane;
+        const float x = (n < N) ? __ldg(p_sqnorm + n) : CUDART_INF_F;
+        if (buf) st.pn[1] = x; else st.pn[0] = x;
+    }
     __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
-                                         uint8_t * /*stage*/, int /*lane*/, int /*buf*/) const {
+                                         uint8_t * /*stage*/, int /*lane*/, int buf) const {
         // all lanes walk the same 32 prototype rows; each lane tests them against its own query's threshold
+        const float pn_lane = buf ? st.pn[1] : st.pn[0];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {   // fully unrolled: v[] must stay in registers
             const int64_t n = static_cast<int64_t>(col0) + j;
-            const float pn = (n < N) ? __ldg(p_sqnorm + n) : CUDART_INF_F;
+            const float pn = __shfl_sync(0xffffffffu, pn_lane, j);
             const float key = fmaf(-2.f, v[j], pn);
             const bool ins = key < st.key[KNN_KC - 1];
             if (__any_sync(0xffffffffu, ins)) {

@@ -167,6 +167,10 @@ struct ac_pipeline {
     int64_t *knn_i, *h_idx;
     void *ws, *ws_topk;
     size_t ws_bytes, ws_topk_bytes, scratch_floats;
+    // the head (fp32 SIMT) and the prototype scan (tensor cores + HBM) are independent given the embeddings: the head
+    // runs on a side stream forked after the encoder and joined before the blend
+    cudaStream_t side;
+    cudaEvent_t ev_emb, ev_head;
 };
 
 extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
@@ -174,6 +178,9 @@ extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
     void *ptrs[] = {pl->ids_dev, pl->p_cls, pl->out_cls, pl->emb, pl->knn_d, pl->p_score, pl->probs, pl->h_val,
                     pl->out_score, pl->scratch, pl->knn_i, pl->h_idx, pl->ws, pl->ws_topk};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (pl->side) cudaStreamDestroy(pl->side);
+    if (pl->ev_emb) cudaEventDestroy(pl->ev_emb);
+    if (pl->ev_head) cudaEventDestroy(pl->ev_head);
     delete pl;
     return AC_OK;
 }
@@ -210,6 +217,9 @@ extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *
     al(reinterpret_cast<void **>(&pl->scratch), sizeof(float) * pl->scratch_floats);
     al(&pl->ws, pl->ws_bytes);
     al(&pl->ws_topk, pl->ws_topk_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_emb, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_head, cudaEventDisableTiming);
     if (e != cudaSuccess) { ac_pipeline_destroy(pl); return check_cuda(e, "ac_pipeline_create cudaMalloc"); }
     *out = pl;
     return AC_OK;
@@ -219,19 +229,24 @@ extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *
 extern "C" int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B,
                                           int32_t *out_cls_dev, float *out_score_dev, ac_stream_t stream) {
     AC_REQUIRE(pl && ids_dev && out_cls_dev && out_score_dev && B > 0 && B <= pl->max_B, "ac_pipeline_predict_device: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = ac_encoder_forward_cls(pl->enc, ids_dev, mask_dev, nullptr, B, pl->S, pl->emb, stream);
     if (rc) return rc;
+    if (pl->has_head) {
+        AC_CUDA(cudaEventRecord(pl->ev_emb, s));
+        AC_CUDA(cudaStreamWaitEvent(pl->side, pl->ev_emb, 0));
+        rc = ac_head_forward(pl->emb, B, &pl->head, AC_ACT_SOFTMAX, pl->probs, pl->scratch, pl->scratch_floats, pl->side);
+        if (rc) return rc;
+        rc = ac_topk_desc(pl->probs, B, pl->head.C, pl->kh, pl->h_val, pl->h_idx, pl->ws_topk, pl->ws_topk_bytes, pl->side);
+        if (rc) return rc;
+        AC_CUDA(cudaEventRecord(pl->ev_head, pl->side));
+    }
     rc = ac_knn_l2_topk(pl->emb, pl->P, pl->p_sqnorm, pl->p_half, B, pl->N, pl->D, pl->k, pl->knn_d, pl->knn_i,
                         pl->row_offset, pl->ws, pl->ws_bytes, AC_KNN_AUTO, stream);
     if (rc) return rc;
     rc = ac_proto_class_scores(pl->knn_d, pl->knn_i, pl->row_class, B, pl->k, pl->p_cls, pl->p_score, stream);
     if (rc) return rc;
-    if (pl->has_head) {
-        rc = ac_head_forward(pl->emb, B, &pl->head, AC_ACT_SOFTMAX, pl->probs, pl->scratch, pl->scratch_floats, stream);
-        if (rc) return rc;
-        rc = ac_topk_desc(pl->probs, B, pl->head.C, pl->kh, pl->h_val, pl->h_idx, pl->ws_topk, pl->ws_topk_bytes, stream);
-        if (rc) return rc;
-    }
+    if (pl->has_head) AC_CUDA(cudaStreamWaitEvent(s, pl->ev_head, 0));
     return ac_blend_topk(pl->p_cls, pl->p_score, pl->h_idx, pl->h_val, B, pl->k, pl->has_head ? pl->kh : 0, 0.7f, 0.3f,
                          out_cls_dev, out_score_dev, stream);
 }
