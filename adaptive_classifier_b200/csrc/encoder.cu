@@ -99,7 +99,7 @@ struct EpiLinear {
     }
 
     __device__ __forceinline__ void tile(State &st, const GemmTileInfo &ti, int row, int col0, const float (&v)[32],
-                                         uint8_t *stage, int lane, int buf) const {
+                                         uint8_t *stage, int lane, int buf, uint32_t /*taddr*/) const {
         const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;        // first row of this warp's TMEM quarter
         if (row_base >= M || col0 >= N) return;                              // warp-uniform
         if (VT && col0 >= vt_col0) {

@@ -68,7 +68,8 @@ struct GemmTileInfo {
 //                __device__ void prefetch(State&, const GemmTileInfo&, int row, int col0, int lane, int buf) const;
 //                      (issue the global loads chunk (col0) will need into State buffer `buf`; called one chunk ahead)
 //                __device__ void tile(State&, const GemmTileInfo&, int row /*global m*/, int col0 /*global n of v[0]*/,
-//                                     const float (&v)[32], uint8_t *stage, int lane, int buf) const;   // 4x per tile per thread
+//                                     const float (&v)[32], uint8_t *stage, int lane, int buf, uint32_t taddr) const;
+//                      (4x per tile per thread; taddr = TMEM address of v[0] for this warp, for re-reading single columns)
 //                      (stage = this warp's private 32 x 80-byte smem tile for transposing to coalesced rows)
 //                __device__ void end_cta(State&, int warp_q, int lane) const; };
 //
@@ -200,7 +201,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane, ci & 1);
+                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane, ci & 1, taddr + c);
             }
             tc_fence_before();
             __syncwarp();

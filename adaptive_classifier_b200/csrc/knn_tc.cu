@@ -35,58 +35,91 @@ constexpr int KNN_KP = 32;   // candidates re-ranked per query
 // ------------------------------------------------------------------------------------------------
 // coarse-pass epilogue
 // ------------------------------------------------------------------------------------------------
+// order-preserving map float -> uint32 (and back) so that atomicMin works on signed keys
+__device__ __forceinline__ uint32_t key_to_ord(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_key(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
 struct EpiKnn {
     const float *p_sqnorm;   // [N]
     float *cand_key;         // [B, slots, KC]  coarse key = ||p||^2 - 2 q.p  (||q||^2 added later)
     int32_t *cand_idx;       // [B, slots, KC]  local row id, -1 = empty
+    uint32_t *gthr;          // [Bp] per query: smallest "worst kept key" published by any list so far (ordered uint)
     int B;                   // queries
     int64_t N;               // rows
-    int tiles_m, slots;      // grid = slots * tiles_m; CTA (blockIdx % tiles_m) owns query tile, slot = blockIdx / tiles_m
+    int tiles_m, slots;      // grid = slots/2 * tiles_m CTAs; every CTA owns one query tile and two lists per query
 
-    static constexpr int kUnrollChunks = 1;   // the insert network is large: keep one copy in the I-cache
+    static constexpr int kUnrollChunks = 1;
     struct State {
         float key[KNN_KC];
         int32_t idx[KNN_KC];
         float pn[2];          // ||p||^2 of the 32 rows of a chunk, one per lane, requested one chunk ahead
+        float gt;             // global bound for this thread's query, refreshed once per tile
     };
 
     __device__ __forceinline__ void begin_cta(State &st, int, int) const {
 #pragma unroll
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
         st.pn[0] = st.pn[1] = CUDART_INF_F;
+        st.gt = CUDART_INF_F;
     }
 
-    // one coalesced 128-byte load per warp and chunk (lane l fetches the norm of row col0 + l), off the critical path
-    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &, int, int col0, int lane, int buf) const {
+    // Every list (74 per query at B = 512) would on its own perform ~KC ln(n/KC) sorted inserts; sharing the best
+    // "KC-th smallest so far" across lists makes all of them reject what no list can need any more.  A row rejected
+    // because key >= gt(t) satisfies key >= gt(final) = min over lists of their worst kept key, which is exactly the
+    // exclusion bound the certification step uses, so the guarantee is unchanged.
+    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &, int row, int col0, int lane, int buf) const {
         const int64_t n = static_cast<int64_t>(col0) + lane;
         const float x = (n < N) ? __ldg(p_sqnorm + n) : CUDART_INF_F;
         if (buf) st.pn[1] = x; else st.pn[0] = x;
+        if (buf == 0) {        // first chunk of a tile: publish this list's bound, pick up the others'
+            if (st.key[KNN_KC - 1] < CUDART_INF_F) atomicMin(gthr + row, key_to_ord(st.key[KNN_KC - 1]));
+            st.gt = ord_to_key(*reinterpret_cast<volatile uint32_t *>(gthr + row));
+        }
     }
-    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
-                                         uint8_t * /*stage*/, int /*lane*/, int buf) const {
-        // all lanes walk the same 32 prototype rows; each lane tests them against its own query's threshold
-        const float pn_lane = buf ? st.pn[1] : st.pn[0];
+
+    __device__ __forceinline__ void insert(State &st, float key, int32_t n) const {
+        // sorted insertion (ascending); strict '<' keeps the earlier (lower id) row on ties.  Slots are visited from the
+        // tail towards the head, so every read sees the pre-insertion value.
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {   // fully unrolled: v[] must stay in registers
-            const int64_t n = static_cast<int64_t>(col0) + j;
+        for (int i = KNN_KC - 1; i > 0; --i) {
+            const bool shift = key < st.key[i - 1];
+            const bool here = !shift && (key < st.key[i]);
+            const float nk = shift ? st.key[i - 1] : (here ? key : st.key[i]);
+            const int32_t ni = shift ? st.idx[i - 1] : (here ? n : st.idx[i]);
+            st.key[i] = nk;
+            st.idx[i] = ni;
+        }
+        if (key < st.key[0]) { st.key[0] = key; st.idx[0] = n; }
+    }
+
+    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
+                                         uint8_t * /*stage*/, int /*lane*/, int buf, uint32_t taddr) const {
+        // fast path: all lanes walk the same 32 prototype rows and only record which ones beat their query's bound
+        const float pn_lane = buf ? st.pn[1] : st.pn[0];
+        const float thr = fminf(st.key[KNN_KC - 1], st.gt);
+        uint32_t hits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
             const float pn = __shfl_sync(0xffffffffu, pn_lane, j);
             const float key = fmaf(-2.f, v[j], pn);
-            const bool ins = key < st.key[KNN_KC - 1];
-            if (__any_sync(0xffffffffu, ins)) {
-                if (ins) {
-                    // sorted insertion (ascending); strict '<' keeps the earlier (lower id) row on ties
-#pragma unroll
-                    for (int i = KNN_KC - 1; i > 0; --i) {
-                        const bool shift = key < st.key[i - 1];
-                        const bool here = !shift && (key < st.key[i]);
-                        const float nk = shift ? st.key[i - 1] : (here ? key : st.key[i]);
-                        const int32_t ni = shift ? st.idx[i - 1] : (here ? static_cast<int32_t>(n) : st.idx[i]);
-                        st.key[i] = nk;
-                        st.idx[i] = ni;
-                    }
-                    if (key < st.key[0]) { st.key[0] = key; st.idx[0] = static_cast<int32_t>(n); }
-                }
-            }
+            hits |= (key < thr) ? (1u << j) : 0u;
+        }
+        // slow path (rare once the bounds are tight): one copy of the insert network, the hit column is read again
+        // from TMEM because v[] cannot be indexed dynamically
+        uint32_t uni = __reduce_or_sync(0xffffffffu, hits);
+        while (uni) {
+            const int j = __ffs(uni) - 1;
+            uni &= uni - 1;
+            const uint32_t r = tmem_ld_32x1(taddr + j);
+            tmem_ld_wait();
+            const float key = fmaf(-2.f, __uint_as_float(r), __shfl_sync(0xffffffffu, pn_lane, j));
+            const int64_t n = static_cast<int64_t>(col0) + j;
+            if (((hits >> j) & 1u) && key < fminf(st.key[KNN_KC - 1], st.gt) && n < N) insert(st, key, static_cast<int32_t>(n));
         }
     }
 
@@ -103,8 +136,6 @@ struct EpiKnn {
     }
 };
 
-// the insertion above reads st.key[i-1] AFTER st.key[i] was rewritten in the same pass only for larger i,
-// so every read sees the pre-insertion value: slots are visited from the tail towards the head.
 
 // ------------------------------------------------------------------------------------------------
 // small kernels around the coarse pass
@@ -228,7 +259,7 @@ __global__ void knn_scatter_results_kernel(const float *__restrict__ d, const in
 // ------------------------------------------------------------------------------------------------
 struct KnnTcPlan {
     int tiles_m, slots, grid, grid_ctas;
-    size_t off_qr, off_qn, off_pn, off_bmax, off_pmax, off_ckey, off_cidx, off_cidx64, off_skey, off_sidx, off_ridx, off_T,
+    size_t off_qr, off_qn, off_gthr, off_pn, off_bmax, off_pmax, off_ckey, off_cidx, off_cidx64, off_skey, off_sidx, off_ridx, off_T,
         off_rd, off_ri, off_fail, off_fq, off_fd, off_fi, off_sel, sel_bytes, off_exact, exact_bytes, total;
 };
 
@@ -248,6 +279,7 @@ static KnnTcPlan plan_knn_tc(int B, int64_t N, int D, int k) {
     const size_t Bp = static_cast<size_t>(p.tiles_m) * GEMM_BLOCK_M;
     p.off_qr = take(Bp * D * 4);
     p.off_qn = take(Bp * 4);
+    p.off_gthr = take(Bp * 4);
     p.off_pn = take(static_cast<size_t>(N) * 4);
     p.off_bmax = take(static_cast<size_t>((N + 7) / 8) * 4);
     p.off_pmax = take(256);
@@ -292,6 +324,7 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     uint8_t *w = static_cast<uint8_t *>(ws);
     float *Qr = reinterpret_cast<float *>(w + pl.off_qr);
     float *qn = reinterpret_cast<float *>(w + pl.off_qn);
+    uint32_t *gthr = reinterpret_cast<uint32_t *>(w + pl.off_gthr);
     float *pn = reinterpret_cast<float *>(w + pl.off_pn);
     float *bmax = reinterpret_cast<float *>(w + pl.off_bmax);
     float *pmax = reinterpret_cast<float *>(w + pl.off_pmax);
@@ -314,6 +347,7 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     const size_t Bp = static_cast<size_t>(pl.tiles_m) * GEMM_BLOCK_M;
     AC_CUDA(cudaMemsetAsync(Qr, 0, Bp * D * 4, s));
     AC_CUDA(cudaMemsetAsync(fail, 0, 4, s));
+    AC_CUDA(cudaMemsetAsync(gthr, 0xFF, Bp * 4, s));   // ordered-uint +max: no bound published yet
     __half *Qh = p_half ? reinterpret_cast<__half *>(Qr) : nullptr;   // the fp16 queries reuse the fp32 query slot
     knn_prep_queries_kernel<<<(B + 3) / 4, 128, 0, s>>>(Q, B, D, Qr, Qh, qn);
     AC_LAUNCH_CHECK();
@@ -331,7 +365,7 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
 
     // ---- coarse pass on the tensor cores
     CUtensorMap ta, tb;
-    EpiKnn epi{pn_use, ckey, cidx, B, N, pl.tiles_m, pl.slots};   // slots = 2 per CTA
+    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots};   // slots = 2 per CTA
     // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16
     // shadow the kernel actually streams 2.N.D bytes (the exact re-rank below still reads fp32 rows)
     if (p_half) {
