@@ -28,7 +28,7 @@ EXPORTS = [
     "ac_version", "ac_last_error", "ac_device_check",
     "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
     "ac_segment_mean",
-    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_grad", "ac_ewc_penalty",
+    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch_workspace_bytes", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
     "ac_proto_class_scores", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
     "ac_pipeline_create", "ac_pipeline_destroy", "ac_pipeline_predict_device", "ac_pipeline_predict_host",
@@ -101,6 +101,9 @@ def load_library() -> ctypes.CDLL:
     L.ac_head_train_workspace_bytes.argtypes = [c_int, POINTER(HeadParams), POINTER(c_size_t)]
     L.ac_head_train_step.argtypes = [c_void_p, c_void_p, c_int, POINTER(HeadParams), POINTER(HeadParams),
                                      POINTER(HeadParams), POINTER(TrainCfg), c_void_p, c_void_p, c_size_t, c_void_p]
+    L.ac_head_train_epoch_workspace_bytes.argtypes = [c_int, POINTER(HeadParams), POINTER(c_size_t)]
+    L.ac_head_train_epoch.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(HeadParams), POINTER(HeadParams),
+                                      POINTER(HeadParams), POINTER(TrainCfg), c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_head_grad.argtypes = [c_void_p, c_void_p, c_int, POINTER(HeadParams), c_int, POINTER(HeadParams),
                                POINTER(HeadParams), c_float, c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_ewc_penalty.argtypes = [POINTER(HeadParams), POINTER(HeadParams), POINTER(HeadParams), c_float, c_float,
@@ -296,6 +299,36 @@ def head_train_step(X, targets, p, m, v, *, step, loss_kind=AC_LOSS_CE, lr=1e-3,
                                ctypes.byref(hv), ctypes.byref(cfg), out_stats.data_ptr(), ws.data_ptr(), ws.numel(),
                                stream_ptr()), "ac_head_train_step")
     return out_stats
+
+
+def head_train_epoch(X, targets, perm, p, m, v, *, first_step, batch, loss_kind=AC_LOSS_CE, lr=1e-3, betas=(0.9, 0.999),
+                     eps=1e-8, weight_decay=0.01, max_norm=1.0, dropout_p=0.1, seed=0, ewc=None, loss_accum=None):
+    """All optimizer steps of one epoch (batches gathered on the device from `perm`).  Returns (loss_accum tensor, steps)."""
+    L = load_library()
+    X = _f32c(X)
+    n = X.shape[0]
+    hp, hm, hv = head_params_struct(p), head_params_struct(m), head_params_struct(v)
+    cfg = TrainCfg()
+    cfg.lr, cfg.beta1, cfg.beta2, cfg.eps = lr, betas[0], betas[1], eps
+    cfg.weight_decay, cfg.max_norm = weight_decay, max_norm
+    cfg.step, cfg.loss_kind, cfg.dropout_p, cfg.seed = first_step, loss_kind, dropout_p, seed
+    keep = []
+    if ewc is not None:
+        fs, ss = head_params_struct(ewc[0]), head_params_struct(ewc[1])
+        keep += [fs, ss]
+        cfg.ewc_fisher, cfg.ewc_star = ctypes.pointer(fs), ctypes.pointer(ss)
+        cfg.ewc_lambda, cfg.ewc_C_old = float(ewc[2]), int(ewc[3])
+    nbytes = c_size_t(0)
+    check(L.ac_head_train_epoch_workspace_bytes(batch, ctypes.byref(hp), ctypes.byref(nbytes)), "ac_head_train_epoch_workspace_bytes")
+    ws = _workspace(nbytes.value, X.device)
+    if loss_accum is None:
+        loss_accum = torch.zeros((1,), dtype=torch.float32, device=X.device)
+    targets = targets.contiguous()
+    perm = perm.to(device=X.device, dtype=torch.int64).contiguous()
+    check(L.ac_head_train_epoch(X.data_ptr(), targets.data_ptr(), perm.data_ptr(), n, batch, ctypes.byref(hp),
+                                ctypes.byref(hm), ctypes.byref(hv), ctypes.byref(cfg), loss_accum.data_ptr(), ws.data_ptr(),
+                                ws.numel(), stream_ptr()), "ac_head_train_epoch")
+    return loss_accum, (n + batch - 1) // batch
 
 
 def head_grad(X, targets, p, *, loss_kind=AC_LOSS_CE, grad_out=None, fisher=None, inv_n_batches=1.0):

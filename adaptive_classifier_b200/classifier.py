@@ -170,16 +170,10 @@ class AdaptiveClassifier:
         seed = int(torch.initial_seed() & 0x7FFFFFFF)
         self.adaptive_head.train()
         for epoch in range(epochs):
-            perm = torch.randperm(n, generator=gen).to(X.device)
-            total = torch.zeros((), dtype=torch.float32, device=X.device)
-            for b in range(n_batches):
-                idx = perm[b * batch_size : (b + 1) * batch_size]
-                xb = X.index_select(0, idx).contiguous()
-                yb = Y.index_select(0, idx).contiguous()
-                step += 1
-                stats = _cabi.head_train_step(xb, yb, p, m, v, step=step, loss_kind=self._loss_kind, lr=lr,
-                                              dropout_p=0.1, seed=seed, ewc=ewc)
-                total = total + stats[0] + stats[1]
+            perm = torch.randperm(n, generator=gen)            # the index lists the reference's DataLoader yields
+            total, nb = _cabi.head_train_epoch(X, Y, perm, p, m, v, first_step=step + 1, batch=batch_size,
+                                               loss_kind=self._loss_kind, lr=lr, dropout_p=0.1, seed=seed, ewc=ewc)
+            step += nb
             avg_loss = float(total.item()) / n_batches
             if use_scheduler:                                   # ReduceLROnPlateau(mode=min, factor .5, patience 2)
                 if avg_loss < sched_best * (1 - 1e-4):

@@ -482,6 +482,10 @@ extern "C" int ac_ewc_penalty(const ac_head_params *p, const ac_head_params *fis
     return AC_OK;
 }
 
+static int train_step_impl(const float *X, const void *targets, int B, ac_head_params *p, ac_head_params *m,
+                           ac_head_params *v, const ac_train_cfg *cfg, int step, float *out_stats, void *workspace,
+                           size_t workspace_bytes, cudaStream_t s);
+
 extern "C" int ac_head_train_step(const float *X, const void *targets, int B, ac_head_params *p, ac_head_params *m,
                                   ac_head_params *v, const ac_train_cfg *cfg, float *out_stats, void *workspace,
                                   size_t workspace_bytes, ac_stream_t stream) {
@@ -489,18 +493,25 @@ extern "C" int ac_head_train_step(const float *X, const void *targets, int B, ac
     if (rc) return rc;
     AC_REQUIRE(X && targets && B > 0 && m && v && cfg && out_stats && workspace, "ac_head_train_step: bad arguments");
     AC_REQUIRE(cfg->step >= 1, "ac_head_train_step: step must be >= 1");
+    return train_step_impl(X, targets, B, p, m, v, cfg, cfg->step, out_stats, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+static int train_step_impl(const float *X, const void *targets, int B, ac_head_params *p, ac_head_params *m,
+                           ac_head_params *v, const ac_train_cfg *cfg, int step, float *out_stats, void *workspace,
+                           size_t workspace_bytes, cudaStream_t s) {
+    int rc;
     TrainWs w;
     const size_t need = carve(w, workspace, B, p);
     if (need > workspace_bytes) { set_error("ac_head_train_step: workspace needs %zu bytes", need); return AC_E_WORKSPACE; }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
 
     const float *mask0 = cfg->mask0, *mask1 = cfg->mask1;
     if (cfg->dropout_p > 0.f && (!mask0 || !mask1)) {
         const int64_t n0 = static_cast<int64_t>(B) * p->H0, n1 = static_cast<int64_t>(B) * p->H1;
         dropout_mask_kernel<<<static_cast<unsigned>((n0 + 255) / 256), 256, 0, s>>>(w.mask0, n0, cfg->dropout_p, cfg->seed,
-                                                                                  2ull * cfg->step);
+                                                                                  2ull * step);
         dropout_mask_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, s>>>(w.mask1, n1, cfg->dropout_p, cfg->seed,
-                                                                                  2ull * cfg->step + 1);
+                                                                                  2ull * step + 1);
         AC_LAUNCH_CHECK();
         mask0 = w.mask0;
         mask1 = w.mask1;
@@ -525,10 +536,75 @@ extern "C" int ac_head_train_step(const float *X, const void *targets, int B, ac
     AC_LAUNCH_CHECK();
     finalize_kernel<<<1, 32, 0, s>>>(w.partial, RED_BLOCKS, 1.f, 1, out_stats + 2);
     AC_LAUNCH_CHECK();
-    const float bc1 = 1.f - powf(cfg->beta1, static_cast<float>(cfg->step));
-    const float bc2 = 1.f - powf(cfg->beta2, static_cast<float>(cfg->step));
+    const float bc1 = 1.f - powf(cfg->beta1, static_cast<float>(step));
+    const float bc2 = 1.f - powf(cfg->beta2, static_cast<float>(step));
     adamw_kernel<<<RED_BLOCKS * 2, 256, 0, s>>>(flat_of(p), g, flat_of(m), flat_of(v), out_stats + 2, cfg->lr, cfg->beta1,
                                                 cfg->beta2, cfg->eps, cfg->weight_decay, cfg->max_norm, bc1, sqrtf(bc2));
     AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// one epoch of the training loops (classifier.py:329-353, :1485-1507; multilabel.py:381-399) in a single call:
+// batches are gathered on the device from a shuffled index list, every optimizer step is launched from here.
+// ------------------------------------------------------------------------------------------------
+namespace ac {
+__global__ void gather_batch_kernel(const float *__restrict__ X, const void *__restrict__ targets, const int64_t *__restrict__ perm,
+                                    int nb, int D, int C, int loss_kind, float *__restrict__ xb, void *__restrict__ yb) {
+    const int r = blockIdx.x;
+    if (r >= nb) return;
+    const int64_t src = perm[r];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) xb[static_cast<int64_t>(r) * D + i] = X[src * D + i];
+    if (loss_kind == AC_LOSS_CE) {
+        if (threadIdx.x == 0) static_cast<int64_t *>(yb)[r] = static_cast<const int64_t *>(targets)[src];
+    } else {
+        for (int i = threadIdx.x; i < C; i += blockDim.x)
+            static_cast<float *>(yb)[static_cast<int64_t>(r) * C + i] = static_cast<const float *>(targets)[src * C + i];
+    }
+}
+__global__ void accum_loss_kernel(const float *__restrict__ stats, float *__restrict__ accum) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) accum[0] += stats[0] + stats[1];
+}
+}  // namespace ac
+
+extern "C" int ac_head_train_epoch_workspace_bytes(int batch, const ac_head_params *p, size_t *bytes) {
+    AC_REQUIRE(p && bytes && batch > 0, "ac_head_train_epoch_workspace_bytes: bad arguments");
+    TrainWs w;
+    const size_t yb = static_cast<size_t>(batch) * (p->C > 2 ? p->C : 2) * sizeof(float);
+    *bytes = carve(w, nullptr, batch, p) + align_up(static_cast<size_t>(batch) * p->D * sizeof(float), 256) + align_up(yb, 256) + 1024;
+    return AC_OK;
+}
+
+extern "C" int ac_head_train_epoch(const float *X, const void *targets, const int64_t *perm, int n, int batch,
+                                   ac_head_params *p, ac_head_params *m, ac_head_params *v, const ac_train_cfg *cfg,
+                                   float *loss_accum, void *workspace, size_t workspace_bytes, ac_stream_t stream) {
+    int rc = check_params(p, "ac_head_train_epoch");
+    if (rc) return rc;
+    AC_REQUIRE(X && targets && perm && n > 0 && batch > 0 && m && v && cfg && loss_accum && workspace,
+               "ac_head_train_epoch: bad arguments");
+    AC_REQUIRE(cfg->step >= 1 && !cfg->mask0 && !cfg->mask1, "ac_head_train_epoch: step >= 1 and no injected masks");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TrainWs w;
+    const size_t step_bytes = carve(w, nullptr, batch, p);
+    const size_t xb_bytes = align_up(static_cast<size_t>(batch) * p->D * sizeof(float), 256);
+    const size_t yb_bytes = align_up(static_cast<size_t>(batch) * (p->C > 2 ? p->C : 2) * sizeof(float), 256);
+    if (step_bytes + xb_bytes + yb_bytes + 256 > workspace_bytes) {
+        set_error("ac_head_train_epoch: workspace needs %zu bytes", step_bytes + xb_bytes + yb_bytes + 256);
+        return AC_E_WORKSPACE;
+    }
+    uint8_t *base = static_cast<uint8_t *>(workspace);
+    float *xb = reinterpret_cast<float *>(base + step_bytes);
+    void *yb = base + step_bytes + xb_bytes;
+    float *stats = reinterpret_cast<float *>(base + step_bytes + xb_bytes + yb_bytes);
+    int step = cfg->step;
+    for (int off = 0; off < n; off += batch, ++step) {
+        const int nb = (n - off < batch) ? n - off : batch;      // DataLoader keeps the last partial batch
+        gather_batch_kernel<<<nb, 128, 0, s>>>(X, targets, perm + off, nb, p->D, p->C, cfg->loss_kind, xb, yb);
+        AC_LAUNCH_CHECK();
+        if ((rc = train_step_impl(xb, yb, nb, p, m, v, cfg, step, stats, workspace, step_bytes, s))) return rc;
+        accum_loss_kernel<<<1, 32, 0, s>>>(stats, loss_accum);
+        AC_LAUNCH_CHECK();
+    }
     return AC_OK;
 }

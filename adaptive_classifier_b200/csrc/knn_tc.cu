@@ -52,6 +52,7 @@ struct EpiKnn {
     int B;                   // queries
     int64_t N;               // rows
     int tiles_m, slots;      // grid = slots/2 * tiles_m CTAs; every CTA owns one query tile and two lists per query
+    int kt;                  // a list publishes its kt-th best key (k + 3 <= kt <= KC): see prefetch()
 
     static constexpr int kUnrollChunks = 1;
     struct State {
@@ -68,16 +69,22 @@ struct EpiKnn {
         st.gt = CUDART_INF_F;
     }
 
-    // Every list (74 per query at B = 512) would on its own perform ~KC ln(n/KC) sorted inserts; sharing the best
-    // "KC-th smallest so far" across lists makes all of them reject what no list can need any more.  A row rejected
-    // because key >= gt(t) satisfies key >= gt(final) = min over lists of their worst kept key, which is exactly the
-    // exclusion bound the certification step uses, so the guarantee is unchanged.
+    // Every list (74 per query at B = 512) would on its own perform ~KC ln(n/KC) sorted inserts; sharing a bound
+    // across lists makes all of them reject what cannot matter any more.  Each list publishes its kt-th best key;
+    // gt = min over lists.  Exclusion bound for the certification: T = min over lists of their FINAL kt-th best
+    // (<= every published value, gt only decreases).  A row with key < T is never rejected (key < T <= gt(t) and
+    // key < T <= list's kt-th best <= list's KC-th best) and never evicted (eviction would put KC better rows in its
+    // list, i.e. that list's kt-th best < key, contradicting key < T).  T >= the global kt-th smallest key, so the
+    // certification is at least as strong as with one global top-kt list.
     __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &, int row, int col0, int lane, int buf) const {
         const int64_t n = static_cast<int64_t>(col0) + lane;
         const float x = (n < N) ? __ldg(p_sqnorm + n) : CUDART_INF_F;
         if (buf) st.pn[1] = x; else st.pn[0] = x;
         if (buf == 0) {        // first chunk of a tile: publish this list's bound, pick up the others'
-            if (st.key[KNN_KC - 1] < CUDART_INF_F) atomicMin(gthr + row, key_to_ord(st.key[KNN_KC - 1]));
+            float pub = CUDART_INF_F;
+#pragma unroll
+            for (int i = 0; i < KNN_KC; ++i) pub = (i == kt - 1) ? st.key[i] : pub;
+            if (pub < CUDART_INF_F) atomicMin(gthr + row, key_to_ord(pub));
             st.gt = ord_to_key(*reinterpret_cast<volatile uint32_t *>(gthr + row));
         }
     }
@@ -203,9 +210,9 @@ __global__ void knn_widen_kernel(const int32_t *__restrict__ in, int64_t n, int6
 
 // after the (key,id) sort of all per-CTA candidates: take the best KP ids for the re-rank and compute
 //   T[b] = ||q||^2 + min( key of the first entry NOT re-ranked, min over CTAs of their worst kept key )
-// sorted_*: [B, KP+1] ascending.  cand_key: [B, slots, KC] (entry KC-1 = worst kept of that CTA).
+// sorted_*: [B, KP+1] ascending.  cand_key: [B, slots, KC] (entry kt-1 = the bound that list published).
 __global__ void knn_pick_kernel(const float *__restrict__ sorted_key, const int64_t *__restrict__ sorted_idx,
-                                const float *__restrict__ cand_key, const float *__restrict__ qn, int B, int slots,
+                                const float *__restrict__ cand_key, const float *__restrict__ qn, int B, int slots, int kt,
                                 int32_t *__restrict__ rerank_idx /*[B,KP]*/, float *__restrict__ T) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -213,7 +220,7 @@ __global__ void knn_pick_kernel(const float *__restrict__ sorted_key, const int6
     const int64_t *si = sorted_idx + static_cast<int64_t>(b) * (KNN_KP + 1);
     for (int j = 0; j < KNN_KP; ++j) rerank_idx[static_cast<int64_t>(b) * KNN_KP + j] = static_cast<int32_t>(si[j]);
     float t = (si[KNN_KP] >= 0) ? sk[KNN_KP] : CUDART_INF_F;
-    for (int s = 0; s < slots; ++s) t = fminf(t, cand_key[(static_cast<int64_t>(b) * slots + s) * KNN_KC + (KNN_KC - 1)]);
+    for (int s = 0; s < slots; ++s) t = fminf(t, cand_key[(static_cast<int64_t>(b) * slots + s) * KNN_KC + (kt - 1)]);
     T[b] = t + qn[b];
 }
 
@@ -365,7 +372,9 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
 
     // ---- coarse pass on the tensor cores
     CUtensorMap ta, tb;
-    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots};   // slots = 2 per CTA
+    int kt = k + 3 > 8 ? k + 3 : 8;
+    if (kt > KNN_KC) kt = KNN_KC;
+    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt};   // slots = 2 per CTA
     // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16
     // shadow the kernel actually streams 2.N.D bytes (the exact re-rank below still reads fp32 rows)
     if (p_half) {
@@ -387,7 +396,7 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     AC_LAUNCH_CHECK();
     const int64_t L = static_cast<int64_t>(pl.slots) * KNN_KC;
     if ((rc = topk_select(ckey, cidx64, B, L, L, 0, KNN_KP + 1, skey, sidx, selws, pl.sel_bytes, s))) return rc;
-    knn_pick_kernel<<<(B + 127) / 128, 128, 0, s>>>(skey, sidx, ckey, qn, B, pl.slots, ridx, T);
+    knn_pick_kernel<<<(B + 127) / 128, 128, 0, s>>>(skey, sidx, ckey, qn, B, pl.slots, kt, ridx, T);
     AC_LAUNCH_CHECK();
 
     // ---- exact re-rank of the candidates, final (d, id) order

@@ -135,6 +135,15 @@ int ac_head_train_step(const float *X, const void *targets, int B,
                        const ac_train_cfg *cfg, float *out_stats,
                        void *workspace, size_t workspace_bytes, ac_stream_t stream);
 
+/* one EPOCH of the reference's training loops (classifier.py:329-353, :1485-1507; multilabel.py:381-399) in one call:
+ * X[n,D], targets (int64[n] or float[n,C]) and the shuffled index list perm[n] (what the reference's DataLoader with
+ * torch.Generator().manual_seed(42) yields) live on the device; batches of `batch` rows (last one partial) are gathered
+ * and stepped here.  cfg->step = 1-based number of the first update; loss_accum[0] += task loss + EWC penalty per step. */
+int ac_head_train_epoch_workspace_bytes(int batch, const ac_head_params *p, size_t *bytes);
+int ac_head_train_epoch(const float *X, const void *targets, const int64_t *perm, int n, int batch,
+                        ac_head_params *p, ac_head_params *m, ac_head_params *v, const ac_train_cfg *cfg,
+                        float *loss_accum, void *workspace, size_t workspace_bytes, ac_stream_t stream);
+
 /* gradient only (no update) of mean CE/BCE wrt all parameters, eval mode: the building block of
  * EWC._compute_fisher (ewc.py:67-92).  fisher += grad^2 * inv_n_batches when fisher != NULL */
 int ac_head_grad(const float *X, const void *targets, int B, const ac_head_params *p, int loss_kind,

@@ -242,6 +242,29 @@ def test_head_train_steps_match_oracle(cabi, loss_kind):
             assert (mg[k].cpu() - m[k]).abs().max() <= 1e-6 + 1e-4 * m[k].abs().max(), (step, k)
 
 
+def test_head_train_epoch_equals_step_sequence(cabi):
+    """ac_head_train_epoch (device-side batch gather, all steps launched from C) == the same steps issued one by one"""
+    n, D, C, bs = 100, 768, 7, 32
+    g = torch.Generator().manual_seed(2)
+    X = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).cuda()
+    y = torch.randint(0, C, (n,), generator=g).cuda()
+    perm = torch.randperm(n, generator=g)
+    _, pa = _head(D, C)
+    pb = {k: v.clone() for k, v in pa.items()}
+    ma, va = ({k: torch.zeros_like(v) for k, v in pa.items()} for _ in range(2))
+    mb, vb = ({k: torch.zeros_like(v) for k, v in pb.items()} for _ in range(2))
+    acc, nb = cabi.head_train_epoch(X, y, perm, pa, ma, va, first_step=5, batch=bs, seed=77)
+    assert nb == 4
+    tot = 0.0
+    for b in range(nb):
+        idx = perm[b * bs:(b + 1) * bs].cuda()
+        st = cabi.head_train_step(X[idx].contiguous(), y[idx].contiguous(), pb, mb, vb, step=5 + b, seed=77)
+        tot += float(st[0] + st[1])
+    for k in pa:
+        assert torch.equal(pa[k], pb[k]) and torch.equal(ma[k], mb[k]) and torch.equal(va[k], vb[k]), k
+    assert abs(float(acc) - tot) < 1e-5
+
+
 def test_ewc_penalty_and_fisher(cabi):
     B, D, C = 20, 768, 6
     g = torch.Generator().manual_seed(4)
