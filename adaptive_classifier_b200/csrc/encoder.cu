@@ -31,21 +31,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// exact-erf GELU 0.5*y*(1+erf(y/sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 + 2 ulp of the two
-// MUFU approximations): 2 MUFU + 11 FP32 ops per element.  The GELU epilogue touches 201 M elements per layer; the issue
-// budget that hides it behind a K = 768 fp16 mainloop is ~24 instructions per element (libdevice erff alone is ~30).
+// exact-erf GELU y*Phi(y) with erfc from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 + 2 ulp of the two MUFU
+// approximations).  With x = |y|/sqrt2, h = erfc(x)/2 = (poly(t)/2) * t * exp(-x^2), t = 1/(1 + p x):
+//     y >= 0: y*(1 - h) = y - y*h        y < 0: y*h            =>   gelu(y) = max(y, 0) - |y*h|
+// 2 MUFU + 12 FP32 ops per element and no branch/select.  The GELU epilogue touches 201 M elements per layer; the
+// issue budget that hides it behind a K = 768 fp16 mainloop is ~24 instructions per element (libdevice erff alone ~30).
 __device__ __forceinline__ float gelu_erf(float y) {
-    const float x = y * 0.70710678118654752440f;
-    const float ax = fabsf(x);
-    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float q = p * t * ex2_approx(-1.4426950408889634f * ax * ax);   // erfc(|x|)
-    const float hy = 0.5f * y;
-    // y >= 0: 0.5*y*(2 - q) = y - hy*q ; y < 0: 0.5*y*q
-    return y >= 0.f ? fmaf(-hy, q, y) : hy * q;
+    const float ay = fabsf(y);
+    const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ay, 1.f));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    const float e = ex2_approx((y * y) * (-0.5f * 1.4426950408889634f));   // exp(-y^2/2)
+    const float h = (p * t) * e;                                             // erfc(|y|/sqrt2) / 2
+    return fmaxf(y, 0.f) - fabsf(y * h);
 }
 
 // ------------------------------------------------------------------------------------------------
