@@ -110,11 +110,142 @@ static int sgemm(const float *A, int64_t sam, int64_t sak, const float *B, int64
     return AC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// skinny linears (M = batch rows, 32 per pass): the 64x64-tile SGEMM above runs them on a dozen CTAs and is
+// latency-bound (~50 us each at M = 32); these two kernels keep every load independent instead.
+//
+// rowdot   Y[b,n] = epi( sum_k X[b,k] * W[n,k] + bias[n] )      W row-major [N,K] (nn.Linear layout), forward
+//          warp = 4 output columns x 32 batch rows, lanes stride K, warp transpose-reduce at the end
+// colacc   Z[b,j] = epi( sum_r G[b,r] * W[r,j] )                W row-major [R,J], backward w.r.t. the input
+//          thread = output column j (coalesced W rows), 8 warps split the reduction, fixed-order smem combine
+// Both sum in a fixed order (deterministic across runs).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float epi_apply(const SgemmEpi &epi, float v, int n, int64_t off) {
+    switch (epi.kind) {
+        case EPI_BIAS: v += epi.bias[n]; break;
+        case EPI_BIAS_RELU: v = fmaxf(v + epi.bias[n], 0.f); break;
+        case EPI_BIAS_RELU_MASK:
+            v = fmaxf(v + epi.bias[n], 0.f);
+            if (epi.mask) v *= epi.mask[off];
+            break;
+        case EPI_RELUGRAD_MASK:
+            if (epi.mask) v *= epi.mask[off];
+            v = (epi.act[off] > 0.f) ? v : 0.f;
+            break;
+        default: break;
+    }
+    return v;
+}
+
+// after the call lane l holds the sum over all lanes of their v[l]
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+constexpr int RD_COLS = 4;      // output columns per warp
+constexpr int RD_WARPS = 8;
+
+__global__ void __launch_bounds__(RD_WARPS * 32)
+rowdot_kernel(const float *__restrict__ X, const float *__restrict__ W, float *__restrict__ Y, int M, int N, int K,
+              SgemmEpi epi) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = (blockIdx.x * RD_WARPS + warp) * RD_COLS;
+    const int b0 = blockIdx.y * 32;
+    if (n0 >= N) return;
+    float acc[RD_COLS][32];
+#pragma unroll
+    for (int c = 0; c < RD_COLS; ++c)
+#pragma unroll
+        for (int b = 0; b < 32; ++b) acc[c][b] = 0.f;
+    const int rows = min(32, M - b0);
+    for (int k = lane; k < K; k += 32) {
+        float w[RD_COLS];
+#pragma unroll
+        for (int c = 0; c < RD_COLS; ++c) w[c] = (n0 + c < N) ? __ldg(W + static_cast<int64_t>(n0 + c) * K + k) : 0.f;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const float x = (b < rows) ? __ldg(X + static_cast<int64_t>(b0 + b) * K + k) : 0.f;
+#pragma unroll
+            for (int c = 0; c < RD_COLS; ++c) acc[c][b] = fmaf(x, w[c], acc[c][b]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < RD_COLS; ++c) {
+        const float s = warp_transpose_reduce(acc[c], lane);     // lane = batch row
+        const int n = n0 + c, m = b0 + lane;
+        if (n < N && lane < rows) {
+            const int64_t off = static_cast<int64_t>(m) * N + n;
+            Y[off] = epi_apply(epi, s, n, off);
+        }
+    }
+}
+
+constexpr int CA_GROUPS = 8;    // reduction split
+
+__global__ void __launch_bounds__(CA_GROUPS * 32)
+colacc_kernel(const float *__restrict__ G, const float *__restrict__ W, float *__restrict__ Z, int M, int R, int J,
+              SgemmEpi epi) {
+    __shared__ float part[CA_GROUPS][32][33];
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 32 + lane;
+    const int b0 = blockIdx.y * 32;
+    const int rows = min(32, M - b0);
+    float acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+    for (int r = g; r < R; r += CA_GROUPS) {
+        const float w = (j < J) ? __ldg(W + static_cast<int64_t>(r) * J + j) : 0.f;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const float gv = (b < rows) ? __ldg(G + static_cast<int64_t>(b0 + b) * R + r) : 0.f;   // warp-uniform address
+            acc[b] = fmaf(gv, w, acc[b]);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b) part[g][b][lane] = acc[b];
+    __syncthreads();
+    // warp g finishes batch rows g, g+8, ...: sum over the groups in index order
+    for (int b = g; b < rows; b += CA_GROUPS) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < CA_GROUPS; ++q) s += part[q][b][lane];
+        if (j < J) {
+            const int64_t off = static_cast<int64_t>(b0 + b) * J + j;
+            Z[off] = epi_apply(epi, s, j, off);
+        }
+    }
+}
+
+static int rowdot(const float *X, const float *W, float *Y, int M, int N, int K, SgemmEpi epi, cudaStream_t s) {
+    if (M <= 0 || N <= 0) return AC_OK;
+    dim3 grid((N + RD_COLS * RD_WARPS - 1) / (RD_COLS * RD_WARPS), (M + 31) / 32);
+    rowdot_kernel<<<grid, RD_WARPS * 32, 0, s>>>(X, W, Y, M, N, K, epi);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+static int colacc(const float *G, const float *W, float *Z, int M, int R, int J, SgemmEpi epi, cudaStream_t s) {
+    if (M <= 0 || J <= 0) return AC_OK;
+    dim3 grid((J + 31) / 32, (M + 31) / 32);
+    colacc_kernel<<<grid, CA_GROUPS * 32, 0, s>>>(G, W, Z, M, R, J, epi);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
 // y[m,n] = act(X W^T + b):  A = X (sam = K, sak = 1), B(k,n) = W[n*K + k] (sbk = 1, sbn = K)
 static int linear_fwd(const float *X, const float *W, const float *b, float *Y, int M, int N, int K, int kind,
                       const float *mask, cudaStream_t s) {
     SgemmEpi e{kind, b, mask, nullptr};
-    return sgemm(X, K, 1, W, 1, K, Y, N, M, N, K, e, s);
+    return rowdot(X, W, Y, M, N, K, e, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -381,12 +512,12 @@ static int fwd_bwd(const float *X, const void *targets, int B, const ac_head_par
     AC_LAUNCH_CHECK();
     // dh1[B,H1] = dz W2, then relu-grad + mask -> da1
     SgemmEpi rg1{EPI_RELUGRAD_MASK, nullptr, mask1, w.h1};
-    if ((rc = sgemm(w.dz, C, 1, p->W2, H1, 1, w.dh1, H1, B, H1, C, rg1, s))) return rc;
+    if ((rc = colacc(w.dz, p->W2, w.dh1, B, C, H1, rg1, s))) return rc;
     if ((rc = sgemm(w.dh1, 1, H1, w.h0, H0, 1, w.g.W1, H0, H1, H0, B, none, s))) return rc;
     colsum_kernel<<<(H1 + 127) / 128, 128, 0, s>>>(w.dh1, B, H1, w.g.b1);
     AC_LAUNCH_CHECK();
     SgemmEpi rg0{EPI_RELUGRAD_MASK, nullptr, mask0, w.h0};
-    if ((rc = sgemm(w.dh1, H1, 1, p->W1, H0, 1, w.dh0, H0, B, H0, H1, rg0, s))) return rc;
+    if ((rc = colacc(w.dh1, p->W1, w.dh0, B, H1, H0, rg0, s))) return rc;
     if ((rc = sgemm(w.dh0, 1, H0, X, D, 1, w.g.W0, D, H0, D, B, none, s))) return rc;
     colsum_kernel<<<(H0 + 127) / 128, 128, 0, s>>>(w.dh0, B, H0, w.g.b0);
     AC_LAUNCH_CHECK();
