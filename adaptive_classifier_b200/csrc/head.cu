@@ -152,9 +152,11 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
     return v[0];
 }
 
-constexpr int RD_COLS = 4;      // output columns per warp
 constexpr int RD_WARPS = 8;
 
+// RD_COLS output columns per warp: 4 when there are many row blocks (re-use of the X loads), 1 for a single 32-row
+// batch so that a 768-column layer still spreads over 96 CTAs
+template <int RD_COLS>
 __global__ void __launch_bounds__(RD_WARPS * 32)
 rowdot_kernel(const float *__restrict__ X, const float *__restrict__ W, float *__restrict__ Y, int M, int N, int K,
               SgemmEpi epi) {
@@ -168,6 +170,7 @@ rowdot_kernel(const float *__restrict__ X, const float *__restrict__ W, float *_
 #pragma unroll
         for (int b = 0; b < 32; ++b) acc[c][b] = 0.f;
     const int rows = min(32, M - b0);
+#pragma unroll 2
     for (int k = lane; k < K; k += 32) {
         float w[RD_COLS];
 #pragma unroll
@@ -228,8 +231,13 @@ colacc_kernel(const float *__restrict__ G, const float *__restrict__ W, float *_
 
 static int rowdot(const float *X, const float *W, float *Y, int M, int N, int K, SgemmEpi epi, cudaStream_t s) {
     if (M <= 0 || N <= 0) return AC_OK;
-    dim3 grid((N + RD_COLS * RD_WARPS - 1) / (RD_COLS * RD_WARPS), (M + 31) / 32);
-    rowdot_kernel<<<grid, RD_WARPS * 32, 0, s>>>(X, W, Y, M, N, K, epi);
+    if (M <= 64) {
+        dim3 grid((N + RD_WARPS - 1) / RD_WARPS, (M + 31) / 32);
+        rowdot_kernel<1><<<grid, RD_WARPS * 32, 0, s>>>(X, W, Y, M, N, K, epi);
+    } else {
+        dim3 grid((N + 4 * RD_WARPS - 1) / (4 * RD_WARPS), (M + 31) / 32);
+        rowdot_kernel<4><<<grid, RD_WARPS * 32, 0, s>>>(X, W, Y, M, N, K, epi);
+    }
     AC_LAUNCH_CHECK();
     return AC_OK;
 }
