@@ -373,6 +373,31 @@ def linear_tc(X, W, bias, residual=None, epi: int = 0, round_out: bool = False, 
     return Y
 
 
+def distilbert_to_bert_state_dict(sd: dict, c):
+    """DistilBERT (HF models/distilbert/modeling_distilbert.py) is the BERT post-LN block without token-type embeddings:
+    rename its parameters to the BERT names the encoder consumes and supply an all-zero single-row type table."""
+    if getattr(c, "activation", "gelu") != "gelu" or getattr(c, "sinusoidal_pos_embds", False):
+        raise AdaptiveB200Error("DistilBERT variant with non-GELU activation / sinusoidal positions is not implemented")
+    out = {
+        "embeddings.word_embeddings.weight": sd["embeddings.word_embeddings.weight"],
+        "embeddings.position_embeddings.weight": sd["embeddings.position_embeddings.weight"],
+        "embeddings.token_type_embeddings.weight": torch.zeros((1, c.dim), dtype=torch.float32),
+        "embeddings.LayerNorm.weight": sd["embeddings.LayerNorm.weight"],
+        "embeddings.LayerNorm.bias": sd["embeddings.LayerNorm.bias"],
+    }
+    ren = {"attention.q_lin": "attention.self.query", "attention.k_lin": "attention.self.key",
+           "attention.v_lin": "attention.self.value", "attention.out_lin": "attention.output.dense",
+           "sa_layer_norm": "attention.output.LayerNorm", "ffn.lin1": "intermediate.dense", "ffn.lin2": "output.dense",
+           "output_layer_norm": "output.LayerNorm"}
+    for l in range(c.n_layers):
+        for src, dst in ren.items():
+            for wb in ("weight", "bias"):
+                out[f"encoder.layer.{l}.{dst}.{wb}"] = sd[f"transformer.layer.{l}.{src}.{wb}"]
+    dims = dict(layers=c.n_layers, hidden=c.dim, heads=c.n_heads, intermediate=c.hidden_dim, vocab=c.vocab_size,
+                max_pos=c.max_position_embeddings, type_vocab=1, ln_eps=1e-12, pad_idx=0)
+    return out, dims
+
+
 class Encoder:
     """Owner of an ac_encoder handle built from an HF BERT/RoBERTa state_dict (CUDA fp32 tensors)."""
 
@@ -420,17 +445,23 @@ class Encoder:
         del keep  # the handle holds its own packed copies
 
     @classmethod
-    def from_hf(cls, model, max_tokens: int = 65536, device="cuda"):
-        """Build from an in-memory HF BertModel / RobertaModel / DistilBert-incompatible models raise."""
+    def from_hf(cls, model, max_tokens: int = 65536, device="cuda", cls_only: bool = True):
+        """Build from an in-memory HF BertModel / RobertaModel / DistilBertModel (post-LN blocks, head_dim 64)."""
         c = model.config
         mt = getattr(c, "model_type", "bert")
+        sd = {k: v for k, v in model.state_dict().items()}
+        if mt == "distilbert":
+            sd, dims = distilbert_to_bert_state_dict(sd, c)
+            return cls(sd, arch="bert", max_tokens=max_tokens, device=device, cls_only=cls_only, **dims)
         if mt not in ("bert", "roberta", "xlm-roberta"):
             raise AdaptiveB200Error(f"encoder architecture '{mt}' is not implemented in the B200 path yet")
-        sd = {k: v for k, v in model.state_dict().items()}
+        if getattr(c, "hidden_act", "gelu") != "gelu" or getattr(c, "position_embedding_type", "absolute") != "absolute":
+            raise AdaptiveB200Error("only exact-erf GELU and absolute position embeddings are implemented")
         return cls(sd, arch="bert" if mt == "bert" else "roberta", layers=c.num_hidden_layers, hidden=c.hidden_size,
                    heads=c.num_attention_heads, intermediate=c.intermediate_size, vocab=c.vocab_size,
                    max_pos=c.max_position_embeddings, type_vocab=c.type_vocab_size, ln_eps=c.layer_norm_eps,
-                   pad_idx=(c.pad_token_id if c.pad_token_id is not None else 0), max_tokens=max_tokens, device=device)
+                   pad_idx=(c.pad_token_id if c.pad_token_id is not None else 0), max_tokens=max_tokens, device=device,
+                   cls_only=cls_only)
 
     def forward_cls(self, ids: torch.Tensor, mask: Optional[torch.Tensor] = None,
                     type_ids: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -55,7 +55,7 @@ class AdaptiveClassifier:
         with torch.cuda.device(torch.device(self.device)):
             self.encoder = _cabi.Encoder.from_hf(hf, max_tokens=self._max_tokens, device=self.device)
 
-        self.embedding_dim = self.model.config.hidden_size
+        self.embedding_dim = getattr(self.model.config, "hidden_size", None) or self.model.config.dim
         self.memory = PrototypeMemory(self.embedding_dim, config=self.config)
         self.adaptive_head = None
         self.label_to_id = {}

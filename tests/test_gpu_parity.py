@@ -338,6 +338,28 @@ def test_encoder_full_last_layer_and_hidden_state(cabi):
     enc_full.close(); enc_cls.close()
 
 
+def test_encoder_distilbert(cabi):
+    """DistilBERT (the encoder of the reference's examples/basic_usage.py:9) through Encoder.from_hf vs HF itself on CPU"""
+    from transformers import DistilBertConfig, DistilBertModel
+    torch.manual_seed(3)
+    cfg = DistilBertConfig(vocab_size=400, dim=128, n_heads=2, n_layers=2, hidden_dim=256, max_position_embeddings=64)
+    m = DistilBertModel(cfg).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "LayerNorm" in n or "layer_norm" in n or n.endswith(".bias"):
+                p.add_(0.1 * torch.randn(p.shape))
+    ids = eo.synthetic_ids(5, 40, vocab=400)
+    mask = torch.ones_like(ids)
+    mask[1, 30:] = 0
+    mask[4, 11:] = 0
+    with torch.no_grad():
+        ref = torch.nn.functional.normalize(m(input_ids=ids, attention_mask=mask).last_hidden_state[:, 0, :], dim=1)
+    enc = cabi.Encoder.from_hf(m, max_tokens=5 * 40)
+    out = enc.forward_cls(ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()).cpu()
+    assert (out - ref).norm(dim=1).max() < 1e-3
+    enc.close()
+
+
 def test_encoder_roberta_positions_and_padding(cabi):
     """RoBERTa position ids (cumsum of non-pad + pad_idx, HF modeling_roberta.py:146-159), hidden 128 / 2 heads"""
     sd, cfg, _ = eo.make_bert_state_dict(5, arch="roberta", num_hidden_layers=2, hidden_size=128, num_attention_heads=2,

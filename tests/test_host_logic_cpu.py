@@ -73,3 +73,21 @@ def test_shard_bounds_cover_rows_exactly():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_distilbert_state_dict_mapping_matches_hf():
+    """DistilBERT -> BERT-named parameters (+ zero type table): the oracle restatement on the mapped weights equals HF"""
+    from transformers import DistilBertConfig, DistilBertModel
+    from adaptive_classifier_b200._cabi import distilbert_to_bert_state_dict
+    from oracle import encoder_oracle as eo
+    torch.manual_seed(3)
+    cfg = DistilBertConfig(vocab_size=400, dim=128, n_heads=2, n_layers=2, hidden_dim=256, max_position_embeddings=64)
+    m = DistilBertModel(cfg).eval()
+    ids = eo.synthetic_ids(3, 20, vocab=400)
+    mask = torch.ones_like(ids)
+    mask[1, 12:] = 0
+    with torch.no_grad():
+        ref = torch.nn.functional.normalize(m(input_ids=ids, attention_mask=mask).last_hidden_state[:, 0, :], dim=1)
+    sd, dims = distilbert_to_bert_state_dict(dict(m.state_dict()), cfg)
+    out = eo.encoder_forward_cls({k: v.float() for k, v in sd.items()}, ids, mask, num_heads=2, ln_eps=1e-12)
+    assert (out - ref).abs().max() < 1e-6 and dims["type_vocab"] == 1 and dims["layers"] == 2
