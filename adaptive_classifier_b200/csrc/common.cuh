@@ -114,24 +114,6 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// same with an L2 cache-policy hint
-__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1,
-                                                 uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 // generic-proxy writes to smem that the async proxy (UMMA / TMA) will read
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -167,19 +149,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(1024 >> 4) << 32;    // stride byte offset between 8-row groups
     d |= static_cast<uint64_t>(1) << 46;            // descriptor version (sm_100)
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
-    return d;
-}
-
-// MN-major operand (e.g. V[key][d] used as B[n = d][k = key]) in the 128-byte-swizzled canonical layout
-// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: 128 B contiguous along MN per K index, 8 K indices per 1024 B
-// group; LBO = byte distance between consecutive 128-byte MN chunks, SBO = distance between 8-K groups.
-__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
 

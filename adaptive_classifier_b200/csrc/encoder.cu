@@ -877,7 +877,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     }
     for (int l = 0; l < c.layers; ++l) {
         EpiQKV eq{e->bqkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H};
-        if ((rc = launch_gemm_tf32<EpiQKV, false, GEMM_KIND_F16>(e->m_xh, e->m_wqkv[l], M, 3 * H, H, eq, s))) return rc;
+        if ((rc = launch_gemm_tc<EpiQKV, false, GEMM_KIND_F16>(e->m_xh, e->m_wqkv[l], M, 3 * H, H, eq, s))) return rc;
         {
             // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
@@ -895,13 +895,13 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             gather_cls_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, e->ctx_cls, e->x_cls);
             AC_LAUNCH_CHECK();
             EpiResid eo{e->bo[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ctx_cls, e->m_wo[l], B, H, H, eo, s))) return rc;
+            if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ctx_cls, e->m_wo[l], B, H, H, eo, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln1w[l], e->ln1b[l], c.ln_eps, B, H, e->x_cls, e->xh_cls);
             AC_LAUNCH_CHECK();
             EpiGelu e1{e->b1[l], nullptr, e->ffn_cls, B, I, I, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_gemm_tf32<EpiGelu, false, GEMM_KIND_F16>(e->m_xh_cls, e->m_w1[l], B, I, H, e1, s))) return rc;
+            if ((rc = launch_gemm_tc<EpiGelu, false, GEMM_KIND_F16>(e->m_xh_cls, e->m_w1[l], B, I, H, e1, s))) return rc;
             EpiResid e2{e->b2[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ffn_cls, e->m_w2[l], B, H, I, e2, s))) return rc;
+            if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ffn_cls, e->m_w2[l], B, H, I, e2, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
             AC_LAUNCH_CHECK();
             cls_normalize_kernel<<<cb, wpb * 32, 0, s>>>(e->x_cls, B, 1, H, out_unit_cls);
@@ -912,13 +912,13 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             return AC_OK;
         }
         EpiResid eo{e->bo[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ctx, e->m_wo[l], M, H, H, eo, s))) return rc;
+        if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ctx, e->m_wo[l], M, H, H, eo, s))) return rc;
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln1w[l], e->ln1b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
         EpiGelu e1{e->b1[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_gemm_tf32<EpiGelu, false, GEMM_KIND_F16>(e->m_xh, e->m_w1[l], M, I, H, e1, s))) return rc;
+        if ((rc = launch_gemm_tc<EpiGelu, false, GEMM_KIND_F16>(e->m_xh, e->m_w1[l], M, I, H, e1, s))) return rc;
         EpiResid e2{e->b2[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_gemm_tf32<EpiResid, false, GEMM_KIND_F16>(e->m_ffn, e->m_w2[l], M, H, I, e2, s))) return rc;
+        if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ffn, e->m_w2[l], M, H, I, e2, s))) return rc;
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln2w[l], e->ln2b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
     }
@@ -947,7 +947,7 @@ template <int MODE, bool OUT_HALF, int KIND>
 static int linear_tc_dispatch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, const float *residual, void *Y,
                               int M, int N, int K, int round_out, cudaStream_t s) {
     EpiLinear<MODE, OUT_HALF, false> e{bias, residual, Y, M, N, N, round_out, nullptr, 0, 0, 0, 0};
-    return launch_gemm_tf32<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
+    return launch_gemm_tc<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
 }
 
 extern "C" int ac_linear_tc(const void *X, const void *W, const float *bias, const float *residual, void *Y, int M, int N,

@@ -78,7 +78,7 @@ struct GemmTileInfo {
 // same B tile: kNN, B = prototype rows streamed once from HBM).
 template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  int M, int N, int K, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -221,10 +221,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 // host-side launcher
 template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32>
-int launch_gemm_tf32(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
+int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
                      cudaStream_t stream, int max_ctas = 0, int prof_cls = PROF_GEMM_LINEAR, double prof_bytes = 0.0) {
     static bool attr_set = false;   // per instantiation
-    auto kern = gemm_tf32_kernel<Epi, kMFastest, kKind>;
+    auto kern = gemm_tc_kernel<Epi, kMFastest, kKind>;
     if (!attr_set) {
         AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         attr_set = true;

@@ -380,13 +380,13 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     if (p_half) {
         if ((rc = make_tmap_2d(&ta, Qh, 2, Bp, D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_M, 64))) return rc;
         if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_N, 64))) return rc;
-        if ((rc = launch_gemm_tf32<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
+        if ((rc = launch_gemm_tc<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
                                                                  pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)))
             return rc;
     } else {
         if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
         if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
-        if ((rc = launch_gemm_tf32<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
+        if ((rc = launch_gemm_tc<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
                                                   PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D))) return rc;
     }
 

@@ -173,7 +173,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    cp = CpuPath()
+    cp = CpuPath(args.rows or N_ROWS)
     t_probe0 = time.time()
     cp.predict(cp.wl.synthetic_ids(8, S).to(torch.int64))
     t_probe0 = time.time()
@@ -362,12 +362,12 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel<EpiLinear<..>, kind::f16> (encoder projections: fp16 operands, fp32 TMEM accumulators)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiLinear<..>, kind::f16> (encoder projections: fp16 operands, fp32 TMEM accumulators)",
                      "achieved": gemm_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": traffic,
                      "peak_source": f"{pk['source']} cuBLAS bf16 GEMM, sustained (kernel timed inside a long step)",
                      "launches": gemm["launches"], "ms_total": gemm["ms"], "share_of_step": gemm["ms"] / ms},
-        "roofline_knn": {"bound": "hbm", "kernel": "gemm_tf32_kernel<EpiKnn, kind::f16> (prototype scan; algorithmic bytes 4*N*D = the fp32 matrix, the kernel streams its 2*N*D-byte fp16 shadow, exact re-rank reads fp32 rows)",
+        "roofline_knn": {"bound": "hbm", "kernel": "gemm_tc_kernel<EpiKnn, kind::f16> (prototype scan; algorithmic bytes 4*N*D = the fp32 matrix, the kernel streams its 2*N*D-byte fp16 shadow, exact re-rank reads fp32 rows)",
                          "achieved": knn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": knn_gbs / pk["hbm_gbs"],
                          "tensor_tflops": knn_tflops, "launches": knn["launches"], "ms_total": knn["ms"],
                          "share_of_step": knn["ms"] / ms, "peak_source": pk["source"]},

@@ -1,4 +1,4 @@
-"""kNN-only workload for ncu: the only gemm_tf32_kernel launches are the prototype scan (fp16 shadow and tf32 variants)."""
+"""kNN-only workload for ncu: the only gemm_tc_kernel launches are the prototype scan (fp16 shadow and tf32 variants)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -10,13 +10,13 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rows 200000 > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-300
 echo "=== ncu full: encoder GEMM"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32_kernel -s 40 -c 4 -f -o gpurun_out/prof_gemm \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 40 -c 4 -f -o gpurun_out/prof_gemm \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rows 200000 > gpurun_out/ncu_gemm.log 2>&1
 tail -2 gpurun_out/ncu_gemm.log | cut -c1-300
 echo "=== kNN only"; timeout 300 python tests/prof_knn.py 2>&1 | tail -2
 echo "=== config 4: add_examples loop"; timeout 600 python tools/bench_add_examples.py --examples 5120 2>&1 | tail -1 | tee gpurun_out/bench_add_examples.json | cut -c1-700
 echo "=== ncu full: kNN scan"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32_kernel -s 4 -c 2 -f -o gpurun_out/prof_knn \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 4 -c 2 -f -o gpurun_out/prof_knn \
     python tests/prof_knn.py > gpurun_out/ncu_knn_only.log 2>&1
 tail -2 gpurun_out/ncu_knn_only.log | cut -c1-300
 echo "=== ncu full: kNN coarse + attention"

@@ -11,6 +11,6 @@ echo "=== kNN only"; timeout 300 python tests/prof_knn.py 2>&1 | tail -2
 echo "=== bench"; timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-400
 tail -3 gpurun_out/bench.err
 echo "=== ncu full: kNN scan"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32_kernel -s 4 -c 2 -f -o gpurun_out/prof_knn \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 4 -c 2 -f -o gpurun_out/prof_knn \
     python tests/prof_knn.py > gpurun_out/ncu_knn_only.log 2>&1
 tail -2 gpurun_out/ncu_knn_only.log | cut -c1-300

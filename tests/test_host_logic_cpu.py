@@ -91,3 +91,28 @@ def test_distilbert_state_dict_mapping_matches_hf():
     sd, dims = distilbert_to_bert_state_dict(dict(m.state_dict()), cfg)
     out = eo.encoder_forward_cls({k: v.float() for k, v in sd.items()}, ids, mask, num_heads=2, ln_eps=1e-12)
     assert (out - ref).abs().max() < 1e-6 and dims["type_vocab"] == 1 and dims["layers"] == 2
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs first) on a reduced index: one JSON line with the
+    contract's keys; rank != 0 exits silently."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--rows", "3000"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "queries/s" and j["value"] > 0 and j["higher_is_better"] is True
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    env["RANK"] = "1"
+    env["WORLD_SIZE"] = "2"
+    out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                           "--rows", "3000"], capture_output=True, text=True, env=env, timeout=120)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
