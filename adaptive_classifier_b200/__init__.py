@@ -1,18 +1,37 @@
-"""adaptive_classifier_b200 -- B200-native predict()/add_examples() hot path of codelion/adaptive-classifier.
+"""B200-native predict()/add_examples() hot path of codelion/adaptive-classifier.
 
-Same public names as /root/reference/src/adaptive_classifier/__init__.py:1-16.  Importing the package needs
-no GPU; constructing a classifier or calling any kernel does (there is no CPU fallback).
+`import adaptive_classifier_b200 as adaptive_classifier` gives the public names of the reference package
+(/root/reference/src/adaptive_classifier/__init__.py:1-16).  Importing needs no GPU; constructing a classifier or
+calling a kernel does -- there is no CPU fallback.  Submodules are loaded on first attribute access.
 """
-from .models import Example, AdaptiveHead, ModelConfig
-from .memory import PrototypeMemory, FlatL2Index
-from .ewc import EWC
-from .classifier import AdaptiveClassifier
-from .multilabel import MultiLabelAdaptiveClassifier, MultiLabelAdaptiveHead
-from ._cabi import AdaptiveB200Error
+import importlib
 
 __version__ = "0.1.0"
 
-__all__ = [
-    "AdaptiveClassifier", "MultiLabelAdaptiveClassifier", "MultiLabelAdaptiveHead", "Example", "AdaptiveHead",
-    "ModelConfig", "PrototypeMemory", "EWC", "FlatL2Index", "AdaptiveB200Error",
-]
+# public name -> submodule that defines it
+_EXPORTS = {
+    "AdaptiveClassifier": "classifier",
+    "MultiLabelAdaptiveClassifier": "multilabel",
+    "MultiLabelAdaptiveHead": "multilabel",
+    "AdaptiveHead": "models",
+    "Example": "models",
+    "ModelConfig": "models",
+    "PrototypeMemory": "memory",
+    "FlatL2Index": "memory",
+    "EWC": "ewc",
+    "AdaptiveB200Error": "_cabi",
+}
+__all__ = sorted(_EXPORTS)
+
+
+def __getattr__(name):
+    sub = _EXPORTS.get(name)
+    if sub is None:
+        raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+    value = getattr(importlib.import_module(f"{__name__}.{sub}"), name)
+    globals()[name] = value
+    return value
+
+
+def __dir__():
+    return sorted(list(globals()) + list(_EXPORTS))
