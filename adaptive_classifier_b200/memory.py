@@ -6,7 +6,9 @@ Same bookkeeping, attribute names and error behaviour; `self.index` is a FlatL2I
 """
 from __future__ import annotations
 
+import functools
 import logging
+import threading
 from collections import defaultdict
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -84,6 +86,16 @@ class FlatL2Index:
         return d.cpu().numpy(), i.cpu().numpy()
 
 
+def _locked(fn):
+    """The reference relies on the GIL for `tests/test_memory.py:226-256` (3 threads adding concurrently); here ctypes
+    releases the GIL while a kernel call is enqueued, so the bookkeeping is serialised explicitly."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self._lock:
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class PrototypeMemory:
     """Memory system that maintains prototypes for each class (memory.py:11-245)."""
 
@@ -97,8 +109,10 @@ class PrototypeMemory:
         self.label_to_index = {}
         self.index_to_label = {}
         self.updates_since_rebuild = 0
+        self._lock = threading.RLock()
 
     # ------------------------------------------------------------------ add path (memory.py:41-83)
+    @_locked
     def add_example(self, example: Example, label: str):
         if example.embedding is None:
             raise ValueError("Example must have an embedding")
@@ -118,6 +132,7 @@ class PrototypeMemory:
         else:
             self.just_rebuilt = False
 
+    @_locked
     def add_examples_batch(self, examples: List[Example], labels: List[str]):
         """Batched equivalent of calling add_example for each pair (same final state): when no class crosses
         max_examples_per_class during the call, prototypes are recomputed once per touched class on the
@@ -180,6 +195,7 @@ class PrototypeMemory:
         out = self.get_nearest_prototypes_batch(q, k)
         return out[0]
 
+    @_locked
     def get_nearest_prototypes_batch(self, queries: torch.Tensor, k: int) -> List[List[Tuple[str, float]]]:
         """Batched form (new): queries [B, D] CUDA fp32 -> per query the list memory.py:85-136 returns."""
         if self.updates_since_rebuild >= self.config.prototype_update_frequency:
@@ -202,6 +218,7 @@ class PrototypeMemory:
         return res
 
     # ------------------------------------------------------------------ prototypes / index maintenance
+    @_locked
     def _update_prototype(self, label: str):
         """memory.py:138-159: prototype = mean of the class's retained examples (device segment mean)."""
         examples = self.examples[label]
@@ -209,6 +226,7 @@ class PrototypeMemory:
             return
         self._update_prototypes_device([label])
 
+    @_locked
     def _rebuild_index(self):
         """memory.py:161-177: rows in sorted(label) order."""
         self.index = FlatL2Index(self.embedding_dim)
@@ -226,6 +244,7 @@ class PrototypeMemory:
         """memory.py:179-194."""
         self._rebuild_index()
 
+    @_locked
     def _prune_examples(self, label: str):
         """memory.py:196-217: keep the max_examples_per_class examples closest (L2) to the class mean."""
         examples = self.examples[label]
@@ -248,6 +267,7 @@ class PrototypeMemory:
             "updates_since_rebuild": self.updates_since_rebuild,
         }
 
+    @_locked
     def clear(self):
         self.examples.clear()
         self.prototypes.clear()
