@@ -284,8 +284,8 @@ class AdaptiveClassifier:
         head_preds = []
         probs = self._head_probs(emb)
         if probs is not None:
-            values, indices = torch.topk(probs[0], len(self.id_to_label))
-            values, indices = values.cpu().tolist(), indices.cpu().tolist()
+            values, indices = _cabi.topk_desc(probs[:1], min(len(self.id_to_label), probs.shape[1]))   # classifier.py:438
+            values, indices = values[0].cpu().tolist(), indices[0].cpu().tolist()
             head_preds = [(self.id_to_label[i], v) for v, i in zip(values, indices)]
         combined_scores = {}
         for label, score in proto_preds:
@@ -318,7 +318,7 @@ class AdaptiveClassifier:
         probs = self._head_probs(emb)
         if probs is not None:
             kk = min(k, len(self.id_to_label))
-            hv, hi = torch.topk(probs, kk, dim=1)
+            hv, hi = _cabi.topk_desc(probs, kk)                   # classifier.py:1347-1350
             head_vals, head_idx = hv.cpu().tolist(), hi.cpu().tolist()
         out = []
         for b in range(emb.shape[0]):
