@@ -25,7 +25,7 @@ AC_ARCH_BERT, AC_ARCH_ROBERTA = 0, 1
 AC_PREC_TF32, AC_PREC_F16 = 0, 1
 
 EXPORTS = [
-    "ac_version", "ac_last_error", "ac_device_check",
+    "ac_version", "ac_last_error", "ac_device_check", "ac_set_option", "ac_get_option",
     "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
     "ac_segment_mean",
     "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch_workspace_bytes", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",

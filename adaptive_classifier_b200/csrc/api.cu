@@ -27,6 +27,17 @@ int check_cuda(cudaError_t e, const char *what) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// run-time options (ac_set_option): experimental kernel variants stay opt-in until they are measured on a B200
+static std::atomic<long long> g_options[OPT_NUM];
+static const char *const g_option_names[OPT_NUM] = {"gemm_pair", "knn_pair"};
+long long option(int id) { return (id >= 0 && id < OPT_NUM) ? g_options[id].load(std::memory_order_relaxed) : 0; }
+static int option_id(const char *name) {
+    if (!name) return -1;
+    for (int i = 0; i < OPT_NUM; ++i)
+        if (strcmp(name, g_option_names[i]) == 0) return i;
+    return -1;
+}
+
 struct ProfSlot { cudaEvent_t a, b; int cls; double flops, bytes; };
 static bool g_prof_on = false;
 static std::vector<ProfSlot> g_prof_slots;
@@ -191,6 +202,19 @@ extern "C" int ac_profile_read(int cls, double *ms, double *flops, double *bytes
     return AC_OK;
 }
 extern "C" const char *ac_last_error(void) { return g_err; }
+
+extern "C" int ac_set_option(const char *name, long long value) {
+    const int id = option_id(name);
+    AC_REQUIRE(id >= 0, "ac_set_option: unknown option '%s'", name ? name : "(null)");
+    g_options[id].store(value, std::memory_order_relaxed);
+    return AC_OK;
+}
+extern "C" int ac_get_option(const char *name, long long *value) {
+    const int id = option_id(name);
+    AC_REQUIRE(id >= 0 && value, "ac_get_option: unknown option '%s' or null output", name ? name : "(null)");
+    *value = g_options[id].load(std::memory_order_relaxed);
+    return AC_OK;
+}
 
 extern "C" int ac_device_check(void) {
     int n = 0;

@@ -14,7 +14,7 @@
 //   attention     one CTA per (sequence, head): Q, K and V^T tiles by TMA, QK^T and PV as tcgen05 MMAs with the score
 //                 tile / output tile in TMEM, thread-per-query-row softmax in between (S <= 128, head_dim 64)
 //   LayerNorm     fp32 residual stream + the fp16 operand copy for the next GEMM
-#include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include <cuda_fp16.h>
 #include <math_constants.h>
 #include <vector>
@@ -710,6 +710,7 @@ struct ac_encoder {
     CUtensorMap m_xh, m_ctx, m_ffn, m_qk_att, m_vt_att;
     int vt_B = -1, vt_S = -1;
     std::vector<CUtensorMap> m_wqkv, m_wo, m_w1, m_w2;
+    std::vector<CUtensorMap> p_wqkv, p_wo, p_w1, p_w2;   // same weights, 128-row boxes (B operand half of a CTA pair)
     std::vector<void *> allocs;
     int last_B = 0, last_S = 0;
     bool last_cls_only = false;
@@ -828,6 +829,13 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
         TRY(make_tmap_2d(&e->m_w1[l], e->w1[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
         TRY(make_tmap_2d(&e->m_w2[l], e->w2[l], 2, H, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_N, 64));
     }
+    e->p_wqkv.resize(L); e->p_wo.resize(L); e->p_w1.resize(L); e->p_w2.resize(L);
+    for (int l = 0; l < L; ++l) {
+        TRY(make_tmap_2d(&e->p_wqkv[l], e->wqkv[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
+        TRY(make_tmap_2d(&e->p_wo[l], e->wo[l], 2, H, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
+        TRY(make_tmap_2d(&e->p_w1[l], e->w1[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
+        TRY(make_tmap_2d(&e->p_w2[l], e->w2[l], 2, H, I, static_cast<uint64_t>(I) * 2, GEMM2_B_ROWS, 64));
+    }
     TRY(check_cuda(cudaDeviceSynchronize(), "encoder_create sync"));
 #undef TRY
     *out = e;
@@ -837,6 +845,15 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
 using EpiQKV = EpiLinear<0, true, true>;      // bias, fp16 out, V third transposed
 using EpiGelu = EpiLinear<1, true, false>;    // bias + GELU, fp16 out
 using EpiResid = EpiLinear<2, false, false>;  // bias + residual, fp32 out (pre-LayerNorm sum)
+
+// one encoder projection: the measured 1-CTA kernel by default, the CTA-pair kernel when option "gemm_pair" is set
+// (tb = weight map with a 256-row box, tb_pair = the same weight with a 128-row box)
+template <class Epi>
+static int launch_linear(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tb_pair, int M, int N, int K,
+                         const Epi &epi, cudaStream_t s) {
+    if (option(OPT_GEMM_PAIR)) return launch_gemm_tc2<Epi, false, GEMM_KIND_F16>(ta, tb_pair, M, N, K, epi, s);
+    return launch_gemm_tc<Epi, false, GEMM_KIND_F16>(ta, tb, M, N, K, epi, s);
+}
 
 extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const int32_t *mask, const int32_t *type_ids,
                                       int B, int S, float *out_unit_cls, ac_stream_t stream) {
@@ -877,7 +894,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     }
     for (int l = 0; l < c.layers; ++l) {
         EpiQKV eq{e->bqkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H};
-        if ((rc = launch_gemm_tc<EpiQKV, false, GEMM_KIND_F16>(e->m_xh, e->m_wqkv[l], M, 3 * H, H, eq, s))) return rc;
+        if ((rc = launch_linear(e->m_xh, e->m_wqkv[l], e->p_wqkv[l], M, 3 * H, H, eq, s))) return rc;
         {
             // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
@@ -895,13 +912,13 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             gather_cls_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, e->ctx_cls, e->x_cls);
             AC_LAUNCH_CHECK();
             EpiResid eo{e->bo[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ctx_cls, e->m_wo[l], B, H, H, eo, s))) return rc;
+            if ((rc = launch_linear(e->m_ctx_cls, e->m_wo[l], e->p_wo[l], B, H, H, eo, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln1w[l], e->ln1b[l], c.ln_eps, B, H, e->x_cls, e->xh_cls);
             AC_LAUNCH_CHECK();
             EpiGelu e1{e->b1[l], nullptr, e->ffn_cls, B, I, I, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_gemm_tc<EpiGelu, false, GEMM_KIND_F16>(e->m_xh_cls, e->m_w1[l], B, I, H, e1, s))) return rc;
+            if ((rc = launch_linear(e->m_xh_cls, e->m_w1[l], e->p_w1[l], B, I, H, e1, s))) return rc;
             EpiResid e2{e->b2[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ffn_cls, e->m_w2[l], B, H, I, e2, s))) return rc;
+            if ((rc = launch_linear(e->m_ffn_cls, e->m_w2[l], e->p_w2[l], B, H, I, e2, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
             AC_LAUNCH_CHECK();
             cls_normalize_kernel<<<cb, wpb * 32, 0, s>>>(e->x_cls, B, 1, H, out_unit_cls);
@@ -912,13 +929,13 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             return AC_OK;
         }
         EpiResid eo{e->bo[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ctx, e->m_wo[l], M, H, H, eo, s))) return rc;
+        if ((rc = launch_linear(e->m_ctx, e->m_wo[l], e->p_wo[l], M, H, H, eo, s))) return rc;
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln1w[l], e->ln1b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
         EpiGelu e1{e->b1[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_gemm_tc<EpiGelu, false, GEMM_KIND_F16>(e->m_xh, e->m_w1[l], M, I, H, e1, s))) return rc;
+        if ((rc = launch_linear(e->m_xh, e->m_w1[l], e->p_w1[l], M, I, H, e1, s))) return rc;
         EpiResid e2{e->b2[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_gemm_tc<EpiResid, false, GEMM_KIND_F16>(e->m_ffn, e->m_w2[l], M, H, I, e2, s))) return rc;
+        if ((rc = launch_linear(e->m_ffn, e->m_w2[l], e->p_w2[l], M, H, I, e2, s))) return rc;
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln2w[l], e->ln2b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
     }
@@ -947,6 +964,8 @@ template <int MODE, bool OUT_HALF, int KIND>
 static int linear_tc_dispatch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, const float *residual, void *Y,
                               int M, int N, int K, int round_out, cudaStream_t s) {
     EpiLinear<MODE, OUT_HALF, false> e{bias, residual, Y, M, N, N, round_out, nullptr, 0, 0, 0, 0};
+    if (option(OPT_GEMM_PAIR))   // tb was built with the pair kernel's 128-row box by ac_linear_tc
+        return launch_gemm_tc2<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
     return launch_gemm_tc<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
 }
 
@@ -963,7 +982,8 @@ extern "C" int ac_linear_tc(const void *X, const void *W, const float *bias, con
     CUtensorMap ta, tb;
     const uint32_t bk = 128 / es;
     if ((rc = make_tmap_2d(&ta, X, es, M, K, static_cast<uint64_t>(K) * es, GEMM_BLOCK_M, bk))) return rc;
-    if ((rc = make_tmap_2d(&tb, W, es, N, K, static_cast<uint64_t>(K) * es, GEMM_BLOCK_N, bk))) return rc;
+    if ((rc = make_tmap_2d(&tb, W, es, N, K, static_cast<uint64_t>(K) * es, option(OPT_GEMM_PAIR) ? GEMM2_B_ROWS : GEMM_BLOCK_N, bk)))
+        return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (precision == AC_PREC_TF32) {
         AC_REQUIRE(!out_half, "ac_linear_tc: tf32 path writes fp32");

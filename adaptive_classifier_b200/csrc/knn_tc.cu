@@ -14,7 +14,7 @@
 //
 // Replaces faiss.IndexFlatL2.search (/root/reference/src/adaptive_classifier/memory.py:110-114) for the
 // batched, large-N configuration of BASELINE.json (configs[1], configs[2]).
-#include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -53,6 +53,7 @@ struct EpiKnn {
     int64_t N;               // rows
     int tiles_m, slots;      // grid = slots/2 * tiles_m CTAs; every CTA owns one query tile and two lists per query
     int kt;                  // a list publishes its kt-th best key (k + 3 <= kt <= KC): see prefetch()
+    int pair;                // != 0: launched as CTA pairs (gemm_tc2.cuh): a cluster owns two consecutive query tiles
 
     static constexpr int kUnrollChunks = 1;
     struct State {
@@ -131,9 +132,17 @@ struct EpiKnn {
     }
 
     __device__ __forceinline__ void end_cta(State &st, int q, int lane) const {
-        const int mt = blockIdx.x % tiles_m;
         // two epilogue warps share a query row (one per 128-column half of every tile): each owns a slot
-        const int slot = (blockIdx.x / tiles_m) * 2 + (((threadIdx.x >> 5) - 2) >> 2);
+        const int chalf = ((threadIdx.x >> 5) - 2) >> 2;
+        int mt, slot;
+        if (pair) {
+            const int cluster = blockIdx.x >> 1, tm2 = tiles_m >> 1;     // tiles_m is even in pair mode
+            mt = (cluster % tm2) * 2 + static_cast<int>(cluster_ctarank());
+            slot = (cluster / tm2) * 2 + chalf;
+        } else {
+            mt = blockIdx.x % tiles_m;
+            slot = (blockIdx.x / tiles_m) * 2 + chalf;
+        }
         const int row = mt * GEMM_BLOCK_M + q * 32 + lane;
         if (row >= B) return;
         float *ck = cand_key + (static_cast<int64_t>(row) * slots + slot) * KNN_KC;
@@ -374,20 +383,28 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     CUtensorMap ta, tb;
     int kt = k + 3 > 8 ? k + 3 : 8;
     if (kt > KNN_KC) kt = KNN_KC;
-    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt};   // slots = 2 per CTA
+    // CTA-pair variant (option "knn_pair"): needs an even number of query tiles so that both CTAs of a pair own real queries
+    const bool pair = option(OPT_KNN_PAIR) != 0 && pl.tiles_m % 2 == 0 && pl.grid_ctas % 2 == 0;
+    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt, pair ? 1 : 0};   // slots = 2 per CTA
+    const uint32_t b_box = pair ? GEMM2_B_ROWS : GEMM_BLOCK_N;
     // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16
     // shadow the kernel actually streams 2.N.D bytes (the exact re-rank below still reads fp32 rows)
     if (p_half) {
         if ((rc = make_tmap_2d(&ta, Qh, 2, Bp, D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_M, 64))) return rc;
-        if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_N, 64))) return rc;
-        if ((rc = launch_gemm_tc<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
-                                                                 pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)))
-            return rc;
+        if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, b_box, 64))) return rc;
+        rc = pair ? launch_gemm_tc2<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
+                                                                   pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
+                  : launch_gemm_tc<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
+                                                                  pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D);
+        if (rc) return rc;
     } else {
         if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
-        if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
-        if ((rc = launch_gemm_tc<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
-                                                  PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D))) return rc;
+        if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, b_box, GEMM_BLOCK_K))) return rc;
+        rc = pair ? launch_gemm_tc2<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
+                                                  PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
+                  : launch_gemm_tc<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
+                                                 PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D);
+        if (rc) return rc;
     }
 
     // ---- merge per-CTA lists, pick KP candidates + exclusion threshold

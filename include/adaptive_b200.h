@@ -39,6 +39,14 @@ int ac_version(void);                 /* ABI version, currently 1 */
 const char *ac_last_error(void);      /* thread-local message of the last failing call */
 int ac_device_check(void);            /* 0 when the current device is sm_100 (B200), else AC_E_CUDA */
 
+/* Run-time options of the library (process-wide, default 0).  They select kernel variants that compute the SAME
+ * results through a different schedule; nothing in the reference corresponds to them.
+ *   "gemm_pair" != 0 : encoder projections / ac_linear_tc run as CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) GEMMs
+ *   "knn_pair"  != 0 : the prototype scan's coarse pass runs as a CTA-pair GEMM
+ * Unknown names return AC_E_INVALID. */
+int ac_set_option(const char *name, long long value);
+int ac_get_option(const char *name, long long *value);
+
 /* ------------------------------------------------------------------------------------------
  * Stage K -- prototype kNN.  Replaces faiss.IndexFlatL2.search at
  *   src/adaptive_classifier/memory.py:110-114 (call sites :34,106,113,114,158,159,164,172,182,190)
