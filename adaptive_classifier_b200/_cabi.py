@@ -126,6 +126,8 @@ def load_library() -> ctypes.CDLL:
     L.ac_pipeline_predict_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_pipeline_debug_copy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ac_profile_enable.argtypes = [c_int]
+    L.ac_set_option.argtypes = [c_char_p, ctypes.c_longlong]
+    L.ac_get_option.argtypes = [c_char_p, POINTER(ctypes.c_longlong)]
     L.ac_profile_read.argtypes = [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                   POINTER(ctypes.c_longlong)]
     for name in EXPORTS:
@@ -533,6 +535,33 @@ def blend_topk(p_cls, p_score, h_idx, h_val, k: int, w_proto: float = 0.7, w_hea
     check(L.ac_blend_topk(p_cls.data_ptr(), p_score.data_ptr(), ptr(h_idx), ptr(neg), B, k, kh, w_proto, w_head,
                           out_cls.data_ptr(), out_sc.data_ptr(), stream_ptr()), "ac_blend_topk")
     return out_cls, out_sc
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide kernel-variant switch (include/adaptive_b200.h): "gemm_pair", "knn_pair", "ln_defer"."""
+    check(load_library().ac_set_option(name.encode(), int(value)), f"ac_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = ctypes.c_longlong(0)
+    check(load_library().ac_get_option(name.encode(), ctypes.byref(v)), f"ac_get_option({name})")
+    return int(v.value)
+
+
+class option:
+    """Context manager: `with option("gemm_pair", 1): ...` restores the previous value on exit."""
+
+    def __init__(self, name: str, value: int):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.prev = get_option(self.name)
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.prev)
+        return False
 
 
 def launch_count() -> int:

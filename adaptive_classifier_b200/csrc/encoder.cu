@@ -54,22 +54,33 @@ __device__ __forceinline__ float gelu_erf(float y) {
 //   VT: columns >= vt_col0 (the V third of the fused QKV projection) are written transposed to
 //       vT[(b*H + feature) * S_pad + key] so that attention can TMA-load V^T as a K-major B operand.
 // ------------------------------------------------------------------------------------------------
-template <int MODE, bool OUT_HALF, bool VT>
+//   DEFER: the A operand was the UN-normalised residual sum y (fp16) and the weights were packed as fp16(gamma * W):
+//       LayerNorm(y) W^T + b = r (acc - mu c1) + c0  with the row statistics (mu, r) of y, c1 = rowsum(W'), and
+//       `bias` holding c0 = W beta + b  (see "deferred LayerNorm" below and oracle/deferred_ln_study.py)
+template <int MODE, bool OUT_HALF, bool VT, bool DEFER = false>
 struct EpiLinear {
-    const float *__restrict__ bias;       // [N]
+    static_assert(!DEFER || (OUT_HALF && MODE != 2), "the deferred-LayerNorm consumer epilogues write fp16 operands");
+    const float *__restrict__ bias;       // [N]   (DEFER: c0)
     const float *__restrict__ residual;   // [M, ldy] (MODE 2)
     void *Y;                              // [M, ldy] fp16 or fp32
     int M, N, ldy;
     int round_out;                        // fp32 output only: round to tf32 (tests of the tf32 path)
     __half *vT;                           // VT only
     int vt_col0, S, S_pad, H;
+    const float *__restrict__ c1;         // DEFER only: [N] row sums of the packed weight
+    const float2 *__restrict__ row_stats; // DEFER only: [M] (mu, 1/sqrt(var + eps)) of the A rows
 
     static constexpr int kUnrollChunks = 4;   // `buf` must be a compile-time constant (register double buffer)
     struct State {
         // residual (MODE 2) of one 32-column chunk in the layout of the transposed phase: [column half][row pass],
         // double-buffered so chunk c+1 is in flight while chunk c is processed
         float4 res[(MODE == 2) ? 2 : 1][(MODE == 2) ? 8 : 1];
+        float mu, r;                      // DEFER: statistics of this thread's accumulator row
     };
+    // accumulator + bias, or the deferred-LayerNorm form r (acc - mu c1) + c0
+    __device__ __forceinline__ float pre(const State &st, float acc, float b, float c1v) const {
+        return DEFER ? fmaf(st.r, fmaf(-st.mu, c1v, acc), b) : acc + b;
+    }
     __device__ __forceinline__ void begin_cta(State &, int, int) const {}
     __device__ __forceinline__ void end_cta(State &, int, int) const {}
 
@@ -80,7 +91,14 @@ struct EpiLinear {
 
     // transposed phase mapping (fp32 staging holds 16 columns at a time): lane = (r8 = lane / 4, c = lane % 4) handles
     // rows r8 + 8*i (i < 4) and the 16-byte column group c of each 16-column half.
-    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &ti, int, int col0, int lane, int buf) const {
+    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &ti, int row, int col0, int lane, int buf) const {
+        if (DEFER) {
+            if (((col0 - ti.n0) & (GEMM_BLOCK_N / 2 - 1)) == 0) {      // first chunk of this warp's column half
+                const float2 ms = (row < M) ? __ldg(row_stats + row) : make_float2(0.f, 0.f);
+                st.mu = ms.x;
+                st.r = ms.y;
+            }
+        }
         if (MODE != 2) return;
         const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;
         const int r8 = lane >> 2, c = lane & 3;
@@ -110,10 +128,11 @@ struct EpiLinear {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + j));
-                    dst[static_cast<int64_t>(j) * S_pad] = __float2half_rn(v[j] + b4.x);
-                    dst[static_cast<int64_t>(j + 1) * S_pad] = __float2half_rn(v[j + 1] + b4.y);
-                    dst[static_cast<int64_t>(j + 2) * S_pad] = __float2half_rn(v[j + 2] + b4.z);
-                    dst[static_cast<int64_t>(j + 3) * S_pad] = __float2half_rn(v[j + 3] + b4.w);
+                    const float4 c4 = DEFER ? __ldg(reinterpret_cast<const float4 *>(c1 + col0 + j)) : make_float4(0, 0, 0, 0);
+                    dst[static_cast<int64_t>(j) * S_pad] = __float2half_rn(pre(st, v[j], b4.x, c4.x));
+                    dst[static_cast<int64_t>(j + 1) * S_pad] = __float2half_rn(pre(st, v[j + 1], b4.y, c4.y));
+                    dst[static_cast<int64_t>(j + 2) * S_pad] = __float2half_rn(pre(st, v[j + 2], b4.z, c4.z));
+                    dst[static_cast<int64_t>(j + 3) * S_pad] = __float2half_rn(pre(st, v[j + 3], b4.w, c4.w));
                 }
             }
             return;
@@ -125,11 +144,13 @@ struct EpiLinear {
             for (int j = 0; j < 4; ++j) {
                 const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 8 * j));
                 const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col0 + 8 * j + 4));
+                const float4 ca = DEFER ? __ldg(reinterpret_cast<const float4 *>(c1 + col0 + 8 * j)) : make_float4(0, 0, 0, 0);
+                const float4 cb = DEFER ? __ldg(reinterpret_cast<const float4 *>(c1 + col0 + 8 * j + 4)) : make_float4(0, 0, 0, 0);
                 float y[8];
-                y[0] = act(v[8 * j] + ba.x); y[1] = act(v[8 * j + 1] + ba.y);
-                y[2] = act(v[8 * j + 2] + ba.z); y[3] = act(v[8 * j + 3] + ba.w);
-                y[4] = act(v[8 * j + 4] + bb.x); y[5] = act(v[8 * j + 5] + bb.y);
-                y[6] = act(v[8 * j + 6] + bb.z); y[7] = act(v[8 * j + 7] + bb.w);
+                y[0] = act(pre(st, v[8 * j], ba.x, ca.x)); y[1] = act(pre(st, v[8 * j + 1], ba.y, ca.y));
+                y[2] = act(pre(st, v[8 * j + 2], ba.z, ca.z)); y[3] = act(pre(st, v[8 * j + 3], ba.w, ca.w));
+                y[4] = act(pre(st, v[8 * j + 4], bb.x, cb.x)); y[5] = act(pre(st, v[8 * j + 5], bb.y, cb.y));
+                y[6] = act(pre(st, v[8 * j + 6], bb.z, cb.z)); y[7] = act(pre(st, v[8 * j + 7], bb.w, cb.w));
                 uint4 pk;
                 __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
                 __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
@@ -186,6 +207,171 @@ struct EpiLinear {
         }
     }
 };
+
+// ------------------------------------------------------------------------------------------------
+// deferred LayerNorm (opt-in, option "ln_defer"): residual epilogue that never materialises LayerNorm
+//
+//   y_new = acc + bias + LN_prev(y_old)          LN_prev(y) = (y - mu) r gamma + beta recomputed from the fp32 y_old, its
+//                                                row statistics and the pending LayerNorm's parameters
+//   writes y_new (fp32, IN PLACE over y_old: every element is read and written by the same thread), fp16(y_new) (the
+//   next GEMM's A operand, consumed through EpiLinear<.., DEFER = true>) and per-row partial (sum, sum of squares) of
+//   this warp's 128 columns into parts[column part][row]; ln_stats_kernel turns the parts into (mu, r).
+//   HBM traffic per half layer at B*S = 65536, H = 768: read y 201 MB, write y 201 MB + fp16 101 MB = 503 MB instead of
+//   905 MB (GEMM epilogue 402 MB + LayerNorm kernel 503 MB); precision: oracle/deferred_ln_study.py.
+// ------------------------------------------------------------------------------------------------
+struct EpiResidDefer {
+    const float *__restrict__ bias;        // [N]
+    float *y;                              // [M, ld] fp32 residual sums: read (old) and written (new) in place
+    __half *yh;                            // [M, ld] fp16 copy of the new sums
+    const float2 *__restrict__ stats_prev; // [M] (mu, r) of the old sums
+    const float *__restrict__ gamma;       // [N] pending LayerNorm of the old sums
+    const float *__restrict__ beta;        // [N]
+    float2 *parts;                         // [N / 128][part_stride] partial (sum, sumsq) of the new sums
+    int64_t part_stride;
+    int M, N, ld;
+
+    static constexpr int kUnrollChunks = 4;
+    struct State {
+        float4 res[2][8];                  // old sums of one 32-column chunk (transposed-phase layout), double-buffered
+        float2 ms[4];                      // (mu, r) of this lane's 4 rows (r8 + 8 i)
+        float sum[4], sq[4];               // running partials of the new sums over this warp's 128 columns
+    };
+    __device__ __forceinline__ void begin_cta(State &, int, int) const {}
+    __device__ __forceinline__ void end_cta(State &, int, int) const {}
+
+    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &ti, int, int col0, int lane, int buf) const {
+        const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;
+        const int r8 = lane >> 2, c = lane & 3;
+        if (((col0 - ti.n0) & (GEMM_BLOCK_N / 2 - 1)) == 0) {           // first chunk of this warp's column half
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int grow = row_base + r8 + 8 * i;
+                st.ms[i] = (grow < M) ? __ldg(stats_prev + grow) : make_float2(0.f, 0.f);
+                st.sum[i] = 0.f;
+                st.sq[i] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int col = col0 + 16 * half + 4 * c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int grow = row_base + r8 + 8 * i;
+                // plain (coherent) load: y is written by this very kernel, although never the element being read here
+                st.res[buf][half * 4 + i] = (grow < M && col + 4 <= N)
+                                                ? *reinterpret_cast<const float4 *>(y + static_cast<int64_t>(grow) * ld + col)
+                                                : make_float4(0, 0, 0, 0);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &ti, int, int col0, const float (&v)[32], uint8_t *stage,
+                                         int lane, int buf, uint32_t) const {
+        const int row_base = ti.m0 + ((threadIdx.x >> 5) & 3) * 32;
+        if (row_base >= M || col0 >= N) return;                              // warp-uniform
+        const int r8 = lane >> 2, c = lane & 3;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int col = col0 + 16 * half + 4 * c;
+            float4 *srow = reinterpret_cast<float4 *>(stage + lane * GEMM_EPI_STAGE_ROW_BYTES);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                srow[j] = make_float4(v[16 * half + 4 * j], v[16 * half + 4 * j + 1], v[16 * half + 4 * j + 2], v[16 * half + 4 * j + 3]);
+            __syncwarp();
+            const bool col_ok = col + 4 <= N;
+            const float4 b4 = col_ok ? __ldg(reinterpret_cast<const float4 *>(bias + col)) : make_float4(0, 0, 0, 0);
+            const float4 g4 = col_ok ? __ldg(reinterpret_cast<const float4 *>(gamma + col)) : make_float4(0, 0, 0, 0);
+            const float4 e4 = col_ok ? __ldg(reinterpret_cast<const float4 *>(beta + col)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = r8 + 8 * i;
+                const int grow = row_base + rr;
+                if (grow < M && col_ok) {
+                    const float4 a = *reinterpret_cast<const float4 *>(stage + rr * GEMM_EPI_STAGE_ROW_BYTES + 16 * c);
+                    const float4 rs = st.res[buf][half * 4 + i];             // old sums, requested one chunk ago
+                    const float mu = st.ms[i].x, r = st.ms[i].y;
+                    float4 o;
+                    o.x = (a.x + b4.x) + fmaf((rs.x - mu) * r, g4.x, e4.x);
+                    o.y = (a.y + b4.y) + fmaf((rs.y - mu) * r, g4.y, e4.y);
+                    o.z = (a.z + b4.z) + fmaf((rs.z - mu) * r, g4.z, e4.z);
+                    o.w = (a.w + b4.w) + fmaf((rs.w - mu) * r, g4.w, e4.w);
+                    *reinterpret_cast<float4 *>(y + static_cast<int64_t>(grow) * ld + col) = o;
+                    const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&h0);
+                    pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+                    *reinterpret_cast<uint2 *>(yh + static_cast<int64_t>(grow) * ld + col) = pk;
+                    st.sum[i] += (o.x + o.y) + (o.z + o.w);
+                    st.sq[i] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+                }
+            }
+            __syncwarp();
+        }
+        if (((col0 - ti.n0) & (GEMM_BLOCK_N / 2 - 1)) == GEMM_BLOCK_N / 2 - 32) {   // last chunk of this warp's column half
+            const int part = col0 / (GEMM_BLOCK_N / 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = st.sum[i], q = st.sq[i];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                q += __shfl_xor_sync(0xffffffffu, q, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                q += __shfl_xor_sync(0xffffffffu, q, 2);
+                const int grow = row_base + r8 + 8 * i;
+                if (c == 0 && grow < M) parts[static_cast<int64_t>(part) * part_stride + grow] = make_float2(s, q);
+            }
+        }
+    }
+};
+
+// (sum, sumsq) partials of every 128-column part -> (mu, 1/sqrt(var + eps)) per row; parts are added in a fixed order
+__global__ void ln_stats_kernel(const float2 *__restrict__ parts, int nparts, int64_t part_stride, int rows, int H, float eps,
+                                float2 *__restrict__ stats) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float s = 0.f, q = 0.f;
+    for (int p = 0; p < nparts; ++p) {
+        const float2 v = parts[static_cast<int64_t>(p) * part_stride + row];
+        s += v.x;
+        q += v.y;
+    }
+    const float mu = s / static_cast<float>(H);
+    const float var = fmaxf(q / static_cast<float>(H) - mu * mu, 0.f);
+    stats[row] = make_float2(mu, 1.f / sqrtf(var + eps));
+}
+
+__global__ void fill_stats_identity_kernel(float2 *__restrict__ stats, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) stats[i] = make_float2(0.f, 1.f);
+}
+__global__ void fill_value_kernel(float *__restrict__ p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// weight packing of a deferred-LayerNorm consumer (one warp per output row n):
+//   Wp[n,k] = fp16(gamma[k] W[n,k]),  c1[n] = sum_k Wp[n,k] (fp32),  c0[n] = sum_k beta[k] W[n,k] + bias[n]
+// gamma / beta NULL = identity LayerNorm (layer 0 consumes the already normalised embeddings)
+__global__ void pack_defer_kernel(const float *__restrict__ W, const float *__restrict__ bias, const float *__restrict__ gamma,
+                                  const float *__restrict__ beta, int N, int K, __half *__restrict__ Wp, float *__restrict__ c1,
+                                  float *__restrict__ c0) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float s1 = 0.f, s0 = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = W[static_cast<int64_t>(n) * K + k];
+        const __half h = __float2half_rn(gamma ? gamma[k] * w : w);
+        Wp[static_cast<int64_t>(n) * K + k] = h;
+        s1 += __half2float(h);
+        s0 = fmaf(beta ? beta[k] : 0.f, w, s0);
+    }
+    s1 = warp_sum(s1);
+    s0 = warp_sum(s0);
+    if (lane == 0) {
+        c1[n] = s1;
+        c0[n] = s0 + bias[n];
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // elementwise / normalisation kernels (one warp per row, float4 lanes; H % 128 == 0, H <= 1024)
@@ -711,9 +897,17 @@ struct ac_encoder {
     int vt_B = -1, vt_S = -1;
     std::vector<CUtensorMap> m_wqkv, m_wo, m_w1, m_w2;
     std::vector<CUtensorMap> p_wqkv, p_wo, p_w1, p_w2;   // same weights, 128-row boxes (B operand half of a CTA pair)
+    // deferred LayerNorm (option "ln_defer"): QKV / FFN1 weights packed as fp16(gamma * W) with their rank-1 correction
+    // vectors, row statistics (ping-pong) and the per-128-column partials the residual epilogues write
+    std::vector<__half *> wqkv_d, w1_d;
+    std::vector<float *> c1qkv, c0qkv, c1f, c0f;
+    std::vector<CUtensorMap> m_wqkv_d, m_w1_d, p_wqkv_d, p_w1_d;
+    float2 *stats_a = nullptr, *stats_b = nullptr, *stats_id = nullptr, *parts = nullptr;
+    float *ones = nullptr, *zeros = nullptr;
     std::vector<void *> allocs;
     int last_B = 0, last_S = 0;
     bool last_cls_only = false;
+    const float *last_hidden = nullptr;   // where the previous full forward left the last hidden state
 };
 
 template <class T>
@@ -792,6 +986,40 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
         TRY(pack_f32(e, &e->ln2w[l], w->out_ln_w[l], H));
         TRY(pack_f32(e, &e->ln2b[l], w->out_ln_b[l], H));
     }
+    // deferred-LayerNorm packing: the QKV projection of layer l consumes the sums whose pending LayerNorm is the output
+    // LayerNorm of layer l-1 (identity for layer 0: the embeddings arrive normalised); FFN1 of layer l consumes the sums
+    // pending the attention-output LayerNorm of layer l
+    e->wqkv_d.assign(L, nullptr); e->w1_d.assign(L, nullptr);
+    e->c1qkv.assign(L, nullptr); e->c0qkv.assign(L, nullptr); e->c1f.assign(L, nullptr); e->c0f.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) {
+        TRY(dev_alloc(e, &e->wqkv_d[l], 3 * HH));
+        TRY(dev_alloc(e, &e->c1qkv[l], 3 * static_cast<size_t>(H)));
+        TRY(dev_alloc(e, &e->c0qkv[l], 3 * static_cast<size_t>(H)));
+        const float *ws[3] = {w->q_w[l], w->k_w[l], w->v_w[l]};
+        const float *bs[3] = {w->q_b[l], w->k_b[l], w->v_b[l]};
+        const float *pg = l ? w->out_ln_w[l - 1] : nullptr, *pb = l ? w->out_ln_b[l - 1] : nullptr;
+        for (int j = 0; j < 3; ++j) {
+            pack_defer_kernel<<<(H + 7) / 8, 256>>>(ws[j], bs[j], pg, pb, H, H, e->wqkv_d[l] + j * HH, e->c1qkv[l] + j * H,
+                                                    e->c0qkv[l] + j * H);
+            TRY(check_cuda(cudaGetLastError(), "pack_defer_kernel qkv"));
+        }
+        TRY(dev_alloc(e, &e->w1_d[l], static_cast<size_t>(I) * H));
+        TRY(dev_alloc(e, &e->c1f[l], I));
+        TRY(dev_alloc(e, &e->c0f[l], I));
+        pack_defer_kernel<<<(I + 7) / 8, 256>>>(w->ff1_w[l], w->ff1_b[l], w->ao_ln_w[l], w->ao_ln_b[l], I, H, e->w1_d[l], e->c1f[l],
+                                                e->c0f[l]);
+        TRY(check_cuda(cudaGetLastError(), "pack_defer_kernel ffn1"));
+    }
+    TRY(dev_alloc(e, &e->stats_a, T));
+    TRY(dev_alloc(e, &e->stats_b, T));
+    TRY(dev_alloc(e, &e->stats_id, T));
+    TRY(dev_alloc(e, &e->parts, static_cast<size_t>(H / 128) * T));
+    TRY(dev_alloc(e, &e->ones, H));
+    TRY(dev_alloc(e, &e->zeros, H));
+    fill_stats_identity_kernel<<<static_cast<unsigned>((T + 255) / 256), 256>>>(e->stats_id, static_cast<int64_t>(T));
+    fill_value_kernel<<<(H + 255) / 256, 256>>>(e->ones, H, 1.f);
+    fill_value_kernel<<<(H + 255) / 256, 256>>>(e->zeros, H, 0.f);
+    TRY(check_cuda(cudaGetLastError(), "deferred-LayerNorm constants"));
     e->vt_elems = 2 * T * H;     // (b, h, d) rows x S_pad keys, S_pad = roundup(S, 8) <= 2*S for S >= 8
     TRY(dev_alloc(e, &e->x, T * H));
     TRY(dev_alloc(e, &e->tmp, T * H));
@@ -829,6 +1057,13 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
         TRY(make_tmap_2d(&e->m_w1[l], e->w1[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
         TRY(make_tmap_2d(&e->m_w2[l], e->w2[l], 2, H, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_N, 64));
     }
+    e->m_wqkv_d.resize(L); e->m_w1_d.resize(L); e->p_wqkv_d.resize(L); e->p_w1_d.resize(L);
+    for (int l = 0; l < L; ++l) {
+        TRY(make_tmap_2d(&e->m_wqkv_d[l], e->wqkv_d[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
+        TRY(make_tmap_2d(&e->m_w1_d[l], e->w1_d[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
+        TRY(make_tmap_2d(&e->p_wqkv_d[l], e->wqkv_d[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
+        TRY(make_tmap_2d(&e->p_w1_d[l], e->w1_d[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
+    }
     e->p_wqkv.resize(L); e->p_wo.resize(L); e->p_w1.resize(L); e->p_w2.resize(L);
     for (int l = 0; l < L; ++l) {
         TRY(make_tmap_2d(&e->p_wqkv[l], e->wqkv[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
@@ -853,6 +1088,104 @@ static int launch_linear(const CUtensorMap &ta, const CUtensorMap &tb, const CUt
                          const Epi &epi, cudaStream_t s) {
     if (option(OPT_GEMM_PAIR)) return launch_gemm_tc2<Epi, false, GEMM_KIND_F16>(ta, tb_pair, M, N, K, epi, s);
     return launch_gemm_tc<Epi, false, GEMM_KIND_F16>(ta, tb, M, N, K, epi, s);
+}
+
+using EpiQKVDefer = EpiLinear<0, true, true, true>;     // r (acc - mu c1) + c0, fp16 out, V third transposed
+using EpiGeluDefer = EpiLinear<1, true, false, true>;   // GELU(r (acc - mu c1) + c0), fp16 out
+
+// last layer, deferred flow: CLS rows of the attention context and of LN_pending(y) (two-pass statistics from the fp32 sums)
+__global__ void gather_cls_ln_kernel(const __half *__restrict__ ctx, const float *__restrict__ y, int B, int S, int H,
+                                     const float *__restrict__ g, const float *__restrict__ b, float eps,
+                                     __half *__restrict__ ctx_cls, float *__restrict__ x_cls) {
+    const int bq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (bq >= B) return;
+    const int64_t src = static_cast<int64_t>(bq) * S * H, dst = static_cast<int64_t>(bq) * H;
+    for (int i = lane; i < H / 8; i += 32)
+        reinterpret_cast<uint4 *>(ctx_cls + dst)[i] = reinterpret_cast<const uint4 *>(ctx + src)[i];
+    const int nv = H / 128;
+    float4 x[LN_MAXV];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (i < nv) x[i] = *reinterpret_cast<const float4 *>(y + src + (lane + 32 * i) * 4);
+    ln_row(x, nv, H, g, b, eps, lane, x_cls + dst, nullptr);
+}
+
+// Layers of the deferred-LayerNorm flow (option "ln_defer"); e->x holds the un-normalised residual sums y, e->xh their
+// fp16 copy, and the LayerNorm that is still pending on y is carried as (gamma, beta, row statistics).
+static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, int S, int S_pad, float *out_unit_cls,
+                                   cudaStream_t s) {
+    const ac_encoder_config &c = e->cfg;
+    const int H = c.hidden, I = c.intermediate, M = B * S;
+    const int wpb = 8;
+    const int nparts = H / 128;
+    const int64_t pstride = static_cast<int64_t>(e->T);
+    int rc;
+    const float *pg = e->ones, *pb = e->zeros;      // pending LayerNorm of the sums in e->x (identity after the embeddings)
+    const float2 *st_in = e->stats_id;
+    for (int l = 0; l < c.layers; ++l) {
+        EpiQKVDefer eq{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
+        if ((rc = launch_linear(e->m_xh, e->m_wqkv_d[l], e->p_wqkv_d[l], M, 3 * H, H, eq, s))) return rc;
+        {
+            const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
+            if (S <= 128)
+                attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+            else
+                attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(
+                    e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+            prof_end(slot, s);
+        }
+        AC_LAUNCH_CHECK();
+        if (l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc) {
+            // ---- CLS-only tail of the last layer (M = B rows): materialise LN_pending on the CLS rows and continue with
+            // the ordinary kernels and the plain (not gamma-scaled) FFN1 weight
+            const int cb = (B + wpb - 1) / wpb;
+            gather_cls_ln_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, pg, pb, c.ln_eps, e->ctx_cls, e->x_cls);
+            AC_LAUNCH_CHECK();
+            EpiResid eo{e->bo[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
+            if ((rc = launch_linear(e->m_ctx_cls, e->m_wo[l], e->p_wo[l], B, H, H, eo, s))) return rc;
+            layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln1w[l], e->ln1b[l], c.ln_eps, B, H, e->x_cls, e->xh_cls);
+            AC_LAUNCH_CHECK();
+            EpiGelu e1{e->b1[l], nullptr, e->ffn_cls, B, I, I, 0, nullptr, 0, 0, 0, 0};
+            if ((rc = launch_linear(e->m_xh_cls, e->m_w1[l], e->p_w1[l], B, I, H, e1, s))) return rc;
+            EpiResid e2{e->b2[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
+            if ((rc = launch_linear(e->m_ffn_cls, e->m_w2[l], e->p_w2[l], B, H, I, e2, s))) return rc;
+            layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
+            AC_LAUNCH_CHECK();
+            cls_normalize_kernel<<<cb, wpb * 32, 0, s>>>(e->x_cls, B, 1, H, out_unit_cls);
+            AC_LAUNCH_CHECK();
+            e->last_B = B;
+            e->last_S = S;
+            e->last_cls_only = true;
+            return AC_OK;
+        }
+        // attention output projection + residual: y <- ctx Wo^T + bo + LN_pending(y); statistics of the new sums
+        EpiResidDefer eo{e->bo[l], e->x, e->xh, st_in, pg, pb, e->parts, pstride, M, H, H};
+        if ((rc = launch_linear(e->m_ctx, e->m_wo[l], e->p_wo[l], M, H, H, eo, s))) return rc;
+        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_b);
+        AC_LAUNCH_CHECK();
+        EpiGeluDefer e1{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
+        if ((rc = launch_linear(e->m_xh, e->m_w1_d[l], e->p_w1_d[l], M, I, H, e1, s))) return rc;
+        // FFN output projection + residual: y <- ffn W2^T + b2 + LN_attention_output(y)
+        EpiResidDefer e2{e->b2[l], e->x, e->xh, e->stats_b, e->ln1w[l], e->ln1b[l], e->parts, pstride, M, H, H};
+        if ((rc = launch_linear(e->m_ffn, e->m_w2[l], e->p_w2[l], M, H, I, e2, s))) return rc;
+        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_a);
+        AC_LAUNCH_CHECK();
+        pg = e->ln2w[l];
+        pb = e->ln2b[l];
+        st_in = e->stats_a;
+    }
+    // full hidden state requested (cls_only = 0): materialise the last LayerNorm for every row (in place, row in registers)
+    const int row_blocks = (M + wpb - 1) / wpb;
+    layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->x, pg, pb, c.ln_eps, M, H, e->tmp, nullptr);
+    AC_LAUNCH_CHECK();
+    cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(e->tmp, B, S, H, out_unit_cls);
+    AC_LAUNCH_CHECK();
+    e->last_B = B;
+    e->last_S = S;
+    e->last_cls_only = false;
+    e->last_hidden = e->tmp;
+    return AC_OK;
 }
 
 extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const int32_t *mask, const int32_t *type_ids,
@@ -892,6 +1225,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
         AC_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTL_SMEM));
         att_attr = true;
     }
+    if (option(OPT_LN_DEFER)) return encoder_layers_deferred(e, mask, B, S, S_pad, out_unit_cls, s);
     for (int l = 0; l < c.layers; ++l) {
         EpiQKV eq{e->bqkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H};
         if ((rc = launch_linear(e->m_xh, e->m_wqkv[l], e->p_wqkv[l], M, 3 * H, H, eq, s))) return rc;
@@ -944,6 +1278,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     e->last_B = B;
     e->last_S = S;
     e->last_cls_only = false;
+    e->last_hidden = e->x;
     return AC_OK;
 }
 
@@ -953,7 +1288,8 @@ extern "C" int ac_encoder_last_hidden(ac_encoder *e, float *out, int64_t n_float
                                   "(create the encoder with cls_only = 0 to keep the full hidden state)");
     const int64_t have = static_cast<int64_t>(e->last_B) * e->last_S * e->cfg.hidden;
     AC_REQUIRE(n_floats <= have, "ac_encoder_last_hidden: asked %lld floats, have %lld", (long long)n_floats, (long long)have);
-    AC_CUDA(cudaMemcpyAsync(out, e->x, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    AC_CUDA(cudaMemcpyAsync(out, e->last_hidden ? e->last_hidden : e->x, n_floats * sizeof(float), cudaMemcpyDeviceToDevice,
+                            static_cast<cudaStream_t>(stream)));
     return AC_OK;
 }
 

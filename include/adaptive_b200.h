@@ -39,10 +39,16 @@ int ac_version(void);                 /* ABI version, currently 1 */
 const char *ac_last_error(void);      /* thread-local message of the last failing call */
 int ac_device_check(void);            /* 0 when the current device is sm_100 (B200), else AC_E_CUDA */
 
-/* Run-time options of the library (process-wide, default 0).  They select kernel variants that compute the SAME
- * results through a different schedule; nothing in the reference corresponds to them.
- *   "gemm_pair" != 0 : encoder projections / ac_linear_tc run as CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) GEMMs
- *   "knn_pair"  != 0 : the prototype scan's coarse pass runs as a CTA-pair GEMM
+/* Run-time options of the library (process-wide, default 0).  They select kernel variants of the same computation;
+ * nothing in the reference corresponds to them.
+ *   "gemm_pair" 1 : encoder projections / ac_linear_tc run as CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) GEMMs;
+ *               2 : the same with the peer CTA's "stage landed" relayed by a thread instead of the TMA unit.
+ *                   Results are bit-identical to the default kernels (measured: profiles/r01_pair_*.log).
+ *   "knn_pair"  1|2 : the prototype scan's coarse pass runs as a CTA-pair GEMM (bit-identical results).
+ *   "ln_defer"  1 : the encoder never materialises LayerNorm between sublayers: residual epilogues write the
+ *                   un-normalised sums + row statistics, the consuming GEMM applies r (acc - mu c1) + c0.  Same math in
+ *                   a different association order (oracle/deferred_ln_study.py: same 4e-4 error vs fp32 as the default).
+ *                   NOT yet run on hardware (written after the round-1 GPU budget was spent).
  * Unknown names return AC_E_INVALID. */
 int ac_set_option(const char *name, long long value);
 int ac_get_option(const char *name, long long *value);

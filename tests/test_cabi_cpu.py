@@ -56,4 +56,4 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/knn_oracle.c", "").replace("oracle/precision_study.py", ""), f
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/knn_oracle.c", "").replace("oracle/precision_study.py", "").replace("oracle/deferred_ln_study.py", ""), f   # comments citing the studies

@@ -4,6 +4,8 @@
 //     ./pair_harness linear    ac_linear_tc on the four encoder projection shapes: outputs compared bit for bit, both timed
 //     ./pair_harness knn       ac_knn_l2_topk (tensor path, fp16 shadow): (d, id) compared bit for bit, both timed
 //     ./pair_harness encoder   full bert-base-shaped forward (random weights), CLS rows compared, both timed
+//     ./pair_harness defer     the same forward with option "ln_defer" (deferred LayerNorm) against the LayerNorm-kernel flow:
+//                              different association order, so a tolerance check; defer_full = without the CLS-only tail
 // Every line is flushed as it is produced: if the experimental kernel traps (mbarrier watchdog), the baseline numbers
 // printed before it are still in the log.  Build: tools/build_harness.sh (nvcc, links ../adaptive_classifier_b200/libadaptive_b200.so).
 #include <cuda_runtime.h>
@@ -213,11 +215,23 @@ static int run_knn() {
     return bad == 0 ? 0 : 1;
 }
 
-static int run_encoder() {
+__global__ void fill_affine(float *p, int64_t n, uint64_t seed, float base, float scale) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        p[i] = base + (static_cast<float>(hash32(seed * 0x9E3779B97F4A7C15ull + i) >> 8) * (1.f / 8388608.f) - 1.f) * scale;
+}
+
+// opt = "gemm_pair" (value g_pair; results must be bit-identical) or "ln_defer" (value 1; same math in a different
+// association order, so the check is a tolerance on the unit CLS rows: the north_star bound is 1e-3 on distances)
+static int run_encoder(const char *opt, int cls_only) {
+    const bool exact = !strcmp(opt, "gemm_pair");
+    const int optval = exact ? g_pair : 1;
     const int L = 12, H = 768, I = 3072, V = 30522, B = 512, S = 128;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     auto mk = [&](size_t n, uint64_t seed, float scale) { float *p = dmalloc<float>(n); fill_f32<<<592, 256>>>(p, static_cast<int64_t>(n), seed, scale); return p; };
-    auto mkc = [&](size_t n, float v) { float *p = dmalloc<float>(n); fill_const<<<64, 256>>>(p, static_cast<int64_t>(n), v); return p; };
+    // LayerNorm parameters away from (1, 0) so that the rank-1 corrections of the deferred flow are exercised
+    uint64_t lnseed = 5000;
+    auto mkc = [&](size_t n, float v) { float *p = dmalloc<float>(n); fill_affine<<<64, 256>>>(p, static_cast<int64_t>(n), ++lnseed, v, v == 0.f ? 0.2f : 0.3f); return p; };
     ac_encoder_weights w{};
     w.word_emb = mk(static_cast<size_t>(V) * H, 100, 0.035f); w.pos_emb = mk(512ull * H, 101, 0.035f); w.type_emb = mk(2ull * H, 102, 0.035f);
     w.emb_ln_w = mkc(H, 1.f); w.emb_ln_b = mkc(H, 0.f);
@@ -239,7 +253,7 @@ static int run_encoder() {
     CK(cudaDeviceSynchronize());
     ac_encoder_config cfg{};
     cfg.arch = AC_ARCH_BERT; cfg.layers = L; cfg.hidden = H; cfg.heads = 12; cfg.intermediate = I; cfg.vocab = V; cfg.max_pos = 512;
-    cfg.type_vocab = 2; cfg.pad_idx = 0; cfg.ln_eps = 1e-12f; cfg.precision = AC_PREC_F16; cfg.max_tokens = B * S; cfg.cls_only = 1;
+    cfg.type_vocab = 2; cfg.pad_idx = 0; cfg.ln_eps = 1e-12f; cfg.precision = AC_PREC_F16; cfg.max_tokens = B * S; cfg.cls_only = cls_only;
     ac_encoder *enc = nullptr;
     AC(ac_encoder_create(&cfg, &w, &enc));
     int32_t *ids = dmalloc<int32_t>(static_cast<size_t>(B) * S);
@@ -247,7 +261,7 @@ static int run_encoder() {
     float *o0 = dmalloc<float>(static_cast<size_t>(B) * H), *o1 = dmalloc<float>(static_cast<size_t>(B) * H);
     CK(cudaDeviceSynchronize());
     for (int variant = 0; variant < 2; ++variant) {
-        AC(ac_set_option("gemm_pair", variant ? g_pair : 0));
+        AC(ac_set_option(opt, variant ? optval : 0));
         float *o = variant ? o1 : o0;
         for (int it = 0; it < 2; ++it) AC(ac_encoder_forward_cls(enc, ids, nullptr, nullptr, B, S, o, nullptr));
         CK(cudaDeviceSynchronize());
@@ -260,26 +274,46 @@ static int run_encoder() {
         AC(ac_profile_enable(0));
         double ms = 0, fl = 0, by = 0; long long n = 0;
         AC(ac_profile_read(0, &ms, &fl, &by, &n));
-        printf("encoder variant=%s B=%d S=%d: forward %.3f ms (%.0f seq/s); projection GEMMs %.3f ms per forward = %.0f TFLOP/s over %lld launches\n",
-               variant ? "pair" : "1cta", B, S, time_ms(e0, e1) / reps, B / (time_ms(e0, e1) / reps * 1e-3), ms / reps, fl / (ms * 1e-3) / 1e12, n);
+        printf("encoder %s=%d cls_only=%d B=%d S=%d: forward %.3f ms (%.0f seq/s); projection GEMMs %.3f ms per forward = %.0f TFLOP/s over %lld launches\n",
+               opt, variant ? optval : 0, cls_only, B, S, time_ms(e0, e1) / reps, B / (time_ms(e0, e1) / reps * 1e-3), ms / reps, fl / (ms * 1e-3) / 1e12, n);
         fflush(stdout);
     }
+    AC(ac_set_option(opt, 0));
     const long long bad = compare("cls_rows", o0, o1, static_cast<size_t>(B) * H * 4, true);
-    printf("encoder: %s\n", bad == 0 ? "PAIR == 1CTA" : "MISMATCH");
+    if (exact) {
+        printf("encoder: %s\n", bad == 0 ? "PAIR == 1CTA" : "MISMATCH");
+        fflush(stdout);
+        return bad == 0 ? 0 : 1;
+    }
+    // tolerance check: largest row-wise L2 distance between the two sets of unit CLS rows
+    std::vector<float> h0(static_cast<size_t>(B) * H), h1(static_cast<size_t>(B) * H);
+    CK(cudaMemcpy(h0.data(), o0, h0.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h1.data(), o1, h1.size() * 4, cudaMemcpyDeviceToHost));
+    double worst = 0;
+    bool finite = true;
+    for (int b = 0; b < B; ++b) {
+        double d2 = 0;
+        for (int i = 0; i < H; ++i) { const double d = static_cast<double>(h0[static_cast<size_t>(b) * H + i]) - h1[static_cast<size_t>(b) * H + i]; d2 += d * d; finite &= (d == d); }
+        worst = fmax(worst, sqrt(d2));
+    }
+    const bool ok = finite && worst < 1e-3;
+    printf("encoder %s: max row ||dq||_2 = %.3e (both flows carry ~4e-4 of fp16 operand rounding against fp32) -> %s\n", opt, worst, ok ? "WITHIN 1e-3" : "OUT OF TOLERANCE");
     fflush(stdout);
-    return bad == 0 ? 0 : 1;
+    return ok ? 0 : 1;
 }
 
 int main(int argc, char **argv) {
     setvbuf(stdout, nullptr, _IOLBF, 0);
-    if (argc < 2) { printf("usage: %s linear|knn|encoder [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
+    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
     if (argc > 2) g_pair = atoi(argv[2]);
     AC(ac_device_check());
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
     printf("device: %s, %d SMs, ABI v%d, test %s, pair option %d\n", pr.name, pr.multiProcessorCount, ac_version(), argv[1], g_pair);
     if (!strcmp(argv[1], "linear")) return run_linear();
     if (!strcmp(argv[1], "knn")) return run_knn();
-    if (!strcmp(argv[1], "encoder")) return run_encoder();
+    if (!strcmp(argv[1], "encoder")) return run_encoder("gemm_pair", 1);
+    if (!strcmp(argv[1], "defer")) return run_encoder("ln_defer", 1);          // production shape: CLS-only tail
+    if (!strcmp(argv[1], "defer_full")) return run_encoder("ln_defer", 0);     // every layer through the deferred epilogues
     printf("unknown test %s\n", argv[1]);
     return 64;
 }
