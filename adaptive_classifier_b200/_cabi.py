@@ -137,6 +137,12 @@ def load_library() -> ctypes.CDLL:
         elif name not in ("ac_last_error",):
             fn.restype = c_int
     _lib = L
+    # kernel variants for a whole process without touching code: AC_OPTIONS="ln_defer=1,head_fused=1" (see set_option)
+    for item in filter(None, os.environ.get("AC_OPTIONS", "").split(",")):
+        name, _, val = item.partition("=")
+        rc = L.ac_set_option(name.strip().encode(), int(val or "1"))
+        if rc != 0:
+            raise AdaptiveB200Error(f"AC_OPTIONS: {L.ac_last_error().decode()}")
     return L
 
 

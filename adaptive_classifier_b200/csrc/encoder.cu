@@ -1140,7 +1140,10 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
             // ---- CLS-only tail of the last layer (M = B rows): materialise LN_pending on the CLS rows and continue with
             // the ordinary kernels and the plain (not gamma-scaled) FFN1 weight
             const int cb = (B + wpb - 1) / wpb;
-            gather_cls_ln_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, pg, pb, c.ln_eps, e->ctx_cls, e->x_cls);
+            if (l == 0)   // single-layer encoder: nothing is pending on the (already normalised) embeddings
+                gather_cls_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, e->ctx_cls, e->x_cls);
+            else
+                gather_cls_ln_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, pg, pb, c.ln_eps, e->ctx_cls, e->x_cls);
             AC_LAUNCH_CHECK();
             EpiResid eo{e->bo[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
             if ((rc = launch_linear(e->m_ctx_cls, e->m_wo[l], e->p_wo[l], B, H, H, eo, s))) return rc;

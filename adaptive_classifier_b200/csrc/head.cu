@@ -11,6 +11,7 @@
 // the step is a fixed launch sequence (graph-capturable: no host sync inside).
 #include "common.cuh"
 #include <math_constants.h>
+#include <vector>
 
 namespace ac {
 
@@ -685,6 +686,420 @@ static int train_step_impl(const float *X, const void *targets, int B, ac_head_p
 
 
 // ------------------------------------------------------------------------------------------------
+// fused epoch (opt-in, option "head_fused"): ONE cooperative persistent kernel runs every optimizer step of an epoch.
+//
+// The step above is ~21 dependent launches of latency-bound kernels (measured 2.9 k steps/s at batch 32, i.e. ~350 us per
+// step for 171 MFLOP: profiles/r01_bench_add_examples_v3.json).  Here the same kernels become PHASES of one kernel,
+// separated by grid barriers (cooperative_groups grid.sync), and every CTA walks the phase's original grid as "virtual
+// blocks".  The bodies below are copies of the kernels above with (a) virtual block indices and (b) plain coherent loads
+// instead of __ldg / __restrict__ (weights, activations and gradients are rewritten by other CTAs inside this kernel, so
+// the non-coherent path is not allowed).  Operation order inside every virtual block is unchanged, so an epoch through
+// this kernel is expected to give the same bits as the launch-per-kernel path (tests/test_gpu_variants.py compares them).
+//
+//   per step:  gather+masks | h0 | h1 | z | loss,dz | gW2,gb2,dh1,loss | gW1,gb1,dh0 | gW0,gb0 | [EWC] | sumsq | AdamW
+//              (9 grid barriers, 10 with EWC; AdamW of step t overlaps the gather of step t+1)
+// Status: written after the round-1 GPU budget was spent; compiles for sm_100a, NOT yet run on hardware.
+// ------------------------------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace ac {
+namespace fused {
+namespace cg = cooperative_groups;
+
+constexpr int FT = 256;                              // threads per CTA
+constexpr int F_SMEM_FLOATS = CA_GROUPS * 32 * 33;   // colacc's partials are the largest user (33.8 KB)
+
+struct EpochArgs {
+    const float *X;            // [n, D]
+    const void *targets;       // int64[n] or float[n, C]
+    const int64_t *perm;       // [n]
+    int n, batch, first_step;
+    ac_head_params p, m, v;    // parameters and AdamW moments (device pointers)
+    TrainWs w;                 // activations, gradients, partials (device pointers)
+    float *xb;                 // [batch, D] gathered rows
+    void *yb;                  // gathered targets
+    float *stats;              // [3] task loss, ewc penalty, grad norm of the current step
+    float *loss_accum;         // += task loss + ewc penalty per step
+    float *partial_ewc;        // [RED_BLOCKS]
+    const float2 *bias_corr;   // [steps] (1 - beta1^t, sqrt(1 - beta2^t)) computed on the host like the per-step path
+    float lr, beta1, beta2, eps, weight_decay, max_norm, dropout_p;
+    int loss_kind;
+    uint64_t seed;
+    int use_ewc, ewc_C_old;
+    float ewc_lambda;
+    ac_head_params fisher, star;
+};
+
+__device__ __forceinline__ void sgemm_vb(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn,
+                                         float *C, int64_t ldc, int M, int N, int K, int vbx, int vby, float *smem) {
+    float(*sA)[SG_BM + 1] = reinterpret_cast<float(*)[SG_BM + 1]>(smem);
+    float(*sB)[SG_BN + 1] = reinterpret_cast<float(*)[SG_BN + 1]>(smem + SG_BK * (SG_BM + 1));
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = vby * SG_BM, n0 = vbx * SG_BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += SG_BK) {
+        for (int e = threadIdx.x; e < SG_BM * SG_BK; e += FT) {
+            int mm, kk;
+            if (sak == 1) { kk = e % SG_BK; mm = e / SG_BK; } else { mm = e % SG_BM; kk = e / SG_BM; }
+            const int m = m0 + mm, k = k0 + kk;
+            sA[kk][mm] = (m < M && k < K) ? A[m * sam + k * sak] : 0.f;
+        }
+        for (int e = threadIdx.x; e < SG_BN * SG_BK; e += FT) {
+            int nn, kk;
+            if (sbk == 1) { kk = e % SG_BK; nn = e / SG_BK; } else { nn = e % SG_BN; kk = e / SG_BN; }
+            const int n = n0 + nn, k = k0 + kk;
+            sB[kk][nn] = (n < N && k < K) ? B[k * sbk + n * sbn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SG_BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n >= N) continue;
+            C[static_cast<int64_t>(m) * ldc + n] = acc[i][j];      // the weight-gradient GEMMs use EPI_NONE
+        }
+    }
+}
+
+// rowdot_kernel<1>: warp = one output column x 32 batch rows
+__device__ __forceinline__ void rowdot_vb(const float *X, const float *W, float *Y, int M, int N, int K, const SgemmEpi &epi,
+                                          int vbx, int vby) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = vbx * RD_WARPS + warp;
+    const int b0 = vby * 32;
+    if (n0 >= N) return;
+    float acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+    const int rows = min(32, M - b0);
+#pragma unroll 2
+    for (int k = lane; k < K; k += 32) {
+        const float w = W[static_cast<int64_t>(n0) * K + k];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const float x = (b < rows) ? X[static_cast<int64_t>(b0 + b) * K + k] : 0.f;
+            acc[b] = fmaf(x, w, acc[b]);
+        }
+    }
+    const float sum = warp_transpose_reduce(acc, lane);     // lane = batch row
+    const int m = b0 + lane;
+    if (lane < rows) {
+        const int64_t off = static_cast<int64_t>(m) * N + n0;
+        Y[off] = epi_apply(epi, sum, n0, off);
+    }
+}
+
+__device__ __forceinline__ void colacc_vb(const float *G, const float *W, float *Z, int M, int R, int J, const SgemmEpi &epi,
+                                          int vbx, int vby, float *smem) {
+    float(*part)[32][33] = reinterpret_cast<float(*)[32][33]>(smem);
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = vbx * 32 + lane;
+    const int b0 = vby * 32;
+    const int rows = min(32, M - b0);
+    float acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+    for (int r = g; r < R; r += CA_GROUPS) {
+        const float w = (j < J) ? W[static_cast<int64_t>(r) * J + j] : 0.f;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const float gv = (b < rows) ? G[static_cast<int64_t>(b0 + b) * R + r] : 0.f;
+            acc[b] = fmaf(gv, w, acc[b]);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b) part[g][b][lane] = acc[b];
+    __syncthreads();
+    for (int b = g; b < rows; b += CA_GROUPS) {
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < CA_GROUPS; ++q) sum += part[q][b][lane];
+        if (j < J) {
+            const int64_t off = static_cast<int64_t>(b0 + b) * J + j;
+            Z[off] = epi_apply(epi, sum, j, off);
+        }
+    }
+    __syncthreads();      // the partials are reused by the next virtual block of this CTA
+}
+
+// loss_grad_kernel for one row (one warp)
+__device__ __forceinline__ void loss_grad_row(const float *z, const void *targets, int B, int C, int loss_kind, float *dz,
+                                              float *row_loss, int row, int lane) {
+    const float *zr = z + static_cast<int64_t>(row) * C;
+    float *dr = dz + static_cast<int64_t>(row) * C;
+    if (loss_kind == AC_LOSS_CE) {
+        const int64_t y = static_cast<const int64_t *>(targets)[row];
+        float mx = -CUDART_INF_F;
+        for (int j = lane; j < C; j += 32) mx = fmaxf(mx, zr[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < C; j += 32) sum += expf(zr[j] - mx);
+        sum = warp_sum(sum);
+        const float lse = mx + logf(sum);
+        const float invB = 1.f / static_cast<float>(B);
+        for (int j = lane; j < C; j += 32) {
+            const float pr = expf(zr[j] - mx) / sum;
+            dr[j] = (pr - (j == y ? 1.f : 0.f)) * invB;
+        }
+        if (lane == 0) row_loss[row] = (y >= 0 && y < C) ? (lse - zr[y]) : 0.f;
+    } else {
+        const float *yr = static_cast<const float *>(targets) + static_cast<int64_t>(row) * C;
+        const float inv = 1.f / (static_cast<float>(B) * static_cast<float>(C));
+        float l = 0.f;
+        for (int j = lane; j < C; j += 32) {
+            const float sg = 1.f / (1.f + expf(-zr[j]));
+            const float y = yr[j];
+            l -= y * fmaxf(logf(sg), -100.f) + (1.f - y) * fmaxf(logf(1.f - sg), -100.f);
+            dr[j] = (sg - y) * inv;
+        }
+        l = warp_sum(l);
+        if (lane == 0) row_loss[row] = l / static_cast<float>(C);
+    }
+}
+
+__device__ __forceinline__ void colsum_vb(const float *dY, int B, int N, float *gb, int vb) {
+    const int n = vb * FT + threadIdx.x;
+    if (n >= N) return;
+    float sum = 0.f;
+    for (int b = 0; b < B; ++b) sum += dY[static_cast<int64_t>(b) * N + n];
+    gb[n] = sum;
+}
+
+// block tree reduction of sumsq_kernel / ewc_grad_penalty_kernel (256 threads)
+__device__ __forceinline__ float block_reduce_256(float local, float *red) {
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+    }
+    const float r = red[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(FT, 1) head_epoch_kernel(const EpochArgs a) {
+    __shared__ float smem[F_SMEM_FLOATS];
+    __shared__ float s_bcast[2];
+    cg::grid_group grid = cg::this_grid();
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = a.p.D, H0 = a.p.H0, H1 = a.p.H1, C = a.p.C;
+    const bool drop = a.dropout_p > 0.f;
+    const float *mask0 = drop ? a.w.mask0 : nullptr, *mask1 = drop ? a.w.mask1 : nullptr;
+    const Flat6 theta = {{a.p.W0, a.p.b0, a.p.W1, a.p.b1, a.p.W2, a.p.b2},
+                         {static_cast<int64_t>(H0) * D, H0, static_cast<int64_t>(H1) * H0, H1, static_cast<int64_t>(C) * H1, C}};
+    const Flat6 mom = {{a.m.W0, a.m.b0, a.m.W1, a.m.b1, a.m.W2, a.m.b2}, {0, 0, 0, 0, 0, 0}};
+    const Flat6 var = {{a.v.W0, a.v.b0, a.v.W1, a.v.b1, a.v.W2, a.v.b2}, {0, 0, 0, 0, 0, 0}};
+    const Flat6 grad = {{a.w.g.W0, a.w.g.b0, a.w.g.W1, a.w.g.b1, a.w.g.W2, a.w.g.b2}, {0, 0, 0, 0, 0, 0}};
+
+    int step = a.first_step;
+    for (int off = 0; off < a.n; off += a.batch, ++step) {
+        const int nb = (a.n - off < a.batch) ? a.n - off : a.batch;
+        const int rb = (nb + 31) / 32;                                   // 32-row blocks of the batch (1 at batch 32)
+        // ---- phase 0: gather the batch rows / targets, dropout masks of this step
+        for (int r = cta; r < nb; r += G) {
+            const int64_t src = a.perm[off + r];
+            for (int i = threadIdx.x; i < D; i += FT) a.xb[static_cast<int64_t>(r) * D + i] = a.X[src * D + i];
+            if (a.loss_kind == AC_LOSS_CE) {
+                if (threadIdx.x == 0) static_cast<int64_t *>(a.yb)[r] = static_cast<const int64_t *>(a.targets)[src];
+            } else {
+                for (int i = threadIdx.x; i < C; i += FT)
+                    static_cast<float *>(a.yb)[static_cast<int64_t>(r) * C + i] = static_cast<const float *>(a.targets)[src * C + i];
+            }
+        }
+        if (drop) {
+            const int64_t n0 = static_cast<int64_t>(nb) * H0, n1 = static_cast<int64_t>(nb) * H1;
+            for (int64_t i = static_cast<int64_t>(cta) * FT + threadIdx.x; i < n0 + n1; i += static_cast<int64_t>(G) * FT) {
+                const bool first = i < n0;
+                const int64_t e = first ? i : i - n0;
+                const uint32_t r = mix32(a.seed * 0x9E3779B97F4A7C15ULL + (2ull * step + (first ? 0 : 1)) * 0xD1B54A32D192ED03ULL +
+                                         static_cast<uint64_t>(e));
+                const float u = (r >> 8) * (1.0f / 16777216.0f);
+                (first ? a.w.mask0 : a.w.mask1)[e] = (u < a.dropout_p) ? 0.f : 1.f / (1.f - a.dropout_p);
+            }
+        }
+        grid.sync();
+        // ---- phase 1..3: forward
+        {
+            const SgemmEpi e0{EPI_BIAS_RELU_MASK, a.p.b0, mask0, nullptr};
+            const int nx = (H0 + RD_WARPS - 1) / RD_WARPS;
+            for (int vb = cta; vb < nx * rb; vb += G) rowdot_vb(a.xb, a.p.W0, a.w.h0, nb, H0, D, e0, vb % nx, vb / nx);
+        }
+        grid.sync();
+        {
+            const SgemmEpi e1{EPI_BIAS_RELU_MASK, a.p.b1, mask1, nullptr};
+            const int nx = (H1 + RD_WARPS - 1) / RD_WARPS;
+            for (int vb = cta; vb < nx * rb; vb += G) rowdot_vb(a.w.h0, a.p.W1, a.w.h1, nb, H1, H0, e1, vb % nx, vb / nx);
+        }
+        grid.sync();
+        {
+            const SgemmEpi e2{EPI_BIAS, a.p.b2, nullptr, nullptr};
+            const int nx = (C + RD_WARPS - 1) / RD_WARPS;
+            for (int vb = cta; vb < nx * rb; vb += G) rowdot_vb(a.w.h1, a.p.W2, a.w.z, nb, C, H1, e2, vb % nx, vb / nx);
+        }
+        grid.sync();
+        // ---- phase 4: loss + dz, one warp per batch row
+        for (int row = cta * (FT / 32) + warp; row < nb; row += G * (FT / 32))
+            loss_grad_row(a.w.z, a.yb, nb, C, a.loss_kind, a.w.dz, a.w.row_loss, row, lane);
+        grid.sync();
+        // ---- phase 5: task loss; gW2 = dz^T h1, gb2, dh1 = (dz W2) * relu' * mask1
+        {
+            const int sx = (H1 + SG_BN - 1) / SG_BN, sy = (C + SG_BM - 1) / SG_BM;     // sgemm grid
+            const int cs = (C + FT - 1) / FT;                                          // colsum blocks
+            const int ax = (H1 + 31) / 32;                                             // colacc grid (x), rb in y
+            const int total = sx * sy + cs + ax * rb + 1;
+            const SgemmEpi rg1{EPI_RELUGRAD_MASK, nullptr, mask1, a.w.h1};
+            for (int it = cta; it < total; it += G) {
+                int t = it;
+                if (t < sx * sy) { sgemm_vb(a.w.dz, 1, C, a.w.h1, H1, 1, a.w.g.W2, H1, C, H1, nb, t % sx, t / sx, smem); continue; }
+                t -= sx * sy;
+                if (t < cs) { colsum_vb(a.w.dz, nb, C, a.w.g.b2, t); continue; }
+                t -= cs;
+                if (t < ax * rb) { colacc_vb(a.w.dz, a.p.W2, a.w.dh1, nb, C, H1, rg1, t % ax, t / ax, smem); continue; }
+                if (threadIdx.x == 0) {                       // reduce_loss_kernel
+                    float sum = 0.f;
+                    for (int i = 0; i < nb; ++i) sum += a.w.row_loss[i];
+                    a.stats[0] = sum / static_cast<float>(nb);
+                }
+            }
+        }
+        grid.sync();
+        // ---- phase 6: gW1 = dh1^T h0, gb1, dh0 = (dh1 W1) * relu' * mask0
+        {
+            const int sx = (H0 + SG_BN - 1) / SG_BN, sy = (H1 + SG_BM - 1) / SG_BM;
+            const int cs = (H1 + FT - 1) / FT;
+            const int ax = (H0 + 31) / 32;
+            const int total = sx * sy + cs + ax * rb;
+            const SgemmEpi rg0{EPI_RELUGRAD_MASK, nullptr, mask0, a.w.h0};
+            for (int it = cta; it < total; it += G) {
+                int t = it;
+                if (t < sx * sy) { sgemm_vb(a.w.dh1, 1, H1, a.w.h0, H0, 1, a.w.g.W1, H0, H1, H0, nb, t % sx, t / sx, smem); continue; }
+                t -= sx * sy;
+                if (t < cs) { colsum_vb(a.w.dh1, nb, H1, a.w.g.b1, t); continue; }
+                t -= cs;
+                colacc_vb(a.w.dh1, a.p.W1, a.w.dh0, nb, H1, H0, rg0, t % ax, t / ax, smem);
+            }
+        }
+        grid.sync();
+        // ---- phase 7: gW0 = dh0^T x, gb0
+        {
+            const int sx = (D + SG_BN - 1) / SG_BN, sy = (H0 + SG_BM - 1) / SG_BM;
+            const int cs = (H0 + FT - 1) / FT;
+            const int total = sx * sy + cs;
+            for (int it = cta; it < total; it += G) {
+                if (it < sx * sy) sgemm_vb(a.w.dh0, 1, H0, a.xb, D, 1, a.w.g.W0, D, H0, D, nb, it % sx, it / sx, smem);
+                else colsum_vb(a.w.dh0, nb, H0, a.w.g.b0, it - sx * sy);
+            }
+        }
+        grid.sync();
+        // ---- phase 8 (EWC): g += 2 lambda / B * F (theta - theta*), penalty partials (ewc_grad_penalty_kernel's virtual grid)
+        if (a.use_ewc) {
+            const Flat6 fis = {{a.fisher.W0, a.fisher.b0, a.fisher.W1, a.fisher.b1, a.fisher.W2, a.fisher.b2}, {0, 0, 0, 0, 0, 0}};
+            const Flat6 sta = {{a.star.W0, a.star.b0, a.star.W1, a.star.b1, a.star.W2, a.star.b2}, {0, 0, 0, 0, 0, 0}};
+            const bool grown = a.ewc_C_old > 0 && a.ewc_C_old < C;
+            const float scale2 = 2.f * (a.ewc_lambda / static_cast<float>(nb));
+            for (int vb = cta; vb < RED_BLOCKS; vb += G) {
+                float local = 0.f;
+                for (int t = 0; t < 6; ++t) {
+                    int64_t lim = theta.n[t];
+                    if (grown && t == 4) lim = static_cast<int64_t>(a.ewc_C_old) * H1;
+                    if (grown && t == 5) lim = a.ewc_C_old;
+                    for (int64_t i = static_cast<int64_t>(vb) * FT + threadIdx.x; i < lim; i += static_cast<int64_t>(RED_BLOCKS) * FT) {
+                        const float diff = theta.p[t][i] - sta.p[t][i];
+                        const float f = fis.p[t][i];
+                        local += f * diff * diff;
+                        grad.p[t][i] += scale2 * f * diff;
+                    }
+                }
+                const float tot = block_reduce_256(local, smem);
+                if (threadIdx.x == 0) a.partial_ewc[vb] = tot;
+            }
+            grid.sync();
+        }
+        // ---- phase 9: partial sums of squares of all gradients (sumsq_kernel's virtual grid); EWC penalty value
+        for (int vb = cta; vb < RED_BLOCKS; vb += G) {
+            float local = 0.f;
+            for (int t = 0; t < 6; ++t)
+                for (int64_t i = static_cast<int64_t>(vb) * FT + threadIdx.x; i < theta.n[t]; i += static_cast<int64_t>(RED_BLOCKS) * FT) {
+                    const float gv = grad.p[t][i];
+                    local = fmaf(gv, gv, local);
+                }
+            const float tot = block_reduce_256(local, smem);
+            if (threadIdx.x == 0) a.w.partial[vb] = tot;
+        }
+        if (cta == G - 1 && threadIdx.x == 0) {
+            float pen = 0.f;
+            if (a.use_ewc) {
+                float sum = 0.f;
+                for (int i = 0; i < RED_BLOCKS; ++i) sum += a.partial_ewc[i];
+                pen = (a.ewc_lambda / static_cast<float>(nb)) * sum;
+            }
+            a.stats[1] = pen;
+        }
+        grid.sync();
+        // ---- phase 10: global-norm clip + AdamW (every CTA recomputes the norm from the partials in finalize_kernel's order)
+        if (threadIdx.x == 0) {
+            float sum = 0.f;
+            for (int i = 0; i < RED_BLOCKS; ++i) sum += a.w.partial[i];
+            s_bcast[0] = sqrtf(sum);
+        }
+        __syncthreads();
+        {
+            const float total = s_bcast[0];
+            float coef = a.max_norm / (total + 1e-6f);
+            coef = coef < 1.f ? coef : 1.f;
+            if (!(a.max_norm > 0.f)) coef = 1.f;
+            const float2 bc = a.bias_corr[step - a.first_step];
+            const float bc1 = bc.x, bc2_sqrt = bc.y;
+            for (int t = 0; t < 6; ++t)
+                for (int64_t i = static_cast<int64_t>(cta) * FT + threadIdx.x; i < theta.n[t]; i += static_cast<int64_t>(G) * FT) {
+                    const float g = grad.p[t][i] * coef;
+                    float pv = theta.p[t][i];
+                    pv = pv * (1.f - a.lr * a.weight_decay);
+                    const float mi = mom.p[t][i] * a.beta1 + g * (1.f - a.beta1);
+                    const float vi = var.p[t][i] * a.beta2 + g * g * (1.f - a.beta2);
+                    const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
+                    pv = pv - (a.lr / bc1) * (mi / denom);
+                    theta.p[t][i] = pv;
+                    mom.p[t][i] = mi;
+                    var.p[t][i] = vi;
+                }
+            if (cta == 0 && threadIdx.x == 0) {
+                a.stats[2] = total;
+                a.loss_accum[0] += a.stats[0] + a.stats[1];
+            }
+        }
+        __syncthreads();    // s_bcast is rewritten next step
+        // no grid barrier here: the next step's gather/mask phase touches nothing AdamW reads or writes, and the barrier
+        // that closes it orders these parameter writes before the next forward
+    }
+}
+
+}  // namespace fused
+}  // namespace ac
+
+// ------------------------------------------------------------------------------------------------
 // one epoch of the training loops (classifier.py:329-353, :1485-1507; multilabel.py:381-399) in a single call:
 // batches are gathered on the device from a shuffled index list, every optimizer step is launched from here.
 // ------------------------------------------------------------------------------------------------
@@ -737,6 +1152,41 @@ extern "C" int ac_head_train_epoch(const float *X, const void *targets, const in
     void *yb = base + step_bytes + xb_bytes;
     float *stats = reinterpret_cast<float *>(base + step_bytes + xb_bytes + yb_bytes);
     int step = cfg->step;
+    if (option(OPT_HEAD_FUSED) && batch <= 64) {
+        // one cooperative persistent kernel for the whole epoch (see fused::head_epoch_kernel)
+        if ((rc = ac_device_check())) return rc;
+        carve(w, workspace, batch, p);
+        const int steps = (n + batch - 1) / batch;
+        std::vector<float2> bc(steps);
+        for (int i = 0; i < steps; ++i)
+            bc[i] = make_float2(1.f - powf(cfg->beta1, static_cast<float>(step + i)),
+                                sqrtf(1.f - powf(cfg->beta2, static_cast<float>(step + i))));
+        float2 *bc_dev = nullptr;
+        float *partial_ewc = nullptr;
+        AC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&bc_dev), steps * sizeof(float2), s));
+        AC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&partial_ewc), RED_BLOCKS * sizeof(float), s));
+        // pageable source: the runtime stages the copy before returning, so `bc` may go out of scope afterwards
+        AC_CUDA(cudaMemcpyAsync(bc_dev, bc.data(), steps * sizeof(float2), cudaMemcpyHostToDevice, s));
+        fused::EpochArgs a{};
+        a.X = X; a.targets = targets; a.perm = perm; a.n = n; a.batch = batch; a.first_step = step;
+        a.p = *p; a.m = *m; a.v = *v; a.w = w; a.xb = xb; a.yb = yb; a.stats = stats; a.loss_accum = loss_accum;
+        a.partial_ewc = partial_ewc; a.bias_corr = bc_dev;
+        a.lr = cfg->lr; a.beta1 = cfg->beta1; a.beta2 = cfg->beta2; a.eps = cfg->eps; a.weight_decay = cfg->weight_decay;
+        a.max_norm = cfg->max_norm; a.dropout_p = cfg->dropout_p; a.loss_kind = cfg->loss_kind; a.seed = cfg->seed;
+        a.use_ewc = (cfg->ewc_fisher && cfg->ewc_star) ? 1 : 0;
+        a.ewc_C_old = cfg->ewc_C_old; a.ewc_lambda = cfg->ewc_lambda;
+        if (a.use_ewc) { a.fisher = *cfg->ewc_fisher; a.star = *cfg->ewc_star; }
+        int per_sm = 0;
+        AC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused::head_epoch_kernel, fused::FT, 0));
+        AC_REQUIRE(per_sm >= 1, "ac_head_train_epoch: the fused epoch kernel does not fit on an SM");
+        void *args[] = {&a};
+        AC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(fused::head_epoch_kernel), dim3(sm_count()),
+                                            dim3(fused::FT), args, 0, s));
+        count_launch();
+        AC_CUDA(cudaFreeAsync(bc_dev, s));
+        AC_CUDA(cudaFreeAsync(partial_ewc, s));
+        return AC_OK;
+    }
     for (int off = 0; off < n; off += batch, ++step) {
         const int nb = (n - off < batch) ? n - off : batch;      // DataLoader keeps the last partial batch
         gather_batch_kernel<<<nb, 128, 0, s>>>(X, targets, perm + off, nb, p->D, p->C, cfg->loss_kind, xb, yb);

@@ -49,6 +49,9 @@ int ac_device_check(void);            /* 0 when the current device is sm_100 (B2
  *                   un-normalised sums + row statistics, the consuming GEMM applies r (acc - mu c1) + c0.  Same math in
  *                   a different association order (oracle/deferred_ln_study.py: same 4e-4 error vs fp32 as the default).
  *                   NOT yet run on hardware (written after the round-1 GPU budget was spent).
+ *   "head_fused" 1 : ac_head_train_epoch runs the whole epoch as ONE cooperative persistent kernel (the per-step kernels
+ *                   become phases separated by grid barriers, same operation order) instead of ~21 launches per step.
+ *                   NOT yet run on hardware.
  * Unknown names return AC_E_INVALID. */
 int ac_set_option(const char *name, long long value);
 int ac_get_option(const char *name, long long *value);

@@ -29,11 +29,11 @@ def _encoder(cabi, sd, cfg, max_tokens, cls_only=True):
 
 
 def test_option_roundtrip(cabi):
-    for name in ("gemm_pair", "knn_pair", "ln_defer"):
-        assert cabi.get_option(name) == 0
-        with cabi.option(name, 1):
-            assert cabi.get_option(name) == 1
-        assert cabi.get_option(name) == 0
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused"):
+        prev = cabi.get_option(name)          # 0 unless AC_OPTIONS preset it for this process
+        with cabi.option(name, 1 - prev):
+            assert cabi.get_option(name) == 1 - prev
+        assert cabi.get_option(name) == prev
     with pytest.raises(cabi.AdaptiveB200Error):
         cabi.set_option("no_such_option", 1)
 
@@ -139,3 +139,45 @@ def test_deferred_layernorm_matches_oracle(cabi, layers, B, S, cls_only, pad):
         keep = mask.bool()
         assert (hidden.view(B, S, -1)[keep] - ref_hidden[keep]).abs().max() < 5e-3
     enc.close()
+
+
+def _head_state(D, C, dev="cuda"):
+    from oracle import head_oracle as ho
+    p = ho.init_head(D, C)
+    pg = {k: v.clone().to(dev).contiguous() for k, v in p.items()}
+    return pg, {k: torch.zeros_like(v) for k, v in pg.items()}, {k: torch.zeros_like(v) for k, v in pg.items()}
+
+
+@experimental
+@pytest.mark.parametrize("n,C,bs,loss,dropout,ewc", [(100, 7, 32, "ce", 0.1, False), (257, 20, 32, "ce", 0.0, True),
+                                                      (90, 5, 32, "bce", 0.1, False), (130, 1000, 64, "ce", 0.1, False)])
+def test_fused_epoch_equals_launch_per_kernel_epoch(cabi, n, C, bs, loss, dropout, ewc):
+    """option "head_fused": one cooperative kernel per epoch, phases = the per-step kernels with the same operation order,
+    so parameters, AdamW moments and the accumulated loss must come out bit-identical to the launch-per-kernel epoch."""
+    D = 768
+    g = torch.Generator().manual_seed(n + C)
+    X = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).cuda()
+    if loss == "ce":
+        y = torch.randint(0, C, (n,), generator=g).cuda()
+        kind = cabi.AC_LOSS_CE
+    else:
+        y = (torch.rand(n, C, generator=g) < 0.3).float().cuda()
+        kind = cabi.AC_LOSS_BCE
+    perm = torch.randperm(n, generator=g)
+    pa, ma, va = _head_state(D, C)
+    pb, mb, vb = _head_state(D, C)
+    ewc_arg_a = ewc_arg_b = None
+    if ewc:
+        fisher = {k: torch.rand(v.shape, generator=g).cuda() for k, v in pa.items()}
+        star = {k: (v + 0.05).contiguous() for k, v in pa.items()}
+        ewc_arg_a = ewc_arg_b = (fisher, star, 100.0, C - 2)      # the head "grew" by two classes
+    kw = dict(first_step=3, batch=bs, seed=11, loss_kind=kind, dropout_p=dropout)
+    acc_a, nb_a = cabi.head_train_epoch(X, y, perm, pa, ma, va, ewc=ewc_arg_a, **kw)
+    with cabi.option("head_fused", 1):
+        acc_b, nb_b = cabi.head_train_epoch(X, y, perm, pb, mb, vb, ewc=ewc_arg_b, **kw)
+    torch.cuda.synchronize()
+    assert nb_a == nb_b
+    for k in pa:
+        assert torch.equal(pa[k], pb[k]), f"parameter {k}"
+        assert torch.equal(ma[k], mb[k]) and torch.equal(va[k], vb[k]), f"moments {k}"
+    assert abs(float(acc_a) - float(acc_b)) <= 1e-6 * max(1.0, abs(float(acc_a)))
