@@ -4,6 +4,7 @@
 //     ./pair_harness linear    ac_linear_tc on the four encoder projection shapes: outputs compared bit for bit, both timed
 //     ./pair_harness knn       ac_knn_l2_topk (tensor path, fp16 shadow): (d, id) compared bit for bit, both timed
 //     ./pair_harness encoder   full bert-base-shaped forward (random weights), CLS rows compared, both timed
+//     ./pair_harness epoch     option "head_fused": one training epoch of the head, fused cooperative kernel vs launch-per-kernel
 //     ./pair_harness defer     the same forward with option "ln_defer" (deferred LayerNorm) against the LayerNorm-kernel flow:
 //                              different association order, so a tolerance check; defer_full = without the CLS-only tail
 // Every line is flushed as it is produced: if the experimental kernel traps (mbarrier watchdog), the baseline numbers
@@ -302,9 +303,70 @@ static int run_encoder(const char *opt, int cls_only) {
     return ok ? 0 : 1;
 }
 
+// option "head_fused": one epoch of the head's training loop (batch 32, dropout 0.1, CE) through the launch-per-kernel path
+// and through the fused cooperative kernel, from identical initial states: parameters and moments must match bit for bit
+static int run_epoch() {
+    const int D = 768, H0 = 768, H1 = 384, C = 20, n = 20000, batch = 32;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float *X = dmalloc<float>(static_cast<size_t>(n) * D);
+    fill_f32<<<592, 256>>>(X, static_cast<int64_t>(n) * D, 21, 1.0f);
+    normalize_rows<<<(n + 7) / 8, 256>>>(X, n, D);
+    std::vector<int64_t> hy(n), hperm(n);
+    for (int i = 0; i < n; ++i) { hy[i] = (i * 7 + i / 13) % C; hperm[i] = (static_cast<int64_t>(i) * 7919) % n; }
+    int64_t *y = dmalloc<int64_t>(n), *perm = dmalloc<int64_t>(n);
+    CK(cudaMemcpy(y, hy.data(), n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(perm, hperm.data(), n * 8, cudaMemcpyHostToDevice));
+    const size_t sizes[6] = {static_cast<size_t>(H0) * D, static_cast<size_t>(H0), static_cast<size_t>(H1) * H0, static_cast<size_t>(H1),
+                             static_cast<size_t>(C) * H1, static_cast<size_t>(C)};
+    auto mkhead = [&](bool zero, uint64_t seed) {
+        ac_head_params h{}; h.D = D; h.H0 = H0; h.H1 = H1; h.C = C;
+        float **slots[6] = {&h.W0, &h.b0, &h.W1, &h.b1, &h.W2, &h.b2};
+        for (int t = 0; t < 6; ++t) {
+            *slots[t] = dmalloc<float>(sizes[t]);
+            if (zero) CK(cudaMemset(*slots[t], 0, sizes[t] * 4));
+            else fill_f32<<<128, 256>>>(*slots[t], static_cast<int64_t>(sizes[t]), seed + t, 0.05f);
+        }
+        return h;
+    };
+    ac_head_params P[2] = {mkhead(false, 300), mkhead(false, 300)}, M[2] = {mkhead(true, 0), mkhead(true, 0)}, V[2] = {mkhead(true, 0), mkhead(true, 0)};
+    size_t wsb = 0;
+    AC(ac_head_train_epoch_workspace_bytes(batch, &P[0], &wsb));
+    void *ws = dmalloc<uint8_t>(wsb);
+    float *acc = dmalloc<float>(2);
+    CK(cudaMemset(acc, 0, 8));
+    ac_train_cfg cfg{};
+    cfg.lr = 1e-3f; cfg.beta1 = 0.9f; cfg.beta2 = 0.999f; cfg.eps = 1e-8f; cfg.weight_decay = 0.01f; cfg.max_norm = 1.0f;
+    cfg.step = 1; cfg.loss_kind = AC_LOSS_CE; cfg.dropout_p = 0.1f; cfg.seed = 42;
+    CK(cudaDeviceSynchronize());
+    for (int variant = 0; variant < 2; ++variant) {
+        AC(ac_set_option("head_fused", variant));
+        CK(cudaEventRecord(e0));
+        AC(ac_head_train_epoch(X, y, perm, n, batch, &P[variant], &M[variant], &V[variant], &cfg, acc + variant, ws, wsb, nullptr));
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        const int steps = (n + batch - 1) / batch;
+        float loss = 0; CK(cudaMemcpy(&loss, acc + variant, 4, cudaMemcpyDeviceToHost));
+        printf("epoch head_fused=%d: %d steps of batch %d in %.2f ms = %.0f steps/s (%.1f us/step), mean loss %.5f\n", variant, steps, batch,
+               time_ms(e0, e1), steps / (time_ms(e0, e1) * 1e-3), time_ms(e0, e1) * 1e3 / steps, loss / steps);
+        fflush(stdout);
+    }
+    AC(ac_set_option("head_fused", 0));
+    long long bad = 0;
+    float *pa[6] = {P[0].W0, P[0].b0, P[0].W1, P[0].b1, P[0].W2, P[0].b2}, *pb[6] = {P[1].W0, P[1].b0, P[1].W1, P[1].b1, P[1].W2, P[1].b2};
+    float *va[6] = {V[0].W0, V[0].b0, V[0].W1, V[0].b1, V[0].W2, V[0].b2}, *vb[6] = {V[1].W0, V[1].b0, V[1].W1, V[1].b1, V[1].W2, V[1].b2};
+    const char *names[6] = {"W0", "b0", "W1", "b1", "W2", "b2"};
+    for (int t = 0; t < 6; ++t) {
+        bad += compare(names[t], pa[t], pb[t], sizes[t] * 4, true);
+        bad += compare("  adam v", va[t], vb[t], sizes[t] * 4, true);
+    }
+    printf("epoch: %s\n", bad == 0 ? "FUSED == LAUNCH-PER-KERNEL" : "MISMATCH");
+    fflush(stdout);
+    return bad == 0 ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
     setvbuf(stdout, nullptr, _IOLBF, 0);
-    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
+    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full|epoch [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
     if (argc > 2) g_pair = atoi(argv[2]);
     AC(ac_device_check());
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
@@ -312,6 +374,7 @@ int main(int argc, char **argv) {
     if (!strcmp(argv[1], "linear")) return run_linear();
     if (!strcmp(argv[1], "knn")) return run_knn();
     if (!strcmp(argv[1], "encoder")) return run_encoder("gemm_pair", 1);
+    if (!strcmp(argv[1], "epoch")) return run_epoch();
     if (!strcmp(argv[1], "defer")) return run_encoder("ln_defer", 1);          // production shape: CLS-only tail
     if (!strcmp(argv[1], "defer_full")) return run_encoder("ln_defer", 0);     // every layer through the deferred epilogues
     printf("unknown test %s\n", argv[1]);
