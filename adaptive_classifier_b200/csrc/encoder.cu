@@ -57,7 +57,9 @@ __device__ __forceinline__ float gelu_erf(float y) {
 //   DEFER: the A operand was the UN-normalised residual sum y (fp16) and the weights were packed as fp16(gamma * W):
 //       LayerNorm(y) W^T + b = r (acc - mu c1) + c0  with the row statistics (mu, r) of y, c1 = rowsum(W'), and
 //       `bias` holding c0 = W beta + b  (see "deferred LayerNorm" below and oracle/deferred_ln_study.py)
-template <int MODE, bool OUT_HALF, bool VT, bool DEFER = false>
+//   COLS:  accumulator columns one epilogue warp drains per tile (128 with 8 epilogue warps, 64 with 16): only the DEFER
+//          variant needs it, to know which chunk is the first of its slice
+template <int MODE, bool OUT_HALF, bool VT, bool DEFER = false, int COLS = GEMM_BLOCK_N / 2>
 struct EpiLinear {
     static_assert(!DEFER || (OUT_HALF && MODE != 2), "the deferred-LayerNorm consumer epilogues write fp16 operands");
     const float *__restrict__ bias;       // [N]   (DEFER: c0)
@@ -93,7 +95,7 @@ struct EpiLinear {
     // rows r8 + 8*i (i < 4) and the 16-byte column group c of each 16-column half.
     __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &ti, int row, int col0, int lane, int buf) const {
         if (DEFER) {
-            if (((col0 - ti.n0) & (GEMM_BLOCK_N / 2 - 1)) == 0) {      // first chunk of this warp's column half
+            if (((col0 - ti.n0) & (COLS - 1)) == 0) {                  // first chunk of this warp's column slice
                 const float2 ms = (row < M) ? __ldg(row_stats + row) : make_float2(0.f, 0.f);
                 st.mu = ms.x;
                 st.r = ms.y;
@@ -1092,6 +1094,17 @@ static int launch_linear(const CUtensorMap &ta, const CUtensorMap &tb, const CUt
 
 using EpiQKVDefer = EpiLinear<0, true, true, true>;     // r (acc - mu c1) + c0, fp16 out, V third transposed
 using EpiGeluDefer = EpiLinear<1, true, false, true>;   // GELU(r (acc - mu c1) + c0), fp16 out
+using EpiQKVDefer16 = EpiLinear<0, true, true, true, 64>;    // the same functors for 16 epilogue warps (64 columns per warp)
+using EpiGeluDefer16 = EpiLinear<1, true, false, true, 64>;
+
+// option "epi16" (bit 0: FFN1 = bias + GELU, bit 1: fused QKV): run that projection through the CTA-pair kernel with 16
+// epilogue warps instead of 8.  Opt-in, not yet run on hardware (the pair protocol itself is: profiles/r01_pair_*.log).
+template <class Epi, class Epi16>
+static int launch_linear_epi16(int bit, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tb_pair, int M, int N,
+                               int K, const Epi &epi, const Epi16 &epi16, cudaStream_t s) {
+    if (option(OPT_EPI16) & bit) return launch_gemm_tc2<Epi16, false, GEMM_KIND_F16, 16>(ta, tb_pair, M, N, K, epi16, s);
+    return launch_linear(ta, tb, tb_pair, M, N, K, epi, s);
+}
 
 // last layer, deferred flow: CLS rows of the attention context and of LN_pending(y) (two-pass statistics from the fp32 sums)
 __global__ void gather_cls_ln_kernel(const __half *__restrict__ ctx, const float *__restrict__ y, int B, int S, int H,
@@ -1125,7 +1138,8 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
     const float2 *st_in = e->stats_id;
     for (int l = 0; l < c.layers; ++l) {
         EpiQKVDefer eq{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
-        if ((rc = launch_linear(e->m_xh, e->m_wqkv_d[l], e->p_wqkv_d[l], M, 3 * H, H, eq, s))) return rc;
+        EpiQKVDefer16 eq16{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
+        if ((rc = launch_linear_epi16(2, e->m_xh, e->m_wqkv_d[l], e->p_wqkv_d[l], M, 3 * H, H, eq, eq16, s))) return rc;
         {
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
             if (S <= 128)
@@ -1168,7 +1182,8 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
         ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_b);
         AC_LAUNCH_CHECK();
         EpiGeluDefer e1{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
-        if ((rc = launch_linear(e->m_xh, e->m_w1_d[l], e->p_w1_d[l], M, I, H, e1, s))) return rc;
+        EpiGeluDefer16 e116{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
+        if ((rc = launch_linear_epi16(1, e->m_xh, e->m_w1_d[l], e->p_w1_d[l], M, I, H, e1, e116, s))) return rc;
         // FFN output projection + residual: y <- ffn W2^T + b2 + LN_attention_output(y)
         EpiResidDefer e2{e->b2[l], e->x, e->xh, e->stats_b, e->ln1w[l], e->ln1b[l], e->parts, pstride, M, H, H};
         if ((rc = launch_linear(e->m_ffn, e->m_w2[l], e->p_w2[l], M, H, I, e2, s))) return rc;
@@ -1231,7 +1246,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     if (option(OPT_LN_DEFER)) return encoder_layers_deferred(e, mask, B, S, S_pad, out_unit_cls, s);
     for (int l = 0; l < c.layers; ++l) {
         EpiQKV eq{e->bqkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H};
-        if ((rc = launch_linear(e->m_xh, e->m_wqkv[l], e->p_wqkv[l], M, 3 * H, H, eq, s))) return rc;
+        if ((rc = launch_linear_epi16(2, e->m_xh, e->m_wqkv[l], e->p_wqkv[l], M, 3 * H, H, eq, eq, s))) return rc;
         {
             // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
@@ -1270,7 +1285,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln1w[l], e->ln1b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
         EpiGelu e1{e->b1[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_linear(e->m_xh, e->m_w1[l], e->p_w1[l], M, I, H, e1, s))) return rc;
+        if ((rc = launch_linear_epi16(1, e->m_xh, e->m_w1[l], e->p_w1[l], M, I, H, e1, e1, s))) return rc;
         EpiResid e2{e->b2[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
         if ((rc = launch_linear(e->m_ffn, e->m_w2[l], e->p_w2[l], M, H, I, e2, s))) return rc;
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln2w[l], e->ln2b[l], c.ln_eps, M, H, e->x, e->xh);

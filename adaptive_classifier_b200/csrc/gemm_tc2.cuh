@@ -29,10 +29,13 @@ constexpr int GEMM2_A_STAGE_BYTES = GEMM_BLOCK_M * 128;                 // 16 KB
 constexpr int GEMM2_B_STAGE_BYTES = GEMM2_B_ROWS * 128;                 // 16 KB
 constexpr int GEMM2_STAGE_BYTES = GEMM2_A_STAGE_BYTES + GEMM2_B_STAGE_BYTES;
 constexpr int GEMM2_STAGES = 6;
-__host__ __device__ constexpr int gemm2_smem_bytes(int stages) {
-    return stages * GEMM2_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+__host__ __device__ constexpr int gemm2_smem_bytes(int stages, int epi_warps = GEMM_EPI_WARPS) {
+    return stages * GEMM2_STAGE_BYTES + epi_warps * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 }
+// 16 epilogue warps (4 per scheduler) for issue-bound epilogues such as bias + GELU: their staging tiles cost one stage
+__host__ __device__ constexpr int gemm2_stages_for(int epi_warps) { return epi_warps > 8 ? GEMM2_STAGES - 1 : GEMM2_STAGES; }
 static_assert(gemm2_smem_bytes(GEMM2_STAGES) <= 227 * 1024, "stage ring does not fit");
+static_assert(gemm2_smem_bytes(gemm2_stages_for(16), 16) <= 227 * 1024, "stage ring does not fit with 16 epilogue warps");
 static_assert(GEMM2_A_STAGE_BYTES == GEMM_A_STAGE_BYTES, "A stage layout is shared with the 1-CTA kernel");
 
 // wait sites, reported by the watchdog so that a broken protocol names the barrier that never completed
@@ -53,8 +56,12 @@ __device__ __forceinline__ void mbar_wait_guarded_cluster(uint64_t *bar, uint32_
 // kRelay = true : every CTA's loads complete on its OWN full barrier; an otherwise idle thread of the peer (warp 1) forwards
 //                 "my stage has landed" to the leader with a remote mbarrier arrive.  Same math, no dependence on the
 //                 cross-CTA completion path of the TMA unit; kept as the fallback / bisecting variant.
-template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kStages = GEMM2_STAGES, bool kRelay = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+// kEpiWarps = 8 (warp w drains lane quarter w%4, column half (w-2)/4) or 16 (column quarter (w-2)/4, 64 columns = 2 chunks):
+//                 the bias + GELU epilogue issues ~17 instructions per element; two warps per scheduler cannot hide its MUFU /
+//                 dependency latency behind a K = 768 mainloop (FFN1 measured 56 % tensor-pipe active), four can.
+template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kStages = GEMM2_STAGES, bool kRelay = false,
+          int kEpiWarps = GEMM_EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 int M, int N, int K, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
@@ -63,7 +70,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kStages * GEMM2_A_STAGE_BYTES;
     uint8_t *epi_stage = smem + kStages * GEMM2_STAGE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES);
+    static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps come in multiples of the 4 TMEM lane quarters");
+    constexpr int kColsPerWarp = GEMM_BLOCK_N / (kEpiWarps / 4);     // 128 or 64 accumulator columns per epilogue warp
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + kEpiWarps * GEMM_EPI_STAGE_BYTES);
     uint64_t *full_bar = bars;                      // [kStages]  used in the leader only (both CTAs' bytes land here)
     uint64_t *empty_bar = bars + kStages;           // [kStages]  one per CTA, multicast commit
     uint64_t *tmem_full = bars + 2 * kStages;       // [2]        one per CTA, multicast commit
@@ -92,8 +101,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 2 * GEMM_EPI_WARPS);
-        mbar_init(&tmem_empty[1], 2 * GEMM_EPI_WARPS);
+        mbar_init(&tmem_empty[0], 2 * kEpiWarps);
+        mbar_init(&tmem_empty[1], 2 * kEpiWarps);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -177,7 +186,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     } else {
         // ---------------- epilogue warps (both CTAs, this CTA's 128 rows) ----------------
         const int q = warp & 3;
-        const int chalf = (warp - 2) >> 2;
+        const int cpart = (warp - 2) >> 2;            // which kColsPerWarp-column slice of the accumulator this warp drains
         typename Epi::State est;
         epi.begin_cta(est, q, lane);
         int acc = 0;
@@ -189,15 +198,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ti.n0 = (kMFastest ? tile / tiles_m : tile % tiles_n) * GEMM_BLOCK_N;
             ti.tile_iter = it;
             const int row = ti.m0 + q * 32 + lane;
-            const int c_lo = chalf * (GEMM_BLOCK_N / 2);
+            const int c_lo = cpart * kColsPerWarp;
             epi.prefetch(est, ti, row, ti.n0 + c_lo, lane, 0);
             mbar_wait_guarded_cluster(&tmem_full[acc], acc_phase, PAIR_SITE_EPI_TMEM_FULL, acc);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BLOCK_N;
 #pragma unroll (Epi::kUnrollChunks)
-            for (int ci = 0; ci < GEMM_BLOCK_N / 2 / 32; ++ci) {
+            for (int ci = 0; ci < kColsPerWarp / 32; ++ci) {
                 const int c = c_lo + 32 * ci;
-                if (ci + 1 < GEMM_BLOCK_N / 2 / 32) epi.prefetch(est, ti, row, ti.n0 + c + 32, lane, (ci + 1) & 1);
+                if (ci + 1 < kColsPerWarp / 32) epi.prefetch(est, ti, row, ti.n0 + c + 32, lane, (ci + 1) & 1);
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
@@ -225,29 +234,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 }
 
 // host-side launcher.  tb must be a tensor map over B with a 128-row box (GEMM2_B_ROWS), ta the usual 128-row A box.
-template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32>
+template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kEpiWarps = GEMM_EPI_WARPS>
 int launch_gemm_tc2(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
                     cudaStream_t stream, int max_ctas = 0, int prof_cls = PROF_GEMM_LINEAR, double prof_bytes = 0.0) {
     static bool attr_set = false;   // per instantiation
-    constexpr int smem = gemm2_smem_bytes(GEMM2_STAGES);
+    constexpr int kStg = gemm2_stages_for(kEpiWarps);
+    constexpr int smem = gemm2_smem_bytes(kStg, kEpiWarps);
     if (!attr_set) {
-        AC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, kMFastest, kKind, GEMM2_STAGES, false>,
+        AC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, false, kEpiWarps>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        AC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, kMFastest, kKind, GEMM2_STAGES, true>,
+        AC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, true, kEpiWarps>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     // option value 2 selects the relay variant (see kRelay above)
     const bool relay = option(prof_cls == PROF_KNN_COARSE ? OPT_KNN_PAIR : OPT_GEMM_PAIR) == 2;
-    auto kern = relay ? gemm_tc2_kernel<Epi, kMFastest, kKind, GEMM2_STAGES, true>
-                      : gemm_tc2_kernel<Epi, kMFastest, kKind, GEMM2_STAGES, false>;
+    auto kern = relay ? gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, true, kEpiWarps>
+                      : gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, false, kEpiWarps>;
     const int tiles = ((M + GEMM2_PAIR_M - 1) / GEMM2_PAIR_M) * ((N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
     int clusters = sm_count() / 2;
     if (max_ctas > 0 && max_ctas / 2 < clusters) clusters = max_ctas / 2;
     if (tiles < clusters) clusters = tiles;
     if (clusters <= 0) return AC_OK;
     const int slot = prof_begin(prof_cls, 2.0 * M * static_cast<double>(N) * K, prof_bytes, stream);
-    kern<<<2 * clusters, GEMM_THREADS, smem, stream>>>(ta, tb, M, N, K, epi);
+    kern<<<2 * clusters, 64 + 32 * kEpiWarps, smem, stream>>>(ta, tb, M, N, K, epi);
     prof_end(slot, stream);
     AC_LAUNCH_CHECK();
     return AC_OK;

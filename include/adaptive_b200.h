@@ -52,6 +52,9 @@ int ac_device_check(void);            /* 0 when the current device is sm_100 (B2
  *   "head_fused" 1 : ac_head_train_epoch runs the whole epoch as ONE cooperative persistent kernel (the per-step kernels
  *                   become phases separated by grid barriers, same operation order) instead of ~21 launches per step.
  *                   NOT yet run on hardware.
+ *   "epi16"  bit 0 : the FFN1 projection (bias + GELU epilogue), bit 1 : the fused QKV projection run through the CTA-pair
+ *                   kernel with 16 epilogue warps instead of 8 (the GELU epilogue is issue-bound with two warps per
+ *                   scheduler).  Same arithmetic per element, so results must be bit-identical.  NOT yet run on hardware.
  * Unknown names return AC_E_INVALID. */
 int ac_set_option(const char *name, long long value);
 int ac_get_option(const char *name, long long *value);

@@ -29,7 +29,7 @@ def _encoder(cabi, sd, cfg, max_tokens, cls_only=True):
 
 
 def test_option_roundtrip(cabi):
-    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused"):
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16"):
         prev = cabi.get_option(name)          # 0 unless AC_OPTIONS preset it for this process
         with cabi.option(name, 1 - prev):
             assert cabi.get_option(name) == 1 - prev
@@ -91,6 +91,23 @@ def test_pair_encoder_bit_identical(cabi):
     ref = enc.forward_cls(ids).clone()
     with cabi.option("gemm_pair", 1):
         out = enc.forward_cls(ids).clone()
+    assert torch.equal(ref.view(torch.int32), out.view(torch.int32))
+    enc.close()
+
+
+@experimental
+@pytest.mark.parametrize("bits,defer", [(1, 0), (3, 0), (3, 1)])
+def test_epi16_encoder_bit_identical(cabi, bits, defer):
+    """16 epilogue warps on FFN1 (bit 0) / QKV (bit 1): per-element arithmetic is unchanged, so the CLS rows must match the
+    8-warp kernels bit for bit, with and without the deferred-LayerNorm flow"""
+    sd, cfg, _ = eo.make_bert_state_dict(1234, num_hidden_layers=2)
+    B, S = 24, 128
+    ids = eo.synthetic_ids(B, S).to(torch.int32).cuda()
+    enc = _encoder(cabi, sd, cfg, max_tokens=B * S)
+    with cabi.option("ln_defer", defer):
+        ref = enc.forward_cls(ids).clone()
+        with cabi.option("epi16", bits):
+            out = enc.forward_cls(ids).clone()
     assert torch.equal(ref.view(torch.int32), out.view(torch.int32))
     enc.close()
 
