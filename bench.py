@@ -356,7 +356,8 @@ def main():
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": G * B_PER_GPU, "seq_len": S, "prototypes": n_rows,
                    "parallelism": f"dp{G} encoder/head, prototype rows sharded x{G}",
-                   "l2": "inputs larger than L2 every step (3.07 GB prototype matrix / G, ~2 GB activations per step)"},
+                   "l2": "inputs larger than L2 every step (3.07 GB prototype matrix / G, ~2 GB activations per step)",
+                   "kernel_variants": os.environ.get("AC_OPTIONS", "") or "default"},
         "e2e": {"value": total_q / (ms_e2e / 1e3), "unit": "queries/s",
                 "h2d_bytes_per_step": B_PER_GPU * S * 4 * G, "d2h_bytes_per_step": B_PER_GPU * K_TOP * 8 * G,
                 "ms_per_step": ms_e2e / args.steps},
