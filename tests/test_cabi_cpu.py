@@ -57,3 +57,28 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/knn_oracle.c", "").replace("oracle/precision_study.py", "").replace("oracle/deferred_ln_study.py", ""), f   # comments citing the studies
+
+
+def test_options_roundtrip_without_a_gpu(cabi):
+    """ac_set_option / ac_get_option are host-only state: they work without a device; unknown names are rejected"""
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16"):
+        prev = cabi.get_option(name)
+        with cabi.option(name, prev + 2):
+            assert cabi.get_option(name) == prev + 2
+        assert cabi.get_option(name) == prev
+    with pytest.raises(cabi.AdaptiveB200Error):
+        cabi.set_option("not_an_option", 1)
+    with pytest.raises(cabi.AdaptiveB200Error):
+        cabi.get_option("not_an_option")
+
+
+def test_ac_options_environment_is_applied_on_load():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); from adaptive_classifier_b200 import _cabi; _cabi.load_library(); "
+            "print(_cabi.get_option('ln_defer'), _cabi.get_option('epi16'), _cabi.get_option('gemm_pair'))" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "AC_OPTIONS": "ln_defer=1,epi16=3"},
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert out.stdout.split() == ["1", "3", "0"]
+    bad = subprocess.run([sys.executable, "-c", code], env={**os.environ, "AC_OPTIONS": "bogus=1"}, capture_output=True, text=True, timeout=300)
+    assert bad.returncode != 0 and "bogus" in bad.stderr
