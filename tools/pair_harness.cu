@@ -224,34 +224,77 @@ __global__ void fill_affine(float *p, int64_t n, uint64_t seed, float base, floa
 
 // opt = "gemm_pair" (value g_pair; results must be bit-identical) or "ln_defer" (value 1; same math in a different
 // association order, so the check is a tolerance on the unit CLS rows: the north_star bound is 1e-3 on distances)
+struct EncoderWeightsOwner {
+    ac_encoder_weights w{};
+    std::vector<const float *> qw, qb, kw, kb, vw, vb, aow, aob, alw, alb, f1w, f1b, f2w, f2b, olw, olb;
+};
+// bert-base-shaped random weights; LayerNorm parameters away from (1, 0) so that the rank-1 corrections of the deferred
+// flow are exercised
+static void make_weights(EncoderWeightsOwner &o, int L, int H, int I, int V) {
+    auto mk = [&](size_t n, uint64_t seed, float scale) { float *p = dmalloc<float>(n); fill_f32<<<592, 256>>>(p, static_cast<int64_t>(n), seed, scale); return p; };
+    uint64_t lnseed = 5000;
+    auto mkc = [&](size_t n, float v) { float *p = dmalloc<float>(n); fill_affine<<<64, 256>>>(p, static_cast<int64_t>(n), ++lnseed, v, v == 0.f ? 0.2f : 0.3f); return p; };
+    ac_encoder_weights &w = o.w;
+    w.word_emb = mk(static_cast<size_t>(V) * H, 100, 0.035f); w.pos_emb = mk(512ull * H, 101, 0.035f); w.type_emb = mk(2ull * H, 102, 0.035f);
+    w.emb_ln_w = mkc(H, 1.f); w.emb_ln_b = mkc(H, 0.f);
+    for (auto *v : {&o.qw, &o.qb, &o.kw, &o.kb, &o.vw, &o.vb, &o.aow, &o.aob, &o.alw, &o.alb, &o.f1w, &o.f1b, &o.f2w, &o.f2b, &o.olw, &o.olb}) v->resize(L);
+    for (int l = 0; l < L; ++l) {
+        const uint64_t s = 1000 + 20 * l;
+        o.qw[l] = mk(static_cast<size_t>(H) * H, s + 0, 0.035f); o.qb[l] = mk(H, s + 1, 0.02f);
+        o.kw[l] = mk(static_cast<size_t>(H) * H, s + 2, 0.035f); o.kb[l] = mk(H, s + 3, 0.02f);
+        o.vw[l] = mk(static_cast<size_t>(H) * H, s + 4, 0.035f); o.vb[l] = mk(H, s + 5, 0.02f);
+        o.aow[l] = mk(static_cast<size_t>(H) * H, s + 6, 0.035f); o.aob[l] = mk(H, s + 7, 0.02f);
+        o.alw[l] = mkc(H, 1.f); o.alb[l] = mkc(H, 0.f);
+        o.f1w[l] = mk(static_cast<size_t>(I) * H, s + 8, 0.035f); o.f1b[l] = mk(I, s + 9, 0.02f);
+        o.f2w[l] = mk(static_cast<size_t>(H) * I, s + 10, 0.035f); o.f2b[l] = mk(H, s + 11, 0.02f);
+        o.olw[l] = mkc(H, 1.f); o.olb[l] = mkc(H, 0.f);
+    }
+    w.q_w = o.qw.data(); w.q_b = o.qb.data(); w.k_w = o.kw.data(); w.k_b = o.kb.data(); w.v_w = o.vw.data(); w.v_b = o.vb.data();
+    w.ao_w = o.aow.data(); w.ao_b = o.aob.data(); w.ao_ln_w = o.alw.data(); w.ao_ln_b = o.alb.data();
+    w.ff1_w = o.f1w.data(); w.ff1_b = o.f1b.data(); w.ff2_w = o.f2w.data(); w.ff2_b = o.f2b.data(); w.out_ln_w = o.olw.data(); w.out_ln_b = o.olb.data();
+    CK(cudaDeviceSynchronize());
+}
+
+// debugging aid for option "ln_defer": encoders of 1, 2, 3, 4 and 12 layers over the same weights, full hidden state of both
+// flows compared -> the first depth at which they part says which epilogue (or the statistics) is wrong
+static int run_defer_layers() {
+    const int H = 768, I = 3072, V = 30522, B = 16, S = 128, Lmax = 12;
+    EncoderWeightsOwner own;
+    make_weights(own, Lmax, H, I, V);
+    int32_t *ids = dmalloc<int32_t>(static_cast<size_t>(B) * S);
+    fill_ids<<<64, 256>>>(ids, static_cast<int64_t>(B) * S, S, V, 7);
+    const size_t nh = static_cast<size_t>(B) * S * H;
+    float *h0 = dmalloc<float>(nh), *h1 = dmalloc<float>(nh), *o = dmalloc<float>(static_cast<size_t>(B) * H);
+    int rc_all = 0;
+    for (int L : {1, 2, 3, 4, 12}) {
+        ac_encoder_config cfg{};
+        cfg.arch = AC_ARCH_BERT; cfg.layers = L; cfg.hidden = H; cfg.heads = 12; cfg.intermediate = I; cfg.vocab = V; cfg.max_pos = 512;
+        cfg.type_vocab = 2; cfg.pad_idx = 0; cfg.ln_eps = 1e-12f; cfg.precision = AC_PREC_F16; cfg.max_tokens = B * S; cfg.cls_only = 0;
+        ac_encoder *enc = nullptr;
+        AC(ac_encoder_create(&cfg, &own.w, &enc));
+        AC(ac_set_option("ln_defer", 0));
+        AC(ac_encoder_forward_cls(enc, ids, nullptr, nullptr, B, S, o, nullptr));
+        AC(ac_encoder_last_hidden(enc, h0, static_cast<int64_t>(nh), nullptr));
+        AC(ac_set_option("ln_defer", 1));
+        AC(ac_encoder_forward_cls(enc, ids, nullptr, nullptr, B, S, o, nullptr));
+        AC(ac_encoder_last_hidden(enc, h1, static_cast<int64_t>(nh), nullptr));
+        AC(ac_set_option("ln_defer", 0));
+        CK(cudaDeviceSynchronize());
+        printf("layers=%d ", L);
+        compare("hidden", h0, h1, nh * 4, true);       // LayerNorm outputs are O(1): expect max_abs_diff ~1e-3 or below
+        AC(ac_encoder_destroy(enc));
+    }
+    return rc_all;
+}
+
 static int run_encoder(const char *opt, int cls_only) {
     const bool exact = strcmp(opt, "ln_defer") != 0;       // pair / 16-epilogue-warp kernels: same arithmetic per element
     const int optval = !strcmp(opt, "gemm_pair") ? g_pair : (!strcmp(opt, "epi16") ? 3 : 1);
     const int L = 12, H = 768, I = 3072, V = 30522, B = 512, S = 128;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    auto mk = [&](size_t n, uint64_t seed, float scale) { float *p = dmalloc<float>(n); fill_f32<<<592, 256>>>(p, static_cast<int64_t>(n), seed, scale); return p; };
-    // LayerNorm parameters away from (1, 0) so that the rank-1 corrections of the deferred flow are exercised
-    uint64_t lnseed = 5000;
-    auto mkc = [&](size_t n, float v) { float *p = dmalloc<float>(n); fill_affine<<<64, 256>>>(p, static_cast<int64_t>(n), ++lnseed, v, v == 0.f ? 0.2f : 0.3f); return p; };
-    ac_encoder_weights w{};
-    w.word_emb = mk(static_cast<size_t>(V) * H, 100, 0.035f); w.pos_emb = mk(512ull * H, 101, 0.035f); w.type_emb = mk(2ull * H, 102, 0.035f);
-    w.emb_ln_w = mkc(H, 1.f); w.emb_ln_b = mkc(H, 0.f);
-    std::vector<const float *> qw(L), qb(L), kw(L), kb(L), vw(L), vb(L), aow(L), aob(L), alw(L), alb(L), f1w(L), f1b(L), f2w(L), f2b(L), olw(L), olb(L);
-    for (int l = 0; l < L; ++l) {
-        const uint64_t s = 1000 + 20 * l;
-        qw[l] = mk(static_cast<size_t>(H) * H, s + 0, 0.035f); qb[l] = mk(H, s + 1, 0.02f);
-        kw[l] = mk(static_cast<size_t>(H) * H, s + 2, 0.035f); kb[l] = mk(H, s + 3, 0.02f);
-        vw[l] = mk(static_cast<size_t>(H) * H, s + 4, 0.035f); vb[l] = mk(H, s + 5, 0.02f);
-        aow[l] = mk(static_cast<size_t>(H) * H, s + 6, 0.035f); aob[l] = mk(H, s + 7, 0.02f);
-        alw[l] = mkc(H, 1.f); alb[l] = mkc(H, 0.f);
-        f1w[l] = mk(static_cast<size_t>(I) * H, s + 8, 0.035f); f1b[l] = mk(I, s + 9, 0.02f);
-        f2w[l] = mk(static_cast<size_t>(H) * I, s + 10, 0.035f); f2b[l] = mk(H, s + 11, 0.02f);
-        olw[l] = mkc(H, 1.f); olb[l] = mkc(H, 0.f);
-    }
-    w.q_w = qw.data(); w.q_b = qb.data(); w.k_w = kw.data(); w.k_b = kb.data(); w.v_w = vw.data(); w.v_b = vb.data();
-    w.ao_w = aow.data(); w.ao_b = aob.data(); w.ao_ln_w = alw.data(); w.ao_ln_b = alb.data();
-    w.ff1_w = f1w.data(); w.ff1_b = f1b.data(); w.ff2_w = f2w.data(); w.ff2_b = f2b.data(); w.out_ln_w = olw.data(); w.out_ln_b = olb.data();
-    CK(cudaDeviceSynchronize());
+    EncoderWeightsOwner own;
+    make_weights(own, L, H, I, V);
+    ac_encoder_weights &w = own.w;
     ac_encoder_config cfg{};
     cfg.arch = AC_ARCH_BERT; cfg.layers = L; cfg.hidden = H; cfg.heads = 12; cfg.intermediate = I; cfg.vocab = V; cfg.max_pos = 512;
     cfg.type_vocab = 2; cfg.pad_idx = 0; cfg.ln_eps = 1e-12f; cfg.precision = AC_PREC_F16; cfg.max_tokens = B * S; cfg.cls_only = cls_only;
@@ -366,7 +409,7 @@ static int run_epoch() {
 
 int main(int argc, char **argv) {
     setvbuf(stdout, nullptr, _IOLBF, 0);
-    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full|epoch|epi16 [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
+    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full|defer_layers|epoch|epi16 [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
     if (argc > 2) g_pair = atoi(argv[2]);
     AC(ac_device_check());
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
@@ -375,6 +418,7 @@ int main(int argc, char **argv) {
     if (!strcmp(argv[1], "knn")) return run_knn();
     if (!strcmp(argv[1], "encoder")) return run_encoder("gemm_pair", 1);
     if (!strcmp(argv[1], "epoch")) return run_epoch();
+    if (!strcmp(argv[1], "defer_layers")) return run_defer_layers();
     if (!strcmp(argv[1], "epi16")) return run_encoder("epi16", 1);             // FFN1 + QKV with 16 epilogue warps
     if (!strcmp(argv[1], "defer")) return run_encoder("ln_defer", 1);          // production shape: CLS-only tail
     if (!strcmp(argv[1], "defer_full")) return run_encoder("ln_defer", 0);     // every layer through the deferred epilogues
