@@ -686,6 +686,206 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// pipelined attention (opt-in, option "attn_pipe"; S <= 128): the same arithmetic as attention_kernel, restructured as a
+// persistent, warp-specialised pipeline so that the load / QK^T of item i+1 overlap the softmax / PV / store of item i.
+//
+//   grid = 2 CTAs per SM, each walks (sequence, head) items i = blockIdx.x, += gridDim.x; two buffers b = i & 1, each
+//   48 KB of smem (Q | K -> later P, V^T) and 128 TMEM columns (scores -> later the output tile).
+//   warp 4, one thread : wait free[b] -> TMA Q, K, V^T (full[b]) -> QK^T MMAs -> commit s_ready[b] -> issue the loads of
+//                        item i+1 -> wait p_ready[b] -> PV MMAs -> commit o_ready[b]
+//   warps 0..3         : key mask -> wait s_ready[b] -> two-pass softmax out of TMEM, P -> smem -> arrive p_ready[b] ->
+//                        wait o_ready[b] -> O / rowsum -> ctx -> arrive free[b]
+// attention_kernel pays TMEM allocation, barrier setup and an exposed TMA round trip per (sequence, head) and measured
+// 111 us per layer against a 61 us traffic floor (403 MB of qk / vT / ctx).  Status: NOT yet run on hardware.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTP_THREADS = 160;
+constexpr int ATTP_BUF = 48 * 1024;
+constexpr int ATTP_SMEM = 2 * ATTP_BUF + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int ATTP_TMEM_COLS = 256;
+
+__global__ void __launch_bounds__(ATTP_THREADS)
+attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
+                      const int32_t *__restrict__ mask, int B, int S, int heads, int H, __half *__restrict__ ctx) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * ATTP_BUF);
+    uint64_t *full = bars, *s_ready = bars + 2, *p_ready = bars + 4, *o_ready = bars + 6, *free_ = bars + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int items = B * heads;
+    const int n_my = (items > static_cast<int>(blockIdx.x)) ? (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap_qk);
+        tma_prefetch_desc(&tmap_vt);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&s_ready[b], 1);
+            mbar_init(&p_ready[b], 4);      // one arrival per softmax warp
+            mbar_init(&o_ready[b], 1);
+            mbar_init(&free_[b], 4);        // one arrival per softmax warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, ATTP_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ---------------- producer + MMA issuer ----------------
+        if (lane == 0) {
+            auto load = [&](int it) {
+                const int b = it & 1;
+                const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+                const int bq = item / heads, h = item % heads;
+                uint8_t *buf = smem + b * ATTP_BUF;
+                mbar_wait_guarded(&free_[b], ((it >> 1) & 1) ^ 1);        // epilogue of item it-2 has released the buffer
+                mbar_arrive_expect_tx(&full[b], 48 * 1024);
+                const int r = bq * S;
+                tma_load_2d(buf, &tmap_qk, &full[b], h * 64, r);
+                tma_load_2d(buf + 16 * 1024, &tmap_qk, &full[b], H + h * 64, r);
+                const int vrow = (bq * heads + h) * 64;
+                tma_load_2d(buf + 32 * 1024, &tmap_vt, &full[b], 0, vrow);
+                tma_load_2d(buf + 40 * 1024, &tmap_vt, &full[b], 64, vrow);
+            };
+            constexpr uint32_t idesc_s = umma_idesc(0 /*f16*/, 128, 128);
+            constexpr uint32_t idesc_o = umma_idesc(0 /*f16*/, 128, 64);
+            if (n_my > 0) load(0);
+            for (int it = 0; it < n_my; ++it) {
+                const int b = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                uint8_t *buf = smem + b * ATTP_BUF;
+                const uint32_t d_tmem = tmem_base + b * 128;
+                mbar_wait_guarded(&full[b], ph);
+                tc_fence_after();
+                {
+                    const uint64_t a = umma_desc_sw128(smem_u32(buf));
+                    const uint64_t bd = umma_desc_sw128(smem_u32(buf + 16 * 1024));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a + 2 * k, bd + 2 * k, idesc_s, k != 0);
+                    tc_commit(&s_ready[b]);
+                }
+                if (it + 1 < n_my) load(it + 1);
+                mbar_wait_guarded(&p_ready[b], ph);
+                tc_fence_after();
+#pragma unroll
+                for (int slab = 0; slab < 2; ++slab) {
+                    const uint64_t a = umma_desc_sw128(smem_u32(buf + slab * 16384));
+                    const uint64_t bd = umma_desc_sw128(smem_u32(buf + 32 * 1024 + slab * 8192));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a + 2 * k, bd + 2 * k, idesc_o, (slab | k) != 0);
+                }
+                tc_commit(&o_ready[b]);
+            }
+        }
+    } else {
+        // ---------------- softmax / epilogue warps: thread = query row (TMEM lane) ----------------
+        const int qrow = warp * 32 + lane;
+        const float scale_log2 = rsqrtf(64.f) * 1.44269504088896340736f;
+        for (int it = 0; it < n_my; ++it) {
+            const int b = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int bq = item / heads, h = item % heads;
+            const int64_t row0 = static_cast<int64_t>(bq) * S;
+            const uint32_t t_s = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + b * 128;
+            uint32_t kmask[4];
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+                const int key = 32 * w4 + lane;
+                const bool ok = (key < S) && (!mask || mask[row0 + key] != 0);
+                kmask[w4] = __ballot_sync(0xffffffffu, ok);
+            }
+            mbar_wait_guarded(&s_ready[b], ph);
+            tc_fence_after();
+            float mx = -CUDART_INF_F;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_s + c, r);
+                tmem_ld_wait();
+                const uint32_t km = c == 0 ? kmask[0] : c == 32 ? kmask[1] : c == 64 ? kmask[2] : kmask[3];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if ((km >> j) & 1u) mx = fmaxf(mx, __uint_as_float(r[j]));
+            }
+            float sum = 0.f;
+            const uint32_t sp_base = smem_u32(smem + b * ATTP_BUF);
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_s + c, r);
+                tmem_ld_wait();
+                uint32_t pk[16];
+                const uint32_t km = c == 0 ? kmask[0] : c == 32 ? kmask[1] : c == 64 ? kmask[2] : kmask[3];
+                const float mxs = mx * scale_log2;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float e0 = ((km >> j) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2, -mxs)) : 0.f;
+                    const float e1 = ((km >> (j + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2, -mxs)) : 0.f;
+                    sum += e0 + e1;
+                    __half2 hh = __floats2half2_rn(e0, e1);
+                    pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
+                }
+                const uint32_t prow = sp_base + (c >> 6) * 16384 + (qrow >> 3) * 1024 + (qrow & 7) * 128;
+                const int ch0 = (c & 63) >> 3;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((ch0 + ch) ^ (qrow & 7)) << 4)),
+                                 "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]), "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
+                                 : "memory");
+                }
+            }
+            // P (generic-proxy smem writes) -> visible to the tensor-core proxy; this warp is done reading its score lanes
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[b]);
+
+            mbar_wait_guarded(&o_ready[b], ph);
+            tc_fence_after();
+            const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_s + c, r);
+                tmem_ld_wait();
+                if (qrow < S) {
+                    __half *dst = ctx + (row0 + qrow) * H + h * 64 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __half2 h0 = __floats2half2_rn(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+                        __half2 h1 = __floats2half2_rn(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+                        __half2 h2 = __floats2half2_rn(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+                        __half2 h3 = __floats2half2_rn(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                        *reinterpret_cast<uint4 *>(dst + j) = pk;
+                    }
+                }
+            }
+            // buffer b (smem + its TMEM columns) may be refilled: the item two ahead reuses it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&free_[b]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ATTP_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention for 128 < S <= 512: one CTA per (sequence, head, 128-query block), key blocks of 128 streamed twice.
 //   pass A  row max over all key blocks        (QK^T only)
 //   pass B  P = exp(scale*(s - max)) per block, O += P V_block accumulated in TMEM, row sums in registers
@@ -1142,7 +1342,10 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
         if ((rc = launch_linear_epi16(2, e->m_xh, e->m_wqkv_d[l], e->p_wqkv_d[l], M, 3 * H, H, eq, eq16, s))) return rc;
         {
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
-            if (S <= 128)
+            if (S <= 128 && option(OPT_ATTN_PIPE)) {
+                const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
+                attention_pipe_kernel<<<ctas, ATTP_THREADS, ATTP_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+            } else if (S <= 128)
                 attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
             else
                 attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(
@@ -1241,6 +1444,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     if (!att_attr) {
         AC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         AC_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTL_SMEM));
+        AC_CUDA(cudaFuncSetAttribute(attention_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTP_SMEM));
         att_attr = true;
     }
     if (option(OPT_LN_DEFER)) return encoder_layers_deferred(e, mask, B, S, S_pad, out_unit_cls, s);
@@ -1250,7 +1454,10 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
         {
             // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
-            if (S <= 128)
+            if (S <= 128 && option(OPT_ATTN_PIPE)) {
+                const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
+                attention_pipe_kernel<<<ctas, ATTP_THREADS, ATTP_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+            } else if (S <= 128)
                 attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
             else
                 attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(

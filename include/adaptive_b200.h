@@ -55,6 +55,9 @@ int ac_device_check(void);            /* 0 when the current device is sm_100 (B2
  *   "epi16"  bit 0 : the FFN1 projection (bias + GELU epilogue), bit 1 : the fused QKV projection run through the CTA-pair
  *                   kernel with 16 epilogue warps instead of 8 (the GELU epilogue is issue-bound with two warps per
  *                   scheduler).  Same arithmetic per element, so results must be bit-identical.  NOT yet run on hardware.
+ *   "attn_pipe" 1 : attention for S <= 128 runs as a persistent, warp-specialised pipeline (2 CTAs per SM, two smem / TMEM
+ *                   buffers: loads and QK^T of the next (sequence, head) overlap softmax / PV / store of the current one).
+ *                   Same arithmetic, so the context rows must be bit-identical.  NOT yet run on hardware.
  * Unknown names return AC_E_INVALID. */
 int ac_set_option(const char *name, long long value);
 int ac_get_option(const char *name, long long *value);

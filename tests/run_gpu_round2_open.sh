@@ -11,7 +11,7 @@ echo "=== 1. harness"; bash tools/run_pair_harness.sh > gpurun_out/harness.log 2
 echo "=== 2. pytest -m gpu with experimental variants"
 AC_TEST_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/ -q -m gpu --timeout 600 -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_experimental.log
 echo "=== 3. bench variants"
-for v in "" "ln_defer=1" "epi16=1" "epi16=3" "ln_defer=1,epi16=1" "gemm_pair=1,ln_defer=1,epi16=1"; do
+for v in "" "ln_defer=1" "epi16=1" "epi16=3" "attn_pipe=1" "ln_defer=1,epi16=1,attn_pipe=1" "gemm_pair=1,ln_defer=1,epi16=1,attn_pipe=1"; do
     name=$(echo "${v:-default}" | tr ',=' '__')
     AC_OPTIONS="$v" timeout 600 python bench.py --no-cpu-baseline 2> gpurun_out/bench_${name}.err | tee gpurun_out/bench_${name}.json | python -c "
 import json,sys
@@ -23,7 +23,7 @@ for v in "" "head_fused=1"; do
     AC_OPTIONS="$v" timeout 900 python tools/bench_add_examples.py --examples 5120 2>&1 | tail -1 | tee gpurun_out/bench_add_examples_${name}.json | cut -c1-420
 done
 echo "=== 5. ncu"
-AC_OPTIONS="ln_defer=1,epi16=1" timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r02_defer.csv \
+AC_OPTIONS="ln_defer=1,epi16=1,attn_pipe=1" timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r02_defer.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 AC_OPTIONS="ln_defer=1,epi16=1" timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 40 -c 8 -o gpurun_out/r02_gemm_defer \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1

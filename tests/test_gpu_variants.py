@@ -29,7 +29,7 @@ def _encoder(cabi, sd, cfg, max_tokens, cls_only=True):
 
 
 def test_option_roundtrip(cabi):
-    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16"):
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe"):
         prev = cabi.get_option(name)          # 0 unless AC_OPTIONS preset it for this process
         with cabi.option(name, 1 - prev):
             assert cabi.get_option(name) == 1 - prev
@@ -109,6 +109,31 @@ def test_epi16_encoder_bit_identical(cabi, bits, defer):
         with cabi.option("epi16", bits):
             out = enc.forward_cls(ids).clone()
     assert torch.equal(ref.view(torch.int32), out.view(torch.int32))
+    enc.close()
+
+
+@experimental
+@pytest.mark.parametrize("B,S,pad", [(24, 128, False), (5, 96, True), (300, 64, False), (3, 17, True)])
+def test_attn_pipe_encoder_bit_identical(cabi, B, S, pad):
+    """persistent pipelined attention: same arithmetic per (sequence, head), so the CLS rows and the full hidden state must
+    match attention_kernel bit for bit (B = 300: more items than CTAs, several items per CTA and both buffers in use)"""
+    sd, cfg, _ = eo.make_bert_state_dict(1234, num_hidden_layers=2)
+    ids = eo.synthetic_ids(B, S)
+    mask = torch.ones_like(ids)
+    if pad:
+        for b in range(B):
+            n = max(2, S - 1 - 2 * b)
+            mask[b, n:] = 0
+            ids[b, n:] = 0
+    ids, mask = ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()
+    enc = _encoder(cabi, sd, cfg, max_tokens=B * S, cls_only=False)
+    ref = enc.forward_cls(ids, mask).clone()
+    ref_h = enc.last_hidden(B, S).clone()
+    with cabi.option("attn_pipe", 1):
+        out = enc.forward_cls(ids, mask).clone()
+        out_h = enc.last_hidden(B, S).clone()
+    assert torch.equal(ref.view(torch.int32), out.view(torch.int32))
+    assert torch.equal(ref_h.view(torch.int32), out_h.view(torch.int32))
     enc.close()
 
 
