@@ -26,6 +26,7 @@ AC_PREC_TF32, AC_PREC_F16 = 0, 1
 
 EXPORTS = [
     "ac_version", "ac_last_error", "ac_device_check", "ac_set_option", "ac_get_option",
+    "ac_peer_scatter", "ac_peer_wait", "ac_encoder_forward_cls_scatter",
     "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
     "ac_segment_mean",
     "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch_workspace_bytes", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",
@@ -38,6 +39,14 @@ EXPORTS = [
 
 class AdaptiveB200Error(RuntimeError):
     pass
+
+
+AC_MAX_PEERS = 16
+
+
+class PeerTable(Structure):
+    """ac_peer_table: NVLink-mapped base pointers of every rank's exchange buffer and of its flag array (one channel)."""
+    _fields_ = [("world", c_int), ("rank", c_int), ("buf", c_void_p * AC_MAX_PEERS), ("flag", c_void_p * AC_MAX_PEERS)]
 
 
 class HeadParams(Structure):
@@ -126,6 +135,10 @@ def load_library() -> ctypes.CDLL:
     L.ac_pipeline_predict_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_pipeline_debug_copy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ac_profile_enable.argtypes = [c_int]
+    L.ac_peer_scatter.argtypes = [c_void_p, c_size_t, c_int, POINTER(PeerTable), c_size_t, ctypes.c_uint32, c_void_p, c_void_p]
+    L.ac_peer_wait.argtypes = [c_void_p, c_int, ctypes.c_uint32, c_void_p]
+    L.ac_encoder_forward_cls_scatter.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, POINTER(PeerTable),
+                                                 c_size_t, ctypes.c_uint32, c_void_p, c_void_p]
     L.ac_set_option.argtypes = [c_char_p, ctypes.c_longlong]
     L.ac_get_option.argtypes = [c_char_p, POINTER(ctypes.c_longlong)]
     L.ac_profile_read.argtypes = [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
@@ -485,6 +498,20 @@ class Encoder:
                                              out.data_ptr(), stream_ptr()), "ac_encoder_forward_cls")
         return out
 
+    def forward_cls_scatter(self, ids: torch.Tensor, table: "PeerTable", dst_offset: int, seq: int, counter: torch.Tensor,
+                            mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """forward_cls whose final kernel also stores the unit CLS rows into every peer's exchange buffer (peer.cu)."""
+        assert ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous()
+        B, S = ids.shape
+        if out is None:
+            out = torch.empty((B, self.hidden), dtype=torch.float32, device=ids.device)
+        if mask is not None:
+            mask = mask.to(torch.int32).contiguous()
+        check(self._L.ac_encoder_forward_cls_scatter(self.handle, ids.data_ptr(), ptr(mask), None, B, S, out.data_ptr(),
+                                                     ctypes.byref(table), dst_offset, seq & 0xFFFFFFFF, counter.data_ptr(),
+                                                     stream_ptr()), "ac_encoder_forward_cls_scatter")
+        return out
+
     def last_hidden(self, B: int, S: int) -> torch.Tensor:
         out = torch.empty((B * S, self.hidden), dtype=torch.float32, device="cuda")
         check(self._L.ac_encoder_last_hidden(self.handle, out.data_ptr(), out.numel(), stream_ptr()),
@@ -541,6 +568,26 @@ def blend_topk(p_cls, p_score, h_idx, h_val, k: int, w_proto: float = 0.7, w_hea
     check(L.ac_blend_topk(p_cls.data_ptr(), p_score.data_ptr(), ptr(h_idx), ptr(neg), B, k, kh, w_proto, w_head,
                           out_cls.data_ptr(), out_sc.data_ptr(), stream_ptr()), "ac_blend_topk")
     return out_cls, out_sc
+
+
+def peer_table(world: int, rank: int, buf_ptrs, flag_ptrs) -> PeerTable:
+    assert world <= AC_MAX_PEERS and len(buf_ptrs) == world and len(flag_ptrs) == world
+    t = PeerTable()
+    t.world, t.rank = world, rank
+    for p in range(world):
+        t.buf[p] = int(buf_ptrs[p])
+        t.flag[p] = int(flag_ptrs[p])
+    return t
+
+
+def peer_scatter(src: torch.Tensor, bytes_per_dst: int, blocks_mode: bool, table: PeerTable, dst_offset: int, seq: int,
+                 counter: torch.Tensor) -> None:
+    check(load_library().ac_peer_scatter(src.data_ptr(), bytes_per_dst, 1 if blocks_mode else 0, ctypes.byref(table), dst_offset,
+                                         seq & 0xFFFFFFFF, counter.data_ptr(), stream_ptr()), "ac_peer_scatter")
+
+
+def peer_wait(flags_local_ptr: int, n_flags: int, seq: int) -> None:
+    check(load_library().ac_peer_wait(flags_local_ptr, n_flags, seq & 0xFFFFFFFF, stream_ptr()), "ac_peer_wait")
 
 
 def set_option(name: str, value: int) -> None:

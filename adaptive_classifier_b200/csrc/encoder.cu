@@ -15,6 +15,7 @@
 //                 tile / output tile in TMEM, thread-per-query-row softmax in between (S <= 128, head_dim 64)
 //   LayerNorm     fp32 residual stream + the fp16 operand copy for the next GEMM
 #include "gemm_tc2.cuh"
+#include "peer.cuh"
 #include <cuda_fp16.h>
 #include <math_constants.h>
 #include <vector>
@@ -486,6 +487,27 @@ __global__ void cls_normalize_kernel(const float *__restrict__ x, int B, int S, 
     for (int i = lane; i < H; i += 32) s = fmaf(src[i], src[i], s);
     const float nrm = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
     for (int i = lane; i < H; i += 32) out[static_cast<int64_t>(bq) * H + i] = src[i] / nrm;
+}
+
+// the same, additionally storing the row into every peer's exchange buffer (NVLink-mapped pointers) and publishing the
+// sequence number once the whole grid has stored: the all-gather of the embeddings for the row-sharded search (peer.cu)
+__global__ void cls_normalize_scatter_kernel(const float *__restrict__ x, int B, int S, int H, float *__restrict__ out,
+                                             ac_peer_table t, size_t dst_off, uint32_t seq, unsigned int *counter) {
+    const int bq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (bq < B) {
+        const float *src = x + static_cast<int64_t>(bq) * S * H;
+        float sq = 0.f;
+        for (int i = lane; i < H; i += 32) sq = fmaf(src[i], src[i], sq);
+        const float nrm = fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+        for (int i = lane; i < H; i += 32) {
+            const float v = src[i] / nrm;
+            out[static_cast<int64_t>(bq) * H + i] = v;
+            for (int p = 0; p < t.world; ++p)
+                reinterpret_cast<float *>(static_cast<uint8_t *>(t.buf[p]) + dst_off)[static_cast<int64_t>(bq) * H + i] = v;
+        }
+    }
+    peer_publish_when_grid_done(t, seq, counter);
 }
 
 // last layer: only the CLS row of every sequence is needed downstream of attention (classifier.py:1272), so the
@@ -1110,7 +1132,25 @@ struct ac_encoder {
     int last_B = 0, last_S = 0;
     bool last_cls_only = false;
     const float *last_hidden = nullptr;   // where the previous full forward left the last hidden state
+    // set for the duration of ac_encoder_forward_cls_scatter: the final normalise kernel also stores to the peers
+    bool sink_on = false;
+    ac_peer_table sink_table;
+    size_t sink_off = 0;
+    uint32_t sink_seq = 0;
+    unsigned int *sink_counter = nullptr;
 };
+
+// final kernel of every forward variant: unit CLS rows, optionally scattered to the peers
+static int launch_cls_normalize(ac_encoder *e, const float *x, int B, int S, int H, float *out, cudaStream_t s) {
+    const int wpb = 8;
+    if (e->sink_on)
+        cls_normalize_scatter_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, B, S, H, out, e->sink_table, e->sink_off, e->sink_seq,
+                                                                          e->sink_counter);
+    else
+        cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, B, S, H, out);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
 
 template <class T>
 static int dev_alloc(ac_encoder *e, T **p, size_t elems) {
@@ -1372,8 +1412,7 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
             if ((rc = launch_linear(e->m_ffn_cls, e->m_w2[l], e->p_w2[l], B, H, I, e2, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
             AC_LAUNCH_CHECK();
-            cls_normalize_kernel<<<cb, wpb * 32, 0, s>>>(e->x_cls, B, 1, H, out_unit_cls);
-            AC_LAUNCH_CHECK();
+            if ((rc = launch_cls_normalize(e, e->x_cls, B, 1, H, out_unit_cls, s))) return rc;
             e->last_B = B;
             e->last_S = S;
             e->last_cls_only = true;
@@ -1400,8 +1439,7 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
     const int row_blocks = (M + wpb - 1) / wpb;
     layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->x, pg, pb, c.ln_eps, M, H, e->tmp, nullptr);
     AC_LAUNCH_CHECK();
-    cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(e->tmp, B, S, H, out_unit_cls);
-    AC_LAUNCH_CHECK();
+    if ((rc = launch_cls_normalize(e, e->tmp, B, S, H, out_unit_cls, s))) return rc;
     e->last_B = B;
     e->last_S = S;
     e->last_cls_only = false;
@@ -1480,8 +1518,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             if ((rc = launch_linear(e->m_ffn_cls, e->m_w2[l], e->p_w2[l], B, H, I, e2, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
             AC_LAUNCH_CHECK();
-            cls_normalize_kernel<<<cb, wpb * 32, 0, s>>>(e->x_cls, B, 1, H, out_unit_cls);
-            AC_LAUNCH_CHECK();
+            if ((rc = launch_cls_normalize(e, e->x_cls, B, 1, H, out_unit_cls, s))) return rc;
             e->last_B = B;
             e->last_S = S;
             e->last_cls_only = true;
@@ -1498,13 +1535,30 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
         layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln2w[l], e->ln2b[l], c.ln_eps, M, H, e->x, e->xh);
         AC_LAUNCH_CHECK();
     }
-    cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(e->x, B, S, H, out_unit_cls);
-    AC_LAUNCH_CHECK();
+    if ((rc = launch_cls_normalize(e, e->x, B, S, H, out_unit_cls, s))) return rc;
     e->last_B = B;
     e->last_S = S;
     e->last_cls_only = false;
     e->last_hidden = e->x;
     return AC_OK;
+}
+
+extern "C" int ac_encoder_forward_cls_scatter(ac_encoder *e, const int32_t *ids, const int32_t *mask, const int32_t *type_ids, int B,
+                                              int S, float *out_unit_cls, const void *peer_table, size_t dst_offset_bytes,
+                                              uint32_t seq, uint32_t *counter, ac_stream_t stream) {
+    const ac_peer_table *t = static_cast<const ac_peer_table *>(peer_table);
+    AC_REQUIRE(e && t && counter, "ac_encoder_forward_cls_scatter: null argument");
+    AC_REQUIRE(t->world >= 1 && t->world <= AC_MAX_PEERS && t->rank >= 0 && t->rank < t->world && dst_offset_bytes % 16 == 0,
+               "ac_encoder_forward_cls_scatter: bad peer table");
+    for (int p = 0; p < t->world; ++p) AC_REQUIRE(t->buf[p] && t->flag[p], "ac_encoder_forward_cls_scatter: null peer pointer %d", p);
+    e->sink_on = true;
+    e->sink_table = *t;
+    e->sink_off = dst_offset_bytes;
+    e->sink_seq = seq;
+    e->sink_counter = counter;
+    const int rc = ac_encoder_forward_cls(e, ids, mask, type_ids, B, S, out_unit_cls, stream);
+    e->sink_on = false;
+    return rc;
 }
 
 extern "C" int ac_encoder_last_hidden(ac_encoder *e, float *out, int64_t n_floats, ac_stream_t stream) {

@@ -275,13 +275,33 @@ def main():
         def step_host():
             return pipe.predict_host(ids_host)
     else:
-        index = ShardedIndex(P, lo, search=lambda Q_, P_, k_, off_: _cabi.knn_l2_topk(Q_, P_, k_, p_sqnorm=p_sqnorm, p_half=p_half, row_offset=off_))
+        search = lambda Q_, P_, k_, off_: _cabi.knn_l2_topk(Q_, P_, k_, p_sqnorm=p_sqnorm, p_half=p_half, row_offset=off_)
+        index = ShardedIndex(P, lo, search=search)
+        # AC_EXCHANGE=peer: the embeddings all-gather and the candidate all-to-all become stores into NVLink-mapped peer
+        # buffers (csrc/peer.cu) instead of NCCL collectives; checked against the NCCL path on the first batch
+        peer = None
+        if os.environ.get("AC_EXCHANGE", "nccl") == "peer":
+            from adaptive_classifier_b200.parallel import PeerExchange
+            peer = PeerExchange(B_PER_GPU, D, K_TOP, device=dev)
+            index_peer = ShardedIndex(P, lo, search=search, exchange=peer)
+            emb0 = enc.forward_cls(ids_dev)
+            d_n, i_n = index.search_local_queries(emb0, K_TOP)
+            d_p, i_p = index_peer.search_local_queries(emb0, K_TOP)
+            torch.cuda.synchronize()
+            if not (torch.equal(d_n, d_p) and torch.equal(i_n, i_p)):
+                raise SystemExit("bench.py: peer-memory exchange disagrees with the NCCL exchange")
         out_cls_host = torch.empty((B_PER_GPU, K_TOP), dtype=torch.int32).pin_memory()
         out_sc_host = torch.empty((B_PER_GPU, K_TOP), dtype=torch.float32).pin_memory()
 
         def step_device(ids=None):
-            emb = enc.forward_cls(ids_dev if ids is None else ids)
-            d, i = index.search_local_queries(emb, K_TOP)
+            if peer is not None:
+                seq, par = peer.next_step()
+                emb = enc.forward_cls_scatter(ids_dev if ids is None else ids, peer.tables[0],
+                                              peer.q_off(par) + rank * B_PER_GPU * D * 4, seq, peer.counter[0:1])
+                d, i = index_peer._search_peer(emb, K_TOP, step=(seq, par), already_scattered=True)
+            else:
+                emb = enc.forward_cls(ids_dev if ids is None else ids)
+                d, i = index.search_local_queries(emb, K_TOP)
             pc, ps = _cabi.proto_class_scores(d, i, row_class)
             probs = _cabi.head_forward(emb, hp, _cabi.AC_ACT_SOFTMAX)
             hv, hi_ = _cabi.topk_desc(probs, K_TOP)
@@ -356,6 +376,7 @@ def main():
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": G * B_PER_GPU, "seq_len": S, "prototypes": n_rows,
                    "parallelism": f"dp{G} encoder/head, prototype rows sharded x{G}",
+                   "exchange": os.environ.get("AC_EXCHANGE", "nccl") if G > 1 else "none",
                    "l2": "inputs larger than L2 every step (3.07 GB prototype matrix / G, ~2 GB activations per step)",
                    "kernel_variants": os.environ.get("AC_OPTIONS", "") or "default"},
         "e2e": {"value": total_q / (ms_e2e / 1e3), "unit": "queries/s",

@@ -223,6 +223,13 @@ int ac_encoder_forward_cls(ac_encoder *enc, const int32_t *ids, const int32_t *m
                            const int32_t *type_ids, int B, int S, float *out_unit_cls,
                            ac_stream_t stream);
 
+/* ac_encoder_forward_cls whose last kernel also stores the unit CLS rows [B,H] at (buf[p] + dst_offset_bytes) of every
+ * peer and then publishes seq in flag[p][rank] (see "Peer-memory exchange" below): the all-gather of the embeddings of the
+ * row-sharded search costs no kernel of its own.  out_unit_cls (local copy) is still written. */
+int ac_encoder_forward_cls_scatter(ac_encoder *enc, const int32_t *ids, const int32_t *mask, const int32_t *type_ids,
+                                   int B, int S, float *out_unit_cls, const void *peer_table /* ac_peer_table* */,
+                                   size_t dst_offset_bytes, uint32_t seq, uint32_t *counter, ac_stream_t stream);
+
 /* debugging / parity: copy the full last hidden state [B*S,H] of the previous forward */
 int ac_encoder_last_hidden(ac_encoder *enc, float *out, int64_t n_floats, ac_stream_t stream);
 
@@ -271,6 +278,28 @@ int ac_pipeline_predict_host(ac_pipeline *pl, const int32_t *ids_host, int B, in
 /* parity tests: copy the last call's unit CLS rows [B,D] and kNN result [B,k] into caller device buffers */
 int ac_pipeline_debug_copy(ac_pipeline *pl, int B, float *emb_out, float *knn_d_out, int64_t *knn_i_out,
                            ac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-memory exchange for the row-sharded index (new; the reference is single-process).
+ * The caller maps every rank's exchange buffer into this process (torch symmetric memory / CUDA IPC: plumbing) and passes
+ * the G base pointers plus G pointers to each rank's flag array of this channel (world uint32 each, zero-initialised).
+ * All ranks use the same layout, so one offset addresses the same slot on every peer.
+ * ------------------------------------------------------------------------------------------ */
+#define AC_MAX_PEERS 16
+typedef struct {
+    int world, rank;
+    void *buf[AC_MAX_PEERS];        /* buf[p]  = base of rank p's exchange buffer as mapped here (buf[rank] = local) */
+    uint32_t *flag[AC_MAX_PEERS];   /* flag[p] = rank p's flag array of this channel; this rank writes flag[p][rank]   */
+} ac_peer_table;
+
+/* blocks_mode 0: the bytes_per_dst bytes at src go to (buf[p] + dst_offset_bytes) of EVERY p (all-gather of embeddings);
+ * blocks_mode 1: block p of src (blocks of bytes_per_dst bytes, contiguous) goes to (buf[p] + dst_offset_bytes)
+ *                (all-to-all of per-shard candidates).  When the whole grid has stored, flag[p][rank] = seq for every p.
+ * counter: one zero-initialised device uint32 per stream (scratch of the "last block" detection). */
+int ac_peer_scatter(const void *src, size_t bytes_per_dst, int blocks_mode, const ac_peer_table *t,
+                    size_t dst_offset_bytes, uint32_t seq, uint32_t *counter, ac_stream_t stream);
+/* returns (in stream order) once flags_local[0..n_flags) have all reached seq; traps after a few seconds otherwise */
+int ac_peer_wait(const uint32_t *flags_local, int n_flags, uint32_t seq, ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): number of kernels launched by this library so far, and optional
