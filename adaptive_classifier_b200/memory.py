@@ -166,16 +166,38 @@ class PrototypeMemory:
             else:
                 self.just_rebuilt = False
 
+    def _class_rows_device(self, label: str) -> torch.Tensor:
+        """[n_c, D] device copy of the class's retained examples, in example order.  With config['b200_cache_rows'] the copy
+        is kept between calls and only the examples appended since are uploaded (the restacking
+        of all retained rows per call is O(n^2) over a continual loop); any reordering / shrinking (pruning, clear, load)
+        drops the cache.  The rows and their order are the same either way, so the means are the same bits."""
+        exs = self.examples[label]
+        if not self.config.config.get("b200_cache_rows", False):
+            return torch.stack([e.embedding.reshape(-1).float() for e in exs]).to(_device())
+        cache = self.__dict__.setdefault("_row_cache", {})
+        have = cache.get(label)
+        n_have = have[0].shape[0] if have is not None else 0
+        # the cache is valid only if it is a prefix of the current list: compare the identity of the cached examples
+        if have is None or n_have > len(exs) or have[1] != [id(e) for e in exs[:n_have]]:
+            have, n_have = None, 0
+        if n_have < len(exs):
+            tail = torch.stack([e.embedding.reshape(-1).float() for e in exs[n_have:]]).to(_device())
+            rows = tail if have is None else torch.cat([have[0], tail], 0)
+            cache[label] = (rows, [id(e) for e in exs])
+            return rows
+        return have[0]
+
     def _update_prototypes_device(self, labels: List[str]):
-        rows, cls = [], []
+        parts, cls = [], []
         for ci, l in enumerate(labels):
-            for ex in self.examples[l]:
-                rows.append(ex.embedding)
-                cls.append(ci)
-        if not rows:
+            if self.examples[l]:
+                rows = self._class_rows_device(l)
+                parts.append(rows)
+                cls.append(torch.full((rows.shape[0],), ci, dtype=torch.int32, device=rows.device))
+        if not parts:
             return
-        X = torch.stack([r.reshape(-1).float() for r in rows]).to(_device())
-        mean, _ = _cabi.segment_mean(X, torch.tensor(cls, dtype=torch.int32, device=X.device), len(labels))
+        X = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+        mean, _ = _cabi.segment_mean(X, cls[0] if len(cls) == 1 else torch.cat(cls, 0), len(labels))
         mean = mean.cpu()
         for ci, l in enumerate(labels):
             self.prototypes[l] = mean[ci].clone()
@@ -269,6 +291,7 @@ class PrototypeMemory:
 
     @_locked
     def clear(self):
+        self.__dict__.pop("_row_cache", None)
         self.examples.clear()
         self.prototypes.clear()
         self.index = FlatL2Index(self.embedding_dim)

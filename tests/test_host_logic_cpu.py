@@ -116,3 +116,49 @@ def test_bench_reference_arm_prints_the_contract_line():
     out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                            "--rows", "3000"], capture_output=True, text=True, env=env, timeout=120)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+def test_prototype_row_cache_matches_restacking(monkeypatch):
+    """with config['b200_cache_rows'] the per-class device rows are kept between calls and only new
+    examples are uploaded; prototypes, pruning and bookkeeping must be exactly what the restacking path produces.  The two
+    device entry points are replaced by torch-CPU stand-ins here (host logic only)."""
+    import torch
+    import adaptive_classifier_b200 as acb
+    from adaptive_classifier_b200 import memory as mem_mod
+
+    def segment_mean(X, cls, C):
+        mean = torch.zeros((C, X.shape[1]), dtype=torch.float32)
+        cnt = torch.zeros((C,), dtype=torch.int32)
+        for c in range(C):
+            rows = X[cls == c]
+            cnt[c] = rows.shape[0]
+            if rows.shape[0]:
+                mean[c] = rows.sum(0) / rows.shape[0]
+        return mean, cnt
+
+    monkeypatch.setattr(mem_mod, "_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(mem_mod._cabi, "segment_mean", segment_mean)
+    D = 16
+    g = torch.Generator().manual_seed(0)
+    mems = []
+    for cached in (False, True):
+        cfg = acb.ModelConfig({"max_examples_per_class": 12, "prototype_update_frequency": 7, "b200_cache_rows": cached})
+        mems.append(acb.PrototypeMemory(D, config=cfg))
+    labels_pool = ["a", "b", "c"]
+    for call in range(14):
+        n = int(torch.randint(1, 6, (1,), generator=g))
+        labs = [labels_pool[int(torch.randint(0, 3, (1,), generator=g))] for _ in range(n)]
+        embs = [torch.nn.functional.normalize(torch.randn(D, generator=g), dim=0) for _ in range(n)]
+        for m in mems:
+            m.add_examples_batch([acb.Example(f"t{call}_{i}", l, e.clone()) for i, (l, e) in enumerate(zip(labs, embs))], labs)
+        a, b = mems
+        assert a.get_stats() == b.get_stats()
+        assert set(a.prototypes) == set(b.prototypes)
+        for l in a.prototypes:
+            assert torch.equal(a.prototypes[l], b.prototypes[l]), (call, l)
+            assert [e.text for e in a.examples[l]] == [e.text for e in b.examples[l]]
+        assert a.label_to_index == b.label_to_index
+    # classes went through pruning (cap 12) during the loop, and the cache survived it
+    assert max(len(v) for v in mems[1].examples.values()) == 12
+    mems[1].clear()
+    assert "_row_cache" not in mems[1].__dict__
