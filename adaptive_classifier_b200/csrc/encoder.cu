@@ -329,6 +329,8 @@ struct EpiResidDefer {
 // (sum, sumsq) partials of every 128-column part -> (mu, 1/sqrt(var + eps)) per row; parts are added in a fixed order
 __global__ void ln_stats_kernel(const float2 *__restrict__ parts, int nparts, int64_t part_stride, int rows, int H, float eps,
                                 float2 *__restrict__ stats) {
+    griddep_launch_dependents();      // option "pdl": no-ops in an ordinary launch
+    griddep_wait();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     float s = 0.f, q = 0.f;
@@ -758,6 +760,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();      // option "pdl" (persistent single-wave kernel): no-ops in an ordinary launch
+    griddep_wait();
 
     if (warp == 4) {
         // ---------------- producer + MMA issuer ----------------
@@ -1384,7 +1388,8 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
             if (S <= 128 && option(OPT_ATTN_PIPE)) {
                 const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
-                attention_pipe_kernel<<<ctas, ATTP_THREADS, ATTP_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+                AC_CUDA(launch_maybe_pdl(attention_pipe_kernel, dim3(ctas), dim3(ATTP_THREADS), ATTP_SMEM, s, option(OPT_PDL) != 0,
+                                         e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx));
             } else if (S <= 128)
                 attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
             else
@@ -1421,7 +1426,8 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
         // attention output projection + residual: y <- ctx Wo^T + bo + LN_pending(y); statistics of the new sums
         EpiResidDefer eo{e->bo[l], e->x, e->xh, st_in, pg, pb, e->parts, pstride, M, H, H};
         if ((rc = launch_linear(e->m_ctx, e->m_wo[l], e->p_wo[l], M, H, H, eo, s))) return rc;
-        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_b);
+        AC_CUDA(launch_maybe_pdl(ln_stats_kernel, dim3((M + 255) / 256), dim3(256), 0, s, option(OPT_PDL) != 0,
+                                 static_cast<const float2 *>(e->parts), nparts, pstride, M, H, c.ln_eps, e->stats_b));
         AC_LAUNCH_CHECK();
         EpiGeluDefer e1{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
         EpiGeluDefer16 e116{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
@@ -1429,7 +1435,8 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
         // FFN output projection + residual: y <- ffn W2^T + b2 + LN_attention_output(y)
         EpiResidDefer e2{e->b2[l], e->x, e->xh, e->stats_b, e->ln1w[l], e->ln1b[l], e->parts, pstride, M, H, H};
         if ((rc = launch_linear(e->m_ffn, e->m_w2[l], e->p_w2[l], M, H, I, e2, s))) return rc;
-        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_a);
+        AC_CUDA(launch_maybe_pdl(ln_stats_kernel, dim3((M + 255) / 256), dim3(256), 0, s, option(OPT_PDL) != 0,
+                                 static_cast<const float2 *>(e->parts), nparts, pstride, M, H, c.ln_eps, e->stats_a));
         AC_LAUNCH_CHECK();
         pg = e->ln2w[l];
         pb = e->ln2b[l];
@@ -1494,7 +1501,8 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
             if (S <= 128 && option(OPT_ATTN_PIPE)) {
                 const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
-                attention_pipe_kernel<<<ctas, ATTP_THREADS, ATTP_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+                AC_CUDA(launch_maybe_pdl(attention_pipe_kernel, dim3(ctas), dim3(ATTP_THREADS), ATTP_SMEM, s, option(OPT_PDL) != 0,
+                                         e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx));
             } else if (S <= 128)
                 attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
             else

@@ -114,6 +114,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     cluster_sync_all();       // barriers of both CTAs are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch (option "pdl"): let the next kernel's CTAs take this SM as soon as this CTA exits, and do
+    // not touch global memory before the previous kernel has completed (both are no-ops in an ordinary launch)
+    griddep_launch_dependents();
+    griddep_wait();
 
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------
@@ -257,7 +261,7 @@ int launch_gemm_tc2(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, 
     if (tiles < clusters) clusters = tiles;
     if (clusters <= 0) return AC_OK;
     const int slot = prof_begin(prof_cls, 2.0 * M * static_cast<double>(N) * K, prof_bytes, stream);
-    kern<<<2 * clusters, 64 + 32 * kEpiWarps, smem, stream>>>(ta, tb, M, N, K, epi);
+    AC_CUDA(launch_maybe_pdl(kern, dim3(2 * clusters), dim3(64 + 32 * kEpiWarps), smem, stream, option(OPT_PDL) != 0, ta, tb, M, N, K, epi));
     prof_end(slot, stream);
     AC_LAUNCH_CHECK();
     return AC_OK;

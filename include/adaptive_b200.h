@@ -58,6 +58,9 @@ int ac_device_check(void);            /* 0 when the current device is sm_100 (B2
  *   "attn_pipe" 1 : attention for S <= 128 runs as a persistent, warp-specialised pipeline (2 CTAs per SM, two smem / TMEM
  *                   buffers: loads and QK^T of the next (sequence, head) overlap softmax / PV / store of the current one).
  *                   Same arithmetic, so the context rows must be bit-identical.  NOT yet run on hardware.
+ *   "pdl" 1 : the opt-in kernels above (pair GEMMs, ln_stats, pipelined attention) are launched with programmatic stream
+ *                   serialization: their prologue overlaps the tail of the previous kernel and they block in
+ *                   griddepcontrol.wait before touching global memory.  NOT yet run on hardware.
  * Unknown names return AC_E_INVALID. */
 int ac_set_option(const char *name, long long value);
 int ac_get_option(const char *name, long long *value);

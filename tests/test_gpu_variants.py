@@ -29,7 +29,7 @@ def _encoder(cabi, sd, cfg, max_tokens, cls_only=True):
 
 
 def test_option_roundtrip(cabi):
-    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe"):
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl"):
         prev = cabi.get_option(name)          # 0 unless AC_OPTIONS preset it for this process
         with cabi.option(name, 1 - prev):
             assert cabi.get_option(name) == 1 - prev
@@ -134,6 +134,23 @@ def test_attn_pipe_encoder_bit_identical(cabi, B, S, pad):
         out_h = enc.last_hidden(B, S).clone()
     assert torch.equal(ref.view(torch.int32), out.view(torch.int32))
     assert torch.equal(ref_h.view(torch.int32), out_h.view(torch.int32))
+    enc.close()
+
+
+@experimental
+def test_pdl_on_the_opted_in_chain_is_bit_identical(cabi):
+    """programmatic dependent launch only changes WHEN the prologues run; with every kernel of the layer loop PDL-aware
+    (pair GEMMs, ln_stats, pipelined attention) the results must not change"""
+    sd, cfg, _ = eo.make_bert_state_dict(1234, num_hidden_layers=3)
+    B, S = 40, 128
+    ids = eo.synthetic_ids(B, S).to(torch.int32).cuda()
+    enc = _encoder(cabi, sd, cfg, max_tokens=B * S)
+    with cabi.option("gemm_pair", 1), cabi.option("ln_defer", 1), cabi.option("attn_pipe", 1):
+        ref = enc.forward_cls(ids).clone()
+        with cabi.option("pdl", 1):
+            outs = [enc.forward_cls(ids).clone() for _ in range(5)]
+    for o in outs:
+        assert torch.equal(ref.view(torch.int32), o.view(torch.int32))
     enc.close()
 
 

@@ -409,7 +409,7 @@ static int run_epoch() {
 
 int main(int argc, char **argv) {
     setvbuf(stdout, nullptr, _IOLBF, 0);
-    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full|defer_layers|epoch|epi16|attn [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
+    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full|defer_layers|epoch|epi16|attn|pdl [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
     if (argc > 2) g_pair = atoi(argv[2]);
     AC(ac_device_check());
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
@@ -421,6 +421,10 @@ int main(int argc, char **argv) {
     if (!strcmp(argv[1], "defer_layers")) return run_defer_layers();
     if (!strcmp(argv[1], "epi16")) return run_encoder("epi16", 1);             // FFN1 + QKV with 16 epilogue warps
     if (!strcmp(argv[1], "attn")) return run_encoder("attn_pipe", 1);          // persistent pipelined attention
+    if (!strcmp(argv[1], "pdl")) {                                             // programmatic dependent launch on the opted-in chain
+        AC(ac_set_option("gemm_pair", 1)); AC(ac_set_option("ln_defer", 1)); AC(ac_set_option("attn_pipe", 1));
+        return run_encoder("pdl", 1);                                          // same kernels, only the launch attribute changes
+    }
     if (!strcmp(argv[1], "defer")) return run_encoder("ln_defer", 1);          // production shape: CLS-only tail
     if (!strcmp(argv[1], "defer_full")) return run_encoder("ln_defer", 0);     // every layer through the deferred epilogues
     printf("unknown test %s\n", argv[1]);
