@@ -1,0 +1,78 @@
+"""Cut the device code (kernels, device functions, plain structs / constants) out of a .cu file so that it can be compiled
+as ordinary C++ against tests/cpu_shim/cuda_shim.h.  TEST INFRASTRUCTURE ONLY.
+
+Host functions (anything with a <<<...>>> launch, the extern "C" entry points, functions returning an error code) are
+dropped; #include lines are dropped (the shim provides what the device code needs); inside cooperative kernels
+`__shared__ T name[N];` becomes a per-block array (all blocks of a cooperative launch are resident at once on the CPU too).
+"""
+import re
+import sys
+
+DROP_PREFIX = ("static int ", "extern \"C\"", "#include", "static size_t knn", "static int\n")
+
+
+def chunks(text):
+    """top-level chunks of a translation unit: namespace lines are emitted on their own, every other entity (up to the `;` or
+    the closing brace at depth 0 relative to the namespaces) is one chunk"""
+    out, cur, depth, ns_depth = [], [], 0, 0
+    in_block_comment = False
+    for line in text.splitlines(keepends=True):
+        stripped = line.strip()
+        if depth == ns_depth and not cur:
+            if re.match(r"namespace\s+\w*\s*(=|\{)", stripped) and stripped.endswith("{"):
+                out.append(("ns", line)); depth += 1; ns_depth += 1
+                continue
+            if stripped.startswith("}") and "namespace" in stripped and ns_depth > 0:
+                out.append(("ns", line)); depth -= 1; ns_depth -= 1
+                continue
+            if not stripped or stripped.startswith("//"):
+                out.append(("c", line))
+                continue
+            if stripped.startswith("#"):                     # preprocessor lines: dropped (the shim supplies the includes)
+                continue
+        cur.append(line)
+        code = re.sub(r"//.*", "", line)
+        code = re.sub(r'"(\\.|[^"\\])*"', '""', code)
+        depth += code.count("{") - code.count("}")
+        if depth == ns_depth and (code.rstrip().endswith(";") or code.rstrip().endswith("}")):
+            out.append(("e", "".join(cur)))
+            cur = []
+    if cur:
+        out.append(("e", "".join(cur)))
+    return out
+
+
+def keep(entity):
+    head = entity.lstrip()
+    if "<<<" in entity:
+        return False
+    if any(head.startswith(p) for p in DROP_PREFIX):
+        return False
+    if re.match(r"static int\b", head):
+        return False
+    return True
+
+
+def per_block_shared(entity):
+    """cooperative kernels: `__shared__ float a[N];` -> one array per resident block"""
+    if "this_grid()" not in entity:
+        return entity
+    def repl(m):
+        ty, name, dim = m.group(1), m.group(2), m.group(3)
+        return f"static {ty} {name}_all[SHIM_MAX_BLOCKS][{dim}]; {ty} *{name} = {name}_all[blockIdx.x];"
+    return re.sub(r"__shared__\s+(\w+)\s+(\w+)\[([^\]]+)\];", repl, entity)
+
+
+def extract(path):
+    text = open(path).read()
+    out = []
+    for kind, body in chunks(text):
+        if kind in ("ns", "c"):
+            out.append(body)
+        elif keep(body):
+            out.append(per_block_shared(body))
+    return "".join(out)
+
+
+if __name__ == "__main__":
+    sys.stdout.write(extract(sys.argv[1]))
