@@ -18,6 +18,18 @@
 #include <random>
 #include <vector>
 
+// CUDA's own host-usable headers supply dim3 / float4 / uint4 / __half ...; their execution-space keywords are then
+// redefined to nothing for the device code compiled as C++
+#include <cuda_fp16.h>
+#include <vector_functions.h>
+#include <vector_types.h>
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __forceinline__
+#undef __restrict__
+#undef __launch_bounds__
+#undef __shared__
 #define __global__
 #define __device__
 #define __host__
@@ -25,18 +37,15 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static          /* kernels launched block by block; the cooperative kernel gets per-block arrays from the extractor */
+#ifndef CUDART_INF_F
 #define CUDART_INF_F (__builtin_inff())
+#endif
 
-struct dim3 {
-    unsigned x, y, z;
-    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
-};
-struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
-static inline float2 make_float2(float x, float y) { return {x, y}; }
-static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 static inline int min(int a, int b) { return a < b ? a : b; }
-static inline float __ldg(const float *p) { return *p; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 namespace shim {
 

@@ -1,0 +1,299 @@
+// epilogue_emul.cpp -- the GEMM epilogue functors and the small kernels of the deferred-LayerNorm flow (csrc/encoder.cu),
+// executed on the CPU (tests/cpu_shim/cuda_shim.h) against element-wise restatements of what they are meant to compute.
+// TEST INFRASTRUCTURE: these were written without GPU access.  The tensor-core mainloop cannot be emulated, so the driver
+// plays its part: it computes the accumulator tile on the CPU and calls prefetch()/tile() for every epilogue warp, chunk by
+// chunk, in the order and with the thread numbering of gemm_tc_kernel / gemm_tc2_kernel (epilogue warps are warps 2..).
+// Checked: every output element is written exactly once at the right address with the right value (ragged M and N,
+// sentinel-filled buffers), row statistics reach the right threads, the per-part (sum, sumsq) partials land in the right
+// slots, the V-transposed addressing, and the 16-epilogue-warp variants (64 columns per warp).
+#include "cuda_shim.h"
+#include "../../include/adaptive_b200.h"
+
+static void __threadfence_system() {}
+static unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p += v; return o; }
+namespace ac {
+static inline float ex2_approx(float x) { return exp2f(x); }
+static inline float rcp_approx(float x) { return 1.f / x; }
+static inline void griddep_wait() {}
+static inline void griddep_launch_dependents() {}
+static inline void st_release_sys(uint32_t *p, uint32_t v) { *p = v; }
+static inline uint32_t ld_acquire_sys(const uint32_t *p) { return *p; }
+}  // namespace ac
+
+#include "_gen_common.inc"
+#include "_gen_gemm_tc.inc"
+#include "_gen_peer.inc"
+#include "_gen_encoder.inc"
+
+using namespace ac;
+
+static int g_fail = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { if (g_fail < 20) { printf("  FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } ++g_fail; } } while (0)
+
+static std::mt19937 g_rng(123);
+static float urand(float s = 1.f) { return std::uniform_real_distribution<float>(-s, s)(g_rng); }
+
+// the epilogue side of gemm_tc_kernel (kEpiWarps = 8) / gemm_tc2_kernel (8 or 16) for one accumulator tile
+template <class Epi, int kEpiWarps>
+static void run_epilogue_tile(const Epi &epi, const std::vector<float> &acc, int ld_acc, int m0, int n0, int tile_iter) {
+    static uint8_t epi_stage[16 * GEMM_EPI_STAGE_BYTES];
+    constexpr int kCols = GEMM_BLOCK_N / (kEpiWarps / 4);
+    shim::launch(dim3(1), dim3(64 + 32 * kEpiWarps), [&] {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp < 2) return;                                    // TMA producer / MMA issuer warps
+        const int q = warp & 3, cpart = (warp - 2) >> 2;
+        typename Epi::State est;
+        epi.begin_cta(est, q, lane);
+        GemmTileInfo ti;
+        ti.m0 = m0; ti.n0 = n0; ti.tile_iter = tile_iter;
+        const int row = m0 + q * 32 + lane;
+        const int c_lo = cpart * kCols;
+        epi.prefetch(est, ti, row, n0 + c_lo, lane, 0);
+        for (int ci = 0; ci < kCols / 32; ++ci) {
+            const int c = c_lo + 32 * ci;
+            if (ci + 1 < kCols / 32) epi.prefetch(est, ti, row, n0 + c + 32, lane, (ci + 1) & 1);
+            float v[32];
+            for (int j = 0; j < 32; ++j) v[j] = acc[static_cast<size_t>(row) * ld_acc + n0 + c + j];
+            epi.tile(est, ti, row, n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane, ci & 1, 0u);
+        }
+        epi.end_cta(est, q, lane);
+    }, 7 + m0 + n0);
+}
+
+template <class Epi, int kEpiWarps>
+static void run_epilogue(const Epi &epi, const std::vector<float> &acc, int ld_acc, int M, int N) {
+    int it = 0;
+    for (int m0 = 0; m0 < M; m0 += GEMM_BLOCK_M)
+        for (int n0 = 0; n0 < N; n0 += GEMM_BLOCK_N) run_epilogue_tile<Epi, kEpiWarps>(epi, acc, ld_acc, m0, n0, it++);
+}
+
+// accumulator of a K-major GEMM with zero-filled out-of-range operands, padded to whole tiles
+static std::vector<float> make_acc(int M, int N, int Mp, int Np) {
+    std::vector<float> acc(static_cast<size_t>(Mp) * Np, 0.f);
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) acc[static_cast<size_t>(m) * Np + n] = urand(3.f);
+    return acc;
+}
+static int pad(int x, int t) { return (x + t - 1) / t * t; }
+static uint16_t hbits(__half h) { uint16_t u; memcpy(&u, &h, 2); return u; }
+
+template <int MODE, int kEpiWarps>
+static void test_consumer(int M, int N) {
+    constexpr int kCols = GEMM_BLOCK_N / (kEpiWarps / 4);
+    using Epi = EpiLinear<MODE, true, false, true, kCols>;
+    const int Mp = pad(M, 128), Np = pad(N, 256), ldy = N + 8;
+    const std::vector<float> acc = make_acc(M, N, Mp, Np);
+    std::vector<float> c0(Np), c1(Np);
+    std::vector<float2> stats(Mp);
+    for (auto &x : c0) x = urand(0.5f);
+    for (auto &x : c1) x = urand(2.f);
+    for (auto &s : stats) s = make_float2(urand(0.5f), 0.5f + fabsf(urand(1.f)));
+    const uint16_t sentinel = 0x7bad;
+    std::vector<__half> Y(static_cast<size_t>(Mp + 4) * ldy);
+    for (auto &h : Y) memcpy(&h, &sentinel, 2);
+    Epi epi{c0.data(), nullptr, Y.data(), M, N, ldy, 0, nullptr, 0, 0, 0, 0, c1.data(), stats.data()};
+    run_epilogue<Epi, kEpiWarps>(epi, acc, Np, M, N);
+    for (int m = 0; m < Mp + 4; ++m)
+        for (int n = 0; n < ldy; ++n) {
+            const uint16_t got = hbits(Y[static_cast<size_t>(m) * ldy + n]);
+            if (m < M && n < N) {
+                float y = fmaf(stats[m].y, fmaf(-stats[m].x, c1[n], acc[static_cast<size_t>(m) * Np + n]), c0[n]);
+                if (MODE == 1) y = gelu_erf(y);
+                CHECK(got == hbits(__float2half_rn(y)), "consumer MODE %d warps %d: (%d,%d) got %04x want %04x", MODE, kEpiWarps, m, n, got, hbits(__float2half_rn(y)));
+            } else {
+                CHECK(got == sentinel, "consumer MODE %d warps %d: (%d,%d) outside the matrix was written", MODE, kEpiWarps, m, n);
+            }
+        }
+    printf("consumer epilogue EpiLinear<%d, fp16, DEFER, COLS=%d> (%d epilogue warps) M=%d N=%d: %s\n", MODE, kCols, kEpiWarps, M, N, g_fail ? "FAIL" : "ok");
+}
+
+// fused QKV with the V third transposed (deferred form)
+template <int kEpiWarps>
+static void test_qkv(int B, int S, int H) {
+    constexpr int kCols = GEMM_BLOCK_N / (kEpiWarps / 4);
+    using Epi = EpiLinear<0, true, true, true, kCols>;
+    const int M = B * S, N = 3 * H, Mp = pad(M, 128), Np = pad(N, 256), S_pad = (S + 7) / 8 * 8, ld = 2 * H;
+    const std::vector<float> acc = make_acc(M, N, Mp, Np);
+    std::vector<float> c0(Np), c1(Np);
+    std::vector<float2> stats(Mp);
+    for (auto &x : c0) x = urand(0.5f);
+    for (auto &x : c1) x = urand(2.f);
+    for (auto &s : stats) s = make_float2(urand(0.5f), 0.5f + fabsf(urand(1.f)));
+    const uint16_t sentinel = 0x7bad;
+    std::vector<__half> qk(static_cast<size_t>(Mp) * ld), vT(static_cast<size_t>(B) * H * S_pad + 64);
+    for (auto &h : qk) memcpy(&h, &sentinel, 2);
+    for (auto &h : vT) memcpy(&h, &sentinel, 2);
+    Epi epi{c0.data(), nullptr, qk.data(), M, N, ld, 0, vT.data(), 2 * H, S, S_pad, H, c1.data(), stats.data()};
+    run_epilogue<Epi, kEpiWarps>(epi, acc, Np, M, N);
+    auto want = [&](int m, int n) { return hbits(__float2half_rn(fmaf(stats[m].y, fmaf(-stats[m].x, c1[n], acc[static_cast<size_t>(m) * Np + n]), c0[n]))); };
+    for (int m = 0; m < Mp; ++m)
+        for (int n = 0; n < ld; ++n) {
+            const uint16_t got = hbits(qk[static_cast<size_t>(m) * ld + n]);
+            if (m < M) CHECK(got == want(m, n), "qkv: qk(%d,%d)", m, n);
+            else CHECK(got == sentinel, "qkv: qk row %d beyond M written", m);
+        }
+    std::vector<uint8_t> seen(vT.size(), 0);
+    for (int m = 0; m < M; ++m)
+        for (int f = 0; f < H; ++f) {
+            const int b = m / S, key = m % S;
+            const size_t at = (static_cast<size_t>(b) * H + f) * S_pad + key;
+            seen[at] = 1;
+            CHECK(hbits(vT[at]) == want(m, 2 * H + f), "qkv: vT(b %d, feature %d, key %d)", b, f, key);
+        }
+    for (size_t i = 0; i < vT.size(); ++i)
+        if (!seen[i]) CHECK(hbits(vT[i]) == sentinel, "qkv: vT[%zu] (padding) was written", i);
+    printf("QKV epilogue EpiLinear<0, fp16, VT, DEFER, COLS=%d> (%d epilogue warps) B=%d S=%d H=%d: %s\n", kCols, kEpiWarps, B, S, H, g_fail ? "FAIL" : "ok");
+}
+
+static void test_resid_defer(int M, int H) {
+    const int N = H, Mp = pad(M, 128), Np = pad(N, 256), nparts = H / 128;
+    const std::vector<float> acc = make_acc(M, N, Mp, Np);
+    std::vector<float> bias(Np), gamma(Np), beta(Np), y(static_cast<size_t>(Mp + 2) * H), y_old;
+    std::vector<float2> stats(Mp), parts(static_cast<size_t>(nparts) * (Mp + 8), make_float2(-777.f, -777.f));
+    for (auto &x : bias) x = urand(0.5f);
+    for (auto &x : gamma) x = 1.f + urand(0.3f);
+    for (auto &x : beta) x = urand(0.2f);
+    for (auto &x : y) x = urand(2.f);
+    for (auto &s : stats) s = make_float2(urand(0.5f), 0.5f + fabsf(urand(1.f)));
+    y_old = y;
+    const uint16_t sentinel = 0x7bad;
+    std::vector<__half> yh(static_cast<size_t>(Mp + 2) * H);
+    for (auto &h : yh) memcpy(&h, &sentinel, 2);
+    EpiResidDefer epi{bias.data(), y.data(), yh.data(), stats.data(), gamma.data(), beta.data(), parts.data(), static_cast<int64_t>(Mp + 8), M, N, H};
+    run_epilogue<EpiResidDefer, 8>(epi, acc, Np, M, N);
+    for (int m = 0; m < Mp + 2; ++m) {
+        std::vector<double> ps(nparts, 0.0), pq(nparts, 0.0);
+        for (int n = 0; n < H; ++n) {
+            const size_t at = static_cast<size_t>(m) * H + n;
+            if (m < M) {
+                const float a = acc[static_cast<size_t>(m) * Np + n];
+                const float o = (a + bias[n]) + fmaf((y_old[at] - stats[m].x) * stats[m].y, gamma[n], beta[n]);
+                CHECK(memcmp(&y[at], &o, 4) == 0, "resid: y(%d,%d) got %g want %g", m, n, y[at], o);
+                CHECK(hbits(yh[at]) == hbits(__float2half_rn(o)), "resid: yh(%d,%d)", m, n);
+                ps[n / 128] += o; pq[n / 128] += static_cast<double>(o) * o;
+            } else {
+                CHECK(memcmp(&y[at], &y_old[at], 4) == 0, "resid: y row %d beyond M was modified", m);
+                CHECK(hbits(yh[at]) == sentinel, "resid: yh row %d beyond M was written", m);
+            }
+        }
+        for (int p = 0; p < nparts; ++p) {
+            const float2 got = parts[static_cast<size_t>(p) * (Mp + 8) + m];
+            if (m < M) {
+                CHECK(fabs(got.x - ps[p]) <= 1e-4 * (1.0 + fabs(ps[p])) && fabs(got.y - pq[p]) <= 1e-4 * (1.0 + fabs(pq[p])),
+                      "resid: parts[%d][%d] = (%g, %g), want (%g, %g)", p, m, got.x, got.y, ps[p], pq[p]);
+            } else if (m < Mp + 8) {
+                CHECK(got.x == -777.f, "resid: parts[%d][%d] beyond M was written", p, m);
+            }
+        }
+    }
+    printf("residual epilogue EpiResidDefer M=%d H=%d (%d parts): %s\n", M, H, nparts, g_fail ? "FAIL" : "ok");
+}
+
+static void test_small_kernels() {
+    // ln_stats_kernel
+    {
+        const int rows = 300, H = 384, nparts = 3, stride = 320;
+        std::vector<float2> parts(static_cast<size_t>(nparts) * stride), stats(rows + 4, make_float2(-1.f, -1.f));
+        for (auto &p : parts) p = make_float2(urand(20.f), 50.f + fabsf(urand(40.f)));
+        shim::launch(dim3((rows + 255) / 256), dim3(256), [&] { ln_stats_kernel(parts.data(), nparts, stride, rows, H, 1e-12f, stats.data()); });
+        for (int r = 0; r < rows + 4; ++r) {
+            if (r >= rows) { CHECK(stats[r].x == -1.f, "ln_stats wrote row %d", r); continue; }
+            float s = 0.f, q = 0.f;
+            for (int p = 0; p < nparts; ++p) { s += parts[static_cast<size_t>(p) * stride + r].x; q += parts[static_cast<size_t>(p) * stride + r].y; }
+            const float mu = s / H, var = fmaxf(q / H - mu * mu, 0.f);
+            CHECK(stats[r].x == mu && stats[r].y == 1.f / sqrtf(var + 1e-12f), "ln_stats row %d", r);
+        }
+    }
+    // pack_defer_kernel: Wp = fp16(gamma * W), c1 = rowsum(Wp), c0 = W beta + b
+    {
+        const int N = 70, K = 96;
+        std::vector<float> W(static_cast<size_t>(N) * K), b(N), g(K), be(K), c1(N + 2, -5.f), c0(N + 2, -5.f);
+        for (auto &x : W) x = urand(0.1f);
+        for (auto &x : b) x = urand(0.1f);
+        for (auto &x : g) x = 1.f + urand(0.3f);
+        for (auto &x : be) x = urand(0.2f);
+        std::vector<__half> Wp(static_cast<size_t>(N) * K);
+        shim::launch(dim3((N + 7) / 8), dim3(256), [&] { pack_defer_kernel(W.data(), b.data(), g.data(), be.data(), N, K, Wp.data(), c1.data(), c0.data()); });
+        for (int n = 0; n < N; ++n) {
+            double s1 = 0, s0 = 0;
+            for (int k = 0; k < K; ++k) {
+                const __half h = __float2half_rn(g[k] * W[static_cast<size_t>(n) * K + k]);
+                CHECK(hbits(Wp[static_cast<size_t>(n) * K + k]) == hbits(h), "pack: Wp(%d,%d)", n, k);
+                s1 += __half2float(h); s0 += static_cast<double>(be[k]) * W[static_cast<size_t>(n) * K + k];
+            }
+            CHECK(fabs(c1[n] - s1) < 1e-4 && fabs(c0[n] - (s0 + b[n])) < 1e-5, "pack: c1/c0 row %d: %g %g vs %g %g", n, c1[n], c0[n], s1, s0 + b[n]);
+        }
+        CHECK(c1[N] == -5.f && c0[N] == -5.f, "pack wrote beyond N");
+        // identity form (gamma / beta null): plain fp16 weights, c0 = bias
+        shim::launch(dim3((N + 7) / 8), dim3(256), [&] { pack_defer_kernel(W.data(), b.data(), nullptr, nullptr, N, K, Wp.data(), c1.data(), c0.data()); });
+        for (int n = 0; n < N; ++n) {
+            CHECK(c0[n] == b[n], "pack identity: c0 row %d", n);
+            for (int k = 0; k < K; ++k) CHECK(hbits(Wp[static_cast<size_t>(n) * K + k]) == hbits(__float2half_rn(W[static_cast<size_t>(n) * K + k])), "pack identity Wp");
+        }
+    }
+    // gather_cls_ln_kernel: CLS rows of ctx copied, LayerNorm of the CLS rows of y
+    {
+        const int B = 11, S = 7, H = 256;
+        std::vector<float> y(static_cast<size_t>(B) * S * H), g(H), be(H), x_cls(static_cast<size_t>(B) * H, -9.f);
+        std::vector<__half> ctx(static_cast<size_t>(B) * S * H), ctx_cls(static_cast<size_t>(B) * H);
+        for (auto &v : y) v = urand(2.f) + 0.3f;
+        for (auto &v : g) v = 1.f + urand(0.3f);
+        for (auto &v : be) v = urand(0.2f);
+        for (auto &h : ctx) h = __float2half_rn(urand(1.f));
+        shim::launch(dim3((B + 7) / 8), dim3(256), [&] { gather_cls_ln_kernel(ctx.data(), y.data(), B, S, H, g.data(), be.data(), 1e-12f, ctx_cls.data(), x_cls.data()); });
+        for (int b = 0; b < B; ++b) {
+            const float *row = &y[static_cast<size_t>(b) * S * H];
+            double mu = 0, var = 0;
+            for (int i = 0; i < H; ++i) mu += row[i];
+            mu /= H;
+            for (int i = 0; i < H; ++i) var += (row[i] - mu) * (row[i] - mu);
+            var /= H;
+            for (int i = 0; i < H; ++i) {
+                const double want = (row[i] - mu) / sqrt(var + 1e-12) * g[i] + be[i];
+                CHECK(fabs(x_cls[static_cast<size_t>(b) * H + i] - want) < 2e-5, "gather_cls_ln x(%d,%d) %g vs %g", b, i, x_cls[static_cast<size_t>(b) * H + i], want);
+                CHECK(hbits(ctx_cls[static_cast<size_t>(b) * H + i]) == hbits(ctx[static_cast<size_t>(b) * S * H + i]), "gather_cls_ln ctx(%d,%d)", b, i);
+            }
+        }
+    }
+    // cls_normalize_scatter_kernel: local output + slot of every "peer" + flags published once by the last block
+    {
+        const int B = 19, S = 3, H = 128, G = 3, rank = 1;
+        std::vector<float> x(static_cast<size_t>(B) * S * H), out(static_cast<size_t>(B) * H);
+        for (auto &v : x) v = urand(2.f);
+        std::vector<std::vector<float>> peer(G, std::vector<float>(static_cast<size_t>(2 * B) * H, -3.f));
+        std::vector<std::vector<uint32_t>> flags(G, std::vector<uint32_t>(G, 0));
+        ac_peer_table t{};
+        t.world = G; t.rank = rank;
+        for (int p = 0; p < G; ++p) { t.buf[p] = peer[p].data(); t.flag[p] = flags[p].data(); }
+        unsigned int counter = 0;
+        const size_t off = static_cast<size_t>(B) * H * 4 / 2;     // some 16-byte aligned offset inside the peer buffers
+        shim::launch(dim3((B + 7) / 8), dim3(256), [&] { cls_normalize_scatter_kernel(x.data(), B, S, H, out.data(), t, off, 41u, &counter); });
+        for (int b = 0; b < B; ++b) {
+            double n2 = 0;
+            for (int i = 0; i < H; ++i) n2 += static_cast<double>(x[static_cast<size_t>(b) * S * H + i]) * x[static_cast<size_t>(b) * S * H + i];
+            for (int i = 0; i < H; ++i) {
+                const double want = x[static_cast<size_t>(b) * S * H + i] / sqrt(n2);
+                CHECK(fabs(out[static_cast<size_t>(b) * H + i] - want) < 1e-6, "cls_normalize_scatter local (%d,%d)", b, i);
+                for (int p = 0; p < G; ++p)
+                    CHECK(peer[p][off / 4 + static_cast<size_t>(b) * H + i] == out[static_cast<size_t>(b) * H + i], "cls_normalize_scatter peer %d (%d,%d)", p, b, i);
+            }
+        }
+        for (int p = 0; p < G; ++p)
+            for (int r = 0; r < G; ++r) CHECK(flags[p][r] == (r == rank ? 41u : 0u), "flag[%d][%d] = %u", p, r, flags[p][r]);
+        CHECK(counter == 0, "the last-block counter was not reset");
+    }
+    printf("ln_stats / pack_defer / gather_cls_ln / cls_normalize_scatter: %s\n", g_fail ? "FAIL" : "ok");
+}
+
+int main() {
+    test_consumer<1, 8>(300, 392);          // FFN1 form: GELU(r (acc - mu c1) + c0), ragged M and N
+    test_consumer<1, 16>(300, 392);         // the same with 16 epilogue warps (64 columns per warp)
+    test_consumer<0, 8>(129, 256);
+    test_qkv<8>(6, 50, 128);                // sequences that straddle warps and tiles, padded key stride
+    test_qkv<16>(3, 128, 128);
+    test_resid_defer(300, 384);             // 3 parts, ragged M, N = 1.5 tiles
+    test_resid_defer(128, 256);
+    test_small_kernels();
+    printf("epilogue_emul: %s (%d failed checks)\n", g_fail ? "FAIL" : "ALL OK", g_fail);
+    return g_fail ? 1 : 0;
+}

@@ -15,9 +15,12 @@ def chunks(text):
     """top-level chunks of a translation unit: namespace lines are emitted on their own, every other entity (up to the `;` or
     the closing brace at depth 0 relative to the namespaces) is one chunk"""
     out, cur, depth, ns_depth = [], [], 0, 0
-    in_block_comment = False
+    in_macro = False
     for line in text.splitlines(keepends=True):
         stripped = line.strip()
+        if in_macro:                                         # continuation lines of a multi-line #define
+            in_macro = stripped.endswith("\\")
+            continue
         if depth == ns_depth and not cur:
             if re.match(r"namespace\s+\w*\s*(=|\{)", stripped) and stripped.endswith("{"):
                 out.append(("ns", line)); depth += 1; ns_depth += 1
@@ -29,6 +32,7 @@ def chunks(text):
                 out.append(("c", line))
                 continue
             if stripped.startswith("#"):                     # preprocessor lines: dropped (the shim supplies the includes)
+                in_macro = stripped.endswith("\\")
                 continue
         cur.append(line)
         code = re.sub(r"//.*", "", line)
@@ -42,9 +46,16 @@ def chunks(text):
     return out
 
 
+# anything that touches tensor cores, TMA, mbarriers, inline PTX or the CUDA runtime cannot be emulated and is dropped
+NOT_EMULATED = re.compile(r"asm\s*(volatile)?\s*\(|CUtensorMap|\btmem_|\bumma_|\btma_|\bmbar_|\btc_fence|\btc_commit|cudaLaunch|cudaStream_t|"
+                          r"cudaError_t|__cvta|cudaEvent|cudaFunc|cudaMalloc|cudaMem|cluster_sync|cluster_ctarank|mapa_shared")
+
+
 def keep(entity):
     head = entity.lstrip()
-    if "<<<" in entity:
+    if "<<<" in entity or NOT_EMULATED.search(entity):
+        return False
+    if re.match(r"(template\s*<[^>]*>\s*)?static\s+int\b", head):
         return False
     if any(head.startswith(p) for p in DROP_PREFIX):
         return False

@@ -1,6 +1,10 @@
 """SIMT kernels that were written without GPU access, executed on the CPU (tests/cpu_shim: every CUDA thread is a fiber,
 barriers / shuffles / cooperative grid sync are fiber barriers, the scheduler shuffles the thread order).
 
+deferred LayerNorm / 16 epilogue warps / peer scatter: the epilogue functors of csrc/encoder.cu are driven tile by tile
+with CPU-computed accumulators in the thread numbering of the GEMM kernels and compared element by element (ragged
+shapes, sentinel-filled buffers), together with ln_stats / pack_defer / gather_cls_ln / cls_normalize_scatter.
+
 head_fused: the device code of csrc/head.cu is cut out of the .cu file and compiled as C++; one training epoch is run through
 the launch-per-kernel sequence and through fused::head_epoch_kernel (cooperative, several blocks) from identical states and
 must give bit-identical parameters, AdamW moments and loss.  A mutant without one grid barrier must fail, otherwise the
@@ -17,6 +21,17 @@ SHIM = os.path.join(ROOT, "tests", "cpu_shim")
 sys.path.insert(0, SHIM)
 
 
+CUDA_INC = "/usr/local/cuda/include"       # host-usable vector / fp16 headers
+
+
+def _gxx(gen, driver, exe):
+    cmd = ["g++", "-std=c++17", "-O1", f"-I{gen}", f"-I{SHIM}", f"-I{CUDA_INC}", os.path.join(SHIM, driver),
+           os.path.join(SHIM, "cuda_shim.cpp"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return exe
+
+
 def _build(tmp_path, mutate=None):
     import extract_device_code as ex
     src = ex.extract(os.path.join(ROOT, "adaptive_classifier_b200", "csrc", "head.cu"))
@@ -25,12 +40,36 @@ def _build(tmp_path, mutate=None):
     gen = tmp_path / "gen"
     gen.mkdir(exist_ok=True)
     (gen / "_gen_head_device.inc").write_text(src)
-    exe = str(tmp_path / ("emul_mut" if mutate else "emul"))
-    cmd = ["g++", "-std=c++17", "-O1", f"-I{gen}", f"-I{SHIM}", os.path.join(SHIM, "head_epoch_emul.cpp"),
-           os.path.join(SHIM, "cuda_shim.cpp"), "-o", exe]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-2000:]
-    return exe
+    return _gxx(gen, "head_epoch_emul.cpp", str(tmp_path / ("emul_mut" if mutate else "emul")))
+
+
+def _build_epilogues(tmp_path, mutate=None):
+    import extract_device_code as ex
+    gen = tmp_path / "gen_enc"
+    gen.mkdir(exist_ok=True)
+    for f in ("common.cuh", "gemm_tc.cuh", "peer.cuh", "encoder.cu"):
+        src = ex.extract(os.path.join(ROOT, "adaptive_classifier_b200", "csrc", f))
+        if mutate and f == "encoder.cu":
+            src = mutate(src)
+        (gen / f"_gen_{f.split('.')[0]}.inc").write_text(src)
+    return _gxx(gen, "epilogue_emul.cpp", str(tmp_path / ("epi_mut" if mutate else "epi")))
+
+
+def test_deferred_layernorm_epilogues_on_the_cpu_emulation(tmp_path):
+    exe = _build_epilogues(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2500:] + r.stderr[-500:]
+
+
+def test_the_epilogue_emulation_detects_a_wrong_column_mask(tmp_path):
+    """mutant: the 16-warp consumer epilogue detects its first chunk with the 8-warp mask -> half of the warps never load
+    their row statistics"""
+    def wrong_mask(src):
+        assert "(COLS - 1)) == 0" in src
+        return src.replace("(COLS - 1)) == 0", "(GEMM_BLOCK_N / 2 - 1)) == 0")
+    exe = _build_epilogues(tmp_path, mutate=wrong_mask)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode != 0 and "16 epilogue warps) M=300 N=392: FAIL" in r.stdout, r.stdout[-1500:]
 
 
 @pytest.fixture(scope="module")
