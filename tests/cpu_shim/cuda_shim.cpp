@@ -18,7 +18,9 @@ static void fiber_entry() {
 }
 
 void run_blocks(const std::vector<dim3> &blocks, dim3 grid, dim3 block, const std::function<void()> &body, unsigned seed) {
-    constexpr size_t kStack = 256 * 1024;
+    constexpr size_t kStack = 128 * 1024;
+    static std::vector<std::unique_ptr<char[]>> stack_pool;      // stacks are reused across launches (no mmap churn)
+    size_t pool_next = 0;
     g_block_dim = block;
     g_grid_dim = grid;
     g_body = &body;
@@ -35,14 +37,15 @@ void run_blocks(const std::vector<dim3> &blocks, dim3 grid, dim3 block, const st
         for (int t = 0; t < tpb; ++t) {
             fibers.emplace_back(new Fiber());
             Fiber *f = fibers.back().get();
-            f->stack.reset(new char[kStack]);
+            if (pool_next == stack_pool.size()) stack_pool.emplace_back(new char[kStack]);
+            char *stk = stack_pool[pool_next++].get();
             f->tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
             f->bid = b;
             f->blk = blk;
             f->warp = &blk->warps[t / 32];
             f->lane = t % 32;
             getcontext(&f->ctx);
-            f->ctx.uc_stack.ss_sp = f->stack.get();
+            f->ctx.uc_stack.ss_sp = stk;
             f->ctx.uc_stack.ss_size = kStack;
             f->ctx.uc_link = &g_sched;
             makecontext(&f->ctx, fiber_entry, 0);

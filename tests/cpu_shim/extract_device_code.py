@@ -51,8 +51,22 @@ NOT_EMULATED = re.compile(r"asm\s*(volatile)?\s*\(|CUtensorMap|\btmem_|\bumma_|\
                           r"cudaError_t|__cvta|cudaEvent|cudaFunc|cudaMalloc|cudaMem|cluster_sync|cluster_ctarank|mapa_shared")
 
 
+# host mode (encoder_emul.cpp): host functions are kept and run against a fake CUDA runtime; only what needs the real
+# tensor-core / TMA / mbarrier hardware is dropped, and kernel launches are rewritten into shim launches
+NOT_EMULATED_HOST = re.compile(r"asm\s*(volatile)?\s*\(|\btmem_|\bumma_|\btma_load|\btma_prefetch|\bmbar_|\btc_fence|\btc_commit|__cvta|"
+                               r"cluster_sync|cluster_ctarank|mapa_shared|cudaLaunchConfig_t|cudaGetDriverEntryPoint")
+HOST_MODE = False
+
+
+def rewrite_launches(entity):
+    """kernel<<<grid, block[, smem[, stream]]>>>(args)  ->  shim_launch(SHIM_CFG(grid, block, ...), kernel, args)"""
+    return re.sub(r"([A-Za-z_][\w:]*)\s*<<<(.*?)>>>\s*\(", lambda m: f"shim_launch(SHIM_CFG({m.group(2)}), {m.group(1)}, ", entity, flags=re.S)
+
+
 def keep(entity):
     head = entity.lstrip()
+    if HOST_MODE:
+        return not NOT_EMULATED_HOST.search(entity) and not head.startswith("#include")
     if "<<<" in entity or NOT_EMULATED.search(entity):
         return False
     if re.match(r"(template\s*<[^>]*>\s*)?static\s+int\b", head):
@@ -74,16 +88,20 @@ def per_block_shared(entity):
     return re.sub(r"__shared__\s+(\w+)\s+(\w+)\[([^\]]+)\];", repl, entity)
 
 
-def extract(path):
+def extract(path, host=False):
+    global HOST_MODE
+    HOST_MODE = host
     text = open(path).read()
     out = []
     for kind, body in chunks(text):
         if kind in ("ns", "c"):
             out.append(body)
         elif keep(body):
-            out.append(per_block_shared(body))
+            body = per_block_shared(body)
+            out.append(rewrite_launches(body) if host else body)
+    HOST_MODE = False
     return "".join(out)
 
 
 if __name__ == "__main__":
-    sys.stdout.write(extract(sys.argv[1]))
+    sys.stdout.write(extract(sys.argv[1], host="--host" in sys.argv))

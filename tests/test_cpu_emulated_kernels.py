@@ -5,6 +5,11 @@ deferred LayerNorm / 16 epilogue warps / peer scatter: the epilogue functors of 
 with CPU-computed accumulators in the thread numbering of the GEMM kernels and compared element by element (ragged
 shapes, sentinel-filled buffers), together with ln_stats / pack_defer / gather_cls_ln / cls_normalize_scatter.
 
+encoder host logic: ac_encoder_create / ac_encoder_forward_cls (default flow, deferred-LayerNorm flow, CLS-only tail, 16-warp
+and pair dispatch) run against a fake CUDA runtime with the real epilogue functors and small kernels; the tensor-core mainloop
+and the attention kernels are replaced by plain CPU stand-ins.  Unit CLS rows and hidden states are compared with the fp32
+oracle.
+
 head_fused: the device code of csrc/head.cu is cut out of the .cu file and compiled as C++; one training epoch is run through
 the launch-per-kernel sequence and through fused::head_epoch_kernel (cooperative, several blocks) from identical states and
 must give bit-identical parameters, AdamW moments and loss.  A mutant without one grid barrier must fail, otherwise the
@@ -99,3 +104,76 @@ def test_the_emulation_detects_a_missing_grid_barrier(tmp_path):
     exe = _build(tmp_path, mutate=drop_second_grid_sync)
     r = subprocess.run([exe] + [str(x) for x in CONFIGS[0]], capture_output=True, text=True, timeout=900)
     assert r.returncode != 0 and "MISMATCH" in r.stdout, r.stdout[-800:]
+
+
+def _build_encoder_host(tmp_path):
+    import extract_device_code as ex
+    gen = tmp_path / "gen_host"
+    gen.mkdir(exist_ok=True)
+    csrc = os.path.join(ROOT, "adaptive_classifier_b200", "csrc")
+    (gen / "_gen_common_host.inc").write_text(ex.extract(os.path.join(csrc, "common.cuh"), host=True))
+    (gen / "_gen_gemm_tc.inc").write_text(ex.extract(os.path.join(csrc, "gemm_tc.cuh")))
+    (gen / "_gen_peer.inc").write_text(ex.extract(os.path.join(csrc, "peer.cuh")))
+    (gen / "_gen_encoder_host.inc").write_text(ex.extract(os.path.join(csrc, "encoder.cu"), host=True))
+    return _gxx(gen, "encoder_emul.cpp", str(tmp_path / "enc_host"))
+
+
+def test_encoder_host_logic_and_deferred_layernorm_flow_on_the_cpu_emulation(tmp_path):
+    import struct
+    import numpy as np
+    import torch
+    from oracle import encoder_oracle as eo
+    exe = _build_encoder_host(tmp_path)
+    L, H, heads, I, V, maxpos, B, S = 3, 128, 2, 256, 200, 64, 3, 20
+    sd, cfg, _ = eo.make_bert_state_dict(1234, vocab_size=V, hidden_size=H, num_hidden_layers=L, num_attention_heads=heads,
+                                         intermediate_size=I, max_position_embeddings=maxpos, type_vocab_size=2)
+    g = torch.Generator().manual_seed(5)
+    for k in list(sd.keys()):                      # LayerNorm parameters away from (1, 0), row means away from 0
+        if k.endswith("LayerNorm.weight"):
+            sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("LayerNorm.bias"):
+            sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("output.dense.bias"):
+            sd[k] = sd[k] + 0.5
+    ids = torch.randint(5, V, (B, S), generator=g)
+    mask = torch.ones_like(ids)
+    for b in range(B):
+        n = S - 1 - 3 * b
+        mask[b, n:] = 0
+        ids[b, n:] = 0
+    ref, ref_hidden = eo.encoder_forward_cls(sd, ids, mask, num_heads=heads, ln_eps=cfg.layer_norm_eps, return_hidden=True)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("11i", L, H, heads, I, V, maxpos, 2, B, S, 1, 0))
+        f.write(struct.pack("f", cfg.layer_norm_eps))
+        w = lambda t: f.write(t.detach().float().contiguous().numpy().tobytes())
+        for k in ("word_embeddings.weight", "position_embeddings.weight", "token_type_embeddings.weight", "LayerNorm.weight", "LayerNorm.bias"):
+            w(sd["embeddings." + k])
+        for l in range(L):
+            p = f"encoder.layer.{l}."
+            for name in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense"):
+                w(sd[p + name + ".weight"]); w(sd[p + name + ".bias"])
+            for name in ("attention.output.LayerNorm.weight", "attention.output.LayerNorm.bias", "intermediate.dense.weight",
+                         "intermediate.dense.bias", "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"):
+                w(sd[p + name])
+        f.write(ids.to(torch.int32).numpy().tobytes())
+        f.write(mask.to(torch.int32).numpy().tobytes())
+    r = subprocess.run([exe, str(fin), str(fout)], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
+    raw = open(fout, "rb").read()
+    off, seen, base = 0, set(), None
+    keep = mask.bool()
+    while off < len(raw):
+        tag = struct.unpack_from("5i", raw, off); off += 20
+        cls = torch.from_numpy(np.frombuffer(raw, np.float32, B * H, off).reshape(B, H).copy()); off += 4 * B * H
+        hid = torch.from_numpy(np.frombuffer(raw, np.float32, B * S * H, off).reshape(B, S, H).copy()); off += 4 * B * S * H
+        seen.add(tag[:4])
+        assert (cls - ref).norm(dim=1).max() < 2e-4, (tag, (cls - ref).norm(dim=1).max())      # encoder tolerance is 1e-3
+        assert (cls.norm(dim=1) - 1).abs().max() < 1e-5
+        if tag[4]:
+            assert (hid[keep] - ref_hidden[keep]).abs().max() < 2e-3, tag
+        if tag[:4] == (0, 0, 0, 0):
+            base = cls
+        elif tag[1]:                                          # deferred flow vs the LayerNorm-kernel flow of the same build
+            assert (cls - base).norm(dim=1).max() < 1e-4, tag
+    assert {(0, 0, 0, 0), (1, 1, 0, 0), (0, 1, 0, 0), (1, 1, 3, 0), (0, 1, 3, 1)} <= seen
