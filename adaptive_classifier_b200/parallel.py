@@ -57,13 +57,18 @@ class PeerExchange:
     satisfies an earlier wait.
     """
 
-    def __init__(self, B: int, D: int, k: int, group=None, device=None):
-        import torch.distributed._symmetric_memory as symm
-        from . import _cabi
+    def __init__(self, B: int, D: int, k: int, group=None, device=None, *, backend=None):
+        """`backend` (tests only) replaces torch's symmetric memory, the process group and the C-ABI binding with stand-ins:
+        an object with .world, .rank, .symm (empty / rendezvous), .cabi (peer_table / peer_scatter / peer_wait), .device."""
+        if backend is None:
+            import torch.distributed._symmetric_memory as symm
+            from . import _cabi
+            self.group = group if group is not None else dist.group.WORLD
+            self.G, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        else:
+            symm, _cabi, self.group, self.G, self.rank, dev = backend.symm, backend.cabi, group, backend.world, backend.rank, backend.device
         self._cabi = _cabi
-        self.group = group if group is not None else dist.group.WORLD
-        self.G = dist.get_world_size(self.group)
-        self.rank = dist.get_rank(self.group)
         self.B, self.D, self.k = B, D, k
         G = self.G
         al = lambda n: (n + 255) // 256 * 256
@@ -73,13 +78,14 @@ class PeerExchange:
         self.par_bytes = self.q_bytes + self.d_bytes + self.i_bytes
         self.flags_off = 2 * self.par_bytes
         total = self.flags_off + al(3 * G * 4)
-        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.buf = symm.empty(total, dtype=torch.uint8, device=dev)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, self.group)
-        torch.cuda.synchronize(dev)
+        if backend is None:
+            torch.cuda.synchronize(dev)
         self.hdl.barrier()                                     # every rank's flags are zero before anyone stores
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.base_ptr = ptrs[self.rank]                        # == self.buf.data_ptr() on a real device
         self.tables = [_cabi.peer_table(G, self.rank, ptrs, [p + self.flags_off + ch * G * 4 for p in ptrs]) for ch in range(3)]
         self.counter = torch.zeros((4,), dtype=torch.int32, device=dev)
         self.seq = 0
@@ -107,7 +113,7 @@ class PeerExchange:
         c, G, B, D = self._cabi, self.G, self.B, self.D
         if not already_scattered:
             c.peer_scatter(q_local.contiguous(), B * D * 4, False, self.tables[0], self.q_off(par) + self.rank * B * D * 4, seq, self.counter[0:1])
-        c.peer_wait(self.buf.data_ptr() + self.flags_off, G, seq)
+        c.peer_wait(self.base_ptr + self.flags_off, G, seq)
         return self._view(self.q_off(par), G * B * D * 4, torch.float32, (G * B, D))
 
     def exchange_candidates(self, d_loc: torch.Tensor, i_loc: torch.Tensor, seq: int, par: int):
@@ -115,7 +121,7 @@ class PeerExchange:
         c, G, B, k = self._cabi, self.G, self.B, self.k
         c.peer_scatter(d_loc.contiguous(), B * k * 4, True, self.tables[1], self.d_off(par) + self.rank * B * k * 4, seq, self.counter[1:2])
         c.peer_scatter(i_loc.contiguous(), B * k * 8, True, self.tables[2], self.i_off(par) + self.rank * B * k * 8, seq, self.counter[2:3])
-        c.peer_wait(self.buf.data_ptr() + self.flags_off + G * 4, 2 * G, seq)
+        c.peer_wait(self.base_ptr + self.flags_off + G * 4, 2 * G, seq)
         return (self._view(self.d_off(par), G * B * k * 4, torch.float32, (G, B, k)),
                 self._view(self.i_off(par), G * B * k * 8, torch.int64, (G, B, k)))
 
@@ -133,6 +139,8 @@ class ShardedIndex:
         self.merge = merge
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if exchange is not None:                               # the exchange knows its world (tests inject one without torch.distributed)
+            self.world, self.rank = exchange.G, exchange.rank
 
     def search_local_queries(self, q_local: torch.Tensor, k: int):
         """q_local [B, D] (this rank's queries) -> (d [B,k], global ids [B,k]) over the WHOLE index."""

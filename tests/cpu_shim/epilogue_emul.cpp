@@ -10,6 +10,8 @@
 #include "../../include/adaptive_b200.h"
 
 static void __threadfence_system() {}
+static void __nanosleep(unsigned) {}
+static void __trap() { printf("__trap() reached\n"); abort(); }
 static unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p += v; return o; }
 namespace ac {
 static inline float ex2_approx(float x) { return exp2f(x); }
@@ -24,6 +26,7 @@ static inline uint32_t ld_acquire_sys(const uint32_t *p) { return *p; }
 #include "_gen_gemm_tc.inc"
 #include "_gen_peer.inc"
 #include "_gen_encoder.inc"
+#include "_gen_peer_cu.inc"
 
 using namespace ac;
 
@@ -285,6 +288,38 @@ static void test_small_kernels() {
     printf("ln_stats / pack_defer / gather_cls_ln / cls_normalize_scatter: %s\n", g_fail ? "FAIL" : "ok");
 }
 
+// peer.cu: scatter of a block to every peer (mode 0) / of block p to peer p (mode 1), flags published once, wait returns
+static void test_peer_kernels() {
+    const int G = 3;
+    const size_t n16 = 37, bytes = n16 * 16;                       // per-destination payload (not a multiple of the block size)
+    for (int mode = 0; mode < 2; ++mode)
+        for (int rank = 0; rank < G; ++rank) {
+            std::vector<std::vector<uint8_t>> peer(G, std::vector<uint8_t>(4096, 0xEE));
+            std::vector<std::vector<uint32_t>> flags(G, std::vector<uint32_t>(G, 0));
+            ac_peer_table t{};
+            t.world = G; t.rank = rank;
+            for (int p = 0; p < G; ++p) { t.buf[p] = peer[p].data(); t.flag[p] = flags[p].data(); }
+            std::vector<uint8_t> src(G * bytes);
+            for (size_t i = 0; i < src.size(); ++i) src[i] = static_cast<uint8_t>(i * 7 + rank);
+            unsigned int counter = 0;
+            const size_t off = 256 + static_cast<size_t>(rank) * bytes;           // slot `rank` of the destination region
+            shim::launch(dim3(3), dim3(256), [&] { peer_scatter_kernel(reinterpret_cast<const uint4 *>(src.data()), n16, t, off, mode, n16, 9u, &counter); });
+            for (int p = 0; p < G; ++p) {
+                const uint8_t *want = src.data() + (mode ? p * bytes : 0);
+                CHECK(memcmp(peer[p].data() + off, want, bytes) == 0, "peer_scatter mode %d rank %d: payload on peer %d", mode, rank, p);
+                for (size_t i = 0; i < peer[p].size(); ++i)
+                    if (i < off || i >= off + bytes) CHECK(peer[p][i] == 0xEE, "peer_scatter mode %d: byte %zu of peer %d outside the slot written", mode, i, p);
+                for (int r = 0; r < G; ++r) CHECK(flags[p][r] == (r == rank ? 9u : 0u), "peer_scatter: flag[%d][%d]", p, r);
+            }
+            CHECK(counter == 0, "peer_scatter: counter not reset");
+            // a wait on flags that are already there returns
+            std::vector<uint32_t> ready(G, 9u);
+            shim::launch(dim3(1), dim3(1024), [&] { peer_wait_kernel(ready.data(), G, 9u); });
+            shim::launch(dim3(1), dim3(1024), [&] { peer_wait_kernel(ready.data(), G, 7u); });       // older step: also satisfied
+        }
+    printf("peer_scatter / peer_wait kernels: %s\n", g_fail ? "FAIL" : "ok");
+}
+
 int main() {
     test_consumer<1, 8>(300, 392);          // FFN1 form: GELU(r (acc - mu c1) + c0), ragged M and N
     test_consumer<1, 16>(300, 392);         // the same with 16 epilogue warps (64 columns per warp)
@@ -294,6 +329,7 @@ int main() {
     test_resid_defer(300, 384);             // 3 parts, ragged M, N = 1.5 tiles
     test_resid_defer(128, 256);
     test_small_kernels();
+    test_peer_kernels();
     printf("epilogue_emul: %s (%d failed checks)\n", g_fail ? "FAIL" : "ALL OK", g_fail);
     return g_fail ? 1 : 0;
 }

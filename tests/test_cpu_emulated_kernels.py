@@ -57,6 +57,7 @@ def _build_epilogues(tmp_path, mutate=None):
         if mutate and f == "encoder.cu":
             src = mutate(src)
         (gen / f"_gen_{f.split('.')[0]}.inc").write_text(src)
+    (gen / "_gen_peer_cu.inc").write_text(ex.extract(os.path.join(ROOT, "adaptive_classifier_b200", "csrc", "peer.cu")))
     return _gxx(gen, "epilogue_emul.cpp", str(tmp_path / ("epi_mut" if mutate else "epi")))
 
 
