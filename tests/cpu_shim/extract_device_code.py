@@ -56,6 +56,17 @@ NOT_EMULATED = re.compile(r"asm\s*(volatile)?\s*\(|CUtensorMap|\btmem_|\bumma_|\
 NOT_EMULATED_HOST = re.compile(r"asm\s*(volatile)?\s*\(|\btmem_|\bumma_|\btma_load|\btma_prefetch|\bmbar_|\btc_fence|\btc_commit|__cvta|"
                                r"cluster_sync|cluster_ctarank|mapa_shared|cudaLaunchConfig_t|cudaGetDriverEntryPoint")
 HOST_MODE = False
+# tc mode (attention_emul.cpp): tests/cpu_shim/tc_emul.h models mbarrier / TMA / tcgen05 / TMEM functionally, so kernels that
+# use the PTX wrappers are kept; the wrappers themselves (inline asm) and anything cluster-related are dropped
+NOT_EMULATED_TC = re.compile(r"asm\s*(volatile)?\s*\(|__cvta|cluster_sync|cluster_ctarank|mapa_shared|cudaLaunch|cudaStream_t|cudaError_t|"
+                             r"cudaEvent|cudaFunc|cudaMalloc|cudaMem|_pair\(")
+TC_MODE = False
+
+
+def rewrite_for_tc(entity):
+    entity = re.sub(r'asm volatile\("st\.shared\.v4\.b32[^"]*"\s*::\s*"r"\((.*?)\),\s*"r"\((.*?)\),\s*"r"\((.*?)\),\s*"r"\((.*?)\),\s*"r"\((.*?)\)\s*:\s*"memory"\);',
+                    r"shim_st_shared_v4(\1, \2, \3, \4, \5);", entity, flags=re.S)
+    return entity.replace("extern __shared__ uint8_t smem_raw[];", "uint8_t *smem_raw = shim::dyn_smem();")
 
 
 def rewrite_launches(entity):
@@ -65,6 +76,10 @@ def rewrite_launches(entity):
 
 def keep(entity):
     head = entity.lstrip()
+    if TC_MODE:
+        if "<<<" in entity or NOT_EMULATED_TC.search(entity):
+            return False
+        return not re.match(r"(template\s*<[^>]*>\s*)?static\s+int\b", head) and not head.startswith("extern \"C\"")
     if HOST_MODE:
         return not NOT_EMULATED_HOST.search(entity) and not head.startswith("#include")
     if "<<<" in entity or NOT_EMULATED.search(entity):
@@ -88,20 +103,23 @@ def per_block_shared(entity):
     return re.sub(r"__shared__\s+(\w+)\s+(\w+)\[([^\]]+)\];", repl, entity)
 
 
-def extract(path, host=False):
-    global HOST_MODE
-    HOST_MODE = host
+def extract(path, host=False, tc=False):
+    global HOST_MODE, TC_MODE
+    HOST_MODE, TC_MODE = host, tc
     text = open(path).read()
     out = []
     for kind, body in chunks(text):
         if kind in ("ns", "c"):
             out.append(body)
-        elif keep(body):
+            continue
+        if tc:
+            body = rewrite_for_tc(body)
+        if keep(body):
             body = per_block_shared(body)
             out.append(rewrite_launches(body) if host else body)
-    HOST_MODE = False
+    HOST_MODE = TC_MODE = False
     return "".join(out)
 
 
 if __name__ == "__main__":
-    sys.stdout.write(extract(sys.argv[1], host="--host" in sys.argv))
+    sys.stdout.write(extract(sys.argv[1], host="--host" in sys.argv, tc="--tc" in sys.argv))

@@ -10,6 +10,11 @@ and pair dispatch) run against a fake CUDA runtime with the real epilogue functo
 and the attention kernels are replaced by plain CPU stand-ins.  Unit CLS rows and hidden states are compared with the fp32
 oracle.
 
+tensor path: tests/cpu_shim/tc_emul.h models mbarrier / TMA (128-byte swizzle) / tcgen05.mma / TMEM functionally.  The
+B200-verified attention_kernel must reproduce a plain reference through the model (this validates the MODEL), then
+attention_pipe_kernel must give the same bits for several grid sizes, and the real gemm_tc_kernel runs all its warp roles
+with the deferred-LayerNorm GELU epilogue.
+
 head_fused: the device code of csrc/head.cu is cut out of the .cu file and compiled as C++; one training epoch is run through
 the launch-per-kernel sequence and through fused::head_epoch_kernel (cooperative, several blocks) from identical states and
 must give bit-identical parameters, AdamW moments and loss.  A mutant without one grid barrier must fail, otherwise the
@@ -178,3 +183,34 @@ def test_encoder_host_logic_and_deferred_layernorm_flow_on_the_cpu_emulation(tmp
         elif tag[1]:                                          # deferred flow vs the LayerNorm-kernel flow of the same build
             assert (cls - base).norm(dim=1).max() < 1e-4, tag
     assert {(0, 0, 0, 0), (1, 1, 0, 0), (0, 1, 0, 0), (1, 1, 3, 0), (0, 1, 3, 1)} <= seen
+
+
+def _build_tensor_path(tmp_path, mutate=None):
+    import extract_device_code as ex
+    gen = tmp_path / "gen_tc"
+    gen.mkdir(exist_ok=True)
+    csrc = os.path.join(ROOT, "adaptive_classifier_b200", "csrc")
+    (gen / "_gen_common_tc.inc").write_text(ex.extract(os.path.join(csrc, "common.cuh"), tc=True))
+    (gen / "_gen_gemm_tc_tc.inc").write_text(ex.extract(os.path.join(csrc, "gemm_tc.cuh"), tc=True))
+    (gen / "_gen_peer.inc").write_text(ex.extract(os.path.join(csrc, "peer.cuh")))
+    src = ex.extract(os.path.join(csrc, "encoder.cu"), tc=True)
+    (gen / "_gen_encoder_tc.inc").write_text(mutate(src) if mutate else src)
+    return _gxx(gen, "attention_emul.cpp", str(tmp_path / ("attn_mut" if mutate else "attn")))
+
+
+def test_pipelined_attention_equals_the_verified_kernel_on_the_blackwell_model(tmp_path):
+    exe = _build_tensor_path(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "attention_emul: ALL OK" in r.stdout, r.stdout[-2500:] + r.stderr[-500:]
+    assert r.stdout.count("attention_pipe == attention_kernel") == 3 and "gemm_tc_kernel<EpiLinear<GELU, DEFER>>" in r.stdout
+
+
+def test_the_blackwell_model_detects_a_wrong_buffer_offset(tmp_path):
+    """mutant: the PV MMA of attention_pipe_kernel reads V^T from the other buffer's slab"""
+    def wrong_slab(src):
+        old = "umma_desc_sw128(smem_u32(buf + 32 * 1024 + slab * 8192))"
+        assert old in src
+        return src.replace(old, "umma_desc_sw128(smem_u32(smem + (b ^ 1) * ATTP_BUF + 32 * 1024 + slab * 8192))")
+    exe = _build_tensor_path(tmp_path, mutate=wrong_slab)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    assert r.returncode != 0 and "outputs differ from attention_kernel" in r.stdout, r.stdout[-1500:]
