@@ -8,9 +8,6 @@
 #include "tc_emul.h"
 #include "../../include/adaptive_b200.h"
 
-uint8_t *shim::g_dyn_smem = nullptr;
-float shim::g_tmem[128][512];
-
 static void __threadfence_system() {}
 static unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p += v; return o; }
 namespace ac {
@@ -126,8 +123,6 @@ static void test_gemm_kernel() {
 }
 
 int main() {
-    static uint8_t *pool = static_cast<uint8_t *>(aligned_alloc(1024, 256 * 1024));
-    shim::g_dyn_smem = pool;
     test_attention(3, 128, 2, false);
     test_attention(5, 50, 2, true);          // ragged S (keys beyond S masked, zero-filled tiles), padding masks, odd item count
     test_attention(2, 17, 1, true);

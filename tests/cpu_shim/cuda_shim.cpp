@@ -28,9 +28,23 @@ void run_blocks(const std::vector<dim3> &blocks, dim3 grid, dim3 block, const st
     if (tpb % 32 != 0) { fprintf(stderr, "cuda_shim: block size must be a multiple of 32\n"); abort(); }
     std::vector<std::unique_ptr<Block>> blks;
     std::vector<std::unique_ptr<Fiber>> fibers;
+    static std::vector<uint8_t *> smem_pool;                    // 256 KB of "shared memory" and a TMEM per resident block
+    static std::vector<float (*)[512]> tmem_pool;
+    static std::vector<Block *> cluster_members;
+    cluster_members.clear();
     for (const dim3 &b : blocks) {
         blks.emplace_back(new Block());
         Block *blk = blks.back().get();
+        const size_t slot = blks.size() - 1;
+        if (slot == smem_pool.size()) {
+            smem_pool.push_back(static_cast<uint8_t *>(aligned_alloc(1024, 256 * 1024)));
+            tmem_pool.push_back(reinterpret_cast<float (*)[512]>(aligned_alloc(64, sizeof(float) * 128 * 512)));
+        }
+        blk->dyn_smem = smem_pool[slot];
+        blk->tmem = tmem_pool[slot];
+        blk->cluster_rank = static_cast<int>(slot);
+        blk->cluster = &cluster_members;
+        cluster_members.push_back(blk);
         blk->bar.n = tpb;
         blk->warps.resize(tpb / 32);
         for (auto &w : blk->warps) w.bar.n = 32;

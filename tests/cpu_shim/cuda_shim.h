@@ -60,6 +60,12 @@ struct Warp {
 struct Block {
     FiberBarrier bar;
     std::vector<Warp> warps;
+    // resources of the functional tensor-path model (tc_emul.h): dynamic shared memory (1024-byte aligned), TMEM, and the
+    // position of this CTA inside its cluster (all blocks of one run_blocks() call form the cluster)
+    uint8_t *dyn_smem = nullptr;
+    float (*tmem)[512] = nullptr;
+    int cluster_rank = 0;
+    std::vector<Block *> *cluster = nullptr;
 };
 struct Fiber {
     ucontext_t ctx;
@@ -96,6 +102,14 @@ void run_blocks(const std::vector<dim3> &blocks, dim3 grid, dim3 block, const st
 inline void launch(dim3 grid, dim3 block, const std::function<void()> &body, unsigned seed = 1) {
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) run_blocks({dim3(bx, by, 0)}, grid, block, body, seed + bx + 977 * by);
+}
+// cluster launch: the `csize` CTAs of a cluster run concurrently (cluster barriers, peer shared memory), clusters one by one
+inline void launch_cluster(dim3 grid, dim3 block, unsigned csize, const std::function<void()> &body, unsigned seed = 1) {
+    for (unsigned c = 0; c < grid.x / csize; ++c) {
+        std::vector<dim3> blocks;
+        for (unsigned r = 0; r < csize; ++r) blocks.push_back(dim3(c * csize + r, 0, 0));
+        run_blocks(blocks, grid, block, body, seed + 31 * c);
+    }
 }
 // cooperative launch: all blocks resident at once (grid.sync works)
 inline void launch_cooperative(dim3 grid, dim3 block, const std::function<void()> &body, unsigned seed = 1) {

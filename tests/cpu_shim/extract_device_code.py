@@ -58,8 +58,7 @@ NOT_EMULATED_HOST = re.compile(r"asm\s*(volatile)?\s*\(|\btmem_|\bumma_|\btma_lo
 HOST_MODE = False
 # tc mode (attention_emul.cpp): tests/cpu_shim/tc_emul.h models mbarrier / TMA / tcgen05 / TMEM functionally, so kernels that
 # use the PTX wrappers are kept; the wrappers themselves (inline asm) and anything cluster-related are dropped
-NOT_EMULATED_TC = re.compile(r"asm\s*(volatile)?\s*\(|__cvta|cluster_sync|cluster_ctarank|mapa_shared|cudaLaunch|cudaStream_t|cudaError_t|"
-                             r"cudaEvent|cudaFunc|cudaMalloc|cudaMem|_pair\(")
+NOT_EMULATED_TC = re.compile(r"asm\s*(volatile)?\s*\(|__cvta|cudaLaunch|cudaStream_t|cudaError_t|cudaEvent|cudaFunc|cudaMalloc|cudaMem")
 TC_MODE = False
 
 

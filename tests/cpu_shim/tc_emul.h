@@ -29,22 +29,23 @@ static inline uint32_t shim_ballot(bool pred) {
 
 namespace shim {
 // per-block dynamic shared memory (1024-byte aligned so that address bits [7:9] used by the swizzle are those of the offset)
-extern uint8_t *g_dyn_smem;
-inline uint8_t *dyn_smem() { return g_dyn_smem; }
-extern float g_tmem[128][512];          // one CTA at a time
+// and TMEM live in the Block (cuda_shim.h); all blocks of one run form the cluster
+inline uint8_t *dyn_smem() { return g_cur->blk->dyn_smem; }
+inline Block *cluster_block(int rank) { return (*g_cur->blk->cluster)[rank]; }
 }  // namespace shim
+#define __cluster_dims__(...)
 
 static inline void shim_st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     uint32_t v[4] = {a, b, c, d};
-    memcpy(shim::g_dyn_smem + addr, v, 16);
+    memcpy(shim::dyn_smem() + addr, v, 16);
 }
 
 namespace ac {
 
-static inline uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(static_cast<const uint8_t *>(p) - shim::g_dyn_smem); }
+static inline uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(static_cast<const uint8_t *>(p) - shim::dyn_smem()); }
 
 // ---- mbarrier: the 64-bit word holds {count:16, pending:16, phase:1, tx bytes:31}
-struct MbarBits { uint64_t count : 16, pending : 16, phase : 1, tx : 31; };
+struct MbarBits { uint64_t count : 16, pending : 16, phase : 1; int64_t tx : 31; };   // tx may go transiently negative (bytes of a peer land before expect_tx)
 static_assert(sizeof(MbarBits) == 8, "mbarrier model must fit the 64-bit word");
 static inline MbarBits *mb(uint64_t *bar) { return reinterpret_cast<MbarBits *>(bar); }
 static inline void mbar_flip_if_complete(uint64_t *bar) {
@@ -63,12 +64,11 @@ static inline void mbar_arrive(uint64_t *bar) {
     mbar_flip_if_complete(bar);
 }
 static inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    mb(bar)->tx += bytes;
+    mb(bar)->tx += static_cast<int64_t>(bytes);
     mbar_arrive(bar);
 }
 static inline void mbar_complete_tx(uint64_t *bar, uint32_t bytes) {
-    if (mb(bar)->tx < bytes) { printf("mbarrier: complete_tx of %u bytes but only %u expected\n", bytes, static_cast<unsigned>(mb(bar)->tx)); abort(); }
-    mb(bar)->tx -= bytes;
+    mb(bar)->tx -= static_cast<int64_t>(bytes);
     mbar_flip_if_complete(bar);
 }
 static inline bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
@@ -114,22 +114,22 @@ static inline void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
         printf("tcgen05.ld: warp %u reads TMEM lane base %u (a warp may only touch lanes 32*(warp %% 4)..)\n", threadIdx.x >> 5, taddr >> 16);
         abort();
     }
-    for (int j = 0; j < 32; ++j) memcpy(&r[j], &shim::g_tmem[lane][col + j], 4);
+    for (int j = 0; j < 32; ++j) memcpy(&r[j], &shim::g_cur->blk->tmem[lane][col + j], 4);
 }
 static inline uint32_t tmem_ld_32x1(uint32_t taddr) {
     uint32_t v;
-    memcpy(&v, &shim::g_tmem[static_cast<int>(taddr >> 16) + shim::g_cur->lane][taddr & 0xffffu], 4);
+    memcpy(&v, &shim::g_cur->blk->tmem[static_cast<int>(taddr >> 16) + shim::g_cur->lane][taddr & 0xffffu], 4);
     return v;
 }
 static inline void tmem_ld_wait() {}
 
 // ---- tcgen05.mma kind::f16, A and B K-major in the SWIZZLE_128B layout, one instruction = K 16
-static inline float umma_operand(uint32_t start_byte, int row, int k /*0..15*/) {
+static inline float umma_operand(const uint8_t *smem, uint32_t start_byte, int row, int k /*0..15*/) {
     // address = start + row * 128 + k * 2; the swizzle XORs address bits [4:6] with bits [7:9]
     uint32_t addr = start_byte + static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>(k) * 2u;
     addr ^= ((addr >> 7) & 7u) << 4;
     __half h;
-    memcpy(&h, shim::g_dyn_smem + addr, 2);
+    memcpy(&h, smem + addr, 2);
     return __half2float(h);
 }
 static inline void umma_tf32(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { printf("umma model: kind::tf32 is not modelled\n"); abort(); }
@@ -141,12 +141,61 @@ static inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, u
     }
     const uint32_t a0 = static_cast<uint32_t>(a_desc & 0x3FFFu) << 4, b0 = static_cast<uint32_t>(b_desc & 0x3FFFu) << 4;
     const int col0 = static_cast<int>(d_tmem & 0xffffu);
+    const uint8_t *smem = shim::dyn_smem();
+    float (*tm)[512] = shim::g_cur->blk->tmem;
     for (int m = 0; m < M; ++m)
         for (int n = 0; n < N; ++n) {
-            float s = accumulate ? shim::g_tmem[m][col0 + n] : 0.f;
-            for (int k = 0; k < 16; ++k) s = fmaf(umma_operand(a0, m, k), umma_operand(b0, n, k), s);
-            shim::g_tmem[m][col0 + n] = s;
+            float s = accumulate ? tm[m][col0 + n] : 0.f;
+            for (int k = 0; k < 16; ++k) s = fmaf(umma_operand(smem, a0, m, k), umma_operand(smem, b0, n, k), s);
+            tm[m][col0 + n] = s;
         }
 }
+
+// ---------------------------------------------------------------- CTA pair (cluster of 2, cta_group::2)
+// shared::cluster addresses: the CTA rank + 1 in bits [24..], the shared::cta offset below
+static inline uint32_t cluster_ctarank() { return static_cast<uint32_t>(shim::g_cur->blk->cluster_rank); }
+static inline uint32_t mapa_shared(uint32_t addr, uint32_t rank) { return addr | ((rank + 1u) << 24); }
+static inline uint64_t *cluster_bar(uint32_t caddr) {
+    const uint32_t r = caddr >> 24;
+    shim::Block *b = r ? shim::cluster_block(static_cast<int>(r) - 1) : shim::g_cur->blk;
+    return reinterpret_cast<uint64_t *>(b->dyn_smem + (caddr & 0xFFFFFFu));
+}
+static inline void cluster_sync_all() { shim::barrier_wait(shim::g_grid_bar); }        // one run = one cluster
+static inline void mbar_arrive_cluster(uint32_t caddr) { mbar_arrive(cluster_bar(caddr)); }
+static inline bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
+static inline void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint32_t bar_caddr, int c0, int c1) {
+    uint64_t scratch;                                   // tma_load_2d signals a barrier: give it a private one, then forward
+    mbar_init(&scratch, 1);
+    mb(&scratch)->tx = static_cast<int64_t>(m->box_rows) * 128;
+    tma_load_2d(smem_dst, m, &scratch, c0, c1);
+    mbar_complete_tx(cluster_bar(bar_caddr), m->box_rows * 128);
+}
+static inline void tmem_alloc_pair(uint32_t *smem_dst, uint32_t) { *smem_dst = 0; }
+static inline void tmem_relinquish_pair() {}
+static inline void tmem_dealloc_pair(uint32_t, uint32_t) {}
+static inline void tc_commit_pair(uint64_t *bar, uint16_t cta_mask) {
+    const uint32_t off = smem_u32(bar);
+    for (int r = 0; r < 2; ++r)
+        if (cta_mask & (1u << r)) mbar_arrive(reinterpret_cast<uint64_t *>(shim::cluster_block(r)->dyn_smem + off));
+}
+// one instruction of the pair: D (256 x N) = A (256 x 16) B^T (N x 16).  CTA r holds rows 128r.. of A and of D (its TMEM)
+// and rows (N/2) r .. of B, each at the SAME shared-memory offsets (this is what ran bit-identically on the B200)
+static inline void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    const int M = static_cast<int>((idesc >> 24) & 31u) << 4, N = static_cast<int>((idesc >> 17) & 63u) << 3;
+    if (M != 256 || ((idesc >> 7) & 7u) != 0 || cluster_ctarank() != 0) { printf("umma pair model: M %d or not the leader\n", M); abort(); }
+    const uint32_t a0 = static_cast<uint32_t>(a_desc & 0x3FFFu) << 4, b0 = static_cast<uint32_t>(b_desc & 0x3FFFu) << 4;
+    const int col0 = static_cast<int>(d_tmem & 0xffffu);
+    for (int r = 0; r < 2; ++r) {
+        shim::Block *cta = shim::cluster_block(r);
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < N; ++n) {
+                const shim::Block *bsrc = shim::cluster_block(n / (N / 2));
+                float s = accumulate ? cta->tmem[m][col0 + n] : 0.f;
+                for (int k = 0; k < 16; ++k) s = fmaf(umma_operand(cta->dyn_smem, a0, m, k), umma_operand(bsrc->dyn_smem, b0, n % (N / 2), k), s);
+                cta->tmem[m][col0 + n] = s;
+            }
+    }
+}
+static inline void umma_tf32_pair(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { printf("umma model: kind::tf32 is not modelled\n"); abort(); }
 
 }  // namespace ac

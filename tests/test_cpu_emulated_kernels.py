@@ -185,17 +185,19 @@ def test_encoder_host_logic_and_deferred_layernorm_flow_on_the_cpu_emulation(tmp
     assert {(0, 0, 0, 0), (1, 1, 0, 0), (0, 1, 0, 0), (1, 1, 3, 0), (0, 1, 3, 1)} <= seen
 
 
-def _build_tensor_path(tmp_path, mutate=None):
+def _build_tensor_path(tmp_path, mutate=None, driver="attention_emul.cpp", mutate_gemm2=None):
     import extract_device_code as ex
     gen = tmp_path / "gen_tc"
     gen.mkdir(exist_ok=True)
     csrc = os.path.join(ROOT, "adaptive_classifier_b200", "csrc")
     (gen / "_gen_common_tc.inc").write_text(ex.extract(os.path.join(csrc, "common.cuh"), tc=True))
     (gen / "_gen_gemm_tc_tc.inc").write_text(ex.extract(os.path.join(csrc, "gemm_tc.cuh"), tc=True))
+    g2 = ex.extract(os.path.join(csrc, "gemm_tc2.cuh"), tc=True)
+    (gen / "_gen_gemm_tc2_tc.inc").write_text(mutate_gemm2(g2) if mutate_gemm2 else g2)
     (gen / "_gen_peer.inc").write_text(ex.extract(os.path.join(csrc, "peer.cuh")))
     src = ex.extract(os.path.join(csrc, "encoder.cu"), tc=True)
     (gen / "_gen_encoder_tc.inc").write_text(mutate(src) if mutate else src)
-    return _gxx(gen, "attention_emul.cpp", str(tmp_path / ("attn_mut" if mutate else "attn")))
+    return _gxx(gen, driver, str(tmp_path / (driver.split(".")[0] + ("_mut" if (mutate or mutate_gemm2) else ""))))
 
 
 def test_pipelined_attention_equals_the_verified_kernel_on_the_blackwell_model(tmp_path):
@@ -214,3 +216,22 @@ def test_the_blackwell_model_detects_a_wrong_buffer_offset(tmp_path):
     exe = _build_tensor_path(tmp_path, mutate=wrong_slab)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
     assert r.returncode != 0 and "outputs differ from attention_kernel" in r.stdout, r.stdout[-1500:]
+
+
+def test_pair_gemm_variants_equal_the_one_cta_kernel_on_the_blackwell_model(tmp_path):
+    """cluster of two concurrently running CTAs: the pair kernel with 8 epilogue warps (ran bit-identically on a B200), the
+    relay variant, 16 epilogue warps / 5 stages with the 64-column functors, and the in-place deferred residual epilogue all
+    give the bits of the 1-CTA kernel"""
+    exe = _build_tensor_path(tmp_path, driver="pair_emul.cpp")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "pair_emul: ALL OK" in r.stdout, r.stdout[-2500:] + r.stderr[-800:]
+
+
+def test_the_pair_model_detects_a_wrong_barrier_count(tmp_path):
+    """mutant: the leader's accumulator-drained barrier still expects 2 x 8 arrivals when 16 epilogue warps arrive per CTA"""
+    def wrong_count(src):
+        assert "mbar_init(&tmem_empty[0], 2 * kEpiWarps);" in src
+        return src.replace("mbar_init(&tmem_empty[0], 2 * kEpiWarps);", "mbar_init(&tmem_empty[0], 2 * GEMM_EPI_WARPS);")
+    exe = _build_tensor_path(tmp_path, driver="pair_emul.cpp", mutate_gemm2=wrong_count)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    assert r.returncode != 0, r.stdout[-800:]
