@@ -253,6 +253,39 @@ int main(int argc, char **argv) {
         printf("variant cls_only=%d ln_defer=%d epi16=%d gemm_pair=%d: %lld launches\n", v[0], v[1], v[2], v[3], ac::g_launches);
         ac::g_launches = 0;
     }
+    // ac_encoder_forward_cls_scatter: the final normalise kernel also stores the rows into every peer's buffer + flags
+    {
+        ac_encoder_config cfg{};
+        cfg.arch = arch; cfg.layers = L; cfg.hidden = H; cfg.heads = heads; cfg.intermediate = I; cfg.vocab = V; cfg.max_pos = maxpos;
+        cfg.type_vocab = typev; cfg.pad_idx = 0; cfg.ln_eps = eps; cfg.precision = AC_PREC_F16; cfg.max_tokens = B * S; cfg.cls_only = 1;
+        for (auto &o : g_options) o = 0;
+        ac_encoder *enc = nullptr;
+        if (ac_encoder_create(&cfg, &w, &enc)) return 5;
+        const int G = 3, rank = 2;
+        const size_t off = 512;
+        std::vector<std::vector<float>> peer(G, std::vector<float>(off / 4 + size_t(B) * H + 16, -9.f));
+        std::vector<std::vector<uint32_t>> flags(G, std::vector<uint32_t>(G, 0));
+        ac_peer_table t{};
+        t.world = G; t.rank = rank;
+        for (int p = 0; p < G; ++p) { t.buf[p] = peer[p].data(); t.flag[p] = flags[p].data(); }
+        uint32_t counter = 0;
+        std::vector<float> cls(size_t(B) * H, -5.f), ref(size_t(B) * H, -5.f);
+        if (ac_encoder_forward_cls(enc, ids.data(), use_mask ? mask.data() : nullptr, nullptr, B, S, ref.data(), nullptr)) return 6;
+        if (ac_encoder_forward_cls_scatter(enc, ids.data(), use_mask ? mask.data() : nullptr, nullptr, B, S, cls.data(), &t, off, 17u, &counter, nullptr)) return 7;
+        int bad = memcmp(cls.data(), ref.data(), cls.size() * 4) != 0;
+        for (int p = 0; p < G; ++p) {
+            bad += memcmp(peer[p].data() + off / 4, ref.data(), ref.size() * 4) != 0;
+            bad += peer[p][off / 4 - 1] != -9.f || peer[p][off / 4 + ref.size()] != -9.f;
+            for (int r = 0; r < G; ++r) bad += flags[p][r] != (r == rank ? 17u : 0u);
+        }
+        // the sink must not leak into the next ordinary forward
+        std::fill(peer[0].begin(), peer[0].end(), -9.f);
+        if (ac_encoder_forward_cls(enc, ids.data(), use_mask ? mask.data() : nullptr, nullptr, B, S, cls.data(), nullptr)) return 8;
+        for (float x : peer[0]) bad += x != -9.f;
+        printf("forward_cls_scatter: %s\n", bad ? "FAIL" : "ok");
+        ac_encoder_destroy(enc);
+        if (bad) return 9;
+    }
     fclose(out);
     return 0;
 }

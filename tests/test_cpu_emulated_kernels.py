@@ -165,7 +165,7 @@ def test_encoder_host_logic_and_deferred_layernorm_flow_on_the_cpu_emulation(tmp
         f.write(ids.to(torch.int32).numpy().tobytes())
         f.write(mask.to(torch.int32).numpy().tobytes())
     r = subprocess.run([exe, str(fin), str(fout)], capture_output=True, text=True, timeout=1500)
-    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
+    assert r.returncode == 0 and "forward_cls_scatter: ok" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
     raw = open(fout, "rb").read()
     off, seen, base = 0, set(), None
     keep = mask.bool()
