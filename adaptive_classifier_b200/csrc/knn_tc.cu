@@ -153,6 +153,51 @@ struct EpiKnn {
 };
 
 
+// Per-lane slow path (opt-in, option "knn_epi"): same lists, cheaper to build.
+//
+// EpiKnn::tile walks the UNION of the 32 lanes' hit columns; every iteration re-reads one accumulator column from TMEM and
+// runs the ~100-instruction insert network for the one or two lanes that hit there, the other lanes idle.  In the middle of
+// the scan every lane still has about one insert per chunk, at a different column than its neighbours, so the union has 20-32
+// members: the ncu capture of the scan shows 19 thread-instructions per accumulator element at 16 of 32 lanes active and a
+// tensor pipe that is busy 48 % of the time (profiles/r01_knn_v2_ncu.txt).  Here every lane walks ITS OWN hits: the chunk's
+// accumulator values go to the warp's private staging tile 16 columns at a time (lane-private rows, stride 17 floats), each
+// lane pops its lowest hit column, reads its own value back and inserts; the loop runs max-over-lanes(hits) times instead of
+// |union| times.  Every lane still inserts its hits in ascending column order, so the lists -- and everything downstream,
+// including the certification argument -- are unchanged bit for bit.  Status: NOT yet run on hardware.
+struct EpiKnnLane : EpiKnn {
+    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
+                                         uint8_t *stage, int lane, int buf, uint32_t /*taddr*/) const {
+        const float pn_lane = buf ? st.pn[1] : st.pn[0];
+        const float thr = fminf(st.key[KNN_KC - 1], st.gt);
+        uint32_t hits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float pn = __shfl_sync(0xffffffffu, pn_lane, j);
+            const float key = fmaf(-2.f, v[j], pn);
+            hits |= (key < thr) ? (1u << j) : 0u;
+        }
+        if (__reduce_or_sync(0xffffffffu, hits) == 0) return;
+        float *srow = reinterpret_cast<float *>(stage) + lane * 17;          // 32 x 17 floats = 2176 B of the 2560 B tile
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t hh = (hits >> (16 * half)) & 0xffffu;
+            if (!__any_sync(0xffffffffu, hh != 0)) continue;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) srow[jj] = v[16 * half + jj];    // lane-private row: no cross-lane hazard
+            while (__any_sync(0xffffffffu, hh != 0)) {
+                const bool act = hh != 0;
+                const int jj = act ? __ffs(hh) - 1 : 0;
+                hh &= hh - 1;
+                const float x = srow[jj];
+                const float pn = __shfl_sync(0xffffffffu, pn_lane, 16 * half + jj);
+                const float key = fmaf(-2.f, x, pn);
+                const int64_t n = static_cast<int64_t>(col0) + 16 * half + jj;
+                if (act && key < fminf(st.key[KNN_KC - 1], st.gt) && n < N) insert(st, key, static_cast<int32_t>(n));
+            }
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // small kernels around the coarse pass
 // ------------------------------------------------------------------------------------------------
@@ -387,6 +432,8 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     const bool pair = option(OPT_KNN_PAIR) != 0 && pl.tiles_m % 2 == 0 && pl.grid_ctas % 2 == 0;
     EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt, pair ? 1 : 0};   // slots = 2 per CTA
     const uint32_t b_box = pair ? GEMM2_B_ROWS : GEMM_BLOCK_N;
+    const bool lane_epi = option(OPT_KNN_EPI) != 0 && !pair;               // per-lane slow path (1-CTA kernel)
+    EpiKnnLane epi_lane{epi};
     // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16
     // shadow the kernel actually streams 2.N.D bytes (the exact re-rank below still reads fp32 rows)
     if (p_half) {
@@ -394,6 +441,8 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
         if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, b_box, 64))) return rc;
         rc = pair ? launch_gemm_tc2<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
                                                                    pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
+             : lane_epi ? launch_gemm_tc<EpiKnnLane, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s,
+                                                                           pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
                   : launch_gemm_tc<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
                                                                   pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D);
         if (rc) return rc;
@@ -402,6 +451,8 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
         if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, b_box, GEMM_BLOCK_K))) return rc;
         rc = pair ? launch_gemm_tc2<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
                                                   PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
+             : lane_epi ? launch_gemm_tc<EpiKnnLane, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s, pl.grid_ctas,
+                                                           PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
                   : launch_gemm_tc<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
                                                  PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D);
         if (rc) return rc;

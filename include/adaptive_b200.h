@@ -61,6 +61,9 @@ int ac_device_check(void);            /* 0 when the current device is sm_100 (B2
  *   "pdl" 1 : the opt-in kernels above (pair GEMMs, ln_stats, pipelined attention) are launched with programmatic stream
  *                   serialization: their prologue overlaps the tail of the previous kernel and they block in
  *                   griddepcontrol.wait before touching global memory.  NOT yet run on hardware.
+ *   "knn_epi" 1 : the prototype scan's epilogue lets every lane walk its own candidate hits (staged through shared memory)
+ *                   instead of the warp walking the union of all lanes' hits: same candidate lists, far fewer
+ *                   instructions.  Results cannot change.  NOT yet run on hardware.
  * Unknown names return AC_E_INVALID. */
 int ac_set_option(const char *name, long long value);
 int ac_get_option(const char *name, long long *value);

@@ -185,7 +185,7 @@ def test_encoder_host_logic_and_deferred_layernorm_flow_on_the_cpu_emulation(tmp
     assert {(0, 0, 0, 0), (1, 1, 0, 0), (0, 1, 0, 0), (1, 1, 3, 0), (0, 1, 3, 1)} <= seen
 
 
-def _build_tensor_path(tmp_path, mutate=None, driver="attention_emul.cpp", mutate_gemm2=None):
+def _build_tensor_path(tmp_path, mutate=None, driver="attention_emul.cpp", mutate_gemm2=None, mutate_knn=None):
     import extract_device_code as ex
     gen = tmp_path / "gen_tc"
     gen.mkdir(exist_ok=True)
@@ -197,7 +197,9 @@ def _build_tensor_path(tmp_path, mutate=None, driver="attention_emul.cpp", mutat
     (gen / "_gen_peer.inc").write_text(ex.extract(os.path.join(csrc, "peer.cuh")))
     src = ex.extract(os.path.join(csrc, "encoder.cu"), tc=True)
     (gen / "_gen_encoder_tc.inc").write_text(mutate(src) if mutate else src)
-    return _gxx(gen, driver, str(tmp_path / (driver.split(".")[0] + ("_mut" if (mutate or mutate_gemm2) else ""))))
+    knn = ex.extract(os.path.join(csrc, "knn_tc.cu"), tc=True)
+    (gen / "_gen_knn_tc_tc.inc").write_text(mutate_knn(knn) if mutate_knn else knn)
+    return _gxx(gen, driver, str(tmp_path / (driver.split(".")[0] + ("_mut" if (mutate or mutate_gemm2 or mutate_knn) else ""))))
 
 
 def test_pipelined_attention_equals_the_verified_kernel_on_the_blackwell_model(tmp_path):
@@ -235,3 +237,22 @@ def test_the_pair_model_detects_a_wrong_barrier_count(tmp_path):
     exe = _build_tensor_path(tmp_path, driver="pair_emul.cpp", mutate_gemm2=wrong_count)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
     assert r.returncode != 0, r.stdout[-800:]
+
+
+def test_knn_coarse_pass_epilogues_on_the_blackwell_model(tmp_path):
+    """gemm_tc_kernel<EpiKnn> (verified on a B200) and <EpiKnnLane> (per-lane slow path, option "knn_epi"): per query, the best k
+    of the union of its candidate lists equals a brute-force scan with the same arithmetic; lists sorted, no row twice"""
+    exe = _build_tensor_path(tmp_path, driver="knn_emul.cpp")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "knn_emul: ALL OK" in r.stdout, r.stdout[-2500:] + r.stderr[-800:]
+
+
+def test_the_knn_model_detects_a_dropped_column_half(tmp_path):
+    """mutant: the per-lane slow path forgets the hits in columns 16..31 of every chunk"""
+    def drop_half(src):
+        old = "for (int half = 0; half < 2; ++half) {\n            uint32_t hh"
+        assert old in src
+        return src.replace(old, "for (int half = 0; half < 1; ++half) {\n            uint32_t hh")
+    exe = _build_tensor_path(tmp_path, driver="knn_emul.cpp", mutate_knn=drop_half)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    assert r.returncode != 0 and "EpiKnnLane" in r.stdout and "FAIL" in r.stdout, r.stdout[-1500:]

@@ -29,7 +29,7 @@ def _encoder(cabi, sd, cfg, max_tokens, cls_only=True):
 
 
 def test_option_roundtrip(cabi):
-    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl"):
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi"):
         prev = cabi.get_option(name)          # 0 unless AC_OPTIONS preset it for this process
         with cabi.option(name, 1 - prev):
             assert cabi.get_option(name) == 1 - prev
@@ -77,6 +77,24 @@ def test_pair_knn_bit_identical(cabi, B, N, shadow):
     ph = cabi.knn_make_shadow(P) if shadow else None
     d0, i0 = cabi.knn_l2_topk(Q, P, k, algo=cabi.AC_KNN_TENSOR, p_half=ph)
     with cabi.option("knn_pair", 1):
+        d1, i1 = cabi.knn_l2_topk(Q, P, k, algo=cabi.AC_KNN_TENSOR, p_half=ph)
+    assert torch.equal(i0, i1) and torch.equal(d0.view(torch.int32), d1.view(torch.int32))
+    de, ie = cabi.knn_l2_topk(Q, P, k, algo=cabi.AC_KNN_EXACT)
+    assert torch.equal(ie, i1) and torch.equal(de.view(torch.int32), d1.view(torch.int32))
+
+
+@experimental
+@pytest.mark.parametrize("B,N,shadow,k", [(512, 60000, True, 5), (256, 30000, False, 5), (300, 20000, True, 12), (64, 5000, True, 1)])
+def test_knn_per_lane_epilogue_bit_identical(cabi, B, N, shadow, k):
+    """option "knn_epi": the same candidate semantics, so the final (d, id) must equal the default tensor path and the exact
+    scan bit for bit"""
+    D = 768
+    rng = np.random.default_rng(B + N + k)
+    P = torch.nn.functional.normalize(torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)), dim=1).cuda()
+    Q = torch.nn.functional.normalize(P[:B] + 0.05 * torch.randn(B, D, device="cuda"), dim=1)
+    ph = cabi.knn_make_shadow(P) if shadow else None
+    d0, i0 = cabi.knn_l2_topk(Q, P, k, algo=cabi.AC_KNN_TENSOR, p_half=ph)
+    with cabi.option("knn_epi", 1):
         d1, i1 = cabi.knn_l2_topk(Q, P, k, algo=cabi.AC_KNN_TENSOR, p_half=ph)
     assert torch.equal(i0, i1) and torch.equal(d0.view(torch.int32), d1.view(torch.int32))
     de, ie = cabi.knn_l2_topk(Q, P, k, algo=cabi.AC_KNN_EXACT)

@@ -161,6 +161,8 @@ static int run_linear() {
     return bad == 0 ? 0 : 1;
 }
 
+static const char *g_knn_option = "knn_pair";   // or "knn_epi" (per-lane slow path of the scan epilogue)
+
 static int run_knn() {
     const int B = 512, D = 768, k = 5;
     const int64_t N = 1000000;
@@ -191,7 +193,7 @@ static int run_knn() {
     int64_t *i0 = dmalloc<int64_t>(B * k), *i1 = dmalloc<int64_t>(B * k);
     CK(cudaDeviceSynchronize());
     for (int variant = 0; variant < 2; ++variant) {
-        AC(ac_set_option("knn_pair", variant ? g_pair : 0));
+        AC(ac_set_option(g_knn_option, variant ? g_pair : 0));
         float *dd = variant ? d1 : d0; int64_t *ii = variant ? i1 : i0;
         for (int it = 0; it < 2; ++it) AC(ac_knn_l2_topk(Q, P, pn, Ph, B, N, D, k, dd, ii, 0, ws, wsb, AC_KNN_TENSOR, nullptr));
         CK(cudaDeviceSynchronize());
@@ -205,7 +207,7 @@ static int run_knn() {
         double ms = 0, fl = 0, by = 0; long long n = 0;
         AC(ac_profile_read(2, &ms, &fl, &by, &n));
         printf("knn variant=%s B=%d N=%lld D=%d k=%d: whole search %.3f ms; coarse scan %.3f ms/launch = %.0f GB/s algorithmic (4ND), %.0f TFLOP/s\n",
-               variant ? "pair" : "1cta", B, static_cast<long long>(N), D, k, time_ms(e0, e1) / reps, ms / n, by / n / (ms / n * 1e-3) / 1e9,
+               variant ? g_knn_option : "default", B, static_cast<long long>(N), D, k, time_ms(e0, e1) / reps, ms / n, by / n / (ms / n * 1e-3) / 1e9,
                fl / n / (ms / n * 1e-3) / 1e12);
         fflush(stdout);
     }
@@ -409,13 +411,14 @@ static int run_epoch() {
 
 int main(int argc, char **argv) {
     setvbuf(stdout, nullptr, _IOLBF, 0);
-    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full|defer_layers|epoch|epi16|attn|pdl [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
+    if (argc < 2) { printf("usage: %s linear|knn|encoder|defer|defer_full|defer_layers|epoch|epi16|attn|pdl|knn_epi [pair option value: 1 (default) | 2 = relay variant]\n", argv[0]); return 64; }
     if (argc > 2) g_pair = atoi(argv[2]);
     AC(ac_device_check());
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
     printf("device: %s, %d SMs, ABI v%d, test %s, pair option %d\n", pr.name, pr.multiProcessorCount, ac_version(), argv[1], g_pair);
     if (!strcmp(argv[1], "linear")) return run_linear();
     if (!strcmp(argv[1], "knn")) return run_knn();
+    if (!strcmp(argv[1], "knn_epi")) { g_knn_option = "knn_epi"; g_pair = 1; return run_knn(); }
     if (!strcmp(argv[1], "encoder")) return run_encoder("gemm_pair", 1);
     if (!strcmp(argv[1], "epoch")) return run_epoch();
     if (!strcmp(argv[1], "defer_layers")) return run_defer_layers();
