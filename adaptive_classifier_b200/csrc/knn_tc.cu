@@ -432,14 +432,16 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     const bool pair = option(OPT_KNN_PAIR) != 0 && pl.tiles_m % 2 == 0 && pl.grid_ctas % 2 == 0;
     EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt, pair ? 1 : 0};   // slots = 2 per CTA
     const uint32_t b_box = pair ? GEMM2_B_ROWS : GEMM_BLOCK_N;
-    const bool lane_epi = option(OPT_KNN_EPI) != 0 && !pair;               // per-lane slow path (1-CTA kernel)
+    const bool lane_epi = option(OPT_KNN_EPI) != 0;                        // per-lane slow path of the epilogue
     EpiKnnLane epi_lane{epi};
     // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16
     // shadow the kernel actually streams 2.N.D bytes (the exact re-rank below still reads fp32 rows)
     if (p_half) {
         if ((rc = make_tmap_2d(&ta, Qh, 2, Bp, D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_M, 64))) return rc;
         if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, b_box, 64))) return rc;
-        rc = pair ? launch_gemm_tc2<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
+        rc = pair && lane_epi ? launch_gemm_tc2<EpiKnnLane, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s,
+                                                                                   pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
+             : pair ? launch_gemm_tc2<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
                                                                    pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
              : lane_epi ? launch_gemm_tc<EpiKnnLane, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s,
                                                                            pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
@@ -449,7 +451,9 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     } else {
         if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
         if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, b_box, GEMM_BLOCK_K))) return rc;
-        rc = pair ? launch_gemm_tc2<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
+        rc = pair && lane_epi ? launch_gemm_tc2<EpiKnnLane, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s, pl.grid_ctas,
+                                                                  PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
+             : pair ? launch_gemm_tc2<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
                                                   PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
              : lane_epi ? launch_gemm_tc<EpiKnnLane, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s, pl.grid_ctas,
                                                            PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)

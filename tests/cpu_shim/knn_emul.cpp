@@ -34,7 +34,7 @@ static int g_fail = 0;
 #define CHECK(cond, ...) do { if (!(cond)) { if (g_fail < 20) { printf("  FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } ++g_fail; } } while (0)
 
 template <class Epi>
-static void run_scan(const char *name, int B, int N, int D, int ctas_per_tile, int k) {
+static void run_scan(const char *name, int B, int N, int D, int ctas_per_tile, int k, bool pair = false) {
     std::mt19937 rng(5);
     std::normal_distribution<float> nd(0.f, 1.f);
     const int tiles_m = (B + 127) / 128, Bp = tiles_m * 128;
@@ -63,9 +63,15 @@ static void run_scan(const char *name, int B, int N, int D, int ctas_per_tile, i
     std::vector<uint32_t> gthr(Bp, 0xFFFFFFFFu);
     CUtensorMap ta{Qh.data(), 2, static_cast<uint64_t>(Bp), static_cast<uint64_t>(D), static_cast<uint64_t>(D) * 2, 128, 64};
     CUtensorMap tb{Ph.data(), 2, static_cast<uint64_t>(N), static_cast<uint64_t>(D), static_cast<uint64_t>(D) * 2, 256, 64};
-    const EpiKnn base{pn.data(), ckey.data(), cidx.data(), gthr.data(), B, static_cast<int64_t>(N), tiles_m, slots, kt, 0};
+    const EpiKnn base{pn.data(), ckey.data(), cidx.data(), gthr.data(), B, static_cast<int64_t>(N), tiles_m, slots, kt, pair ? 1 : 0};
     Epi epi{base};
-    shim::launch(dim3(grid), dim3(GEMM_THREADS), [&] { gemm_tc_kernel<Epi, true, GEMM_KIND_F16>(ta, tb, Bp, N, D, epi); });
+    if (pair) {      // a cluster owns two consecutive query tiles; B rows split between the two CTAs (128-row boxes)
+        CUtensorMap tb2 = tb;
+        tb2.box_rows = 128;
+        shim::launch_cluster(dim3(grid), dim3(GEMM_THREADS), 2, [&] { gemm_tc2_kernel<Epi, true, GEMM_KIND_F16, 6, false, 8>(ta, tb2, Bp, N, D, epi); });
+    } else {
+        shim::launch(dim3(grid), dim3(GEMM_THREADS), [&] { gemm_tc_kernel<Epi, true, GEMM_KIND_F16>(ta, tb, Bp, N, D, epi); });
+    }
 
     long long inserted = 0;
     for (int b = 0; b < B; ++b) {
@@ -99,6 +105,8 @@ int main() {
     run_scan<EpiKnn>("EpiKnn    ", 200, 3000, 128, 2, 5);
     run_scan<EpiKnnLane>("EpiKnnLane", 200, 3000, 128, 2, 5);
     run_scan<EpiKnnLane>("EpiKnnLane", 70, 1000, 64, 1, 10);       // ragged query tile, ragged last prototype tile, kt = 13
+    run_scan<EpiKnn>("EpiKnn     pair", 200, 3000, 128, 2, 5, true);     // pair kernel (ran on the B200 with EpiKnn)
+    run_scan<EpiKnnLane>("EpiKnnLane pair", 200, 3000, 128, 2, 5, true);
     printf("knn_emul: %s (%d failed checks)\n", g_fail ? "FAIL" : "ALL OK", g_fail);
     return g_fail ? 1 : 0;
 }
