@@ -1,7 +1,8 @@
 #!/bin/bash
-# FIRST GPU call of round 2 (about 8-10 minutes of box time): everything written after the round-1 GPU budget ran out is
+# FIRST GPU call of round 2 (about 20 minutes of box time; trim the bench variant list in step 3 if the budget is tight): everything written after the round-1 GPU budget ran out is
 # checked and measured here in one go.  Nothing in this script changes defaults; it only produces evidence in gpurun_out/.
-#   1. torch-free C-ABI harness: pair kernels (re-check), deferred LayerNorm, fused head epoch, 16 epilogue warps
+#   1. torch-free C-ABI harness: pair kernels (re-check), deferred LayerNorm, fused head epoch, 16 epilogue warps, pipelined
+#      attention, per-lane kNN epilogue, programmatic dependent launch
 #   2. the GPU suite with the experimental tests enabled
 #   3. bench.py: default, and with each variant / the combination switched on through AC_OPTIONS
 #   4. config 4 (add_examples loop) with and without the fused epoch
