@@ -29,7 +29,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // run-time options (ac_set_option): experimental kernel variants stay opt-in until they are measured on a B200
 static std::atomic<long long> g_options[OPT_NUM];
-static const char *const g_option_names[OPT_NUM] = {"gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi"};
+static const char *const g_option_names[OPT_NUM] = {"gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi", "cls_attn"};
 long long option(int id) { return (id >= 0 && id < OPT_NUM) ? g_options[id].load(std::memory_order_relaxed) : 0; }
 static int option_id(const char *name) {
     if (!name) return -1;

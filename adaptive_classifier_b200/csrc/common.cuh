@@ -45,7 +45,7 @@ int prof_begin(int cls, double flops, double bytes, cudaStream_t s);   // slot i
 void prof_end(int slot, cudaStream_t s);
 
 // run-time options set through ac_set_option (api.cu)
-enum { OPT_GEMM_PAIR = 0, OPT_KNN_PAIR = 1, OPT_LN_DEFER = 2, OPT_HEAD_FUSED = 3, OPT_EPI16 = 4, OPT_ATTN_PIPE = 5, OPT_PDL = 6, OPT_KNN_EPI = 7, OPT_NUM = 8 };
+enum { OPT_GEMM_PAIR = 0, OPT_KNN_PAIR = 1, OPT_LN_DEFER = 2, OPT_HEAD_FUSED = 3, OPT_EPI16 = 4, OPT_ATTN_PIPE = 5, OPT_PDL = 6, OPT_KNN_EPI = 7, OPT_CLS_ATTN = 8, OPT_NUM = 9 };
 long long option(int id);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

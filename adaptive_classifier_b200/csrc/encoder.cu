@@ -1097,6 +1097,94 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CLS-only attention of the last layer (opt-in, option "cls_attn").  Downstream of the last layer's attention only row 0
+// of every sequence is read (gather_cls_kernel / gather_cls_ln_kernel; classifier.py:1272 pools the CLS token), so
+// softmax(Q K^T) V shrinks to one query row per (sequence, head): S dot products of length 64 and a [1 x S] x [S x 64]
+// product.  One warp per (b, h): lanes over keys for the scores (the K row of a key is 128 contiguous bytes), lanes over
+// head dims for the output (row d of the transposed V buffer is S_pad contiguous keys).  Same arithmetic as
+// attention_kernel: masked two-pass softmax in base 2, P rounded to fp16 before PV, fp32 sums, 1 / rowsum at the end.
+// Reads 2 x B x S x H halves (K and V once), writes B x H halves: ~100 MB for the bench batch against the 403 MB and the
+// 128 x 128 tensor-core tiles of the full kernel.  Rows other than the CLS rows of ctx are left stale - the CLS-only tail
+// never reads them.  Status: NOT yet run on hardware (CPU-emulated through the encoder host path).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTC_WARPS = 8;
+constexpr int ATTC_MAX_S = 512;
+
+__global__ void __launch_bounds__(ATTC_WARPS * 32)
+attention_cls_kernel(const __half *__restrict__ qk, const __half *__restrict__ vT, const int32_t *__restrict__ mask, int B, int S,
+                     int S_pad, int heads, int H, __half *__restrict__ ctx) {
+    __shared__ float sq[ATTC_WARPS][64];
+    __shared__ float sp[ATTC_WARPS][ATTC_MAX_S];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * ATTC_WARPS + warp;
+    if (item >= B * heads) return;                                    // warp-uniform
+    const int b = item / heads, h = item % heads;
+    const int64_t row0 = static_cast<int64_t>(b) * S;
+    const int64_t ld = 2 * static_cast<int64_t>(H);                   // Q | K row of the qk buffer
+    {
+        const float2 f = __half22float2(reinterpret_cast<const __half2 *>(qk + row0 * ld + h * 64)[lane]);
+        sq[warp][2 * lane] = f.x;
+        sq[warp][2 * lane + 1] = f.y;
+    }
+    __syncwarp();
+    // ---- scores of the CLS query against every key; invalid keys (padding) are remembered as -inf
+    float mx = -CUDART_INF_F;
+    for (int key = lane; key < S; key += 32) {
+        const uint4 *kr = reinterpret_cast<const uint4 *>(qk + (row0 + key) * ld + H + h * 64);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = kr[c];
+            const __half2 *hp = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hp[j]);
+                s = fmaf(sq[warp][8 * c + 2 * j], f.x, s);
+                s = fmaf(sq[warp][8 * c + 2 * j + 1], f.y, s);
+            }
+        }
+        const bool ok = !mask || mask[row0 + key] != 0;
+        sp[warp][key] = ok ? s : -CUDART_INF_F;
+        if (ok) mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float scale_log2 = rsqrtf(64.f) * 1.44269504088896340736f;
+    const float mxs = mx * scale_log2;
+    float sum = 0.f;
+    for (int key = lane; key < S; key += 32) {
+        const float s = sp[warp][key];
+        const float e = (s != -CUDART_INF_F) ? ex2_approx(fmaf(s, scale_log2, -mxs)) : 0.f;
+        sum += e;
+        sp[warp][key] = __half2float(__float2half_rn(e));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
+    // ---- out[d] = sum_key P[key] V[key, d]; lane owns head dims lane and lane + 32
+    const int S8 = S & ~7;
+#pragma unroll
+    for (int dd = 0; dd < 2; ++dd) {
+        const int d = lane + 32 * dd;
+        const __half *vr = vT + (static_cast<int64_t>(b) * H + h * 64 + d) * S_pad;
+        float acc = 0.f;
+        for (int k0 = 0; k0 < S8; k0 += 8) {
+            const uint4 u = *reinterpret_cast<const uint4 *>(vr + k0);
+            const __half2 *hp = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hp[j]);
+                acc = fmaf(sp[warp][k0 + 2 * j], f.x, acc);
+                acc = fmaf(sp[warp][k0 + 2 * j + 1], f.y, acc);
+            }
+        }
+        for (int k = S8; k < S; ++k) acc = fmaf(sp[warp][k], __half2float(vr[k]), acc);
+        ctx[row0 * H + h * 64 + d] = __float2half_rn(acc * inv);
+    }
+}
+
 }  // namespace ac
 
 // ================================================================================================
@@ -1152,6 +1240,36 @@ static int launch_cls_normalize(ac_encoder *e, const float *x, int B, int S, int
                                                                           e->sink_counter);
     else
         cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, B, S, H, out);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+// softmax(Q K^T / 8 + mask) V of layer l out of e->qk / e->vT into e->ctx
+static int launch_attention(ac_encoder *e, const int32_t *mask, int B, int S, int S_pad, int l, cudaStream_t s) {
+    const ac_encoder_config &c = e->cfg;
+    const int H = c.hidden;
+    const bool cls_tail = l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc;
+    if (cls_tail && option(OPT_CLS_ATTN)) {
+        // the CLS-only tail reads row 0 of every sequence only: one query row per (sequence, head)
+        const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * 64, 0.0, s);
+        attention_cls_kernel<<<(B * c.heads + ATTC_WARPS - 1) / ATTC_WARPS, ATTC_WARPS * 32, 0, s>>>(e->qk, e->vT, mask, B, S, S_pad,
+                                                                                                  c.heads, H, e->ctx);
+        prof_end(slot, s);
+        AC_LAUNCH_CHECK();
+        return AC_OK;
+    }
+    // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
+    const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
+    if (S <= 128 && option(OPT_ATTN_PIPE)) {
+        const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
+        AC_CUDA(launch_maybe_pdl(attention_pipe_kernel, dim3(ctas), dim3(ATTP_THREADS), ATTP_SMEM, s, option(OPT_PDL) != 0, e->m_qk_att,
+                                 e->m_vt_att, mask, B, S, c.heads, H, e->ctx));
+    } else if (S <= 128)
+        attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
+    else
+        attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S,
+                                                                                                c.heads, H, e->ctx);
+    prof_end(slot, s);
     AC_LAUNCH_CHECK();
     return AC_OK;
 }
@@ -1384,20 +1502,7 @@ static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, in
         EpiQKVDefer eq{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
         EpiQKVDefer16 eq16{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
         if ((rc = launch_linear_epi16(2, e->m_xh, e->m_wqkv_d[l], e->p_wqkv_d[l], M, 3 * H, H, eq, eq16, s))) return rc;
-        {
-            const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
-            if (S <= 128 && option(OPT_ATTN_PIPE)) {
-                const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
-                AC_CUDA(launch_maybe_pdl(attention_pipe_kernel, dim3(ctas), dim3(ATTP_THREADS), ATTP_SMEM, s, option(OPT_PDL) != 0,
-                                         e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx));
-            } else if (S <= 128)
-                attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
-            else
-                attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(
-                    e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
-            prof_end(slot, s);
-        }
-        AC_LAUNCH_CHECK();
+        if ((rc = launch_attention(e, mask, B, S, S_pad, l, s))) return rc;
         if (l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc) {
             // ---- CLS-only tail of the last layer (M = B rows): materialise LN_pending on the CLS rows and continue with
             // the ordinary kernels and the plain (not gamma-scaled) FFN1 weight
@@ -1496,21 +1601,7 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     for (int l = 0; l < c.layers; ++l) {
         EpiQKV eq{e->bqkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H};
         if ((rc = launch_linear_epi16(2, e->m_xh, e->m_wqkv[l], e->p_wqkv[l], M, 3 * H, H, eq, eq, s))) return rc;
-        {
-            // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
-            const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
-            if (S <= 128 && option(OPT_ATTN_PIPE)) {
-                const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
-                AC_CUDA(launch_maybe_pdl(attention_pipe_kernel, dim3(ctas), dim3(ATTP_THREADS), ATTP_SMEM, s, option(OPT_PDL) != 0,
-                                         e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx));
-            } else if (S <= 128)
-                attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
-            else
-                attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(
-                    e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
-            prof_end(slot, s);
-        }
-        AC_LAUNCH_CHECK();
+        if ((rc = launch_attention(e, mask, B, S, S_pad, l, s))) return rc;
         if (l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc) {
             // ---- CLS-only tail of the last layer: M = B rows
             const int cb = (B + wpb - 1) / wpb;

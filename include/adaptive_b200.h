@@ -64,6 +64,9 @@ int ac_device_check(void);            /* 0 when the current device is sm_100 (B2
  *   "knn_epi" 1 : the prototype scan's epilogue lets every lane walk its own candidate hits (staged through shared memory)
  *                   instead of the warp walking the union of all lanes' hits: same candidate lists, far fewer
  *                   instructions.  Results cannot change.  NOT yet run on hardware.
+ *   "cls_attn" 1 : with cls_only = 1 the last layer's attention computes the CLS query row of every (sequence, head) only
+ *                   (one warp each, no tensor core): the CLS-only tail reads nothing else.  Same formula, fp32 sums in a
+ *                   different order: CLS rows agree to rounding (within the 1e-3 encoder tolerance).  NOT yet run on hardware.
  * Unknown names return AC_E_INVALID. */
 int ac_set_option(const char *name, long long value);
 int ac_get_option(const char *name, long long *value);

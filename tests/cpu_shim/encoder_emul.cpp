@@ -44,6 +44,7 @@ typedef struct CUtensorMap_st {
 #define __grid_constant__
 
 static void __threadfence_system() {}
+static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 static unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p += v; return o; }
 
 static long long g_options[16] = {0};
@@ -229,14 +230,16 @@ int main(int argc, char **argv) {
     fclose(f);
 
     FILE *out = fopen(argv[2], "wb");
-    // variants: {cls_only, ln_defer, epi16, gemm_pair}
-    const int variants[][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {0, 1, 0, 0}, {1, 1, 0, 0}, {1, 1, 3, 0}, {1, 0, 1, 1}, {0, 1, 3, 1}};
+    // variants: {cls_only, ln_defer, epi16, gemm_pair, cls_attn}
+    const int variants[][5] = {{0, 0, 0, 0, 0}, {1, 0, 0, 0, 0}, {0, 1, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 1, 3, 0, 0}, {1, 0, 1, 1, 0}, {0, 1, 3, 1, 0},
+                               {1, 0, 0, 0, 1}, {1, 1, 0, 0, 1}, {0, 0, 0, 0, 1}};
     for (const auto &v : variants) {
         ac_encoder_config cfg{};
         cfg.arch = arch; cfg.layers = L; cfg.hidden = H; cfg.heads = heads; cfg.intermediate = I; cfg.vocab = V; cfg.max_pos = maxpos;
         cfg.type_vocab = typev; cfg.pad_idx = arch == AC_ARCH_ROBERTA ? 1 : 0; cfg.ln_eps = eps; cfg.precision = AC_PREC_F16; cfg.max_tokens = B * S;
         cfg.cls_only = v[0];
         g_options[ac::OPT_LN_DEFER] = v[1]; g_options[ac::OPT_EPI16] = v[2]; g_options[ac::OPT_GEMM_PAIR] = v[3];
+        g_options[ac::OPT_CLS_ATTN] = v[4];
         ac_encoder *enc = nullptr;
         int rc = ac_encoder_create(&cfg, &w, &enc);
         if (rc) { printf("create failed: %s\n", g_err); return 3; }
@@ -245,12 +248,12 @@ int main(int argc, char **argv) {
         if (rc) { printf("forward failed: %s\n", g_err); return 4; }
         int32_t have_hidden = 0;
         if (!v[0]) { rc = ac_encoder_last_hidden(enc, hidden.data(), int64_t(B) * S * H, nullptr); have_hidden = rc == 0; }
-        const int32_t tag[5] = {v[0], v[1], v[2], v[3], have_hidden};
-        fwrite(tag, 4, 5, out);
+        const int32_t tag[6] = {v[0], v[1], v[2], v[3], v[4], have_hidden};
+        fwrite(tag, 4, 6, out);
         fwrite(cls.data(), 4, cls.size(), out);
         fwrite(hidden.data(), 4, hidden.size(), out);
         ac_encoder_destroy(enc);
-        printf("variant cls_only=%d ln_defer=%d epi16=%d gemm_pair=%d: %lld launches\n", v[0], v[1], v[2], v[3], ac::g_launches);
+        printf("variant cls_only=%d ln_defer=%d epi16=%d gemm_pair=%d cls_attn=%d: %lld launches\n", v[0], v[1], v[2], v[3], v[4], ac::g_launches);
         ac::g_launches = 0;
     }
     // ac_encoder_forward_cls_scatter: the final normalise kernel also stores the rows into every peer's buffer + flags
@@ -285,6 +288,41 @@ int main(int argc, char **argv) {
         printf("forward_cls_scatter: %s\n", bad ? "FAIL" : "ok");
         ac_encoder_destroy(enc);
         if (bad) return 9;
+    }
+    // attention_cls_kernel (one query row per (sequence, head)) against the stand-in of the full kernel, on the Q | K and V^T
+    // buffers the last layer of a full forward left behind: CLS rows bit for bit, every other row of ctx untouched
+    {
+        ac_encoder_config cfg{};
+        cfg.arch = arch; cfg.layers = L; cfg.hidden = H; cfg.heads = heads; cfg.intermediate = I; cfg.vocab = V; cfg.max_pos = maxpos;
+        cfg.type_vocab = typev; cfg.pad_idx = 0; cfg.ln_eps = eps; cfg.precision = AC_PREC_F16; cfg.max_tokens = B * S; cfg.cls_only = 0;
+        for (auto &o : g_options) o = 0;
+        ac_encoder *enc = nullptr;
+        if (ac_encoder_create(&cfg, &w, &enc)) return 10;
+        std::vector<float> cls(size_t(B) * H);
+        if (ac_encoder_forward_cls(enc, ids.data(), use_mask ? mask.data() : nullptr, nullptr, B, S, cls.data(), nullptr)) return 11;
+        const int S_pad = (S + 7) / 8 * 8;
+        int bad = 0;
+        for (int round = 0; round < 3; ++round) {
+            std::vector<int32_t> m2 = mask;
+            if (round == 1) for (int k = 0; k < S; ++k) m2[size_t(B > 1 ? 1 : 0) * S + k] = 0;      // one sequence with no valid key
+            const int32_t *mp = round == 2 ? nullptr : m2.data();
+            std::vector<__half> full(size_t(B) * S * H), one(size_t(B) * S * H);
+            memset(full.data(), 0x7b, full.size() * 2);
+            memset(one.data(), 0x7b, one.size() * 2);
+            shim::launch(dim3(B * heads), dim3(128), [&] { ac::attention_kernel(enc->m_qk_att, enc->m_vt_att, mp, B, S, heads, H, full.data()); });
+            shim::launch(dim3((B * heads + ac::ATTC_WARPS - 1) / ac::ATTC_WARPS), dim3(ac::ATTC_WARPS * 32),
+                         [&] { ac::attention_cls_kernel(enc->qk, enc->vT, mp, B, S, S_pad, heads, H, one.data()); });
+            for (int b = 0; b < B; ++b)
+                for (int t = 0; t < S; ++t) {
+                    const __half *x = &one[(size_t(b) * S + t) * H], *y = &full[(size_t(b) * S + t) * H];
+                    if (t == 0) bad += memcmp(x, y, size_t(H) * 2) != 0;
+                    else
+                        for (int j = 0; j < H; ++j) { uint16_t u; memcpy(&u, &x[j], 2); bad += u != 0x7b7b; }
+                }
+        }
+        printf("attention_cls_kernel == attention stand-in on the CLS rows: %s\n", bad ? "FAIL" : "ok");
+        ac_encoder_destroy(enc);
+        if (bad) return 12;
     }
     fclose(out);
     return 0;

@@ -12,7 +12,7 @@ echo "=== 1. harness"; bash tools/run_pair_harness.sh > gpurun_out/harness.log 2
 echo "=== 2. pytest -m gpu with experimental variants"
 AC_TEST_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/ -q -m gpu --timeout 600 -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_experimental.log
 echo "=== 3. bench variants"
-for v in "" "knn_epi=1" "ln_defer=1" "epi16=1" "epi16=3" "attn_pipe=1" "ln_defer=1,epi16=1,attn_pipe=1" "gemm_pair=1,ln_defer=1,epi16=1,attn_pipe=1" "gemm_pair=1,ln_defer=1,epi16=1,attn_pipe=1,pdl=1,knn_epi=1"; do
+for v in "" "knn_epi=1" "cls_attn=1" "ln_defer=1" "epi16=1" "epi16=3" "attn_pipe=1" "ln_defer=1,epi16=1,attn_pipe=1" "gemm_pair=1,ln_defer=1,epi16=1,attn_pipe=1" "gemm_pair=1,ln_defer=1,epi16=1,attn_pipe=1,pdl=1,knn_epi=1,cls_attn=1"; do
     name=$(echo "${v:-default}" | tr ',=' '__')
     AC_OPTIONS="$v" timeout 600 python bench.py --no-cpu-baseline 2> gpurun_out/bench_${name}.err | tee gpurun_out/bench_${name}.json | python -c "
 import json,sys

@@ -61,7 +61,7 @@ def test_product_package_never_imports_the_oracle():
 
 def test_options_roundtrip_without_a_gpu(cabi):
     """ac_set_option / ac_get_option are host-only state: they work without a device; unknown names are rejected"""
-    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi"):
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi", "cls_attn"):
         prev = cabi.get_option(name)
         with cabi.option(name, prev + 2):
             assert cabi.get_option(name) == prev + 2

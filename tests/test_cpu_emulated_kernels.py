@@ -170,19 +170,22 @@ def test_encoder_host_logic_and_deferred_layernorm_flow_on_the_cpu_emulation(tmp
     off, seen, base = 0, set(), None
     keep = mask.bool()
     while off < len(raw):
-        tag = struct.unpack_from("5i", raw, off); off += 20
+        tag = struct.unpack_from("6i", raw, off); off += 24
         cls = torch.from_numpy(np.frombuffer(raw, np.float32, B * H, off).reshape(B, H).copy()); off += 4 * B * H
         hid = torch.from_numpy(np.frombuffer(raw, np.float32, B * S * H, off).reshape(B, S, H).copy()); off += 4 * B * S * H
-        seen.add(tag[:4])
+        seen.add(tag[:5])
         assert (cls - ref).norm(dim=1).max() < 2e-4, (tag, (cls - ref).norm(dim=1).max())      # encoder tolerance is 1e-3
         assert (cls.norm(dim=1) - 1).abs().max() < 1e-5
-        if tag[4]:
+        if tag[5]:
             assert (hid[keep] - ref_hidden[keep]).abs().max() < 2e-3, tag
-        if tag[:4] == (0, 0, 0, 0):
+        if tag[:5] == (0, 0, 0, 0, 0):
             base = cls
+        elif tag[4] and not tag[1]:                           # CLS-only attention: the same arithmetic on one query row
+            assert torch.equal(cls, base), tag
         elif tag[1]:                                          # deferred flow vs the LayerNorm-kernel flow of the same build
             assert (cls - base).norm(dim=1).max() < 1e-4, tag
-    assert {(0, 0, 0, 0), (1, 1, 0, 0), (0, 1, 0, 0), (1, 1, 3, 0), (0, 1, 3, 1)} <= seen
+    assert {(0, 0, 0, 0, 0), (1, 1, 0, 0, 0), (0, 1, 0, 0, 0), (1, 1, 3, 0, 0), (0, 1, 3, 1, 0), (1, 0, 0, 0, 1), (1, 1, 0, 0, 1)} <= seen
+    assert "attention_cls_kernel == attention stand-in on the CLS rows: ok" in r.stdout
 
 
 def _build_tensor_path(tmp_path, mutate=None, driver="attention_emul.cpp", mutate_gemm2=None, mutate_knn=None):

@@ -29,7 +29,7 @@ def _encoder(cabi, sd, cfg, max_tokens, cls_only=True):
 
 
 def test_option_roundtrip(cabi):
-    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi"):
+    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi", "cls_attn"):
         prev = cabi.get_option(name)          # 0 unless AC_OPTIONS preset it for this process
         with cabi.option(name, 1 - prev):
             assert cabi.get_option(name) == 1 - prev
@@ -152,6 +152,31 @@ def test_attn_pipe_encoder_bit_identical(cabi, B, S, pad):
         out_h = enc.last_hidden(B, S).clone()
     assert torch.equal(ref.view(torch.int32), out.view(torch.int32))
     assert torch.equal(ref_h.view(torch.int32), out_h.view(torch.int32))
+    enc.close()
+
+
+@experimental
+@pytest.mark.parametrize("B,S,pad", [(24, 128, False), (5, 96, True), (300, 64, False), (3, 17, True), (4, 200, True)])
+def test_cls_attn_last_layer_matches_the_full_kernel(cabi, B, S, pad):
+    """option "cls_attn": the last layer's attention computes the CLS query row only (SIMT, fp32 sums in a different order
+    from the tensor core), so the unit CLS rows agree with the full kernel to rounding and with the fp32 oracle within the
+    encoder tolerance (1e-3)"""
+    sd, cfg, _ = eo.make_bert_state_dict(1234, num_hidden_layers=2)
+    ids = eo.synthetic_ids(B, S)
+    mask = torch.ones_like(ids)
+    if pad:
+        for b in range(B):
+            n = max(2, S - 1 - 2 * b)
+            mask[b, n:] = 0
+            ids[b, n:] = 0
+    want = eo.encoder_forward_cls(sd, ids, mask, num_heads=cfg.num_attention_heads, ln_eps=cfg.layer_norm_eps)
+    ids, mask = ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()
+    enc = _encoder(cabi, sd, cfg, max_tokens=B * S, cls_only=True)
+    ref = enc.forward_cls(ids, mask).clone()
+    with cabi.option("cls_attn", 1):
+        out = enc.forward_cls(ids, mask).clone()
+    assert (out - ref).norm(dim=1).max().item() < 1e-4
+    assert (out.cpu() - want).norm(dim=1).max().item() < 1e-3
     enc.close()
 
 

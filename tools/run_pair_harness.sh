@@ -4,7 +4,7 @@
 # variants written after the round-1 GPU budget was spent.
 mkdir -p gpurun_out
 cd tools
-for t in "linear 1" "knn 1" "encoder 1" "linear 2" "knn 2" "defer" "defer_full" "defer_layers" "epoch" "epi16" "attn" "pdl" "knn_epi"; do
+for t in "linear 1" "knn 1" "encoder 1" "linear 2" "knn 2" "defer" "defer_full" "defer_layers" "epoch" "epi16" "attn" "pdl" "knn_epi" "cls_attn"; do
     name=${t// /_}
     timeout 40 ./pair_harness $t > ../gpurun_out/pair_${name}.log 2>&1
     echo "exit=$?" >> ../gpurun_out/pair_${name}.log
