@@ -694,7 +694,7 @@ static int train_step_impl(const float *X, const void *targets, int B, ac_head_p
 // blocks".  The bodies below are copies of the kernels above with (a) virtual block indices and (b) plain coherent loads
 // instead of __ldg / __restrict__ (weights, activations and gradients are rewritten by other CTAs inside this kernel, so
 // the non-coherent path is not allowed).  Operation order inside every virtual block is unchanged, so an epoch through
-// this kernel is expected to give the same bits as the launch-per-kernel path (tests/test_gpu_variants.py compares them).
+// this kernel is expected to give the same bits as the launch-per-kernel path (tests/test_gpu_zzz_variants.py compares them).
 //
 //   per step:  gather+masks | h0 | h1 | z | loss,dz | gW2,gb2,dh1,loss | gW1,gb1,dh0 | gW0,gb0 | [EWC] | sumsq | AdamW
 //              (9 grid barriers, 10 with EWC; AdamW of step t overlaps the gather of step t+1)

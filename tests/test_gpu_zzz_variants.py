@@ -1,3 +1,4 @@
+# Runs after every hardware-verified GPU test (file order): checks of the opt-in kernel variants.
 """Kernel variants selected with ac_set_option (include/adaptive_b200.h).
 
 * CTA-pair GEMMs ("gemm_pair", "knn_pair"): must be BIT-IDENTICAL to the default kernels -- same MMA K order, same
