@@ -18,7 +18,6 @@ static inline float rcp_approx(float x) { return 1.f / x; }
 static inline void griddep_wait() {}
 static inline void griddep_launch_dependents() {}
 }  // namespace ac
-static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 
 #include "_gen_common_tc.inc"
 #include "_gen_gemm_tc_tc.inc"

@@ -44,6 +44,7 @@
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 

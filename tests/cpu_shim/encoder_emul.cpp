@@ -44,7 +44,6 @@ typedef struct CUtensorMap_st {
 #define __grid_constant__
 
 static void __threadfence_system() {}
-static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 static unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p += v; return o; }
 
 static long long g_options[16] = {0};

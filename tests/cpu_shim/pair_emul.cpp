@@ -18,7 +18,6 @@ static inline void griddep_launch_dependents() {}
 static inline void st_release_sys(uint32_t *p, uint32_t v) { *p = v; }
 static inline uint32_t ld_acquire_sys(const uint32_t *p) { return *p; }
 }  // namespace ac
-static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 
 #include "_gen_common_tc.inc"
 #include "_gen_gemm_tc_tc.inc"
