@@ -19,34 +19,27 @@ LIB_PATH = os.path.join(_HERE, "libadaptive_b200.so")
 
 AC_KNN_AUTO, AC_KNN_EXACT, AC_KNN_TENSOR = 0, 1, 2
 AC_KNN_MAX_K = 2048
+AC_KNN_TENSOR_MAX_K = 1024
 AC_ACT_LOGITS, AC_ACT_SOFTMAX, AC_ACT_SIGMOID = 0, 1, 2
 AC_LOSS_CE, AC_LOSS_BCE = 0, 1
 AC_ARCH_BERT, AC_ARCH_ROBERTA = 0, 1
 AC_PREC_TF32, AC_PREC_F16 = 0, 1
 
 EXPORTS = [
-    "ac_version", "ac_last_error", "ac_device_check", "ac_set_option", "ac_get_option",
-    "ac_peer_scatter", "ac_peer_wait", "ac_encoder_forward_cls_scatter",
+    "ac_version", "ac_last_error", "ac_device_check",
     "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
     "ac_segment_mean",
-    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch_workspace_bytes", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",
+    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
     "ac_proto_class_scores", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
     "ac_pipeline_create", "ac_pipeline_destroy", "ac_pipeline_predict_device", "ac_pipeline_predict_host",
-    "ac_pipeline_debug_copy", "ac_launch_count", "ac_profile_enable", "ac_profile_read",
+    "ac_pipeline_encode", "ac_pipeline_embeddings", "ac_pipeline_search_shard", "ac_pipeline_finish_sharded",
+    "ac_pipeline_debug_copy", "ac_pipeline_knn_stats", "ac_launch_count", "ac_profile_enable", "ac_profile_read",
 ]
 
 
 class AdaptiveB200Error(RuntimeError):
     pass
-
-
-AC_MAX_PEERS = 16
-
-
-class PeerTable(Structure):
-    """ac_peer_table: NVLink-mapped base pointers of every rank's exchange buffer and of its flag array (one channel)."""
-    _fields_ = [("world", c_int), ("rank", c_int), ("buf", c_void_p * AC_MAX_PEERS), ("flag", c_void_p * AC_MAX_PEERS)]
 
 
 class HeadParams(Structure):
@@ -100,19 +93,18 @@ def load_library() -> ctypes.CDLL:
     L.ac_device_check.restype = c_int
     L.ac_knn_workspace_bytes.argtypes = [c_int, c_int64, c_int, c_int, c_int, POINTER(c_size_t)]
     L.ac_knn_l2_topk.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
-                                 c_int64, c_void_p, c_size_t, c_int, c_void_p]
+                                 c_int64, c_void_p, c_size_t, c_int, c_void_p, c_void_p]
     L.ac_knn_make_shadow.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
     L.ac_row_sqnorm.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
     L.ac_topk_merge.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_proto_scores.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.ac_segment_mean.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_head_forward.argtypes = [c_void_p, c_int, POINTER(HeadParams), c_int, c_void_p, c_void_p, c_size_t, c_void_p]
-    L.ac_head_train_workspace_bytes.argtypes = [c_int, POINTER(HeadParams), POINTER(c_size_t)]
+    L.ac_head_train_workspace_bytes.argtypes = [c_int, c_int, POINTER(HeadParams), POINTER(c_size_t)]
     L.ac_head_train_step.argtypes = [c_void_p, c_void_p, c_int, POINTER(HeadParams), POINTER(HeadParams),
                                      POINTER(HeadParams), POINTER(TrainCfg), c_void_p, c_void_p, c_size_t, c_void_p]
-    L.ac_head_train_epoch_workspace_bytes.argtypes = [c_int, POINTER(HeadParams), POINTER(c_size_t)]
     L.ac_head_train_epoch.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(HeadParams), POINTER(HeadParams),
-                                      POINTER(HeadParams), POINTER(TrainCfg), c_void_p, c_void_p, c_size_t, c_void_p]
+                                      POINTER(HeadParams), POINTER(TrainCfg), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_head_grad.argtypes = [c_void_p, c_void_p, c_int, POINTER(HeadParams), c_int, POINTER(HeadParams),
                                POINTER(HeadParams), c_float, c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_ewc_penalty.argtypes = [POINTER(HeadParams), POINTER(HeadParams), POINTER(HeadParams), c_float, c_float,
@@ -129,18 +121,17 @@ def load_library() -> ctypes.CDLL:
     L.ac_blend_topk.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]
     L.ac_pipeline_create.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(HeadParams),
-                                     c_int, c_int, c_int, c_int64, POINTER(c_void_p)]
+                                     c_int, c_int, c_int, c_int64, c_int, POINTER(c_void_p)]
+    L.ac_pipeline_encode.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.ac_pipeline_embeddings.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.ac_pipeline_search_shard.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    L.ac_pipeline_finish_sharded.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_pipeline_destroy.argtypes = [c_void_p]
     L.ac_pipeline_predict_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_pipeline_predict_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_pipeline_debug_copy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ac_profile_enable.argtypes = [c_int]
-    L.ac_peer_scatter.argtypes = [c_void_p, c_size_t, c_int, POINTER(PeerTable), c_size_t, ctypes.c_uint32, c_void_p, c_void_p]
-    L.ac_peer_wait.argtypes = [c_void_p, c_int, ctypes.c_uint32, c_void_p]
-    L.ac_encoder_forward_cls_scatter.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, POINTER(PeerTable),
-                                                 c_size_t, ctypes.c_uint32, c_void_p, c_void_p]
-    L.ac_set_option.argtypes = [c_char_p, ctypes.c_longlong]
-    L.ac_get_option.argtypes = [c_char_p, POINTER(ctypes.c_longlong)]
+    L.ac_pipeline_knn_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.ac_profile_read.argtypes = [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                   POINTER(ctypes.c_longlong)]
     for name in EXPORTS:
@@ -150,12 +141,6 @@ def load_library() -> ctypes.CDLL:
         elif name not in ("ac_last_error",):
             fn.restype = c_int
     _lib = L
-    # kernel variants for a whole process without touching code: AC_OPTIONS="ln_defer=1,head_fused=1" (see set_option)
-    for item in filter(None, os.environ.get("AC_OPTIONS", "").split(",")):
-        name, _, val = item.partition("=")
-        rc = L.ac_set_option(name.strip().encode(), int(val or "1"))
-        if rc != 0:
-            raise AdaptiveB200Error(f"AC_OPTIONS: {L.ac_last_error().decode()}")
     return L
 
 
@@ -203,7 +188,10 @@ def knn_make_shadow(P: torch.Tensor) -> torch.Tensor:
 
 
 def knn_l2_topk(Q: torch.Tensor, P: torch.Tensor, k: int, *, p_sqnorm: Optional[torch.Tensor] = None,
-                p_half: Optional[torch.Tensor] = None, row_offset: int = 0, algo: int = AC_KNN_AUTO):
+                p_half: Optional[torch.Tensor] = None, row_offset: int = 0, algo: int = AC_KNN_AUTO,
+                stats: Optional[torch.Tensor] = None):
+    """stats: optional CUDA int32[4] accumulator (see ac_knn_l2_topk): with it the call never synchronises and the CALLER must
+    check stats[1] (buffer overflow -> redo those queries with AC_KNN_EXACT); without it the library does both itself."""
     L = load_library()
     Q = _f32c(Q)
     P = _f32c(P)
@@ -216,7 +204,7 @@ def knn_l2_topk(Q: torch.Tensor, P: torch.Tensor, k: int, *, p_sqnorm: Optional[
     out_d = torch.empty((B, k), dtype=torch.float32, device=Q.device)
     out_i = torch.empty((B, k), dtype=torch.int64, device=Q.device)
     check(L.ac_knn_l2_topk(Q.data_ptr(), P.data_ptr(), ptr(p_sqnorm), ptr(p_half), B, N, D, k, out_d.data_ptr(),
-                           out_i.data_ptr(), row_offset, ws.data_ptr(), ws.numel(), algo, stream_ptr()), "ac_knn_l2_topk")
+                           out_i.data_ptr(), row_offset, ws.data_ptr(), ws.numel(), algo, ptr(stats), stream_ptr()), "ac_knn_l2_topk")
     return out_d, out_i
 
 
@@ -311,7 +299,7 @@ def head_train_step(X, targets, p, m, v, *, step, loss_kind=AC_LOSS_CE, lr=1e-3,
         cfg.ewc_fisher, cfg.ewc_star = ctypes.pointer(fs), ctypes.pointer(ss)
         cfg.ewc_lambda, cfg.ewc_C_old = float(ewc[2]), int(ewc[3])
     nbytes = c_size_t(0)
-    check(L.ac_head_train_workspace_bytes(B, ctypes.byref(hp), ctypes.byref(nbytes)), "ac_head_train_workspace_bytes")
+    check(L.ac_head_train_workspace_bytes(B, 1, ctypes.byref(hp), ctypes.byref(nbytes)), "ac_head_train_workspace_bytes")
     ws = _workspace(nbytes.value, X.device)
     if out_stats is None:
         out_stats = torch.zeros((4,), dtype=torch.float32, device=X.device)
@@ -323,8 +311,11 @@ def head_train_step(X, targets, p, m, v, *, step, loss_kind=AC_LOSS_CE, lr=1e-3,
 
 
 def head_train_epoch(X, targets, perm, p, m, v, *, first_step, batch, loss_kind=AC_LOSS_CE, lr=1e-3, betas=(0.9, 0.999),
-                     eps=1e-8, weight_decay=0.01, max_norm=1.0, dropout_p=0.1, seed=0, ewc=None, loss_accum=None):
-    """All optimizer steps of one epoch (batches gathered on the device from `perm`).  Returns (loss_accum tensor, steps)."""
+                     eps=1e-8, weight_decay=0.01, max_norm=1.0, dropout_p=0.1, seed=0, ewc=None, loss_accum=None,
+                     step_stats=None):
+    """All optimizer steps of one epoch in ONE kernel launch (batches gathered on the device from `perm`).
+    step_stats: optional CUDA fp32 [steps, 3] receiving (task loss, EWC penalty, grad norm) of every step.
+    Returns (loss_accum tensor, steps)."""
     L = load_library()
     X = _f32c(X)
     n = X.shape[0]
@@ -340,16 +331,19 @@ def head_train_epoch(X, targets, perm, p, m, v, *, first_step, batch, loss_kind=
         cfg.ewc_fisher, cfg.ewc_star = ctypes.pointer(fs), ctypes.pointer(ss)
         cfg.ewc_lambda, cfg.ewc_C_old = float(ewc[2]), int(ewc[3])
     nbytes = c_size_t(0)
-    check(L.ac_head_train_epoch_workspace_bytes(batch, ctypes.byref(hp), ctypes.byref(nbytes)), "ac_head_train_epoch_workspace_bytes")
+    steps = (n + batch - 1) // batch
+    check(L.ac_head_train_workspace_bytes(batch, steps, ctypes.byref(hp), ctypes.byref(nbytes)), "ac_head_train_workspace_bytes")
     ws = _workspace(nbytes.value, X.device)
+    if step_stats is not None:
+        assert step_stats.is_cuda and step_stats.dtype == torch.float32 and step_stats.is_contiguous() and step_stats.numel() >= 3 * steps
     if loss_accum is None:
         loss_accum = torch.zeros((1,), dtype=torch.float32, device=X.device)
     targets = targets.contiguous()
     perm = perm.to(device=X.device, dtype=torch.int64).contiguous()
     check(L.ac_head_train_epoch(X.data_ptr(), targets.data_ptr(), perm.data_ptr(), n, batch, ctypes.byref(hp),
-                                ctypes.byref(hm), ctypes.byref(hv), ctypes.byref(cfg), loss_accum.data_ptr(), ws.data_ptr(),
-                                ws.numel(), stream_ptr()), "ac_head_train_epoch")
-    return loss_accum, (n + batch - 1) // batch
+                                ctypes.byref(hm), ctypes.byref(hv), ctypes.byref(cfg), loss_accum.data_ptr(), ptr(step_stats),
+                                ws.data_ptr(), ws.numel(), stream_ptr()), "ac_head_train_epoch")
+    return loss_accum, steps
 
 
 def head_grad(X, targets, p, *, loss_kind=AC_LOSS_CE, grad_out=None, fisher=None, inv_n_batches=1.0):
@@ -360,7 +354,7 @@ def head_grad(X, targets, p, *, loss_kind=AC_LOSS_CE, grad_out=None, fisher=None
     g = head_params_struct(grad_out) if grad_out is not None else None
     f = head_params_struct(fisher) if fisher is not None else None
     nbytes = c_size_t(0)
-    check(L.ac_head_train_workspace_bytes(B, ctypes.byref(hp), ctypes.byref(nbytes)), "ac_head_train_workspace_bytes")
+    check(L.ac_head_train_workspace_bytes(B, 1, ctypes.byref(hp), ctypes.byref(nbytes)), "ac_head_train_workspace_bytes")
     ws = _workspace(nbytes.value, X.device)
     loss = torch.zeros((1,), dtype=torch.float32, device=X.device)
     targets = targets.contiguous()
@@ -498,20 +492,6 @@ class Encoder:
                                              out.data_ptr(), stream_ptr()), "ac_encoder_forward_cls")
         return out
 
-    def forward_cls_scatter(self, ids: torch.Tensor, table: "PeerTable", dst_offset: int, seq: int, counter: torch.Tensor,
-                            mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """forward_cls whose final kernel also stores the unit CLS rows into every peer's exchange buffer (peer.cu)."""
-        assert ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous()
-        B, S = ids.shape
-        if out is None:
-            out = torch.empty((B, self.hidden), dtype=torch.float32, device=ids.device)
-        if mask is not None:
-            mask = mask.to(torch.int32).contiguous()
-        check(self._L.ac_encoder_forward_cls_scatter(self.handle, ids.data_ptr(), ptr(mask), None, B, S, out.data_ptr(),
-                                                     ctypes.byref(table), dst_offset, seq & 0xFFFFFFFF, counter.data_ptr(),
-                                                     stream_ptr()), "ac_encoder_forward_cls_scatter")
-        return out
-
     def last_hidden(self, B: int, S: int) -> torch.Tensor:
         out = torch.empty((B * S, self.hidden), dtype=torch.float32, device="cuda")
         check(self._L.ac_encoder_last_hidden(self.handle, out.data_ptr(), out.numel(), stream_ptr()),
@@ -570,53 +550,6 @@ def blend_topk(p_cls, p_score, h_idx, h_val, k: int, w_proto: float = 0.7, w_hea
     return out_cls, out_sc
 
 
-def peer_table(world: int, rank: int, buf_ptrs, flag_ptrs) -> PeerTable:
-    assert world <= AC_MAX_PEERS and len(buf_ptrs) == world and len(flag_ptrs) == world
-    t = PeerTable()
-    t.world, t.rank = world, rank
-    for p in range(world):
-        t.buf[p] = int(buf_ptrs[p])
-        t.flag[p] = int(flag_ptrs[p])
-    return t
-
-
-def peer_scatter(src: torch.Tensor, bytes_per_dst: int, blocks_mode: bool, table: PeerTable, dst_offset: int, seq: int,
-                 counter: torch.Tensor) -> None:
-    check(load_library().ac_peer_scatter(src.data_ptr(), bytes_per_dst, 1 if blocks_mode else 0, ctypes.byref(table), dst_offset,
-                                         seq & 0xFFFFFFFF, counter.data_ptr(), stream_ptr()), "ac_peer_scatter")
-
-
-def peer_wait(flags_local_ptr: int, n_flags: int, seq: int) -> None:
-    check(load_library().ac_peer_wait(flags_local_ptr, n_flags, seq & 0xFFFFFFFF, stream_ptr()), "ac_peer_wait")
-
-
-def set_option(name: str, value: int) -> None:
-    """Process-wide kernel-variant switch (include/adaptive_b200.h): "gemm_pair", "knn_pair", "ln_defer"."""
-    check(load_library().ac_set_option(name.encode(), int(value)), f"ac_set_option({name})")
-
-
-def get_option(name: str) -> int:
-    v = ctypes.c_longlong(0)
-    check(load_library().ac_get_option(name.encode(), ctypes.byref(v)), f"ac_get_option({name})")
-    return int(v.value)
-
-
-class option:
-    """Context manager: `with option("gemm_pair", 1): ...` restores the previous value on exit."""
-
-    def __init__(self, name: str, value: int):
-        self.name, self.value = name, value
-
-    def __enter__(self):
-        self.prev = get_option(self.name)
-        set_option(self.name, self.value)
-        return self
-
-    def __exit__(self, *exc):
-        set_option(self.name, self.prev)
-        return False
-
-
 def launch_count() -> int:
     return int(load_library().ac_launch_count())
 
@@ -633,12 +566,20 @@ def profile_read(cls: int):
     return {"ms": ms.value, "flops": fl.value, "bytes": by.value, "launches": n.value}
 
 
+class _ExternalCudaBuffer:
+    """__cuda_array_interface__ view of a device buffer owned by a C handle (fp32, row-major)"""
+
+    def __init__(self, ptr_value: int, shape, device):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr_value), False), "version": 3,
+                                         "strides": None}
+
+
 class Pipeline:
     """ids -> E -> K -> class scores -> H -> blend, device or host (pinned) buffers at the boundary."""
 
     def __init__(self, enc: Encoder, P: torch.Tensor, max_B: int, S: int, k: int, *, head: Optional[dict] = None,
                  row_class: Optional[torch.Tensor] = None, p_sqnorm: Optional[torch.Tensor] = None,
-                 p_half: Optional[torch.Tensor] = None, row_offset: int = 0):
+                 p_half: Optional[torch.Tensor] = None, row_offset: int = 0, shards: int = 1):
         L = load_library()
         self._L = L
         self.enc, self.P, self.p_sqnorm, self.row_class, self.p_half = enc, _f32c(P), p_sqnorm, row_class, p_half
@@ -648,8 +589,9 @@ class Pipeline:
         h = c_void_p()
         check(L.ac_pipeline_create(enc.handle, self.P.data_ptr(), ptr(p_sqnorm), ptr(p_half), ptr(row_class), self.P.shape[0],
                                    self.P.shape[1], ctypes.byref(hp) if hp is not None else None, max_B, S, k,
-                                   row_offset, ctypes.byref(h)), "ac_pipeline_create")
+                                   row_offset, shards, ctypes.byref(h)), "ac_pipeline_create")
         self.handle = h
+        self.shards = shards
         self.out_cls_host = torch.empty((max_B, k), dtype=torch.int32).pin_memory()
         self.out_score_host = torch.empty((max_B, k), dtype=torch.float32).pin_memory()
         self.out_cls = torch.empty((max_B, k), dtype=torch.int32, device=self.P.device)
@@ -668,6 +610,36 @@ class Pipeline:
         check(self._L.ac_pipeline_predict_host(self.handle, ids_host.data_ptr(), B, self.out_cls_host.data_ptr(),
                                                self.out_score_host.data_ptr(), stream_ptr()), "ac_pipeline_predict_host")
         return self.out_cls_host[:B], self.out_score_host[:B]
+
+    # ---- phases of the row-sharded multi-GPU step (parallel.ShardedPipeline runs the collectives between them)
+    def encode(self, ids_dev: torch.Tensor, mask_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """E (+ the head forked onto the side stream); returns a [B, D] view of the pipeline's embedding buffer"""
+        B = ids_dev.shape[0]
+        check(self._L.ac_pipeline_encode(self.handle, ids_dev.data_ptr(), ptr(mask_dev), B, stream_ptr()), "ac_pipeline_encode")
+        if getattr(self, "_emb_view", None) is None:
+            p = c_void_p()
+            check(self._L.ac_pipeline_embeddings(self.handle, ctypes.byref(p)), "ac_pipeline_embeddings")
+            D = self.P.shape[1]
+            # wrap the handle-owned device buffer without copying (lifetime = the pipeline's)
+            self._emb_store = _ExternalCudaBuffer(p.value, (self.max_B, D), self.P.device)
+            self._emb_view = torch.as_tensor(self._emb_store, device=self.P.device)
+        return self._emb_view[:B]
+
+    def search_shard(self, q_all: torch.Tensor, G: int, B: int, packed: torch.Tensor) -> None:
+        check(self._L.ac_pipeline_search_shard(self.handle, _f32c(q_all).data_ptr(), G, B, packed.data_ptr(), stream_ptr()),
+              "ac_pipeline_search_shard")
+
+    def finish_sharded(self, received: torch.Tensor, G: int, B: int):
+        check(self._L.ac_pipeline_finish_sharded(self.handle, received.data_ptr(), G, B, self.out_cls.data_ptr(),
+                                                 self.out_score.data_ptr(), stream_ptr()), "ac_pipeline_finish_sharded")
+        return self.out_cls[:B], self.out_score[:B]
+
+    def knn_stats(self, reset: bool = True) -> dict:
+        """search statistics since the last reset (synchronises): queries that took the second tensor pass, queries whose
+        candidate buffer overflowed (results not exact -> redo with AC_KNN_EXACT), max rows collected, searches"""
+        out = (ctypes.c_int32 * 4)()
+        check(self._L.ac_pipeline_knn_stats(self.handle, out, 1 if reset else 0, stream_ptr()), "ac_pipeline_knn_stats")
+        return {"second_pass_queries": int(out[0]), "overflow_queries": int(out[1]), "max_collected": int(out[2]), "searches": int(out[3])}
 
     def debug_views(self, B: int):
         """(emb [B,D], knn_d [B,k], knn_i [B,k]) of the last call."""

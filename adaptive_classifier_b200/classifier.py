@@ -27,10 +27,25 @@ from .models import AdaptiveHead, Example, ModelConfig
 logger = logging.getLogger(__name__)
 
 
+def dataloader_epoch_permutation(gen: torch.Generator, n: int) -> torch.Tensor:
+    """The index order one epoch of the reference's `DataLoader(dataset, shuffle=True, generator=gen)` yields
+    (classifier.py:315-320, :1453-1459), reproduced draw for draw from the same generator:
+      1. `_BaseDataLoaderIter.__init__` draws an int64 `_base_seed` when the epoch's iterator is created,
+      2. `RandomSampler.__iter__` draws `randperm(n)` -- the epoch's order,
+      3. on exhaustion it draws a second `randperm(n)` whose `[:num_samples % n]` (empty) slice is discarded.
+    Pinned against a real DataLoader in tests/test_host_logic_cpu.py and against the reference run's recorded batches
+    (tests/golden/golden_training.npz)."""
+    torch.empty((), dtype=torch.int64).random_(generator=gen)
+    perm = torch.randperm(n, generator=gen)
+    torch.randperm(n, generator=gen)
+    return perm
+
+
 class AdaptiveClassifier:
     """A flexible classifier that can adapt to new classes and examples (classifier.py:27)."""
 
     _loss_kind = _cabi.AC_LOSS_CE
+    _dropout_p = 0.1              # nn.Dropout(0.1) of the reference head (models.py:59); parity tests replay with 0
 
     def __init__(self, model_name: str, device: Optional[str] = None, config: Optional[Dict[str, Any]] = None,
                  seed: int = 42, use_onnx: Optional[Union[bool, str]] = "auto", trust_remote_code: bool = False):
@@ -157,7 +172,7 @@ class AdaptiveClassifier:
     def _run_epochs(self, X: torch.Tensor, Y: torch.Tensor, *, epochs: int, batch_size: int, use_scheduler: bool,
                     ewc=None, ewc_zero_term: bool = False):
         """Shared optimizer loop of classifier.py:322-365 / :1484-1520: shuffled batches from
-        torch.Generator().manual_seed(42) (same index lists as the reference's DataLoader), fresh AdamW,
+        torch.Generator().manual_seed(42) consumed exactly like the reference's DataLoader (dataloader_epoch_permutation), fresh AdamW,
         optional ReduceLROnPlateau(0.5, patience 2), early stopping patience 3."""
         n = X.shape[0]
         p, m, v = self._head_blocks()
@@ -168,20 +183,30 @@ class AdaptiveClassifier:
         step = 0
         n_batches = (n + batch_size - 1) // batch_size
         seed = int(torch.initial_seed() & 0x7FFFFFFF)
+        trace = {"loss": [], "ewc": [], "gnorm": [], "steps_per_epoch": [], "lr": []}
         self.adaptive_head.train()
         for epoch in range(epochs):
-            perm = torch.randperm(n, generator=gen)            # the index lists the reference's DataLoader yields
+            perm = dataloader_epoch_permutation(gen, n)        # the index lists the reference's DataLoader yields
+            step_stats = torch.zeros((n_batches, 3), dtype=torch.float32, device=X.device)
             total, nb = _cabi.head_train_epoch(X, Y, perm, p, m, v, first_step=step + 1, batch=batch_size,
-                                               loss_kind=self._loss_kind, lr=lr, dropout_p=0.1, seed=seed, ewc=ewc)
+                                               loss_kind=self._loss_kind, lr=lr, dropout_p=self._dropout_p, seed=seed, ewc=ewc,
+                                               step_stats=step_stats)
             step += nb
-            avg_loss = float(total.item()) / n_batches
-            if use_scheduler:                                   # ReduceLROnPlateau(mode=min, factor .5, patience 2)
+            st = step_stats.cpu()                               # the epoch's one host sync (the reference syncs per step: loss.item())
+            trace["loss"] += st[:, 0].tolist()
+            trace["ewc"] += st[:, 1].tolist()
+            trace["gnorm"] += st[:, 2].tolist()
+            trace["steps_per_epoch"].append(nb)
+            trace["lr"].append(lr)
+            # `total_loss += loss.item()` then `/ len(loader)` (classifier.py:353-355, :1507-1509): a Python float sum in step order
+            avg_loss = sum(float(a) + float(b) for a, b in zip(st[:, 0].tolist(), st[:, 1].tolist())) / n_batches
+            if use_scheduler:                                   # ReduceLROnPlateau(mode=min, factor .5, patience 2, rel 1e-4)
                 if avg_loss < sched_best * (1 - 1e-4):
                     sched_best, sched_bad = avg_loss, 0
                 else:
                     sched_bad += 1
-                    if sched_bad > 2:
-                        lr, sched_bad = lr * 0.5, 0
+                if sched_bad > 2:
+                    lr, sched_bad = lr * 0.5, 0
             if avg_loss < best_loss:
                 best_loss, patience_counter = avg_loss, 0
             else:
@@ -189,6 +214,7 @@ class AdaptiveClassifier:
                 if patience_counter >= patience:
                     logger.debug(f"Early stopping at epoch {epoch + 1}")
                     break
+        self.last_training_trace = trace
         self.adaptive_head.eval()
 
     def _training_matrix(self):

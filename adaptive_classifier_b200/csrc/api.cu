@@ -27,17 +27,6 @@ int check_cuda(cudaError_t e, const char *what) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// run-time options (ac_set_option): experimental kernel variants stay opt-in until they are measured on a B200
-static std::atomic<long long> g_options[OPT_NUM];
-static const char *const g_option_names[OPT_NUM] = {"gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi", "cls_attn"};
-long long option(int id) { return (id >= 0 && id < OPT_NUM) ? g_options[id].load(std::memory_order_relaxed) : 0; }
-static int option_id(const char *name) {
-    if (!name) return -1;
-    for (int i = 0; i < OPT_NUM; ++i)
-        if (strcmp(name, g_option_names[i]) == 0) return i;
-    return -1;
-}
-
 struct ProfSlot { cudaEvent_t a, b; int cls; double flops, bytes; };
 static bool g_prof_on = false;
 static std::vector<ProfSlot> g_prof_slots;
@@ -130,11 +119,11 @@ int launch_knn_rerank(const float *Q, const float *P, int B, int64_t N, int D, i
                       int64_t *out_i, int64_t row_offset, cudaStream_t stream);
 size_t topk_select_workspace(int B, int64_t L, int k);
 int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in_stride, int64_t id_offset, int k,
-                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream);
+                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream, const float *row_gate = nullptr);
 // from knn_tc.cu
 size_t knn_tc_workspace(int B, int64_t N, int D, int k);
 int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N, int D, int k,
-                  float *out_d, int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, cudaStream_t stream);
+                  float *out_d, int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, int32_t *stats, cudaStream_t stream);
 
 // exact path processes the queries in blocks so the [qb, N] distance slab stays bounded
 static int exact_query_block(int B, int64_t N) {
@@ -173,7 +162,7 @@ static int knn_exact(const float *Q, const float *P, int B, int64_t N, int D, in
 static int resolve_algo(int algo, int B, int64_t N, int D, int k) {
     if (algo != AC_KNN_AUTO) return algo;
     // tensor path pays off once the scan is compute-bound on the SIMT pipes (B >~ 8) and the index is big
-    if (B >= 16 && k <= 16 && N >= 4096 && D % 32 == 0) return AC_KNN_TENSOR;
+    if (B >= 16 && k <= AC_KNN_TENSOR_MAX_K && N >= 4096 && N >= 8ll * k && D % 32 == 0) return AC_KNN_TENSOR;
     return AC_KNN_EXACT;
 }
 
@@ -202,19 +191,6 @@ extern "C" int ac_profile_read(int cls, double *ms, double *flops, double *bytes
     return AC_OK;
 }
 extern "C" const char *ac_last_error(void) { return g_err; }
-
-extern "C" int ac_set_option(const char *name, long long value) {
-    const int id = option_id(name);
-    AC_REQUIRE(id >= 0, "ac_set_option: unknown option '%s'", name ? name : "(null)");
-    g_options[id].store(value, std::memory_order_relaxed);
-    return AC_OK;
-}
-extern "C" int ac_get_option(const char *name, long long *value) {
-    const int id = option_id(name);
-    AC_REQUIRE(id >= 0 && value, "ac_get_option: unknown option '%s' or null output", name ? name : "(null)");
-    *value = g_options[id].load(std::memory_order_relaxed);
-    return AC_OK;
-}
 
 extern "C" int ac_device_check(void) {
     int n = 0;
@@ -245,7 +221,7 @@ extern "C" int ac_knn_workspace_bytes(int B, int64_t N, int D, int k, int algo, 
 
 extern "C" int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N,
                               int D, int k, float *out_d, int64_t *out_i, int64_t row_offset, void *workspace,
-                              size_t workspace_bytes, int algo, ac_stream_t stream) {
+                              size_t workspace_bytes, int algo, int32_t *stats, ac_stream_t stream) {
     AC_REQUIRE(Q && out_d && out_i && B >= 0 && N >= 0 && D > 0, "ac_knn_l2_topk: bad arguments");
     AC_REQUIRE(k >= 1 && k <= AC_KNN_MAX_K, "ac_knn_l2_topk: k=%d outside [1,%d]", k, AC_KNN_MAX_K);
     AC_REQUIRE(N == 0 || P, "ac_knn_l2_topk: null index");
@@ -259,9 +235,9 @@ extern "C" int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqn
     AC_REQUIRE(workspace && workspace_bytes > slack, "ac_knn_l2_topk: null/empty workspace");
     const size_t avail = workspace_bytes - slack;
     if (a == AC_KNN_TENSOR) {
-        AC_REQUIRE(k <= 16 && D % 32 == 0, "ac_knn_l2_topk: tensor path needs k <= 16 and D %% 32 == 0");
+        AC_REQUIRE(k <= AC_KNN_TENSOR_MAX_K && D % 32 == 0, "ac_knn_l2_topk: tensor path needs k <= %d and D %% 32 == 0", AC_KNN_TENSOR_MAX_K);
         AC_REQUIRE(!p_half || D % 64 == 0, "ac_knn_l2_topk: the fp16 shadow path needs D %% 64 == 0");
-        return knn_tc_search(Q, P, p_sqnorm, p_half, B, N, D, k, out_d, out_i, row_offset, ws, avail, s);
+        return knn_tc_search(Q, P, p_sqnorm, p_half, B, N, D, k, out_d, out_i, row_offset, ws, avail, stats, s);
     }
     return knn_exact(Q, P, B, N, D, k, out_d, out_i, row_offset, ws, avail, s);
 }

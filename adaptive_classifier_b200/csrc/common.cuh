@@ -40,13 +40,9 @@ void count_launch();
     } while (0)
 
 // optional CUDA-event timing of individual launches on their own stream (roofline numbers of bench.py)
-enum { PROF_GEMM_LINEAR = 0, PROF_ATTENTION = 1, PROF_KNN_COARSE = 2, PROF_KNN_EXACT = 3, PROF_NUM = 4 };
+enum { PROF_GEMM_LINEAR = 0, PROF_ATTENTION = 1, PROF_KNN_COARSE = 2, PROF_KNN_EXACT = 3, PROF_KNN_PASS2 = 4, PROF_NUM = 5 };
 int prof_begin(int cls, double flops, double bytes, cudaStream_t s);   // slot id or -1 when disabled
 void prof_end(int slot, cudaStream_t s);
-
-// run-time options set through ac_set_option (api.cu)
-enum { OPT_GEMM_PAIR = 0, OPT_KNN_PAIR = 1, OPT_LN_DEFER = 2, OPT_HEAD_FUSED = 3, OPT_EPI16 = 4, OPT_ATTN_PIPE = 5, OPT_PDL = 6, OPT_KNN_EPI = 7, OPT_CLS_ATTN = 8, OPT_NUM = 9 };
-long long option(int id);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
@@ -216,16 +212,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ uint32_t cluster_id_x() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctaid_x() {   // number of clusters in the grid (x)
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
-    return r;
-}
 // shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -301,31 +287,6 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
         "}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-
-// ---------------------------------------------------------------- programmatic dependent launch (opt-in, option "pdl")
-// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the stream is
-// still running: its CTAs are placed as SM resources free up, run their prologue (barrier init, TMEM allocation, descriptor
-// prefetch) and then block in griddepcontrol.wait until the predecessor has completed and flushed.  Only persistent,
-// single-wave kernels call launch_dependents early (a multi-wave predecessor that still has to place CTAs needing TMEM
-// could otherwise wait forever for TMEM held by a blocked dependent).  Both instructions are no-ops in ordinary launches.
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-template <class... KArgs, class... Args>
-static inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
-                                           Args &&...args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---------------------------------------------------------------- host: TMA descriptor creation

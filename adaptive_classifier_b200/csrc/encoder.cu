@@ -13,9 +13,10 @@
 //                 bias | bias+GELU(erf) | bias+residual, fp16 or fp32 output, V written TRANSPOSED per (sequence, head)
 //   attention     one CTA per (sequence, head): Q, K and V^T tiles by TMA, QK^T and PV as tcgen05 MMAs with the score
 //                 tile / output tile in TMEM, thread-per-query-row softmax in between (S <= 128, head_dim 64)
-//   LayerNorm     fp32 residual stream + the fp16 operand copy for the next GEMM
+//   LayerNorm     never materialised inside the layer stack: the residual epilogues keep the un-normalised sums y (fp32) and
+//                 per-row (sum, sumsq) partials, the consuming projections run on gamma-scaled weights and apply the
+//                 rank-1 correction r (acc - mu c1) + c0 in their epilogue ("deferred LayerNorm" below)
 #include "gemm_tc2.cuh"
-#include "peer.cuh"
 #include <cuda_fp16.h>
 #include <math_constants.h>
 #include <vector>
@@ -57,7 +58,7 @@ __device__ __forceinline__ float gelu_erf(float y) {
 // ------------------------------------------------------------------------------------------------
 //   DEFER: the A operand was the UN-normalised residual sum y (fp16) and the weights were packed as fp16(gamma * W):
 //       LayerNorm(y) W^T + b = r (acc - mu c1) + c0  with the row statistics (mu, r) of y, c1 = rowsum(W'), and
-//       `bias` holding c0 = W beta + b  (see "deferred LayerNorm" below and oracle/deferred_ln_study.py)
+//       `bias` holding c0 = W beta + b  (see "deferred LayerNorm" below)
 //   COLS:  accumulator columns one epilogue warp drains per tile (128 with 8 epilogue warps, 64 with 16): only the DEFER
 //          variant needs it, to know which chunk is the first of its slice
 template <int MODE, bool OUT_HALF, bool VT, bool DEFER = false, int COLS = GEMM_BLOCK_N / 2>
@@ -212,7 +213,7 @@ struct EpiLinear {
 };
 
 // ------------------------------------------------------------------------------------------------
-// deferred LayerNorm (opt-in, option "ln_defer"): residual epilogue that never materialises LayerNorm
+// deferred LayerNorm: residual epilogue that never materialises LayerNorm
 //
 //   y_new = acc + bias + LN_prev(y_old)          LN_prev(y) = (y - mu) r gamma + beta recomputed from the fp32 y_old, its
 //                                                row statistics and the pending LayerNorm's parameters
@@ -220,7 +221,7 @@ struct EpiLinear {
 //   next GEMM's A operand, consumed through EpiLinear<.., DEFER = true>) and per-row partial (sum, sum of squares) of
 //   this warp's 128 columns into parts[column part][row]; ln_stats_kernel turns the parts into (mu, r).
 //   HBM traffic per half layer at B*S = 65536, H = 768: read y 201 MB, write y 201 MB + fp16 101 MB = 503 MB instead of
-//   905 MB (GEMM epilogue 402 MB + LayerNorm kernel 503 MB); precision: oracle/deferred_ln_study.py.
+//   905 MB (GEMM epilogue 402 MB + LayerNorm kernel 503 MB); precision: oracle/deferred_ln_study.py (CPU emulation) and tests/test_gpu_parity.py (non-trivial gamma / beta).
 // ------------------------------------------------------------------------------------------------
 struct EpiResidDefer {
     const float *__restrict__ bias;        // [N]
@@ -329,8 +330,6 @@ struct EpiResidDefer {
 // (sum, sumsq) partials of every 128-column part -> (mu, 1/sqrt(var + eps)) per row; parts are added in a fixed order
 __global__ void ln_stats_kernel(const float2 *__restrict__ parts, int nparts, int64_t part_stride, int rows, int H, float eps,
                                 float2 *__restrict__ stats) {
-    griddep_launch_dependents();      // option "pdl": no-ops in an ordinary launch
-    griddep_wait();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     float s = 0.f, q = 0.f;
@@ -489,27 +488,6 @@ __global__ void cls_normalize_kernel(const float *__restrict__ x, int B, int S, 
     for (int i = lane; i < H; i += 32) s = fmaf(src[i], src[i], s);
     const float nrm = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
     for (int i = lane; i < H; i += 32) out[static_cast<int64_t>(bq) * H + i] = src[i] / nrm;
-}
-
-// the same, additionally storing the row into every peer's exchange buffer (NVLink-mapped pointers) and publishing the
-// sequence number once the whole grid has stored: the all-gather of the embeddings for the row-sharded search (peer.cu)
-__global__ void cls_normalize_scatter_kernel(const float *__restrict__ x, int B, int S, int H, float *__restrict__ out,
-                                             ac_peer_table t, size_t dst_off, uint32_t seq, unsigned int *counter) {
-    const int bq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (bq < B) {
-        const float *src = x + static_cast<int64_t>(bq) * S * H;
-        float sq = 0.f;
-        for (int i = lane; i < H; i += 32) sq = fmaf(src[i], src[i], sq);
-        const float nrm = fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
-        for (int i = lane; i < H; i += 32) {
-            const float v = src[i] / nrm;
-            out[static_cast<int64_t>(bq) * H + i] = v;
-            for (int p = 0; p < t.world; ++p)
-                reinterpret_cast<float *>(static_cast<uint8_t *>(t.buf[p]) + dst_off)[static_cast<int64_t>(bq) * H + i] = v;
-        }
-    }
-    peer_publish_when_grid_done(t, seq, counter);
 }
 
 // last layer: only the CLS row of every sequence is needed downstream of attention (classifier.py:1272), so the
@@ -710,208 +688,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
-// pipelined attention (opt-in, option "attn_pipe"; S <= 128): the same arithmetic as attention_kernel, restructured as a
-// persistent, warp-specialised pipeline so that the load / QK^T of item i+1 overlap the softmax / PV / store of item i.
-//
-//   grid = 2 CTAs per SM, each walks (sequence, head) items i = blockIdx.x, += gridDim.x; two buffers b = i & 1, each
-//   48 KB of smem (Q | K -> later P, V^T) and 128 TMEM columns (scores -> later the output tile).
-//   warp 4, one thread : wait free[b] -> TMA Q, K, V^T (full[b]) -> QK^T MMAs -> commit s_ready[b] -> issue the loads of
-//                        item i+1 -> wait p_ready[b] -> PV MMAs -> commit o_ready[b]
-//   warps 0..3         : key mask -> wait s_ready[b] -> two-pass softmax out of TMEM, P -> smem -> arrive p_ready[b] ->
-//                        wait o_ready[b] -> O / rowsum -> ctx -> arrive free[b]
-// attention_kernel pays TMEM allocation, barrier setup and an exposed TMA round trip per (sequence, head) and measured
-// 111 us per layer against a 61 us traffic floor (403 MB of qk / vT / ctx).  Status: NOT yet run on hardware.
-// ------------------------------------------------------------------------------------------------
-constexpr int ATTP_THREADS = 160;
-constexpr int ATTP_BUF = 48 * 1024;
-constexpr int ATTP_SMEM = 2 * ATTP_BUF + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int ATTP_TMEM_COLS = 256;
-
-__global__ void __launch_bounds__(ATTP_THREADS)
-attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
-                      const int32_t *__restrict__ mask, int B, int S, int heads, int H, __half *__restrict__ ctx) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * ATTP_BUF);
-    uint64_t *full = bars, *s_ready = bars + 2, *p_ready = bars + 4, *o_ready = bars + 6, *free_ = bars + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int items = B * heads;
-    const int n_my = (items > static_cast<int>(blockIdx.x)) ? (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
-
-    if (tid == 0) {
-        tma_prefetch_desc(&tmap_qk);
-        tma_prefetch_desc(&tmap_vt);
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&full[b], 1);
-            mbar_init(&s_ready[b], 1);
-            mbar_init(&p_ready[b], 4);      // one arrival per softmax warp
-            mbar_init(&o_ready[b], 1);
-            mbar_init(&free_[b], 4);        // one arrival per softmax warp
-        }
-        fence_mbar_init();
-    }
-    if (warp == 4) {
-        tmem_alloc(tmem_slot, ATTP_TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    griddep_launch_dependents();      // option "pdl" (persistent single-wave kernel): no-ops in an ordinary launch
-    griddep_wait();
-
-    if (warp == 4) {
-        // ---------------- producer + MMA issuer ----------------
-        if (lane == 0) {
-            auto load = [&](int it) {
-                const int b = it & 1;
-                const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-                const int bq = item / heads, h = item % heads;
-                uint8_t *buf = smem + b * ATTP_BUF;
-                mbar_wait_guarded(&free_[b], ((it >> 1) & 1) ^ 1);        // epilogue of item it-2 has released the buffer
-                mbar_arrive_expect_tx(&full[b], 48 * 1024);
-                const int r = bq * S;
-                tma_load_2d(buf, &tmap_qk, &full[b], h * 64, r);
-                tma_load_2d(buf + 16 * 1024, &tmap_qk, &full[b], H + h * 64, r);
-                const int vrow = (bq * heads + h) * 64;
-                tma_load_2d(buf + 32 * 1024, &tmap_vt, &full[b], 0, vrow);
-                tma_load_2d(buf + 40 * 1024, &tmap_vt, &full[b], 64, vrow);
-            };
-            constexpr uint32_t idesc_s = umma_idesc(0 /*f16*/, 128, 128);
-            constexpr uint32_t idesc_o = umma_idesc(0 /*f16*/, 128, 64);
-            if (n_my > 0) load(0);
-            for (int it = 0; it < n_my; ++it) {
-                const int b = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                uint8_t *buf = smem + b * ATTP_BUF;
-                const uint32_t d_tmem = tmem_base + b * 128;
-                mbar_wait_guarded(&full[b], ph);
-                tc_fence_after();
-                {
-                    const uint64_t a = umma_desc_sw128(smem_u32(buf));
-                    const uint64_t bd = umma_desc_sw128(smem_u32(buf + 16 * 1024));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a + 2 * k, bd + 2 * k, idesc_s, k != 0);
-                    tc_commit(&s_ready[b]);
-                }
-                if (it + 1 < n_my) load(it + 1);
-                mbar_wait_guarded(&p_ready[b], ph);
-                tc_fence_after();
-#pragma unroll
-                for (int slab = 0; slab < 2; ++slab) {
-                    const uint64_t a = umma_desc_sw128(smem_u32(buf + slab * 16384));
-                    const uint64_t bd = umma_desc_sw128(smem_u32(buf + 32 * 1024 + slab * 8192));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a + 2 * k, bd + 2 * k, idesc_o, (slab | k) != 0);
-                }
-                tc_commit(&o_ready[b]);
-            }
-        }
-    } else {
-        // ---------------- softmax / epilogue warps: thread = query row (TMEM lane) ----------------
-        const int qrow = warp * 32 + lane;
-        const float scale_log2 = rsqrtf(64.f) * 1.44269504088896340736f;
-        for (int it = 0; it < n_my; ++it) {
-            const int b = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-            const int bq = item / heads, h = item % heads;
-            const int64_t row0 = static_cast<int64_t>(bq) * S;
-            const uint32_t t_s = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + b * 128;
-            uint32_t kmask[4];
-#pragma unroll
-            for (int w4 = 0; w4 < 4; ++w4) {
-                const int key = 32 * w4 + lane;
-                const bool ok = (key < S) && (!mask || mask[row0 + key] != 0);
-                kmask[w4] = __ballot_sync(0xffffffffu, ok);
-            }
-            mbar_wait_guarded(&s_ready[b], ph);
-            tc_fence_after();
-            float mx = -CUDART_INF_F;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_s + c, r);
-                tmem_ld_wait();
-                const uint32_t km = c == 0 ? kmask[0] : c == 32 ? kmask[1] : c == 64 ? kmask[2] : kmask[3];
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if ((km >> j) & 1u) mx = fmaxf(mx, __uint_as_float(r[j]));
-            }
-            float sum = 0.f;
-            const uint32_t sp_base = smem_u32(smem + b * ATTP_BUF);
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_s + c, r);
-                tmem_ld_wait();
-                uint32_t pk[16];
-                const uint32_t km = c == 0 ? kmask[0] : c == 32 ? kmask[1] : c == 64 ? kmask[2] : kmask[3];
-                const float mxs = mx * scale_log2;
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float e0 = ((km >> j) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2, -mxs)) : 0.f;
-                    const float e1 = ((km >> (j + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2, -mxs)) : 0.f;
-                    sum += e0 + e1;
-                    __half2 hh = __floats2half2_rn(e0, e1);
-                    pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
-                }
-                const uint32_t prow = sp_base + (c >> 6) * 16384 + (qrow >> 3) * 1024 + (qrow & 7) * 128;
-                const int ch0 = (c & 63) >> 3;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((ch0 + ch) ^ (qrow & 7)) << 4)),
-                                 "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]), "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
-                                 : "memory");
-                }
-            }
-            // P (generic-proxy smem writes) -> visible to the tensor-core proxy; this warp is done reading its score lanes
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_ready[b]);
-
-            mbar_wait_guarded(&o_ready[b], ph);
-            tc_fence_after();
-            const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_s + c, r);
-                tmem_ld_wait();
-                if (qrow < S) {
-                    __half *dst = ctx + (row0 + qrow) * H + h * 64 + c;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __half2 h0 = __floats2half2_rn(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-                        __half2 h1 = __floats2half2_rn(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-                        __half2 h2 = __floats2half2_rn(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-                        __half2 h3 = __floats2half2_rn(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-                        uint4 pk;
-                        pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                        *reinterpret_cast<uint4 *>(dst + j) = pk;
-                    }
-                }
-            }
-            // buffer b (smem + its TMEM columns) may be refilled: the item two ahead reuses it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&free_[b]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, ATTP_TMEM_COLS);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // attention for 128 < S <= 512: one CTA per (sequence, head, 128-query block), key blocks of 128 streamed twice.
 //   pass A  row max over all key blocks        (QK^T only)
 //   pass B  P = exp(scale*(s - max)) per block, O += P V_block accumulated in TMEM, row sums in registers
@@ -1097,92 +873,22 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// CLS-only attention of the last layer (opt-in, option "cls_attn").  Downstream of the last layer's attention only row 0
-// of every sequence is read (gather_cls_kernel / gather_cls_ln_kernel; classifier.py:1272 pools the CLS token), so
-// softmax(Q K^T) V shrinks to one query row per (sequence, head): S dot products of length 64 and a [1 x S] x [S x 64]
-// product.  One warp per (b, h): lanes over keys for the scores (the K row of a key is 128 contiguous bytes), lanes over
-// head dims for the output (row d of the transposed V buffer is S_pad contiguous keys).  Same arithmetic as
-// attention_kernel: masked two-pass softmax in base 2, P rounded to fp16 before PV, fp32 sums, 1 / rowsum at the end.
-// Reads 2 x B x S x H halves (K and V once), writes B x H halves: ~100 MB for the bench batch against the 403 MB and the
-// 128 x 128 tensor-core tiles of the full kernel.  Rows other than the CLS rows of ctx are left stale - the CLS-only tail
-// never reads them.  Status: NOT yet run on hardware (CPU-emulated through the encoder host path).
-// ------------------------------------------------------------------------------------------------
-constexpr int ATTC_WARPS = 8;
-constexpr int ATTC_MAX_S = 512;
-
-__global__ void __launch_bounds__(ATTC_WARPS * 32)
-attention_cls_kernel(const __half *__restrict__ qk, const __half *__restrict__ vT, const int32_t *__restrict__ mask, int B, int S,
-                     int S_pad, int heads, int H, __half *__restrict__ ctx) {
-    __shared__ float sq[ATTC_WARPS][64];
-    __shared__ float sp[ATTC_WARPS][ATTC_MAX_S];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * ATTC_WARPS + warp;
-    if (item >= B * heads) return;                                    // warp-uniform
-    const int b = item / heads, h = item % heads;
-    const int64_t row0 = static_cast<int64_t>(b) * S;
-    const int64_t ld = 2 * static_cast<int64_t>(H);                   // Q | K row of the qk buffer
-    {
-        const float2 f = __half22float2(reinterpret_cast<const __half2 *>(qk + row0 * ld + h * 64)[lane]);
-        sq[warp][2 * lane] = f.x;
-        sq[warp][2 * lane + 1] = f.y;
-    }
-    __syncwarp();
-    // ---- scores of the CLS query against every key; invalid keys (padding) are remembered as -inf
-    float mx = -CUDART_INF_F;
-    for (int key = lane; key < S; key += 32) {
-        const uint4 *kr = reinterpret_cast<const uint4 *>(qk + (row0 + key) * ld + H + h * 64);
-        float s = 0.f;
+// last layer, deferred flow: CLS rows of the attention context and of LN_pending(y) (two-pass statistics from the fp32 sums)
+__global__ void gather_cls_ln_kernel(const __half *__restrict__ ctx, const float *__restrict__ y, int B, int S, int H,
+                                     const float *__restrict__ g, const float *__restrict__ b, float eps,
+                                     __half *__restrict__ ctx_cls, float *__restrict__ x_cls) {
+    const int bq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (bq >= B) return;
+    const int64_t src = static_cast<int64_t>(bq) * S * H, dst = static_cast<int64_t>(bq) * H;
+    for (int i = lane; i < H / 8; i += 32)
+        reinterpret_cast<uint4 *>(ctx_cls + dst)[i] = reinterpret_cast<const uint4 *>(ctx + src)[i];
+    const int nv = H / 128;
+    float4 x[LN_MAXV];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = kr[c];
-            const __half2 *hp = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(hp[j]);
-                s = fmaf(sq[warp][8 * c + 2 * j], f.x, s);
-                s = fmaf(sq[warp][8 * c + 2 * j + 1], f.y, s);
-            }
-        }
-        const bool ok = !mask || mask[row0 + key] != 0;
-        sp[warp][key] = ok ? s : -CUDART_INF_F;
-        if (ok) mx = fmaxf(mx, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float scale_log2 = rsqrtf(64.f) * 1.44269504088896340736f;
-    const float mxs = mx * scale_log2;
-    float sum = 0.f;
-    for (int key = lane; key < S; key += 32) {
-        const float s = sp[warp][key];
-        const float e = (s != -CUDART_INF_F) ? ex2_approx(fmaf(s, scale_log2, -mxs)) : 0.f;
-        sum += e;
-        sp[warp][key] = __half2float(__float2half_rn(e));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncwarp();
-    const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
-    // ---- out[d] = sum_key P[key] V[key, d]; lane owns head dims lane and lane + 32
-    const int S8 = S & ~7;
-#pragma unroll
-    for (int dd = 0; dd < 2; ++dd) {
-        const int d = lane + 32 * dd;
-        const __half *vr = vT + (static_cast<int64_t>(b) * H + h * 64 + d) * S_pad;
-        float acc = 0.f;
-        for (int k0 = 0; k0 < S8; k0 += 8) {
-            const uint4 u = *reinterpret_cast<const uint4 *>(vr + k0);
-            const __half2 *hp = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(hp[j]);
-                acc = fmaf(sp[warp][k0 + 2 * j], f.x, acc);
-                acc = fmaf(sp[warp][k0 + 2 * j + 1], f.y, acc);
-            }
-        }
-        for (int k = S8; k < S; ++k) acc = fmaf(sp[warp][k], __half2float(vr[k]), acc);
-        ctx[row0 * H + h * 64 + d] = __float2half_rn(acc * inv);
-    }
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (i < nv) x[i] = *reinterpret_cast<const float4 *>(y + src + (lane + 32 * i) * 4);
+    ln_row(x, nv, H, g, b, eps, lane, x_cls + dst, nullptr);
 }
 
 }  // namespace ac
@@ -1196,9 +902,13 @@ struct ac_encoder {
     ac_encoder_config cfg;
     // packed weights (device): fp16 GEMM operands, fp32 everything else
     float *word = nullptr, *pos = nullptr, *type = nullptr, *emb_ln_w = nullptr, *emb_ln_b = nullptr;
-    std::vector<__half *> wqkv, wo, w1, w2;
-    std::vector<float *> bqkv, bo, ln1w, ln1b, b1, b2, ln2w, ln2b;
-    // activations: fp32 residual stream x / pre-LN sum tmp; fp16 GEMM operands xh, qk, vT, ctx, ffn
+    // QKV / FFN1 consume un-normalised residual sums: their weights are packed as fp16(gamma * W) with the rank-1 correction
+    // vectors c1 (row sums of the packed weight) and c0 (W beta + bias), see pack_defer_kernel
+    std::vector<__half *> wqkv_d, wo, w1_d, w2;
+    std::vector<float *> c1qkv, c0qkv, c1f, c0f, bo, ln1w, ln1b, b2, ln2w, ln2b;
+    __half *w1_last = nullptr;            // plain fp16 FFN1 weight of the last layer (CLS-only tail runs on materialised LayerNorm rows)
+    float *b1_last = nullptr;
+    // activations: fp32 residual sums x (+ tmp for a materialised final LayerNorm); fp16 GEMM operands xh, qk, vT, ctx, ffn
     float *x = nullptr, *tmp = nullptr;
     __half *xh = nullptr, *qk = nullptr, *vT = nullptr, *ctx = nullptr, *ffn = nullptr;
     size_t T = 0;           // token capacity (multiple of 128)
@@ -1208,63 +918,43 @@ struct ac_encoder {
     float *x_cls = nullptr, *tmp_cls = nullptr;
     __half *xh_cls = nullptr, *ctx_cls = nullptr, *ffn_cls = nullptr;
     CUtensorMap m_xh_cls, m_ctx_cls, m_ffn_cls;
-    // cached TMA descriptors
+    // cached TMA descriptors: A operands (128-row boxes) and weights (128-row boxes = the B half one CTA of a pair stages)
     CUtensorMap m_xh, m_ctx, m_ffn, m_qk_att, m_vt_att;
     int vt_B = -1, vt_S = -1;
-    std::vector<CUtensorMap> m_wqkv, m_wo, m_w1, m_w2;
-    std::vector<CUtensorMap> p_wqkv, p_wo, p_w1, p_w2;   // same weights, 128-row boxes (B operand half of a CTA pair)
-    // deferred LayerNorm (option "ln_defer"): QKV / FFN1 weights packed as fp16(gamma * W) with their rank-1 correction
-    // vectors, row statistics (ping-pong) and the per-128-column partials the residual epilogues write
-    std::vector<__half *> wqkv_d, w1_d;
-    std::vector<float *> c1qkv, c0qkv, c1f, c0f;
-    std::vector<CUtensorMap> m_wqkv_d, m_w1_d, p_wqkv_d, p_w1_d;
+    std::vector<CUtensorMap> p_wqkv_d, p_wo, p_w1_d, p_w2;
+    CUtensorMap p_w1_last;
+    // row statistics (ping-pong) and the per-128-column partials the residual epilogues write
     float2 *stats_a = nullptr, *stats_b = nullptr, *stats_id = nullptr, *parts = nullptr;
     float *ones = nullptr, *zeros = nullptr;
     std::vector<void *> allocs;
     int last_B = 0, last_S = 0;
     bool last_cls_only = false;
     const float *last_hidden = nullptr;   // where the previous full forward left the last hidden state
-    // set for the duration of ac_encoder_forward_cls_scatter: the final normalise kernel also stores to the peers
-    bool sink_on = false;
-    ac_peer_table sink_table;
-    size_t sink_off = 0;
-    uint32_t sink_seq = 0;
-    unsigned int *sink_counter = nullptr;
 };
 
-// final kernel of every forward variant: unit CLS rows, optionally scattered to the peers
-static int launch_cls_normalize(ac_encoder *e, const float *x, int B, int S, int H, float *out, cudaStream_t s) {
+static int launch_cls_normalize(const float *x, int B, int S, int H, float *out, cudaStream_t s) {
     const int wpb = 8;
-    if (e->sink_on)
-        cls_normalize_scatter_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, B, S, H, out, e->sink_table, e->sink_off, e->sink_seq,
-                                                                          e->sink_counter);
-    else
-        cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, B, S, H, out);
+    cls_normalize_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, B, S, H, out);
     AC_LAUNCH_CHECK();
     return AC_OK;
 }
 
-// softmax(Q K^T / 8 + mask) V of layer l out of e->qk / e->vT into e->ctx
-static int launch_attention(ac_encoder *e, const int32_t *mask, int B, int S, int S_pad, int l, cudaStream_t s) {
+// softmax(Q K^T / 8 + mask) V out of e->qk / e->vT into e->ctx
+static int launch_attention(ac_encoder *e, const int32_t *mask, int B, int S, cudaStream_t s) {
     const ac_encoder_config &c = e->cfg;
     const int H = c.hidden;
-    const bool cls_tail = l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc;
-    if (cls_tail && option(OPT_CLS_ATTN)) {
-        // the CLS-only tail reads row 0 of every sequence only: one query row per (sequence, head)
-        const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * 64, 0.0, s);
-        attention_cls_kernel<<<(B * c.heads + ATTC_WARPS - 1) / ATTC_WARPS, ATTC_WARPS * 32, 0, s>>>(e->qk, e->vT, mask, B, S, S_pad,
-                                                                                                  c.heads, H, e->ctx);
-        prof_end(slot, s);
-        AC_LAUNCH_CHECK();
-        return AC_OK;
+    // per-device: the attribute is a property of the (function, device) pair
+    static bool att_attr[64] = {};
+    int dev = 0;
+    AC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !att_attr[dev]) {
+        AC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        AC_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTL_SMEM));
+        if (dev >= 0 && dev < 64) att_attr[dev] = true;
     }
     // algorithmic flops of softmax(QK^T)V at the true sequence length (the 128-wide tile does more)
     const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * c.heads * static_cast<double>(S) * S * 64, 0.0, s);
-    if (S <= 128 && option(OPT_ATTN_PIPE)) {
-        const int ctas = (B * c.heads < 2 * sm_count()) ? B * c.heads : 2 * sm_count();
-        AC_CUDA(launch_maybe_pdl(attention_pipe_kernel, dim3(ctas), dim3(ATTP_THREADS), ATTP_SMEM, s, option(OPT_PDL) != 0, e->m_qk_att,
-                                 e->m_vt_att, mask, B, S, c.heads, H, e->ctx));
-    } else if (S <= 128)
+    if (S <= 128)
         attention_kernel<<<B * c.heads, ATT_THREADS, ATT_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S, c.heads, H, e->ctx);
     else
         attention_long_kernel<<<dim3(B * c.heads, (S + 127) / 128), ATT_THREADS, ATTL_SMEM, s>>>(e->m_qk_att, e->m_vt_att, mask, B, S,
@@ -1325,37 +1015,14 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
     TRY(pack_f32(e, &e->type, w->type_emb, static_cast<size_t>(cfg->type_vocab) * H));
     TRY(pack_f32(e, &e->emb_ln_w, w->emb_ln_w, H));
     TRY(pack_f32(e, &e->emb_ln_b, w->emb_ln_b, H));
-    e->wqkv.assign(L, nullptr); e->wo.assign(L, nullptr); e->w1.assign(L, nullptr); e->w2.assign(L, nullptr);
-    e->bqkv.assign(L, nullptr); e->bo.assign(L, nullptr); e->ln1w.assign(L, nullptr); e->ln1b.assign(L, nullptr);
-    e->b1.assign(L, nullptr); e->b2.assign(L, nullptr); e->ln2w.assign(L, nullptr); e->ln2b.assign(L, nullptr);
+    e->wqkv_d.assign(L, nullptr); e->wo.assign(L, nullptr); e->w1_d.assign(L, nullptr); e->w2.assign(L, nullptr);
+    e->c1qkv.assign(L, nullptr); e->c0qkv.assign(L, nullptr); e->c1f.assign(L, nullptr); e->c0f.assign(L, nullptr);
+    e->bo.assign(L, nullptr); e->ln1w.assign(L, nullptr); e->ln1b.assign(L, nullptr);
+    e->b2.assign(L, nullptr); e->ln2w.assign(L, nullptr); e->ln2b.assign(L, nullptr);
     const size_t HH = static_cast<size_t>(H) * H;
     for (int l = 0; l < L; ++l) {
-        // fused QKV operand [3H, H] fp16 and bias [3H] fp32
-        TRY(dev_alloc(e, &e->wqkv[l], 3 * HH));
-        TRY(dev_alloc(e, &e->bqkv[l], 3 * static_cast<size_t>(H)));
-        const float *ws[3] = {w->q_w[l], w->k_w[l], w->v_w[l]};
-        const float *bs[3] = {w->q_b[l], w->k_b[l], w->v_b[l]};
-        for (int j = 0; j < 3; ++j) {
-            to_half_kernel<<<256, 256>>>(ws[j], e->wqkv[l] + j * HH, static_cast<int64_t>(HH));
-            round_copy_kernel<<<8, 256>>>(bs[j], e->bqkv[l] + j * H, H, 0);
-        }
-        TRY(pack_f16(e, &e->wo[l], w->ao_w[l], HH));
-        TRY(pack_f32(e, &e->bo[l], w->ao_b[l], H));
-        TRY(pack_f32(e, &e->ln1w[l], w->ao_ln_w[l], H));
-        TRY(pack_f32(e, &e->ln1b[l], w->ao_ln_b[l], H));
-        TRY(pack_f16(e, &e->w1[l], w->ff1_w[l], static_cast<size_t>(I) * H));
-        TRY(pack_f32(e, &e->b1[l], w->ff1_b[l], I));
-        TRY(pack_f16(e, &e->w2[l], w->ff2_w[l], static_cast<size_t>(H) * I));
-        TRY(pack_f32(e, &e->b2[l], w->ff2_b[l], H));
-        TRY(pack_f32(e, &e->ln2w[l], w->out_ln_w[l], H));
-        TRY(pack_f32(e, &e->ln2b[l], w->out_ln_b[l], H));
-    }
-    // deferred-LayerNorm packing: the QKV projection of layer l consumes the sums whose pending LayerNorm is the output
-    // LayerNorm of layer l-1 (identity for layer 0: the embeddings arrive normalised); FFN1 of layer l consumes the sums
-    // pending the attention-output LayerNorm of layer l
-    e->wqkv_d.assign(L, nullptr); e->w1_d.assign(L, nullptr);
-    e->c1qkv.assign(L, nullptr); e->c0qkv.assign(L, nullptr); e->c1f.assign(L, nullptr); e->c0f.assign(L, nullptr);
-    for (int l = 0; l < L; ++l) {
+        // fused QKV operand [3H, H]: the projection of layer l consumes the sums whose pending LayerNorm is the output
+        // LayerNorm of layer l-1 (identity for layer 0: the embeddings arrive normalised)
         TRY(dev_alloc(e, &e->wqkv_d[l], 3 * HH));
         TRY(dev_alloc(e, &e->c1qkv[l], 3 * static_cast<size_t>(H)));
         TRY(dev_alloc(e, &e->c0qkv[l], 3 * static_cast<size_t>(H)));
@@ -1367,12 +1034,25 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
                                                     e->c0qkv[l] + j * H);
             TRY(check_cuda(cudaGetLastError(), "pack_defer_kernel qkv"));
         }
+        TRY(pack_f16(e, &e->wo[l], w->ao_w[l], HH));
+        TRY(pack_f32(e, &e->bo[l], w->ao_b[l], H));
+        TRY(pack_f32(e, &e->ln1w[l], w->ao_ln_w[l], H));
+        TRY(pack_f32(e, &e->ln1b[l], w->ao_ln_b[l], H));
+        // FFN1 of layer l consumes the sums pending the attention-output LayerNorm of layer l
         TRY(dev_alloc(e, &e->w1_d[l], static_cast<size_t>(I) * H));
         TRY(dev_alloc(e, &e->c1f[l], I));
         TRY(dev_alloc(e, &e->c0f[l], I));
         pack_defer_kernel<<<(I + 7) / 8, 256>>>(w->ff1_w[l], w->ff1_b[l], w->ao_ln_w[l], w->ao_ln_b[l], I, H, e->w1_d[l], e->c1f[l],
                                                 e->c0f[l]);
         TRY(check_cuda(cudaGetLastError(), "pack_defer_kernel ffn1"));
+        TRY(pack_f16(e, &e->w2[l], w->ff2_w[l], static_cast<size_t>(H) * I));
+        TRY(pack_f32(e, &e->b2[l], w->ff2_b[l], H));
+        TRY(pack_f32(e, &e->ln2w[l], w->out_ln_w[l], H));
+        TRY(pack_f32(e, &e->ln2b[l], w->out_ln_b[l], H));
+    }
+    if (cfg->cls_only) {
+        TRY(pack_f16(e, &e->w1_last, w->ff1_w[L - 1], static_cast<size_t>(I) * H));
+        TRY(pack_f32(e, &e->b1_last, w->ff1_b[L - 1], I));
     }
     TRY(dev_alloc(e, &e->stats_a, T));
     TRY(dev_alloc(e, &e->stats_b, T));
@@ -1414,149 +1094,31 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
     TRY(make_tmap_2d(&e->m_xh_cls, e->xh_cls, 2, e->Bc, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_M, 64));
     TRY(make_tmap_2d(&e->m_ctx_cls, e->ctx_cls, 2, e->Bc, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_M, 64));
     TRY(make_tmap_2d(&e->m_ffn_cls, e->ffn_cls, 2, e->Bc, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_M, 64));
-    e->m_wqkv.resize(L); e->m_wo.resize(L); e->m_w1.resize(L); e->m_w2.resize(L);
+    e->p_wqkv_d.resize(L); e->p_wo.resize(L); e->p_w1_d.resize(L); e->p_w2.resize(L);
     for (int l = 0; l < L; ++l) {
-        TRY(make_tmap_2d(&e->m_wqkv[l], e->wqkv[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
-        TRY(make_tmap_2d(&e->m_wo[l], e->wo[l], 2, H, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
-        TRY(make_tmap_2d(&e->m_w1[l], e->w1[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
-        TRY(make_tmap_2d(&e->m_w2[l], e->w2[l], 2, H, I, static_cast<uint64_t>(I) * 2, GEMM_BLOCK_N, 64));
-    }
-    e->m_wqkv_d.resize(L); e->m_w1_d.resize(L); e->p_wqkv_d.resize(L); e->p_w1_d.resize(L);
-    for (int l = 0; l < L; ++l) {
-        TRY(make_tmap_2d(&e->m_wqkv_d[l], e->wqkv_d[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
-        TRY(make_tmap_2d(&e->m_w1_d[l], e->w1_d[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM_BLOCK_N, 64));
         TRY(make_tmap_2d(&e->p_wqkv_d[l], e->wqkv_d[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
-        TRY(make_tmap_2d(&e->p_w1_d[l], e->w1_d[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
-    }
-    e->p_wqkv.resize(L); e->p_wo.resize(L); e->p_w1.resize(L); e->p_w2.resize(L);
-    for (int l = 0; l < L; ++l) {
-        TRY(make_tmap_2d(&e->p_wqkv[l], e->wqkv[l], 2, 3 * H, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
         TRY(make_tmap_2d(&e->p_wo[l], e->wo[l], 2, H, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
-        TRY(make_tmap_2d(&e->p_w1[l], e->w1[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
+        TRY(make_tmap_2d(&e->p_w1_d[l], e->w1_d[l], 2, I, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
         TRY(make_tmap_2d(&e->p_w2[l], e->w2[l], 2, H, I, static_cast<uint64_t>(I) * 2, GEMM2_B_ROWS, 64));
     }
+    if (cfg->cls_only) TRY(make_tmap_2d(&e->p_w1_last, e->w1_last, 2, I, H, static_cast<uint64_t>(H) * 2, GEMM2_B_ROWS, 64));
     TRY(check_cuda(cudaDeviceSynchronize(), "encoder_create sync"));
 #undef TRY
     *out = e;
     return AC_OK;
 }
 
-using EpiQKV = EpiLinear<0, true, true>;      // bias, fp16 out, V third transposed
-using EpiGelu = EpiLinear<1, true, false>;    // bias + GELU, fp16 out
-using EpiResid = EpiLinear<2, false, false>;  // bias + residual, fp32 out (pre-LayerNorm sum)
+using EpiGelu = EpiLinear<1, true, false>;                  // bias + GELU, fp16 out                       (CLS-only tail)
+using EpiResid = EpiLinear<2, false, false>;                // bias + residual, fp32 out (pre-LayerNorm sum, CLS-only tail)
+using EpiQKVDefer = EpiLinear<0, true, true, true>;         // r (acc - mu c1) + c0, fp16 out, V third transposed
+using EpiGeluDefer16 = EpiLinear<1, true, false, true, 64>; // GELU(r (acc - mu c1) + c0), fp16 out; 16 epilogue warps x 64 columns
 
-// one encoder projection: the measured 1-CTA kernel by default, the CTA-pair kernel when option "gemm_pair" is set
-// (tb = weight map with a 256-row box, tb_pair = the same weight with a 128-row box)
-template <class Epi>
-static int launch_linear(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tb_pair, int M, int N, int K,
-                         const Epi &epi, cudaStream_t s) {
-    if (option(OPT_GEMM_PAIR)) return launch_gemm_tc2<Epi, false, GEMM_KIND_F16>(ta, tb_pair, M, N, K, epi, s);
-    return launch_gemm_tc<Epi, false, GEMM_KIND_F16>(ta, tb, M, N, K, epi, s);
-}
-
-using EpiQKVDefer = EpiLinear<0, true, true, true>;     // r (acc - mu c1) + c0, fp16 out, V third transposed
-using EpiGeluDefer = EpiLinear<1, true, false, true>;   // GELU(r (acc - mu c1) + c0), fp16 out
-using EpiQKVDefer16 = EpiLinear<0, true, true, true, 64>;    // the same functors for 16 epilogue warps (64 columns per warp)
-using EpiGeluDefer16 = EpiLinear<1, true, false, true, 64>;
-
-// option "epi16" (bit 0: FFN1 = bias + GELU, bit 1: fused QKV): run that projection through the CTA-pair kernel with 16
-// epilogue warps instead of 8.  Opt-in, not yet run on hardware (the pair protocol itself is: profiles/r01_pair_*.log).
-template <class Epi, class Epi16>
-static int launch_linear_epi16(int bit, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tb_pair, int M, int N,
-                               int K, const Epi &epi, const Epi16 &epi16, cudaStream_t s) {
-    if (option(OPT_EPI16) & bit) return launch_gemm_tc2<Epi16, false, GEMM_KIND_F16, 16>(ta, tb_pair, M, N, K, epi16, s);
-    return launch_linear(ta, tb, tb_pair, M, N, K, epi, s);
-}
-
-// last layer, deferred flow: CLS rows of the attention context and of LN_pending(y) (two-pass statistics from the fp32 sums)
-__global__ void gather_cls_ln_kernel(const __half *__restrict__ ctx, const float *__restrict__ y, int B, int S, int H,
-                                     const float *__restrict__ g, const float *__restrict__ b, float eps,
-                                     __half *__restrict__ ctx_cls, float *__restrict__ x_cls) {
-    const int bq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (bq >= B) return;
-    const int64_t src = static_cast<int64_t>(bq) * S * H, dst = static_cast<int64_t>(bq) * H;
-    for (int i = lane; i < H / 8; i += 32)
-        reinterpret_cast<uint4 *>(ctx_cls + dst)[i] = reinterpret_cast<const uint4 *>(ctx + src)[i];
-    const int nv = H / 128;
-    float4 x[LN_MAXV];
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-        if (i < nv) x[i] = *reinterpret_cast<const float4 *>(y + src + (lane + 32 * i) * 4);
-    ln_row(x, nv, H, g, b, eps, lane, x_cls + dst, nullptr);
-}
-
-// Layers of the deferred-LayerNorm flow (option "ln_defer"); e->x holds the un-normalised residual sums y, e->xh their
-// fp16 copy, and the LayerNorm that is still pending on y is carried as (gamma, beta, row statistics).
-static int encoder_layers_deferred(ac_encoder *e, const int32_t *mask, int B, int S, int S_pad, float *out_unit_cls,
-                                   cudaStream_t s) {
-    const ac_encoder_config &c = e->cfg;
-    const int H = c.hidden, I = c.intermediate, M = B * S;
-    const int wpb = 8;
-    const int nparts = H / 128;
-    const int64_t pstride = static_cast<int64_t>(e->T);
-    int rc;
-    const float *pg = e->ones, *pb = e->zeros;      // pending LayerNorm of the sums in e->x (identity after the embeddings)
-    const float2 *st_in = e->stats_id;
-    for (int l = 0; l < c.layers; ++l) {
-        EpiQKVDefer eq{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
-        EpiQKVDefer16 eq16{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
-        if ((rc = launch_linear_epi16(2, e->m_xh, e->m_wqkv_d[l], e->p_wqkv_d[l], M, 3 * H, H, eq, eq16, s))) return rc;
-        if ((rc = launch_attention(e, mask, B, S, S_pad, l, s))) return rc;
-        if (l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc) {
-            // ---- CLS-only tail of the last layer (M = B rows): materialise LN_pending on the CLS rows and continue with
-            // the ordinary kernels and the plain (not gamma-scaled) FFN1 weight
-            const int cb = (B + wpb - 1) / wpb;
-            if (l == 0)   // single-layer encoder: nothing is pending on the (already normalised) embeddings
-                gather_cls_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, e->ctx_cls, e->x_cls);
-            else
-                gather_cls_ln_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, pg, pb, c.ln_eps, e->ctx_cls, e->x_cls);
-            AC_LAUNCH_CHECK();
-            EpiResid eo{e->bo[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_linear(e->m_ctx_cls, e->m_wo[l], e->p_wo[l], B, H, H, eo, s))) return rc;
-            layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln1w[l], e->ln1b[l], c.ln_eps, B, H, e->x_cls, e->xh_cls);
-            AC_LAUNCH_CHECK();
-            EpiGelu e1{e->b1[l], nullptr, e->ffn_cls, B, I, I, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_linear(e->m_xh_cls, e->m_w1[l], e->p_w1[l], B, I, H, e1, s))) return rc;
-            EpiResid e2{e->b2[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_linear(e->m_ffn_cls, e->m_w2[l], e->p_w2[l], B, H, I, e2, s))) return rc;
-            layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
-            AC_LAUNCH_CHECK();
-            if ((rc = launch_cls_normalize(e, e->x_cls, B, 1, H, out_unit_cls, s))) return rc;
-            e->last_B = B;
-            e->last_S = S;
-            e->last_cls_only = true;
-            return AC_OK;
-        }
-        // attention output projection + residual: y <- ctx Wo^T + bo + LN_pending(y); statistics of the new sums
-        EpiResidDefer eo{e->bo[l], e->x, e->xh, st_in, pg, pb, e->parts, pstride, M, H, H};
-        if ((rc = launch_linear(e->m_ctx, e->m_wo[l], e->p_wo[l], M, H, H, eo, s))) return rc;
-        AC_CUDA(launch_maybe_pdl(ln_stats_kernel, dim3((M + 255) / 256), dim3(256), 0, s, option(OPT_PDL) != 0,
-                                 static_cast<const float2 *>(e->parts), nparts, pstride, M, H, c.ln_eps, e->stats_b));
-        AC_LAUNCH_CHECK();
-        EpiGeluDefer e1{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
-        EpiGeluDefer16 e116{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
-        if ((rc = launch_linear_epi16(1, e->m_xh, e->m_w1_d[l], e->p_w1_d[l], M, I, H, e1, e116, s))) return rc;
-        // FFN output projection + residual: y <- ffn W2^T + b2 + LN_attention_output(y)
-        EpiResidDefer e2{e->b2[l], e->x, e->xh, e->stats_b, e->ln1w[l], e->ln1b[l], e->parts, pstride, M, H, H};
-        if ((rc = launch_linear(e->m_ffn, e->m_w2[l], e->p_w2[l], M, H, I, e2, s))) return rc;
-        AC_CUDA(launch_maybe_pdl(ln_stats_kernel, dim3((M + 255) / 256), dim3(256), 0, s, option(OPT_PDL) != 0,
-                                 static_cast<const float2 *>(e->parts), nparts, pstride, M, H, c.ln_eps, e->stats_a));
-        AC_LAUNCH_CHECK();
-        pg = e->ln2w[l];
-        pb = e->ln2b[l];
-        st_in = e->stats_a;
-    }
-    // full hidden state requested (cls_only = 0): materialise the last LayerNorm for every row (in place, row in registers)
-    const int row_blocks = (M + wpb - 1) / wpb;
-    layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->x, pg, pb, c.ln_eps, M, H, e->tmp, nullptr);
-    AC_LAUNCH_CHECK();
-    if ((rc = launch_cls_normalize(e, e->tmp, B, S, H, out_unit_cls, s))) return rc;
-    e->last_B = B;
-    e->last_S = S;
-    e->last_cls_only = false;
-    e->last_hidden = e->tmp;
-    return AC_OK;
+// One encoder projection = one CTA-pair GEMM (gemm_tc2.cuh).  tb is the weight's 128-row-box map.  The bias + GELU epilogue of
+// FFN1 issues ~17 instructions per element, which two warps per scheduler cannot hide behind a K = 768 mainloop: it runs with
+// 16 epilogue warps (measured on a B200: -0.65 ms per 12-layer forward at B*S = 65536, profiles/r02_variants.md).
+template <class Epi, int kEpiWarps = GEMM_EPI_WARPS>
+static int launch_linear(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi, cudaStream_t s) {
+    return launch_gemm_tc2<Epi, false, GEMM_KIND_F16, kEpiWarps>(ta, tb, M, N, K, epi, s);
 }
 
 extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const int32_t *mask, const int32_t *type_ids,
@@ -1585,79 +1147,71 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
     }
     const int wpb = 8;
     const int row_blocks = (M + wpb - 1) / wpb;
+    const int nparts = H / 128;
+    const int64_t pstride = static_cast<int64_t>(e->T);
 
+    // e->x holds the un-normalised residual sums y, e->xh their fp16 copy; the LayerNorm still pending on y is carried as
+    // (gamma, beta, row statistics).  The embeddings arrive normalised: identity LayerNorm pending.
     embed_ln_kernel<<<row_blocks, wpb * 32, 0, s>>>(ids, type_ids, e->word, e->pos, e->type, e->emb_ln_w, e->emb_ln_b,
                                                     c.ln_eps, B, S, H, c.arch, c.pad_idx, c.vocab, c.max_pos,
                                                     c.type_vocab, e->x, e->xh);
     AC_LAUNCH_CHECK();
-    static bool att_attr = false;
-    if (!att_attr) {
-        AC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        AC_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTL_SMEM));
-        AC_CUDA(cudaFuncSetAttribute(attention_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTP_SMEM));
-        att_attr = true;
-    }
-    if (option(OPT_LN_DEFER)) return encoder_layers_deferred(e, mask, B, S, S_pad, out_unit_cls, s);
+    const float *pg = e->ones, *pb = e->zeros;
+    const float2 *st_in = e->stats_id;
     for (int l = 0; l < c.layers; ++l) {
-        EpiQKV eq{e->bqkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H};
-        if ((rc = launch_linear_epi16(2, e->m_xh, e->m_wqkv[l], e->p_wqkv[l], M, 3 * H, H, eq, eq, s))) return rc;
-        if ((rc = launch_attention(e, mask, B, S, S_pad, l, s))) return rc;
+        EpiQKVDefer eq{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
+        if ((rc = launch_linear(e->m_xh, e->p_wqkv_d[l], M, 3 * H, H, eq, s))) return rc;
+        if ((rc = launch_attention(e, mask, B, S, s))) return rc;
         if (l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc) {
-            // ---- CLS-only tail of the last layer: M = B rows
+            // ---- CLS-only tail of the last layer (classifier.py:1272 pools row 0): M = B rows.  LN_pending is materialised on
+            // the CLS rows and the tail runs on ordinary LayerNorm kernels and the plain (not gamma-scaled) FFN1 weight
             const int cb = (B + wpb - 1) / wpb;
-            gather_cls_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, e->ctx_cls, e->x_cls);
+            if (l == 0)   // single-layer encoder: nothing is pending on the (already normalised) embeddings
+                gather_cls_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, e->ctx_cls, e->x_cls);
+            else
+                gather_cls_ln_kernel<<<cb, wpb * 32, 0, s>>>(e->ctx, e->x, B, S, H, pg, pb, c.ln_eps, e->ctx_cls, e->x_cls);
             AC_LAUNCH_CHECK();
             EpiResid eo{e->bo[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_linear(e->m_ctx_cls, e->m_wo[l], e->p_wo[l], B, H, H, eo, s))) return rc;
+            if ((rc = launch_linear(e->m_ctx_cls, e->p_wo[l], B, H, H, eo, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln1w[l], e->ln1b[l], c.ln_eps, B, H, e->x_cls, e->xh_cls);
             AC_LAUNCH_CHECK();
-            EpiGelu e1{e->b1[l], nullptr, e->ffn_cls, B, I, I, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_linear(e->m_xh_cls, e->m_w1[l], e->p_w1[l], B, I, H, e1, s))) return rc;
+            EpiGelu e1{e->b1_last, nullptr, e->ffn_cls, B, I, I, 0, nullptr, 0, 0, 0, 0};
+            if ((rc = launch_linear(e->m_xh_cls, e->p_w1_last, B, I, H, e1, s))) return rc;
             EpiResid e2{e->b2[l], e->x_cls, e->tmp_cls, B, H, H, 0, nullptr, 0, 0, 0, 0};
-            if ((rc = launch_linear(e->m_ffn_cls, e->m_w2[l], e->p_w2[l], B, H, I, e2, s))) return rc;
+            if ((rc = launch_linear(e->m_ffn_cls, e->p_w2[l], B, H, I, e2, s))) return rc;
             layernorm_kernel<<<cb, wpb * 32, 0, s>>>(e->tmp_cls, e->ln2w[l], e->ln2b[l], c.ln_eps, B, H, e->x_cls, nullptr);
             AC_LAUNCH_CHECK();
-            if ((rc = launch_cls_normalize(e, e->x_cls, B, 1, H, out_unit_cls, s))) return rc;
+            if ((rc = launch_cls_normalize(e->x_cls, B, 1, H, out_unit_cls, s))) return rc;
             e->last_B = B;
             e->last_S = S;
             e->last_cls_only = true;
             return AC_OK;
         }
-        EpiResid eo{e->bo[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_linear(e->m_ctx, e->m_wo[l], e->p_wo[l], M, H, H, eo, s))) return rc;
-        layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln1w[l], e->ln1b[l], c.ln_eps, M, H, e->x, e->xh);
+        // attention output projection + residual: y <- ctx Wo^T + bo + LN_pending(y); statistics of the new sums
+        EpiResidDefer eo{e->bo[l], e->x, e->xh, st_in, pg, pb, e->parts, pstride, M, H, H};
+        if ((rc = launch_linear(e->m_ctx, e->p_wo[l], M, H, H, eo, s))) return rc;
+        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_b);
         AC_LAUNCH_CHECK();
-        EpiGelu e1{e->b1[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_linear_epi16(1, e->m_xh, e->m_w1[l], e->p_w1[l], M, I, H, e1, e1, s))) return rc;
-        EpiResid e2{e->b2[l], e->x, e->tmp, M, H, H, 0, nullptr, 0, 0, 0, 0};
-        if ((rc = launch_linear(e->m_ffn, e->m_w2[l], e->p_w2[l], M, H, I, e2, s))) return rc;
-        layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->tmp, e->ln2w[l], e->ln2b[l], c.ln_eps, M, H, e->x, e->xh);
+        EpiGeluDefer16 e1{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
+        if ((rc = launch_linear<EpiGeluDefer16, 16>(e->m_xh, e->p_w1_d[l], M, I, H, e1, s))) return rc;
+        // FFN output projection + residual: y <- ffn W2^T + b2 + LN_attention_output(y)
+        EpiResidDefer e2{e->b2[l], e->x, e->xh, e->stats_b, e->ln1w[l], e->ln1b[l], e->parts, pstride, M, H, H};
+        if ((rc = launch_linear(e->m_ffn, e->p_w2[l], M, H, I, e2, s))) return rc;
+        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_a);
         AC_LAUNCH_CHECK();
+        pg = e->ln2w[l];
+        pb = e->ln2b[l];
+        st_in = e->stats_a;
     }
-    if ((rc = launch_cls_normalize(e, e->x, B, S, H, out_unit_cls, s))) return rc;
+    // full hidden state requested (cls_only = 0): materialise the last LayerNorm for every row
+    layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->x, pg, pb, c.ln_eps, M, H, e->tmp, nullptr);
+    AC_LAUNCH_CHECK();
+    if ((rc = launch_cls_normalize(e->tmp, B, S, H, out_unit_cls, s))) return rc;
     e->last_B = B;
     e->last_S = S;
     e->last_cls_only = false;
-    e->last_hidden = e->x;
+    e->last_hidden = e->tmp;
     return AC_OK;
-}
-
-extern "C" int ac_encoder_forward_cls_scatter(ac_encoder *e, const int32_t *ids, const int32_t *mask, const int32_t *type_ids, int B,
-                                              int S, float *out_unit_cls, const void *peer_table, size_t dst_offset_bytes,
-                                              uint32_t seq, uint32_t *counter, ac_stream_t stream) {
-    const ac_peer_table *t = static_cast<const ac_peer_table *>(peer_table);
-    AC_REQUIRE(e && t && counter, "ac_encoder_forward_cls_scatter: null argument");
-    AC_REQUIRE(t->world >= 1 && t->world <= AC_MAX_PEERS && t->rank >= 0 && t->rank < t->world && dst_offset_bytes % 16 == 0,
-               "ac_encoder_forward_cls_scatter: bad peer table");
-    for (int p = 0; p < t->world; ++p) AC_REQUIRE(t->buf[p] && t->flag[p], "ac_encoder_forward_cls_scatter: null peer pointer %d", p);
-    e->sink_on = true;
-    e->sink_table = *t;
-    e->sink_off = dst_offset_bytes;
-    e->sink_seq = seq;
-    e->sink_counter = counter;
-    const int rc = ac_encoder_forward_cls(e, ids, mask, type_ids, B, S, out_unit_cls, stream);
-    e->sink_on = false;
-    return rc;
 }
 
 extern "C" int ac_encoder_last_hidden(ac_encoder *e, float *out, int64_t n_floats, ac_stream_t stream) {
@@ -1671,16 +1225,14 @@ extern "C" int ac_encoder_last_hidden(ac_encoder *e, float *out, int64_t n_float
     return AC_OK;
 }
 
-// generic tensor-core linear exposed for parity tests / roofline measurement.
+// generic tensor-core linear exposed for parity tests / roofline measurement (the encoder's CTA-pair GEMM with a plain epilogue).
 //   precision AC_PREC_TF32: X, W fp32 (used as stored, tf32 truncation by the MMA unless pre-rounded), Y fp32
 //   precision AC_PREC_F16 : X, W fp16, Y fp32 (out_half = 0) or fp16 (out_half = 1)
 template <int MODE, bool OUT_HALF, int KIND>
 static int linear_tc_dispatch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, const float *residual, void *Y,
                               int M, int N, int K, int round_out, cudaStream_t s) {
     EpiLinear<MODE, OUT_HALF, false> e{bias, residual, Y, M, N, N, round_out, nullptr, 0, 0, 0, 0};
-    if (option(OPT_GEMM_PAIR))   // tb was built with the pair kernel's 128-row box by ac_linear_tc
-        return launch_gemm_tc2<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
-    return launch_gemm_tc<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
+    return launch_gemm_tc2<EpiLinear<MODE, OUT_HALF, false>, false, KIND>(ta, tb, M, N, K, e, s);
 }
 
 extern "C" int ac_linear_tc(const void *X, const void *W, const float *bias, const float *residual, void *Y, int M, int N,
@@ -1696,8 +1248,7 @@ extern "C" int ac_linear_tc(const void *X, const void *W, const float *bias, con
     CUtensorMap ta, tb;
     const uint32_t bk = 128 / es;
     if ((rc = make_tmap_2d(&ta, X, es, M, K, static_cast<uint64_t>(K) * es, GEMM_BLOCK_M, bk))) return rc;
-    if ((rc = make_tmap_2d(&tb, W, es, N, K, static_cast<uint64_t>(K) * es, option(OPT_GEMM_PAIR) ? GEMM2_B_ROWS : GEMM_BLOCK_N, bk)))
-        return rc;
+    if ((rc = make_tmap_2d(&tb, W, es, N, K, static_cast<uint64_t>(K) * es, GEMM2_B_ROWS, bk))) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (precision == AC_PREC_TF32) {
         AC_REQUIRE(!out_half, "ac_linear_tc: tf32 path writes fp32");

@@ -11,8 +11,8 @@
 //                 lane quarter w%4 and the column half (w-2)/4 of the 128 x 256 accumulator
 //
 // Two TMEM accumulator buffers (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile
-// i+1.  The epilogue is a functor so the same mainloop serves the encoder linears (bias / GELU /
-// residual) and the kNN coarse pass (running per-query top-k' over prototype tiles).
+// i+1.  The epilogue is a functor; this 1-CTA mainloop serves the kNN scans (running per-query top-k' lists / threshold
+// collection over prototype tiles), the encoder linears run the CTA-pair variant of gemm_tc2.cuh with the same functor concept.
 #pragma once
 #include "common.cuh"
 
@@ -64,6 +64,7 @@ struct GemmTileInfo {
 
 // Epilogue concept (parameters live in the functor, per-thread running state in Epi::State):
 //   struct Epi { struct State {...};
+//                __device__ bool skip_kernel() const;   (gemm_tc_kernel only: true => every thread returns immediately)
 //                __device__ void begin_cta(State&, int warp_q, int lane) const;
 //                __device__ void prefetch(State&, const GemmTileInfo&, int row, int col0, int lane, int buf) const;
 //                      (issue the global loads chunk (col0) will need into State buffer `buf`; called one chunk ahead)
@@ -80,6 +81,9 @@ template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  int M, int N, int K, Epi epi) {
+    // device-conditional launch: an epilogue may declare the whole launch unnecessary (kNN pass 2 when every query was
+    // certified) from a device-side counter, before any barrier / TMEM state exists -- uniform over the grid
+    if (epi.skip_kernel()) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem;
@@ -223,11 +227,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32>
 int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
                      cudaStream_t stream, int max_ctas = 0, int prof_cls = PROF_GEMM_LINEAR, double prof_bytes = 0.0) {
-    static bool attr_set = false;   // per instantiation
     auto kern = gemm_tc_kernel<Epi, kMFastest, kKind>;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per instantiation and per device
+    int dev = 0;
+    AC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
     int ctas = sm_count();

@@ -16,8 +16,9 @@
 //   warps 2..9  : epilogue of this CTA's 128 accumulator rows (identical to gemm_tc.cuh); "accumulator drained" arrives on
 //                 the leader's barrier (remote arrive from the peer)
 //
-// Status: written in round 1 after the GPU budget was spent -- compiles for sm_100a, NOT yet run on hardware.  It is
-// therefore opt-in (ac_set_option("gemm_pair", 1)); the default path stays the measured 1-CTA kernel.
+// Status: every encoder projection runs through this kernel.  Measured on a B200 (profiles/r02_variants.md): bit-identical to
+// the 1-CTA kernel on all encoder shapes; 12-layer forward at B*S = 65536 with deferred LayerNorm and the 16-warp GELU epilogue
+// 15.02 -> 14.31 ms per step against the 1-CTA mainloop.  The kNN coarse pass stays on gemm_tc.cuh (no gain there).
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -39,8 +40,7 @@ static_assert(gemm2_smem_bytes(gemm2_stages_for(16), 16) <= 227 * 1024, "stage r
 static_assert(GEMM2_A_STAGE_BYTES == GEMM_A_STAGE_BYTES, "A stage layout is shared with the 1-CTA kernel");
 
 // wait sites, reported by the watchdog so that a broken protocol names the barrier that never completed
-enum { PAIR_SITE_PRODUCER_EMPTY = 0, PAIR_SITE_MMA_TMEM_EMPTY = 1, PAIR_SITE_MMA_FULL = 2, PAIR_SITE_EPI_TMEM_FULL = 3,
-       PAIR_SITE_RELAY_FULL = 4, PAIR_SITE_MMA_PEER_FULL = 5 };
+enum { PAIR_SITE_PRODUCER_EMPTY = 0, PAIR_SITE_MMA_TMEM_EMPTY = 1, PAIR_SITE_MMA_FULL = 2, PAIR_SITE_EPI_TMEM_FULL = 3 };
 __device__ __forceinline__ void mbar_wait_guarded_cluster(uint64_t *bar, uint32_t parity, int site, int index) {
     uint32_t spins = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
@@ -52,15 +52,11 @@ __device__ __forceinline__ void mbar_wait_guarded_cluster(uint64_t *bar, uint32_
     }
 }
 
-// kRelay = false: both CTAs' TMA loads count their bytes on the leader's full barrier (.cta_group::2 loads, the CUTLASS scheme).
-// kRelay = true : every CTA's loads complete on its OWN full barrier; an otherwise idle thread of the peer (warp 1) forwards
-//                 "my stage has landed" to the leader with a remote mbarrier arrive.  Same math, no dependence on the
-//                 cross-CTA completion path of the TMA unit; kept as the fallback / bisecting variant.
+// Both CTAs' TMA loads count their bytes on the leader's full barrier (.cta_group::2 loads with a mapa'd barrier address).
 // kEpiWarps = 8 (warp w drains lane quarter w%4, column half (w-2)/4) or 16 (column quarter (w-2)/4, 64 columns = 2 chunks):
 //                 the bias + GELU epilogue issues ~17 instructions per element; two warps per scheduler cannot hide its MUFU /
 //                 dependency latency behind a K = 768 mainloop (FFN1 measured 56 % tensor-pipe active), four can.
-template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kStages = GEMM2_STAGES, bool kRelay = false,
-          int kEpiWarps = GEMM_EPI_WARPS>
+template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kStages = GEMM2_STAGES, int kEpiWarps = GEMM_EPI_WARPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 int M, int N, int K, Epi epi) {
@@ -77,8 +73,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t *empty_bar = bars + kStages;           // [kStages]  one per CTA, multicast commit
     uint64_t *tmem_full = bars + 2 * kStages;       // [2]        one per CTA, multicast commit
     uint64_t *tmem_empty = bars + 2 * kStages + 2;  // [2]        leader only: 2 x GEMM_EPI_WARPS arrivals
-    uint64_t *peer_full = bars + 2 * kStages + 4;   // [kStages]  leader only, kRelay: "the peer's stage has landed"
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kStages + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -97,7 +92,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
-            mbar_init(&peer_full[s], 1);
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
@@ -114,10 +108,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     cluster_sync_all();       // barriers of both CTAs are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // programmatic dependent launch (option "pdl"): let the next kernel's CTAs take this SM as soon as this CTA exits, and do
-    // not touch global memory before the previous kernel has completed (both are no-ops in an ordinary launch)
-    griddep_launch_dependents();
-    griddep_wait();
 
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------
@@ -130,16 +120,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 for (int kb = 0; kb < num_kb; ++kb) {
                     // arrival = the leader's multicast commit
                     mbar_wait_guarded_cluster(&empty_bar[stage], phase ^ 1, PAIR_SITE_PRODUCER_EMPTY, stage);
-                    if (kRelay) {
-                        mbar_arrive_expect_tx(&full_bar[stage], GEMM2_STAGE_BYTES);
-                        tma_load_2d(smem_a + stage * GEMM2_A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0);
-                        tma_load_2d(smem_b + stage * GEMM2_B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n0);
-                    } else {
-                        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);
-                        tma_load_2d_pair(smem_a + stage * GEMM2_A_STAGE_BYTES, &tmap_a, full_leader, kb * BK, m0);
-                        tma_load_2d_pair(smem_b + stage * GEMM2_B_STAGE_BYTES, &tmap_b, full_leader, kb * BK, n0);
-                    }
+                    const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);
+                    tma_load_2d_pair(smem_a + stage * GEMM2_A_STAGE_BYTES, &tmap_a, full_leader, kb * BK, m0);
+                    tma_load_2d_pair(smem_b + stage * GEMM2_B_STAGE_BYTES, &tmap_b, full_leader, kb * BK, n0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -160,7 +144,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 for (int kb = 0; kb < num_kb; ++kb) {
                     // both CTAs' operand bytes have landed
                     mbar_wait_guarded_cluster(&full_bar[stage], phase, PAIR_SITE_MMA_FULL, stage);
-                    if (kRelay) mbar_wait_guarded_cluster(&peer_full[stage], phase, PAIR_SITE_MMA_PEER_FULL, stage);
                     tc_fence_after();
                     const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + stage * GEMM2_A_STAGE_BYTES));
                     const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + stage * GEMM2_B_STAGE_BYTES));
@@ -174,17 +157,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
                 tc_commit_pair(&tmem_full[acc], 0x3);          // accumulator complete -> both epilogues
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            }
-        } else if (kRelay && rank == 1 && lane == 0) {
-            // ---------------- relay (peer CTA): forward "stage landed" to the leader ----------------
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait_guarded_cluster(&full_bar[stage], phase, PAIR_SITE_RELAY_FULL, stage);
-                    mbar_arrive_cluster(mapa_shared(smem_u32(&peer_full[stage]), 0));
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
             }
         }
     } else {
@@ -241,27 +213,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kEpiWarps = GEMM_EPI_WARPS>
 int launch_gemm_tc2(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const Epi &epi,
                     cudaStream_t stream, int max_ctas = 0, int prof_cls = PROF_GEMM_LINEAR, double prof_bytes = 0.0) {
-    static bool attr_set = false;   // per instantiation
     constexpr int kStg = gemm2_stages_for(kEpiWarps);
     constexpr int smem = gemm2_smem_bytes(kStg, kEpiWarps);
-    if (!attr_set) {
-        AC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, false, kEpiWarps>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        AC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, true, kEpiWarps>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+    auto kern = gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, kEpiWarps>;
+    static bool attr_set[64] = {};   // per instantiation and per device (the attribute belongs to the (function, device) pair)
+    int dev = 0;
+    AC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    // option value 2 selects the relay variant (see kRelay above)
-    const bool relay = option(prof_cls == PROF_KNN_COARSE ? OPT_KNN_PAIR : OPT_GEMM_PAIR) == 2;
-    auto kern = relay ? gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, true, kEpiWarps>
-                      : gemm_tc2_kernel<Epi, kMFastest, kKind, kStg, false, kEpiWarps>;
     const int tiles = ((M + GEMM2_PAIR_M - 1) / GEMM2_PAIR_M) * ((N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N);
     int clusters = sm_count() / 2;
     if (max_ctas > 0 && max_ctas / 2 < clusters) clusters = max_ctas / 2;
     if (tiles < clusters) clusters = tiles;
     if (clusters <= 0) return AC_OK;
     const int slot = prof_begin(prof_cls, 2.0 * M * static_cast<double>(N) * K, prof_bytes, stream);
-    AC_CUDA(launch_maybe_pdl(kern, dim3(2 * clusters), dim3(64 + 32 * kEpiWarps), smem, stream, option(OPT_PDL) != 0, ta, tb, M, N, K, epi));
+    kern<<<2 * clusters, 64 + 32 * kEpiWarps, smem, stream>>>(ta, tb, M, N, K, epi);
     prof_end(slot, stream);
     AC_LAUNCH_CHECK();
     return AC_OK;

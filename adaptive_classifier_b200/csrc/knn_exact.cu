@@ -224,12 +224,14 @@ __device__ __forceinline__ bool cand_less(float da, long long ia, float db, long
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_chunk_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx, int64_t L, int64_t in_stride,
                   int64_t id_offset, int k, float *__restrict__ out_d, int64_t *__restrict__ out_i,
-                  int64_t out_stride /* per query */, int n2 /* power of two >= entries of a chunk, <= SEL_CHUNK */) {
+                  int64_t out_stride /* per query */, int n2 /* power of two >= entries of a chunk, <= SEL_CHUNK */,
+                  const float *__restrict__ row_gate /* nullable: rows with gate == -inf are left untouched */) {
     extern __shared__ __align__(16) uint8_t sel_smem[];
     float *sd = reinterpret_cast<float *>(sel_smem);
     long long *si = reinterpret_cast<long long *>(sel_smem + SEL_CHUNK * sizeof(float));
 
     const int b = blockIdx.y;
+    if (row_gate && row_gate[b] == -CUDART_INF_F) return;        // block-uniform
     const int chunk = blockIdx.x;
     const int64_t base = static_cast<int64_t>(chunk) * SEL_CHUNK;
     const float *db = d + static_cast<int64_t>(b) * in_stride;
@@ -295,15 +297,12 @@ size_t topk_select_workspace(int B, int64_t L, int k) {
 }
 
 // d[B, L] (+ idx or implicit ids) -> out_d[B,k], out_i[B,k] sorted ascending by (d, id)
+// row_gate (nullable, [B]): queries whose gate is -inf are skipped (their output rows keep their contents)
 int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in_stride, int64_t id_offset, int k,
-                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream, const float *row_gate = nullptr) {
     AC_REQUIRE(k >= 1 && k <= AC_KNN_MAX_K, "topk_select: k=%d outside [1,%d]", k, AC_KNN_MAX_K);
-    static bool attr_set = false;
     const int smem = SEL_CHUNK * (sizeof(float) + sizeof(long long));
-    if (!attr_set) {
-        AC_CUDA(cudaFuncSetAttribute(topk_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    AC_CUDA(cudaFuncSetAttribute(topk_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (B <= 0) return AC_OK;
     uint8_t *wp = static_cast<uint8_t *>(ws);
     size_t used = 0;
@@ -323,14 +322,14 @@ int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in
         int64_t *ni = reinterpret_cast<int64_t *>(wp + used + bd);
         used += bd + bi;
         topk_chunk_kernel<<<dim3(static_cast<unsigned>(chunks), B), SEL_THREADS, smem, stream>>>(
-            cur_d, cur_i, cur_L, cur_stride, cur_off, k, nd, ni, out_len, SEL_CHUNK);
+            cur_d, cur_i, cur_L, cur_stride, cur_off, k, nd, ni, out_len, SEL_CHUNK, row_gate);
         AC_LAUNCH_CHECK();
         cur_d = nd; cur_i = ni; cur_L = out_len; cur_stride = out_len; cur_off = 0;
     }
     int n2 = 32;
     while (n2 < cur_L) n2 <<= 1;            // the final list is short (candidates, head classes): sort only that much
     topk_chunk_kernel<<<dim3(1, B), SEL_THREADS, smem, stream>>>(cur_d, cur_i, cur_L, cur_stride, cur_off, k, out_d,
-                                                                 out_i, k, n2);
+                                                                 out_i, k, n2, row_gate);
     AC_LAUNCH_CHECK();
     return AC_OK;
 }
@@ -463,11 +462,7 @@ extern "C" int ac_topk_merge(const float *d, const int64_t *i, int G, int B, int
     if (B == 0) return AC_OK;
     // one CTA per query gathers its G*k candidates from the [G,B,k] slabs and sorts them by (d, id)
     const int smem = SEL_CHUNK * (sizeof(float) + sizeof(long long));
-    static bool attr_set = false;
-    if (!attr_set) {
-        AC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    AC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     topk_merge_kernel<<<B, SEL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(d, i, G, B, k, out_d, out_i);
     AC_LAUNCH_CHECK();
     return AC_OK;

@@ -1,20 +1,28 @@
 // knn_tc.cu -- stage K, tensor path: brute-force squared-L2 kNN over a large prototype matrix.
 //
-//   coarse pass   d~(q,p) = ||q||^2 + ||p||^2 - 2 q.p   with q.p on tcgen05 (kind::tf32) through the GEMM
-//                 mainloop of gemm_tc.cuh: M = queries (128 per CTA, fixed per CTA), N = prototype rows
-//                 streamed ONCE from HBM by TMA (4.N.D algorithmic bytes), fp32 accumulators in TMEM.
-//                 Epilogue: thread = query row; running top-16 (coarse key, row id) in registers.
-//   merge         per query, the per-CTA lists are sorted by (d~, id); the best KP = 32 become candidates.
-//   re-rank       exact fp32 distances of the candidates in the oracle's lane order (knn_exact.cu).
-//   certify       T = smallest coarse distance any non-candidate row can have, eps = rigorous bound on
-//                 |d~ - d| for tf32 operands (q rounded RNE: 2^-11, p truncated by the MMA: 2^-10);
-//                 a query is certified when d_exact[k-1] < T - eps: then no excluded row can enter or tie
-//                 the top-k, so indices are identical to the exact scan.  Uncertified queries are recomputed
-//                 by the exact scan (knn_exact.cu).  Result: bit-identical (d, id) to the exact path.
+//   pass 1        d~(q,p) = ||q||^2 + ||p||^2 - 2 q.p   with q.p on tcgen05 (kind::f16 over the fp16 shadow of the rows, or
+//                 kind::tf32 on the fp32 rows) through the GEMM mainloop of gemm_tc.cuh: M = queries (128 per CTA, fixed per
+//                 CTA), N = prototype rows streamed ONCE from HBM by TMA, fp32 accumulators in TMEM.
+//                 Epilogue EpiKnn: thread = query row; running top-16 (coarse key, row id) per (query, CTA, column half).
+//   k <= 16       merge the lists, exact fp32 re-rank of the best KP = 32 candidates in the oracle's lane order
+//                 (knn_exact.cu), CERTIFY: T = smallest coarse distance any non-candidate row can have, eps = rigorous bound
+//                 on |d~ - d|; d_exact[k-1] < T - eps => no excluded row can enter or tie the top-k.
+//   pass 2        for the queries pass 1 could not certify, and for every query when k > 16: with tau = the k-th smallest
+//                 coarse distance among the merged candidates (real rows, so the exact k-th distance is <= tau + eps), a
+//                 second tensor pass (EpiKnnCollect) appends EVERY row with d~ <= tau + 2 eps to a per-query buffer -- a
+//                 superset of the true top-k -- which is then re-ranked exactly and selected by (d, id).
+//                 The pass is launched unconditionally and exits at once when a device-side counter says nobody needs it:
+//                 no host synchronisation anywhere, the whole search is capturable in a CUDA graph, and the worst case
+//                 (every query uncertified, e.g. near-duplicate rows closer than eps) costs one more scan instead of a
+//                 full fp32 SIMT scan per query.
+//   overflow      a query with more than `cap` rows inside the 2 eps band (thousands of near-identical rows) is reported
+//                 in stats[1]; without a stats pointer the call synchronises and recomputes those queries by the exact scan.
+// Result: (d, id) bit-identical to the exact path / the oracle.
 //
 // Replaces faiss.IndexFlatL2.search (/root/reference/src/adaptive_classifier/memory.py:110-114) for the
-// batched, large-N configuration of BASELINE.json (configs[1], configs[2]).
-#include "gemm_tc2.cuh"
+// batched, large-N configurations of BASELINE.json (configs[1], configs[2], configs[4]); k = num_classes (predict(),
+// classifier.py:424-425) stays on the tensor path up to k = 1024.
+#include "gemm_tc.cuh"
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -24,7 +32,7 @@ int launch_knn_rerank(const float *Q, const float *P, int B, int64_t N, int D, i
                       int64_t *out_i, int64_t row_offset, cudaStream_t stream);
 size_t topk_select_workspace(int B, int64_t L, int k);
 int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in_stride, int64_t id_offset, int k,
-                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream);
+                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream, const float *row_gate = nullptr);
 int knn_exact_subset(const float *Q, const float *P, int B, int64_t N, int D, int k, float *out_d, int64_t *out_i,
                      int64_t row_offset, void *ws, size_t ws_bytes, cudaStream_t s);
 size_t knn_exact_workspace_pub(int B, int64_t N, int k);
@@ -53,7 +61,6 @@ struct EpiKnn {
     int64_t N;               // rows
     int tiles_m, slots;      // grid = slots/2 * tiles_m CTAs; every CTA owns one query tile and two lists per query
     int kt;                  // a list publishes its kt-th best key (k + 3 <= kt <= KC): see prefetch()
-    int pair;                // != 0: launched as CTA pairs (gemm_tc2.cuh): a cluster owns two consecutive query tiles
 
     static constexpr int kUnrollChunks = 1;
     struct State {
@@ -63,6 +70,7 @@ struct EpiKnn {
         float gt;             // global bound for this thread's query, refreshed once per tile
     };
 
+    __device__ __forceinline__ bool skip_kernel() const { return false; }
     __device__ __forceinline__ void begin_cta(State &st, int, int) const {
 #pragma unroll
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
@@ -134,15 +142,8 @@ struct EpiKnn {
     __device__ __forceinline__ void end_cta(State &st, int q, int lane) const {
         // two epilogue warps share a query row (one per 128-column half of every tile): each owns a slot
         const int chalf = ((threadIdx.x >> 5) - 2) >> 2;
-        int mt, slot;
-        if (pair) {
-            const int cluster = blockIdx.x >> 1, tm2 = tiles_m >> 1;     // tiles_m is even in pair mode
-            mt = (cluster % tm2) * 2 + static_cast<int>(cluster_ctarank());
-            slot = (cluster / tm2) * 2 + chalf;
-        } else {
-            mt = blockIdx.x % tiles_m;
-            slot = (blockIdx.x / tiles_m) * 2 + chalf;
-        }
+        const int mt = blockIdx.x % tiles_m;
+        const int slot = (blockIdx.x / tiles_m) * 2 + chalf;
         const int row = mt * GEMM_BLOCK_M + q * 32 + lane;
         if (row >= B) return;
         float *ck = cand_key + (static_cast<int64_t>(row) * slots + slot) * KNN_KC;
@@ -152,51 +153,57 @@ struct EpiKnn {
     }
 };
 
+// pass 2: append every row whose coarse key is <= thr[query] to the query's candidate buffer (thr = -inf: query not flagged).
+// Hits are rare (about k per query over the whole scan), so the fast path is one FFMA + compare per accumulator element.
+struct EpiKnnCollect {
+    const float *p_sqnorm;   // [N]
+    const float *thr;        // [Bp] key-domain threshold: tau_key + 2 eps, or -inf
+    int32_t *buf;            // [B, cap] local row ids
+    int32_t *cnt;            // [Bp] rows found (may exceed cap: overflow, reported by the re-rank)
+    const int32_t *need;     // [0] = number of flagged queries; 0 => the whole kernel exits at once
+    int cap, B;
+    int64_t N;
+    int tiles_m;
 
-// Per-lane slow path (opt-in, option "knn_epi"): same lists, cheaper to build.
-//
-// EpiKnn::tile walks the UNION of the 32 lanes' hit columns; every iteration re-reads one accumulator column from TMEM and
-// runs the ~100-instruction insert network for the one or two lanes that hit there, the other lanes idle.  In the middle of
-// the scan every lane still has about one insert per chunk, at a different column than its neighbours, so the union has 20-32
-// members: the ncu capture of the scan shows 19 thread-instructions per accumulator element at 16 of 32 lanes active and a
-// tensor pipe that is busy 48 % of the time (profiles/r01_knn_v2_ncu.txt).  Here every lane walks ITS OWN hits: the chunk's
-// accumulator values go to the warp's private staging tile 16 columns at a time (lane-private rows, stride 17 floats), each
-// lane pops its lowest hit column, reads its own value back and inserts; the loop runs max-over-lanes(hits) times instead of
-// |union| times.  Every lane still inserts its hits in ascending column order, so the lists -- and everything downstream,
-// including the certification argument -- are unchanged bit for bit.  Status: NOT yet run on hardware.
-struct EpiKnnLane : EpiKnn {
-    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int /*row*/, int col0, const float (&v)[32],
-                                         uint8_t *stage, int lane, int buf, uint32_t /*taddr*/) const {
-        const float pn_lane = buf ? st.pn[1] : st.pn[0];
-        const float thr = fminf(st.key[KNN_KC - 1], st.gt);
+    static constexpr int kUnrollChunks = 1;
+    struct State {
+        float pn[2];
+        float thr;
+    };
+    __device__ __forceinline__ bool skip_kernel() const { return *reinterpret_cast<const volatile int32_t *>(need) == 0; }
+    __device__ __forceinline__ void begin_cta(State &st, int q, int lane) const {
+        const int row = (blockIdx.x % tiles_m) * GEMM_BLOCK_M + q * 32 + lane;     // a CTA keeps one query tile (kMFastest)
+        st.thr = (row < B) ? thr[row] : -CUDART_INF_F;
+        st.pn[0] = st.pn[1] = CUDART_INF_F;
+    }
+    __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &, int, int col0, int lane, int buf_) const {
+        const int64_t n = static_cast<int64_t>(col0) + lane;
+        const float x = (n < N) ? __ldg(p_sqnorm + n) : CUDART_INF_F;
+        if (buf_) st.pn[1] = x; else st.pn[0] = x;
+    }
+    __device__ __forceinline__ void tile(State &st, const GemmTileInfo &, int row, int col0, const float (&v)[32], uint8_t *,
+                                         int, int buf_, uint32_t) const {
+        const float pn_lane = buf_ ? st.pn[1] : st.pn[0];
         uint32_t hits = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const float pn = __shfl_sync(0xffffffffu, pn_lane, j);
             const float key = fmaf(-2.f, v[j], pn);
-            hits |= (key < thr) ? (1u << j) : 0u;
+            hits |= (key <= st.thr) ? (1u << j) : 0u;
         }
-        if (__reduce_or_sync(0xffffffffu, hits) == 0) return;
-        float *srow = reinterpret_cast<float *>(stage) + lane * 17;          // 32 x 17 floats = 2176 B of the 2560 B tile
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t hh = (hits >> (16 * half)) & 0xffffu;
-            if (!__any_sync(0xffffffffu, hh != 0)) continue;
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) srow[jj] = v[16 * half + jj];    // lane-private row: no cross-lane hazard
-            while (__any_sync(0xffffffffu, hh != 0)) {
-                const bool act = hh != 0;
-                const int jj = act ? __ffs(hh) - 1 : 0;
-                hh &= hh - 1;
-                const float x = srow[jj];
-                const float pn = __shfl_sync(0xffffffffu, pn_lane, 16 * half + jj);
-                const float key = fmaf(-2.f, x, pn);
-                const int64_t n = static_cast<int64_t>(col0) + 16 * half + jj;
-                if (act && key < fminf(st.key[KNN_KC - 1], st.gt) && n < N) insert(st, key, static_cast<int32_t>(n));
+        while (hits) {                                   // per-lane: this thread's own hits, ascending row order
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int64_t n = static_cast<int64_t>(col0) + j;
+            if (n < N) {
+                const int pos = atomicAdd(cnt + row, 1);
+                if (pos < cap) buf[static_cast<int64_t>(row) * cap + pos] = static_cast<int32_t>(n);
             }
         }
     }
+    __device__ __forceinline__ void end_cta(State &, int, int) const {}
 };
+
 
 // ------------------------------------------------------------------------------------------------
 // small kernels around the coarse pass
@@ -278,23 +285,85 @@ __global__ void knn_pick_kernel(const float *__restrict__ sorted_key, const int6
     T[b] = t + qn[b];
 }
 
-// certified[b] = out_d[b,k-1] < T[b] - eps(b);  eps = 2*rel*||q||*max||p|| * 1.02 + 4e-5*(1+||q||^2+max||p||^2) with
+// rigorous bound on |coarse - exact| for query b: 2*rel*||q||*max||p|| * 1.02 + 4e-5*(1+||q||^2+max||p||^2) with
 //   rel = 2^-10 + 2^-11 + 2^-21 (fp32 rows truncated to tf32 by the MMA, queries rounded RNE), or
 //   rel = 2^-11 + 2^-11 + 2^-22 (fp16 shadow rows and fp16 queries, both RNE; the subnormal tail adds < 1e-6)
+__device__ __forceinline__ float knn_eps(float qn2, float pm2, float rel) {
+    return 2.f * rel * 1.02f * sqrtf(qn2) * sqrtf(pm2) + 4e-5f * (1.f + qn2 + pm2);
+}
+
+// k <= 16: certified[b] = out_d[b,k-1] < T[b] - eps(b).  An uncertified query is flagged for pass 2 with the key-domain
+// threshold  thr = (k-th smallest coarse key among the merged candidates) + 2 eps  (see the header: a superset of the top-k).
+// sorted_key / sorted_idx: [B, KP+1] merged candidates ascending.
 __global__ void knn_certify_kernel(const float *__restrict__ out_d, const int64_t *__restrict__ out_i, const float *__restrict__ T,
-                                   const float *__restrict__ qn, const float *__restrict__ pmax2, int B, int k, float rel,
-                                   int32_t *__restrict__ fail_list, int32_t *__restrict__ fail_count) {
+                                   const float *__restrict__ qn, const float *__restrict__ pmax2, const float *__restrict__ sorted_key,
+                                   const int64_t *__restrict__ sorted_idx, int B, int Bp, int k, float rel, float *__restrict__ thr,
+                                   int32_t *__restrict__ cnt, int32_t *__restrict__ need) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const float qn2 = qn[b], pm2 = pmax2[0];
-    const float eps = 2.f * rel * 1.02f * sqrtf(qn2) * sqrtf(pm2) + 4e-5f * (1.f + qn2 + pm2);
+    if (b >= Bp) return;
+    cnt[b] = 0;
+    if (b >= B) { thr[b] = -CUDART_INF_F; return; }
+    const float eps = knn_eps(qn[b], pmax2[0], rel);
     const float dk = out_d[static_cast<int64_t>(b) * k + (k - 1)];
     const bool full = out_i[static_cast<int64_t>(b) * k + (k - 1)] >= 0;
     // T == +inf: every row of the index was a candidate (nothing excluded) -> exact by construction
     const bool ok = (T[b] == CUDART_INF_F) || (full && dk < T[b] - eps);
-    if (!ok) {
-        const int slot = atomicAdd(fail_count, 1);
-        fail_list[slot] = b;
+    if (ok) { thr[b] = -CUDART_INF_F; return; }
+    const bool have_k = sorted_idx[static_cast<int64_t>(b) * (KNN_KP + 1) + (k - 1)] >= 0;
+    thr[b] = have_k ? sorted_key[static_cast<int64_t>(b) * (KNN_KP + 1) + (k - 1)] + 2.f * eps : CUDART_INF_F;
+    atomicAdd(need, 1);
+}
+
+// k > 16: every query takes pass 2; sorted_key / sorted_idx: [B, k] merged candidates ascending
+__global__ void knn_threshold_kernel(const float *__restrict__ sorted_key, const int64_t *__restrict__ sorted_idx,
+                                     const float *__restrict__ qn, const float *__restrict__ pmax2, int B, int Bp, int k, float rel,
+                                     float *__restrict__ thr, int32_t *__restrict__ cnt, int32_t *__restrict__ need) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Bp) return;
+    cnt[b] = 0;
+    if (b >= B) { thr[b] = -CUDART_INF_F; return; }
+    const bool have_k = sorted_idx[static_cast<int64_t>(b) * k + (k - 1)] >= 0;
+    thr[b] = have_k ? sorted_key[static_cast<int64_t>(b) * k + (k - 1)] + 2.f * knn_eps(qn[b], pmax2[0], rel) : CUDART_INF_F;
+    if (b == 0) need[0] = B;
+}
+
+// exact distance (oracle lane order, as knn_rerank_kernel) of the rows pass 2 collected; one 8-lane group per buffer slot.
+// Slots >= cnt[b] are written as padding; queries that were not flagged are skipped.  Overflowing queries are counted.
+__global__ void knn_rerank_collected_kernel(const float *__restrict__ Q, const float *__restrict__ P, int B, int64_t N, int D, int cap,
+                                            const float *__restrict__ thr, const int32_t *__restrict__ cnt,
+                                            const int32_t *__restrict__ buf, float *__restrict__ out_d, int64_t *__restrict__ out_i,
+                                            int64_t row_offset, int32_t *__restrict__ stats, int32_t *__restrict__ over_list) {
+    const int b = blockIdx.y;
+    if (thr[b] == -CUDART_INF_F) return;                                         // block-uniform
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int j = threadIdx.x & 7;
+    const int have = cnt[b];
+    const int n_use = have < cap ? have : cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(stats + 0, 1);
+        atomicMax(stats + 2, have);
+        if (have > cap) over_list[atomicAdd(stats + 1, 1)] = b;
+    }
+    const bool valid = slot < cap;
+    int32_t r = -1;
+    if (valid && slot < n_use) r = buf[static_cast<int64_t>(b) * cap + slot];
+    float acc = 0.f;
+    if (r >= 0 && r < N) {
+        const float *q = Q + static_cast<int64_t>(b) * D;
+        const float *p = P + static_cast<int64_t>(r) * D;
+        for (int i = j; i < D; i += 8) {
+            const float t = __fsub_rn(q[i], p[i]);
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+    }
+    const unsigned m = 0xffffffffu;
+    const float s4 = __fadd_rn(acc, __shfl_xor_sync(m, acc, 4));
+    const float s1 = __fadd_rn(s4, __shfl_xor_sync(m, s4, 1));
+    const float s2 = __fadd_rn(s1, __shfl_xor_sync(m, s1, 2));
+    if (valid && j == 0) {
+        const bool ok = (r >= 0 && r < N);
+        out_d[static_cast<int64_t>(b) * cap + slot] = ok ? s2 : CUDART_INF_F;
+        out_i[static_cast<int64_t>(b) * cap + slot] = ok ? (static_cast<int64_t>(r) + row_offset) : -1;
     }
 }
 
@@ -314,14 +383,21 @@ __global__ void knn_scatter_results_kernel(const float *__restrict__ d, const in
     out_d[static_cast<int64_t>(list[r]) * k + j] = d[t];
     out_i[static_cast<int64_t>(list[r]) * k + j] = idx[t];
 }
+__global__ void knn_add_stats_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out) {
+    if (threadIdx.x == 0) { out[0] += in[0]; out[1] += in[1]; out[2] = max(out[2], in[2]); out[3] += 1; }
+}
 
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
+constexpr int KNN_SMALL_K = 16;        // certification path (lists of KNN_KC per (query, CTA, half))
+constexpr int KNN_QUERY_BLOCK = 512;   // k > 16: queries per pass so that every query has >= 74 lists x 16 >= 1024 candidates
+static int knn_cap(int k) { return k <= KNN_SMALL_K ? 256 : 2048; }
+
 struct KnnTcPlan {
-    int tiles_m, slots, grid, grid_ctas;
+    int tiles_m, slots, grid_ctas, cap, ksel;
     size_t off_qr, off_qn, off_gthr, off_pn, off_bmax, off_pmax, off_ckey, off_cidx, off_cidx64, off_skey, off_sidx, off_ridx, off_T,
-        off_rd, off_ri, off_fail, off_fq, off_fd, off_fi, off_sel, sel_bytes, off_exact, exact_bytes, total;
+        off_rd, off_ri, off_thr, off_cnt, off_stats, off_over, off_buf, off_rd2, off_ri2, off_sel, sel_bytes, total;
 };
 
 static KnnTcPlan plan_knn_tc(int B, int64_t N, int D, int k) {
@@ -332,9 +408,10 @@ static KnnTcPlan plan_knn_tc(int B, int64_t N, int D, int k) {
     if (p.slots < 1) p.slots = 1;
     const int64_t tiles_n = (N + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
     if (p.slots > tiles_n) p.slots = static_cast<int>(tiles_n);
-    p.grid = p.slots * p.tiles_m;
-    p.grid_ctas = p.grid;
+    p.grid_ctas = p.slots * p.tiles_m;
     p.slots *= 2;   // candidate lists per query: one per (CTA, accumulator column half)
+    p.cap = knn_cap(k);
+    p.ksel = k <= KNN_SMALL_K ? KNN_KP + 1 : k;      // how many merged candidates are kept sorted
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t Bp = static_cast<size_t>(p.tiles_m) * GEMM_BLOCK_M;
@@ -348,32 +425,61 @@ static KnnTcPlan plan_knn_tc(int B, int64_t N, int D, int k) {
     p.off_ckey = take(nc * 4);
     p.off_cidx = take(nc * 4);
     p.off_cidx64 = take(nc * 8);
-    p.off_skey = take(static_cast<size_t>(B) * (KNN_KP + 1) * 4);
-    p.off_sidx = take(static_cast<size_t>(B) * (KNN_KP + 1) * 8);
+    p.off_skey = take(static_cast<size_t>(B) * p.ksel * 4);
+    p.off_sidx = take(static_cast<size_t>(B) * p.ksel * 8);
     p.off_ridx = take(static_cast<size_t>(B) * KNN_KP * 4);
     p.off_T = take(static_cast<size_t>(B) * 4);
     p.off_rd = take(static_cast<size_t>(B) * KNN_KP * 4);
     p.off_ri = take(static_cast<size_t>(B) * KNN_KP * 8);
-    p.off_fail = take(static_cast<size_t>(B + 1) * 4);
-    p.sel_bytes = topk_select_workspace(B, static_cast<int64_t>(p.slots) * KNN_KC, KNN_KP + 1) + 256;
+    p.off_thr = take(Bp * 4);
+    p.off_cnt = take(Bp * 4);
+    p.off_stats = take(256);                          // [0] flagged, [1] overflowed, [2] max collected, [4] need (pass-2 gate)
+    p.off_over = take(static_cast<size_t>(B) * 4);
+    p.off_buf = take(static_cast<size_t>(B) * p.cap * 4);
+    p.off_rd2 = take(static_cast<size_t>(B) * p.cap * 4);
+    p.off_ri2 = take(static_cast<size_t>(B) * p.cap * 8);
+    size_t sel = topk_select_workspace(B, static_cast<int64_t>(p.slots) * KNN_KC, p.ksel);
+    const size_t sel2 = topk_select_workspace(B, p.cap, k);
+    if (sel2 > sel) sel = sel2;
+    p.sel_bytes = sel + 256;
     p.off_sel = take(p.sel_bytes);
     p.total = off;
-    (void)k;
     return p;
 }
 
+static int knn_block(int B, int k) { return (k > KNN_SMALL_K && B > KNN_QUERY_BLOCK) ? KNN_QUERY_BLOCK : B; }
+
 size_t knn_tc_workspace(int B, int64_t N, int D, int k) {
-    KnnTcPlan p = plan_knn_tc(B, N, D, k);
-    // fallback staging for uncertified queries: gathered queries + their results
-    const size_t fb = align_up(static_cast<size_t>(B) * D * 4, 256) + align_up(static_cast<size_t>(B) * k * 4, 256) +
-                      align_up(static_cast<size_t>(B) * k * 8, 256);
-    return p.total + fb + 1024;
+    const int Bb = knn_block(B, k);
+    KnnTcPlan p = plan_knn_tc(Bb, N, D, k);
+    // exact-scan staging for overflowed queries (synchronous mode only): gathered queries + their results + the scan's scratch
+    const size_t fb = align_up(static_cast<size_t>(Bb) * D * 4, 256) + align_up(static_cast<size_t>(Bb) * k * 4, 256) +
+                      align_up(static_cast<size_t>(Bb) * k * 8, 256);
+    return p.total + fb + knn_exact_workspace_pub(Bb, N, k) + 1024;
 }
 
-int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N, int D, int k,
-                  float *out_d, int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, cudaStream_t s) {
-    int rc = ac_device_check();
-    if (rc) return rc;
+template <class Epi>
+static int launch_scan(const float *Qr, const float *P, const void *p_half, size_t Bp, int64_t N, int D, const Epi &epi, int grid_ctas,
+                       int prof_cls, cudaStream_t s) {
+    CUtensorMap ta, tb;
+    int rc;
+    // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16 shadow
+    // the kernel actually streams 2.N.D bytes (the exact re-rank still reads fp32 rows): both are reported by bench.py
+    const double bytes = 4.0 * static_cast<double>(N) * D;
+    if (p_half) {
+        if ((rc = make_tmap_2d(&ta, Qr, 2, Bp, D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_M, 64))) return rc;
+        if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_N, 64))) return rc;
+        return launch_gemm_tc<Epi, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, grid_ctas, prof_cls, bytes);
+    }
+    if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
+    if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_N, GEMM_BLOCK_K))) return rc;
+    return launch_gemm_tc<Epi, true, GEMM_KIND_TF32>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, grid_ctas, prof_cls, bytes);
+}
+
+static int knn_tc_block(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N, int D, int k,
+                        float *out_d, int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, int32_t *stats_out,
+                        cudaStream_t s) {
+    int rc;
     KnnTcPlan pl = plan_knn_tc(B, N, D, k);
     const size_t fb_q = align_up(static_cast<size_t>(B) * D * 4, 256), fb_d = align_up(static_cast<size_t>(B) * k * 4, 256),
                  fb_i = align_up(static_cast<size_t>(B) * k * 8, 256);
@@ -398,7 +504,14 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     float *T = reinterpret_cast<float *>(w + pl.off_T);
     float *rd = reinterpret_cast<float *>(w + pl.off_rd);
     int64_t *ri = reinterpret_cast<int64_t *>(w + pl.off_ri);
-    int32_t *fail = reinterpret_cast<int32_t *>(w + pl.off_fail);   // [0] = count, [1..] = list
+    float *thr = reinterpret_cast<float *>(w + pl.off_thr);
+    int32_t *cnt = reinterpret_cast<int32_t *>(w + pl.off_cnt);
+    int32_t *stats = reinterpret_cast<int32_t *>(w + pl.off_stats);
+    int32_t *need = stats + 4;
+    int32_t *over = reinterpret_cast<int32_t *>(w + pl.off_over);
+    int32_t *buf = reinterpret_cast<int32_t *>(w + pl.off_buf);
+    float *rd2 = reinterpret_cast<float *>(w + pl.off_rd2);
+    int64_t *ri2 = reinterpret_cast<int64_t *>(w + pl.off_ri2);
     uint8_t *selws = w + pl.off_sel;
     uint8_t *fbq = w + pl.total;
     uint8_t *fbd = fbq + fb_q;
@@ -407,7 +520,7 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
 
     const size_t Bp = static_cast<size_t>(pl.tiles_m) * GEMM_BLOCK_M;
     AC_CUDA(cudaMemsetAsync(Qr, 0, Bp * D * 4, s));
-    AC_CUDA(cudaMemsetAsync(fail, 0, 4, s));
+    AC_CUDA(cudaMemsetAsync(stats, 0, 32, s));
     AC_CUDA(cudaMemsetAsync(gthr, 0xFF, Bp * 4, s));   // ordered-uint +max: no bound published yet
     __half *Qh = p_half ? reinterpret_cast<__half *>(Qr) : nullptr;   // the fp16 queries reuse the fp32 query slot
     knn_prep_queries_kernel<<<(B + 3) / 4, 128, 0, s>>>(Q, B, D, Qr, Qh, qn);
@@ -424,73 +537,75 @@ int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const v
     knn_reduce_max_kernel<<<1, 256, 0, s>>>(bmax, rb, pmax);
     AC_LAUNCH_CHECK();
 
-    // ---- coarse pass on the tensor cores
-    CUtensorMap ta, tb;
-    int kt = k + 3 > 8 ? k + 3 : 8;
-    if (kt > KNN_KC) kt = KNN_KC;
-    // CTA-pair variant (option "knn_pair"): needs an even number of query tiles so that both CTAs of a pair own real queries
-    const bool pair = option(OPT_KNN_PAIR) != 0 && pl.tiles_m % 2 == 0 && pl.grid_ctas % 2 == 0;
-    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt, pair ? 1 : 0};   // slots = 2 per CTA
-    const uint32_t b_box = pair ? GEMM2_B_ROWS : GEMM_BLOCK_N;
-    const bool lane_epi = option(OPT_KNN_EPI) != 0;                        // per-lane slow path of the epilogue
-    EpiKnnLane epi_lane{epi};
-    // algorithmic work of the scan: 2.B.N.D flops, one read of the fp32 prototype matrix (4.N.D bytes); with the fp16
-    // shadow the kernel actually streams 2.N.D bytes (the exact re-rank below still reads fp32 rows)
-    if (p_half) {
-        if ((rc = make_tmap_2d(&ta, Qh, 2, Bp, D, static_cast<uint64_t>(D) * 2, GEMM_BLOCK_M, 64))) return rc;
-        if ((rc = make_tmap_2d(&tb, p_half, 2, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 2, b_box, 64))) return rc;
-        rc = pair && lane_epi ? launch_gemm_tc2<EpiKnnLane, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s,
-                                                                                   pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
-             : pair ? launch_gemm_tc2<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
-                                                                   pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
-             : lane_epi ? launch_gemm_tc<EpiKnnLane, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s,
-                                                                           pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
-                  : launch_gemm_tc<EpiKnn, true, GEMM_KIND_F16>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s,
-                                                                  pl.grid_ctas, PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D);
-        if (rc) return rc;
-    } else {
-        if ((rc = make_tmap_2d(&ta, Qr, 4, Bp, D, static_cast<uint64_t>(D) * 4, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
-        if ((rc = make_tmap_2d(&tb, P, 4, static_cast<uint64_t>(N), D, static_cast<uint64_t>(D) * 4, b_box, GEMM_BLOCK_K))) return rc;
-        rc = pair && lane_epi ? launch_gemm_tc2<EpiKnnLane, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s, pl.grid_ctas,
-                                                                  PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
-             : pair ? launch_gemm_tc2<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
-                                                  PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
-             : lane_epi ? launch_gemm_tc<EpiKnnLane, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi_lane, s, pl.grid_ctas,
-                                                           PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D)
-                  : launch_gemm_tc<EpiKnn, true>(ta, tb, static_cast<int>(Bp), static_cast<int>(N), D, epi, s, pl.grid_ctas,
-                                                 PROF_KNN_COARSE, 4.0 * static_cast<double>(N) * D);
-        if (rc) return rc;
-    }
+    // ---- pass 1 on the tensor cores: per-(query, CTA, half) top-16 lists
+    const bool small_k = k <= KNN_SMALL_K;
+    int kt = KNN_KC;
+    if (small_k) { kt = k + 3 > 8 ? k + 3 : 8; if (kt > KNN_KC) kt = KNN_KC; }
+    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt};
+    if ((rc = launch_scan(Qr, P, p_half, Bp, N, D, epi, pl.grid_ctas, PROF_KNN_COARSE, s))) return rc;
 
-    // ---- merge per-CTA lists, pick KP candidates + exclusion threshold
+    // ---- merge the lists (sorted by (key, id))
     const int64_t nc = static_cast<int64_t>(B) * pl.slots * KNN_KC;
     knn_widen_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, s>>>(cidx, nc, cidx64);
     AC_LAUNCH_CHECK();
     const int64_t L = static_cast<int64_t>(pl.slots) * KNN_KC;
-    if ((rc = topk_select(ckey, cidx64, B, L, L, 0, KNN_KP + 1, skey, sidx, selws, pl.sel_bytes, s))) return rc;
-    knn_pick_kernel<<<(B + 127) / 128, 128, 0, s>>>(skey, sidx, ckey, qn, B, pl.slots, kt, ridx, T);
-    AC_LAUNCH_CHECK();
-
-    // ---- exact re-rank of the candidates, final (d, id) order
-    if ((rc = launch_knn_rerank(Q, P, B, N, D, KNN_KP, ridx, rd, ri, row_offset, s))) return rc;
-    if ((rc = topk_select(rd, ri, B, KNN_KP, KNN_KP, 0, k, out_d, out_i, selws, pl.sel_bytes, s))) return rc;
-
-    // ---- certification + exact recomputation of the (rare) uncertified queries
+    if ((rc = topk_select(ckey, cidx64, B, L, L, 0, pl.ksel, skey, sidx, selws, pl.sel_bytes, s))) return rc;
     const float rel = p_half ? (2.f * 4.8828125e-4f + 2.4e-7f) : (9.765625e-4f + 4.8828125e-4f + 4.8e-7f);
-    knn_certify_kernel<<<(B + 127) / 128, 128, 0, s>>>(out_d, out_i, T, qn, pmax, B, k, rel, fail + 1, fail);
+    const unsigned bp_blocks = static_cast<unsigned>((Bp + 127) / 128);
+    if (small_k) {
+        // exact re-rank of the best KP candidates, final (d, id) order, certification
+        knn_pick_kernel<<<(B + 127) / 128, 128, 0, s>>>(skey, sidx, ckey, qn, B, pl.slots, kt, ridx, T);
+        AC_LAUNCH_CHECK();
+        if ((rc = launch_knn_rerank(Q, P, B, N, D, KNN_KP, ridx, rd, ri, row_offset, s))) return rc;
+        if ((rc = topk_select(rd, ri, B, KNN_KP, KNN_KP, 0, k, out_d, out_i, selws, pl.sel_bytes, s))) return rc;
+        knn_certify_kernel<<<bp_blocks, 128, 0, s>>>(out_d, out_i, T, qn, pmax, skey, sidx, B, static_cast<int>(Bp), k, rel, thr, cnt,
+                                                     need);
+    } else {
+        knn_threshold_kernel<<<bp_blocks, 128, 0, s>>>(skey, sidx, qn, pmax, B, static_cast<int>(Bp), k, rel, thr, cnt, need);
+    }
     AC_LAUNCH_CHECK();
-    int32_t nfail = 0;
-    AC_CUDA(cudaMemcpyAsync(&nfail, fail, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+
+    // ---- pass 2 (device-conditional): collect the superset, exact re-rank, final selection for the flagged queries
+    EpiKnnCollect epi2{pn_use, thr, buf, cnt, need, pl.cap, B, N, pl.tiles_m};
+    if ((rc = launch_scan(Qr, P, p_half, Bp, N, D, epi2, pl.grid_ctas, PROF_KNN_PASS2, s))) return rc;
+    knn_rerank_collected_kernel<<<dim3(static_cast<unsigned>((pl.cap * 8 + 255) / 256), B), 256, 0, s>>>(
+        Q, P, B, N, D, pl.cap, thr, cnt, buf, rd2, ri2, row_offset, stats, over);
+    AC_LAUNCH_CHECK();
+    if ((rc = topk_select(rd2, ri2, B, pl.cap, pl.cap, 0, k, out_d, out_i, selws, pl.sel_bytes, s, thr))) return rc;
+
+    if (stats_out) {
+        knn_add_stats_kernel<<<1, 32, 0, s>>>(stats, stats_out);
+        AC_LAUNCH_CHECK();
+        return AC_OK;
+    }
+    // synchronous mode: queries whose 2-eps band overflowed the buffer are recomputed by the exact scan
+    int32_t h[4] = {0, 0, 0, 0};
+    AC_CUDA(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, s));
     AC_CUDA(cudaStreamSynchronize(s));
-    if (nfail > 0) {
+    const int nover = h[1];
+    if (nover > 0) {
         float *gq = reinterpret_cast<float *>(fbq);
         float *gd = reinterpret_cast<float *>(fbd);
         int64_t *gi = reinterpret_cast<int64_t *>(fbi);
-        knn_gather_rows_kernel<<<nfail, 128, 0, s>>>(Q, fail + 1, nfail, D, gq);
+        knn_gather_rows_kernel<<<nover, 128, 0, s>>>(Q, over, nover, D, gq);
         AC_LAUNCH_CHECK();
-        if ((rc = knn_exact_subset(gq, P, nfail, N, D, k, gd, gi, row_offset, exws, exact_ws, s))) return rc;
-        knn_scatter_results_kernel<<<(nfail * k + 127) / 128, 128, 0, s>>>(gd, gi, fail + 1, nfail, k, out_d, out_i);
+        if ((rc = knn_exact_subset(gq, P, nover, N, D, k, gd, gi, row_offset, exws, exact_ws, s))) return rc;
+        knn_scatter_results_kernel<<<(nover * k + 127) / 128, 128, 0, s>>>(gd, gi, over, nover, k, out_d, out_i);
         AC_LAUNCH_CHECK();
+    }
+    return AC_OK;
+}
+
+int knn_tc_search(const float *Q, const float *P, const float *p_sqnorm, const void *p_half, int B, int64_t N, int D, int k,
+                  float *out_d, int64_t *out_i, int64_t row_offset, void *ws, size_t ws_bytes, int32_t *stats_out, cudaStream_t s) {
+    int rc = ac_device_check();
+    if (rc) return rc;
+    const int Bb = knn_block(B, k);
+    for (int b0 = 0; b0 < B; b0 += Bb) {
+        const int nb = (B - b0 < Bb) ? B - b0 : Bb;
+        if ((rc = knn_tc_block(Q + static_cast<int64_t>(b0) * D, P, p_sqnorm, p_half, nb, N, D, k, out_d + static_cast<int64_t>(b0) * k,
+                               out_i + static_cast<int64_t>(b0) * k, row_offset, ws, ws_bytes, stats_out, s)))
+            return rc;
     }
     return AC_OK;
 }

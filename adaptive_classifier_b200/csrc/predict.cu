@@ -14,7 +14,7 @@
 namespace ac {
 size_t topk_select_workspace(int B, int64_t L, int k);
 int topk_select(const float *d, const int64_t *idx, int B, int64_t L, int64_t in_stride, int64_t id_offset, int k,
-                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream);
+                float *out_d, int64_t *out_i, void *ws, size_t ws_bytes, cudaStream_t stream, const float *row_gate = nullptr);
 
 constexpr int BLEND_MAX_K = 32;
 
@@ -161,22 +161,26 @@ struct ac_pipeline {
     ac_head_params head;
     bool has_head;
     int64_t N, row_offset;
-    int D, max_B, S, k, kh;
+    int D, max_B, S, k, kh, shards;
     int32_t *ids_dev, *p_cls, *out_cls;
     float *emb, *knn_d, *p_score, *probs, *h_val, *out_score, *scratch;
     int64_t *knn_i, *h_idx;
+    float *loc_d;            // [shards * max_B, k]  this shard's candidates for every rank's queries (sharded mode)
+    int64_t *loc_i;
     void *ws, *ws_topk;
     size_t ws_bytes, ws_topk_bytes, scratch_floats;
     // the head (fp32 SIMT) and the prototype scan (tensor cores + HBM) are independent given the embeddings: the head
     // runs on a side stream forked after the encoder and joined before the blend
     cudaStream_t side;
     cudaEvent_t ev_emb, ev_head;
+    // search statistics accumulated on the device (ac_knn_l2_topk stats): no host synchronisation inside a predict call
+    int32_t *knn_stats;
 };
 
 extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
     if (!pl) return AC_OK;
     void *ptrs[] = {pl->ids_dev, pl->p_cls, pl->out_cls, pl->emb, pl->knn_d, pl->p_score, pl->probs, pl->h_val,
-                    pl->out_score, pl->scratch, pl->knn_i, pl->h_idx, pl->ws, pl->ws_topk};
+                    pl->out_score, pl->scratch, pl->knn_i, pl->h_idx, pl->ws, pl->ws_topk, pl->knn_stats, pl->loc_d, pl->loc_i};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (pl->side) cudaStreamDestroy(pl->side);
     if (pl->ev_emb) cudaEventDestroy(pl->ev_emb);
@@ -187,16 +191,17 @@ extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
 
 extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const void *p_half,
                                   const int32_t *row_class, int64_t N, int D, const ac_head_params *head, int max_B, int S,
-                                  int k, int64_t row_offset, ac_pipeline **out) {
+                                  int k, int64_t row_offset, int shards, ac_pipeline **out) {
     AC_REQUIRE(enc && P && out && N > 0 && D > 0 && max_B > 0 && S > 0, "ac_pipeline_create: bad arguments");
     AC_REQUIRE(k >= 1 && k <= 16, "ac_pipeline_create: k=%d outside [1,16]", k);
+    AC_REQUIRE(shards >= 1 && shards <= 64 && static_cast<int64_t>(shards) * k <= 4096, "ac_pipeline_create: shards=%d", shards);
     ac_pipeline *pl = new ac_pipeline();
     memset(pl, 0, sizeof(*pl));
     pl->enc = enc; pl->P = P; pl->p_sqnorm = p_sqnorm; pl->p_half = p_half; pl->row_class = row_class; pl->N = N; pl->row_offset = row_offset;
-    pl->D = D; pl->max_B = max_B; pl->S = S; pl->k = k;
+    pl->D = D; pl->max_B = max_B; pl->S = S; pl->k = k; pl->shards = shards;
     pl->has_head = head != nullptr;
     if (head) { pl->head = *head; pl->kh = k < head->C ? k : head->C; }
-    int rc = ac_knn_workspace_bytes(max_B, N, D, k, AC_KNN_AUTO, &pl->ws_bytes);
+    int rc = ac_knn_workspace_bytes(max_B * shards, N, D, k, AC_KNN_AUTO, &pl->ws_bytes);
     if (rc) { delete pl; return rc; }
     const size_t C = head ? head->C : 1;
     pl->scratch_floats = head ? static_cast<size_t>(max_B) * (head->H0 + head->H1) : 1;
@@ -217,6 +222,12 @@ extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *
     al(reinterpret_cast<void **>(&pl->scratch), sizeof(float) * pl->scratch_floats);
     al(&pl->ws, pl->ws_bytes);
     al(&pl->ws_topk, pl->ws_topk_bytes);
+    if (shards > 1) {
+        al(reinterpret_cast<void **>(&pl->loc_d), sizeof(float) * max_B * shards * k);
+        al(reinterpret_cast<void **>(&pl->loc_i), sizeof(int64_t) * max_B * shards * k);
+    }
+    al(reinterpret_cast<void **>(&pl->knn_stats), 4 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(pl->knn_stats, 0, 4 * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_emb, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_head, cudaEventDisableTiming);
@@ -225,10 +236,11 @@ extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *
     return AC_OK;
 }
 
-// device entry: ids_dev[B,S] int32 (device) -> out_cls_dev[B,k] int32, out_score_dev[B,k] fp32 (device)
-extern "C" int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B,
-                                          int32_t *out_cls_dev, float *out_score_dev, ac_stream_t stream) {
-    AC_REQUIRE(pl && ids_dev && out_cls_dev && out_score_dev && B > 0 && B <= pl->max_B, "ac_pipeline_predict_device: bad arguments");
+// ---- phases of one predict step (the single-GPU entry below chains them; the row-sharded multi-GPU step interleaves the two
+// NCCL exchanges of parallel.py between them -- same kernels, same side-stream overlap of the head)
+// E: ids -> unit CLS rows (pl->emb); the head (fp32 SIMT) is forked onto the side stream as soon as the embeddings exist
+extern "C" int ac_pipeline_encode(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B, ac_stream_t stream) {
+    AC_REQUIRE(pl && ids_dev && B > 0 && B <= pl->max_B, "ac_pipeline_encode: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = ac_encoder_forward_cls(pl->enc, ids_dev, mask_dev, nullptr, B, pl->S, pl->emb, stream);
     if (rc) return rc;
@@ -241,14 +253,86 @@ extern "C" int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_de
         if (rc) return rc;
         AC_CUDA(cudaEventRecord(pl->ev_head, pl->side));
     }
-    rc = ac_knn_l2_topk(pl->emb, pl->P, pl->p_sqnorm, pl->p_half, B, pl->N, pl->D, pl->k, pl->knn_d, pl->knn_i,
-                        pl->row_offset, pl->ws, pl->ws_bytes, AC_KNN_AUTO, stream);
-    if (rc) return rc;
-    rc = ac_proto_class_scores(pl->knn_d, pl->knn_i, pl->row_class, B, pl->k, pl->p_cls, pl->p_score, stream);
+    return AC_OK;
+}
+extern "C" int ac_pipeline_embeddings(ac_pipeline *pl, const float **emb_dev) {
+    AC_REQUIRE(pl && emb_dev, "ac_pipeline_embeddings: bad arguments");
+    *emb_dev = pl->emb;
+    return AC_OK;
+}
+
+// class scores of pl->knn_d / pl->knn_i -> join the head -> blend
+static int pipeline_finish(ac_pipeline *pl, int B, int32_t *out_cls_dev, float *out_score_dev, ac_stream_t stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = ac_proto_class_scores(pl->knn_d, pl->knn_i, pl->row_class, B, pl->k, pl->p_cls, pl->p_score, stream);
     if (rc) return rc;
     if (pl->has_head) AC_CUDA(cudaStreamWaitEvent(s, pl->ev_head, 0));
     return ac_blend_topk(pl->p_cls, pl->p_score, pl->h_idx, pl->h_val, B, pl->k, pl->has_head ? pl->kh : 0, 0.7f, 0.3f,
                          out_cls_dev, out_score_dev, stream);
+}
+
+namespace ac {
+// per-shard candidate lists [G*B, k] (block g = the queries of rank g) -> one byte buffer of G chunks, chunk g =
+// d[B,k] fp32 | id[B,k] int64: ONE all-to-all moves distances and ids together
+__global__ void pack_candidates_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx, int G, int bk /* B*k */,
+                                       uint8_t *__restrict__ packed) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<int64_t>(G) * bk) return;
+    const int g = static_cast<int>(t / bk), e = static_cast<int>(t % bk);
+    uint8_t *chunk = packed + static_cast<int64_t>(g) * bk * 12;
+    reinterpret_cast<float *>(chunk)[e] = d[t];
+    reinterpret_cast<int64_t *>(chunk + static_cast<int64_t>(bk) * 4)[e] = idx[t];
+}
+// received buffer (chunk g = shard g's list of MY queries) -> [G, B, k] slabs for ac_topk_merge
+__global__ void unpack_candidates_kernel(const uint8_t *__restrict__ packed, int G, int bk, float *__restrict__ d,
+                                         int64_t *__restrict__ idx) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<int64_t>(G) * bk) return;
+    const int g = static_cast<int>(t / bk), e = static_cast<int>(t % bk);
+    const uint8_t *chunk = packed + static_cast<int64_t>(g) * bk * 12;
+    d[t] = reinterpret_cast<const float *>(chunk)[e];
+    idx[t] = reinterpret_cast<const int64_t *>(chunk + static_cast<int64_t>(bk) * 4)[e];
+}
+}  // namespace ac
+
+// K over THIS shard for the queries of every rank: q_all[G*B, D] (all-gathered unit embeddings, rank-major) -> packed[G * B*k*12]
+extern "C" int ac_pipeline_search_shard(ac_pipeline *pl, const float *q_all, int G, int B, void *packed, ac_stream_t stream) {
+    AC_REQUIRE(pl && q_all && packed && G >= 1 && G <= pl->shards && B > 0 && B <= pl->max_B, "ac_pipeline_search_shard: bad arguments");
+    AC_REQUIRE((static_cast<int64_t>(B) * pl->k) % 2 == 0, "ac_pipeline_search_shard: B*k must be even (8-byte alignment of the id block)");
+    int rc = ac_knn_l2_topk(q_all, pl->P, pl->p_sqnorm, pl->p_half, G * B, pl->N, pl->D, pl->k, pl->loc_d, pl->loc_i, pl->row_offset,
+                            pl->ws, pl->ws_bytes, AC_KNN_AUTO, pl->knn_stats, stream);
+    if (rc) return rc;
+    const int64_t n = static_cast<int64_t>(G) * B * pl->k;
+    pack_candidates_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pl->loc_d, pl->loc_i, G, B * pl->k, static_cast<uint8_t *>(packed));
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+// received[G * B*k*12] (chunk g = shard g's candidates for MY queries) -> merge by (d, global id) -> class scores -> H -> blend
+extern "C" int ac_pipeline_finish_sharded(ac_pipeline *pl, const void *received, int G, int B, int32_t *out_cls_dev,
+                                          float *out_score_dev, ac_stream_t stream) {
+    AC_REQUIRE(pl && received && out_cls_dev && out_score_dev && G >= 1 && G <= pl->shards && B > 0 && B <= pl->max_B,
+               "ac_pipeline_finish_sharded: bad arguments");
+    const int64_t n = static_cast<int64_t>(G) * B * pl->k;
+    unpack_candidates_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t *>(received), G, B * pl->k, pl->loc_d, pl->loc_i);
+    AC_LAUNCH_CHECK();
+    int rc = ac_topk_merge(pl->loc_d, pl->loc_i, G, B, pl->k, pl->knn_d, pl->knn_i, stream);
+    if (rc) return rc;
+    return pipeline_finish(pl, B, out_cls_dev, out_score_dev, stream);
+}
+
+// device entry: ids_dev[B,S] int32 (device) -> out_cls_dev[B,k] int32, out_score_dev[B,k] fp32 (device)
+extern "C" int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B,
+                                          int32_t *out_cls_dev, float *out_score_dev, ac_stream_t stream) {
+    AC_REQUIRE(pl && ids_dev && out_cls_dev && out_score_dev && B > 0 && B <= pl->max_B, "ac_pipeline_predict_device: bad arguments");
+    int rc = ac_pipeline_encode(pl, ids_dev, mask_dev, B, stream);
+    if (rc) return rc;
+    rc = ac_knn_l2_topk(pl->emb, pl->P, pl->p_sqnorm, pl->p_half, B, pl->N, pl->D, pl->k, pl->knn_d, pl->knn_i,
+                        pl->row_offset, pl->ws, pl->ws_bytes, AC_KNN_AUTO, pl->knn_stats, stream);
+    if (rc) return rc;
+    return pipeline_finish(pl, B, out_cls_dev, out_score_dev, stream);
 }
 
 // host entry: ids_host[B,S] (pinned) -> H2D -> predict -> D2H of [B,k] class ids + scores, stream-synchronised
@@ -261,6 +345,18 @@ extern "C" int ac_pipeline_predict_host(ac_pipeline *pl, const int32_t *ids_host
     if (rc) return rc;
     AC_CUDA(cudaMemcpyAsync(out_cls_host, pl->out_cls, sizeof(int32_t) * B * pl->k, cudaMemcpyDeviceToHost, s));
     AC_CUDA(cudaMemcpyAsync(out_score_host, pl->out_score, sizeof(float) * B * pl->k, cudaMemcpyDeviceToHost, s));
+    AC_CUDA(cudaStreamSynchronize(s));
+    return AC_OK;
+}
+
+// search statistics since the previous read (synchronises the stream): out[0] queries that took the second tensor pass,
+// out[1] queries whose candidate buffer overflowed (their results are not exact: redo with AC_KNN_EXACT), out[2] max rows
+// collected for one query, out[3] searches.  reset != 0 clears the counters.
+extern "C" int ac_pipeline_knn_stats(ac_pipeline *pl, int32_t *out4_host, int reset, ac_stream_t stream) {
+    AC_REQUIRE(pl && out4_host, "ac_pipeline_knn_stats: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AC_CUDA(cudaMemcpyAsync(out4_host, pl->knn_stats, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (reset) AC_CUDA(cudaMemsetAsync(pl->knn_stats, 0, 4 * sizeof(int32_t), s));
     AC_CUDA(cudaStreamSynchronize(s));
     return AC_OK;
 }

@@ -32,16 +32,17 @@ def class_centres(C: int, D: int, device="cpu") -> torch.Tensor:
 
 
 def synthetic_rows(lo: int, hi: int, D: int, C: int, seed: int, device="cuda", chunk: int = 131072) -> torch.Tensor:
-    """rows [lo,hi) of the synthetic index: normalize(centre[j mod C] + 0.5*randn/sqrt(D)); generated on `device`
-    in chunks with a device generator seeded by (seed, chunk start)."""
+    """rows [lo,hi) of the synthetic index: normalize(centre[j mod C] + 0.5*randn/sqrt(D)); generated on `device` in chunks
+    with a device generator seeded by (seed, GLOBAL chunk start): any row range of the same index has the same bits, so a row
+    shard equals the corresponding slice of the unsharded matrix (the N > 1 parity check of bench.py relies on it)."""
     cen = class_centres(C, D, device)
     out = torch.empty((hi - lo, D), dtype=torch.float32, device=device)
-    for s in range(lo, hi, chunk):
-        e = min(hi, s + chunk)
+    for s in range(lo - lo % chunk, hi, chunk):
         g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + s)
-        noise = torch.randn((e - s, D), generator=g, device=device) * (0.5 / D ** 0.5)
-        j = torch.arange(s, e, device=device) % C
-        out[s - lo : e - lo] = torch.nn.functional.normalize(cen[j] + noise, dim=1)
+        noise = torch.randn((chunk, D), generator=g, device=device) * (0.5 / D ** 0.5)
+        a, e = max(s, lo), min(hi, s + chunk)
+        j = torch.arange(a, e, device=device) % C
+        out[a - lo : e - lo] = torch.nn.functional.normalize(cen[j] + noise[a - s : e - s], dim=1)
     return out
 
 

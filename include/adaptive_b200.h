@@ -39,37 +39,6 @@ int ac_version(void);                 /* ABI version, currently 1 */
 const char *ac_last_error(void);      /* thread-local message of the last failing call */
 int ac_device_check(void);            /* 0 when the current device is sm_100 (B200), else AC_E_CUDA */
 
-/* Run-time options of the library (process-wide, default 0).  They select kernel variants of the same computation;
- * nothing in the reference corresponds to them.
- *   "gemm_pair" 1 : encoder projections / ac_linear_tc run as CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) GEMMs;
- *               2 : the same with the peer CTA's "stage landed" relayed by a thread instead of the TMA unit.
- *                   Results are bit-identical to the default kernels (measured: profiles/r01_pair_*.log).
- *   "knn_pair"  1|2 : the prototype scan's coarse pass runs as a CTA-pair GEMM (bit-identical results).
- *   "ln_defer"  1 : the encoder never materialises LayerNorm between sublayers: residual epilogues write the
- *                   un-normalised sums + row statistics, the consuming GEMM applies r (acc - mu c1) + c0.  Same math in
- *                   a different association order (oracle/deferred_ln_study.py: same 4e-4 error vs fp32 as the default).
- *                   NOT yet run on hardware (written after the round-1 GPU budget was spent).
- *   "head_fused" 1 : ac_head_train_epoch runs the whole epoch as ONE cooperative persistent kernel (the per-step kernels
- *                   become phases separated by grid barriers, same operation order) instead of ~21 launches per step.
- *                   NOT yet run on hardware.
- *   "epi16"  bit 0 : the FFN1 projection (bias + GELU epilogue), bit 1 : the fused QKV projection run through the CTA-pair
- *                   kernel with 16 epilogue warps instead of 8 (the GELU epilogue is issue-bound with two warps per
- *                   scheduler).  Same arithmetic per element, so results must be bit-identical.  NOT yet run on hardware.
- *   "attn_pipe" 1 : attention for S <= 128 runs as a persistent, warp-specialised pipeline (2 CTAs per SM, two smem / TMEM
- *                   buffers: loads and QK^T of the next (sequence, head) overlap softmax / PV / store of the current one).
- *                   Same arithmetic, so the context rows must be bit-identical.  NOT yet run on hardware.
- *   "pdl" 1 : the opt-in kernels above (pair GEMMs, ln_stats, pipelined attention) are launched with programmatic stream
- *                   serialization: their prologue overlaps the tail of the previous kernel and they block in
- *                   griddepcontrol.wait before touching global memory.  NOT yet run on hardware.
- *   "knn_epi" 1 : the prototype scan's epilogue lets every lane walk its own candidate hits (staged through shared memory)
- *                   instead of the warp walking the union of all lanes' hits: same candidate lists, far fewer
- *                   instructions.  Results cannot change.  NOT yet run on hardware.
- *   "cls_attn" 1 : with cls_only = 1 the last layer's attention computes the CLS query row of every (sequence, head) only
- *                   (one warp each, no tensor core): the CLS-only tail reads nothing else.  Same formula, fp32 sums in a
- *                   different order: CLS rows agree to rounding (within the 1e-3 encoder tolerance).  NOT yet run on hardware.
- * Unknown names return AC_E_INVALID. */
-int ac_set_option(const char *name, long long value);
-int ac_get_option(const char *name, long long *value);
 
 /* ------------------------------------------------------------------------------------------
  * Stage K -- prototype kNN.  Replaces faiss.IndexFlatL2.search at
@@ -80,11 +49,14 @@ int ac_get_option(const char *name, long long *value);
 enum {
     AC_KNN_AUTO = 0,
     AC_KNN_EXACT = 1,   /* fp32 SIMT exact scan + radix select (any k <= AC_KNN_MAX_K)       */
-    AC_KNN_TENSOR = 2   /* tcgen05 kind::tf32 coarse pass + exact fp32 re-rank, k <= 16,
-                           every query certified against the coarse error bound, uncertified
-                           queries recomputed by the exact scan (indices identical either way) */
+    AC_KNN_TENSOR = 2   /* tcgen05 coarse pass (kind::f16 over the fp16 shadow, or kind::tf32) + exact fp32 re-rank,
+                           k <= AC_KNN_TENSOR_MAX_K.  k <= 16: per-query certification against the rigorous coarse
+                           error bound; uncertified queries -- and every query when k > 16 -- take a second,
+                           device-conditional tensor pass that collects the provable superset {d~ <= tau + 2 eps},
+                           re-ranked exactly (indices identical to AC_KNN_EXACT either way; no host sync) */
 };
 #define AC_KNN_MAX_K 2048
+#define AC_KNN_TENSOR_MAX_K 1024
 
 /* bytes of scratch ac_knn_l2_topk needs for these sizes (device memory, 256-byte aligned) */
 int ac_knn_workspace_bytes(int B, int64_t N, int D, int k, int algo, size_t *bytes);
@@ -97,11 +69,15 @@ int ac_knn_workspace_bytes(int B, int64_t N, int D, int k, int algo, size_t *byt
  * p_half (nullable) = fp16 shadow copy of P[N,D] (ac_knn_make_shadow): the tensor path then runs its coarse pass as
  *   tcgen05 kind::f16 over 2.N.D bytes (D %% 64 == 0); candidates are still re-ranked on the fp32 rows, so the
  *   result is the same bits either way.
+ * stats (nullable, device int32[4], ACCUMULATED): [0] queries that needed the second tensor pass, [1] queries whose
+ *   2-eps band overflowed the candidate buffer (their rows of out_d/out_i are NOT exact: the caller must redo them with
+ *   AC_KNN_EXACT), [2] max rows collected for one query, [3] searches.  With stats != NULL the call never synchronises
+ *   (graph-capturable); with stats == NULL it synchronises once at the end and recomputes overflowed queries itself.
  */
 int ac_knn_l2_topk(const float *Q, const float *P, const float *p_sqnorm, const void *p_half,
                    int B, int64_t N, int D, int k,
                    float *out_d, int64_t *out_i, int64_t row_offset,
-                   void *workspace, size_t workspace_bytes, int algo, ac_stream_t stream);
+                   void *workspace, size_t workspace_bytes, int algo, int32_t *stats, ac_stream_t stream);
 
 /* fp16 (RNE) shadow of the prototype matrix for the tensor path's coarse pass; out_half holds N*D halves */
 int ac_knn_make_shadow(const float *P, int64_t N, int D, void *out_half, ac_stream_t stream);
@@ -156,10 +132,11 @@ typedef struct {
     int ewc_C_old;
 } ac_train_cfg;
 
-/* bytes of workspace for one train step at batch B */
-int ac_head_train_workspace_bytes(int B, const ac_head_params *p, size_t *bytes);
+/* bytes of workspace for a training / gradient call with `batch` rows per step and n_steps steps (1 for a single step) */
+int ac_head_train_workspace_bytes(int batch, int n_steps, const ac_head_params *p, size_t *bytes);
 
-/* one optimizer step: fwd(train) + loss + bwd + [EWC grad] + global-norm clip + AdamW.
+/* one optimizer step: fwd(train) + loss + bwd + [EWC grad] + global-norm clip + AdamW, as one launch of the persistent
+ * cooperative kernel of csrc/head_train.cuh (B <= 64; D, H0, H1 multiples of 4).
  * m, v: AdamW moments (same shapes as p).  out_stats[0] = task loss, [1] = ewc penalty,
  * [2] = grad norm before clipping (device floats). */
 int ac_head_train_step(const float *X, const void *targets, int B,
@@ -170,11 +147,14 @@ int ac_head_train_step(const float *X, const void *targets, int B,
 /* one EPOCH of the reference's training loops (classifier.py:329-353, :1485-1507; multilabel.py:381-399) in one call:
  * X[n,D], targets (int64[n] or float[n,C]) and the shuffled index list perm[n] (what the reference's DataLoader with
  * torch.Generator().manual_seed(42) yields) live on the device; batches of `batch` rows (last one partial) are gathered
- * and stepped here.  cfg->step = 1-based number of the first update; loss_accum[0] += task loss + EWC penalty per step. */
-int ac_head_train_epoch_workspace_bytes(int batch, const ac_head_params *p, size_t *bytes);
+ * and stepped inside ONE kernel launch (the grid stays resident for the whole epoch: parameters live in shared memory, six
+ * grid barriers per step).  cfg->step = 1-based number of the first update.  loss_accum (nullable): [0] += task loss + EWC
+ * penalty per step.  step_stats (nullable): [ceil(n / batch), 3] = (task loss, EWC penalty, grad norm before clipping) of
+ * every step -- what the reference's loop reads back with loss.item() (classifier.py:353, :1507).
+ * workspace: ac_head_train_workspace_bytes(batch, ceil(n / batch), ...). */
 int ac_head_train_epoch(const float *X, const void *targets, const int64_t *perm, int n, int batch,
                         ac_head_params *p, ac_head_params *m, ac_head_params *v, const ac_train_cfg *cfg,
-                        float *loss_accum, void *workspace, size_t workspace_bytes, ac_stream_t stream);
+                        float *loss_accum, float *step_stats, void *workspace, size_t workspace_bytes, ac_stream_t stream);
 
 /* gradient only (no update) of mean CE/BCE wrt all parameters, eval mode: the building block of
  * EWC._compute_fisher (ewc.py:67-92).  fisher += grad^2 * inv_n_batches when fisher != NULL */
@@ -232,12 +212,6 @@ int ac_encoder_forward_cls(ac_encoder *enc, const int32_t *ids, const int32_t *m
                            const int32_t *type_ids, int B, int S, float *out_unit_cls,
                            ac_stream_t stream);
 
-/* ac_encoder_forward_cls whose last kernel also stores the unit CLS rows [B,H] at (buf[p] + dst_offset_bytes) of every
- * peer and then publishes seq in flag[p][rank] (see "Peer-memory exchange" below): the all-gather of the embeddings of the
- * row-sharded search costs no kernel of its own.  out_unit_cls (local copy) is still written. */
-int ac_encoder_forward_cls_scatter(ac_encoder *enc, const int32_t *ids, const int32_t *mask, const int32_t *type_ids,
-                                   int B, int S, float *out_unit_cls, const void *peer_table /* ac_peer_table* */,
-                                   size_t dst_offset_bytes, uint32_t seq, uint32_t *counter, ac_stream_t stream);
 
 /* debugging / parity: copy the full last hidden state [B*S,H] of the previous forward */
 int ac_encoder_last_hidden(ac_encoder *enc, float *out, int64_t n_floats, ac_stream_t stream);
@@ -276,7 +250,7 @@ int ac_blend_topk(const int32_t *proto_cls, const float *proto_score, const int6
 typedef struct ac_pipeline ac_pipeline;
 int ac_pipeline_create(ac_encoder *enc, const float *P, const float *p_sqnorm, const void *p_half,
                        const int32_t *row_class, int64_t N, int D, const ac_head_params *head, int max_B, int S, int k,
-                       int64_t row_offset, ac_pipeline **out);
+                       int64_t row_offset, int shards /* 1, or the number of GPUs the rows are sharded over */, ac_pipeline **out);
 int ac_pipeline_destroy(ac_pipeline *pl);
 /* device buffers at the boundary (bench.py `value`) */
 int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B,
@@ -284,36 +258,28 @@ int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const in
 /* HOST buffers at the boundary (bench.py `e2e`): H2D of ids and D2H of the [B,k] result inside the call */
 int ac_pipeline_predict_host(ac_pipeline *pl, const int32_t *ids_host, int B, int32_t *out_cls_host,
                              float *out_score_host, ac_stream_t stream);
+/* The phases of one step, for the row-sharded multi-GPU search: the caller (parallel.py) runs the
+ * two collectives between them on the same stream -- all-gather of the unit embeddings, ONE all-to-all of the packed
+ * (distance, id) candidates -- so that N > 1 executes the same kernels, with the same side-stream overlap of the head, as N = 1.
+ *   ac_pipeline_encode         ids -> unit CLS rows (ac_pipeline_embeddings returns the device pointer, [B, D])
+ *   ac_pipeline_search_shard   q_all[G*B, D] (rank-major) over THIS shard -> packed: G chunks of (d[B,k] fp32 | id[B,k] int64)
+ *   ac_pipeline_finish_sharded received chunks (chunk g = shard g's candidates of MY queries) -> merge by (d, global id)
+ *                              [bit-identical to the unsharded search] -> class scores -> head -> blend */
+int ac_pipeline_encode(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B, ac_stream_t stream);
+int ac_pipeline_embeddings(ac_pipeline *pl, const float **emb_dev);
+int ac_pipeline_search_shard(ac_pipeline *pl, const float *q_all, int G, int B, void *packed, ac_stream_t stream);
+int ac_pipeline_finish_sharded(ac_pipeline *pl, const void *received, int G, int B, int32_t *out_cls_dev, float *out_score_dev,
+                               ac_stream_t stream);
+/* search statistics accumulated since the last reset (synchronises): see ac_knn_l2_topk `stats` */
+int ac_pipeline_knn_stats(ac_pipeline *pl, int32_t *out4_host, int reset, ac_stream_t stream);
 /* parity tests: copy the last call's unit CLS rows [B,D] and kNN result [B,k] into caller device buffers */
 int ac_pipeline_debug_copy(ac_pipeline *pl, int B, float *emb_out, float *knn_d_out, int64_t *knn_i_out,
                            ac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Peer-memory exchange for the row-sharded index (new; the reference is single-process).
- * The caller maps every rank's exchange buffer into this process (torch symmetric memory / CUDA IPC: plumbing) and passes
- * the G base pointers plus G pointers to each rank's flag array of this channel (world uint32 each, zero-initialised).
- * All ranks use the same layout, so one offset addresses the same slot on every peer.
- * ------------------------------------------------------------------------------------------ */
-#define AC_MAX_PEERS 16
-typedef struct {
-    int world, rank;
-    void *buf[AC_MAX_PEERS];        /* buf[p]  = base of rank p's exchange buffer as mapped here (buf[rank] = local) */
-    uint32_t *flag[AC_MAX_PEERS];   /* flag[p] = rank p's flag array of this channel; this rank writes flag[p][rank]   */
-} ac_peer_table;
-
-/* blocks_mode 0: the bytes_per_dst bytes at src go to (buf[p] + dst_offset_bytes) of EVERY p (all-gather of embeddings);
- * blocks_mode 1: block p of src (blocks of bytes_per_dst bytes, contiguous) goes to (buf[p] + dst_offset_bytes)
- *                (all-to-all of per-shard candidates).  When the whole grid has stored, flag[p][rank] = seq for every p.
- * counter: one zero-initialised device uint32 per stream (scratch of the "last block" detection). */
-int ac_peer_scatter(const void *src, size_t bytes_per_dst, int blocks_mode, const ac_peer_table *t,
-                    size_t dst_offset_bytes, uint32_t seq, uint32_t *counter, ac_stream_t stream);
-/* returns (in stream order) once flags_local[0..n_flags) have all reached seq; traps after a few seconds otherwise */
-int ac_peer_wait(const uint32_t *flags_local, int n_flags, uint32_t seq, ac_stream_t stream);
-
-/* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): number of kernels launched by this library so far, and optional
  * CUDA-event timing of the dominant kernels on their launching stream.
- * classes: 0 encoder tcgen05 GEMM, 1 attention, 2 kNN coarse pass, 3 kNN exact scan
+ * classes: 0 encoder tcgen05 GEMM, 1 attention, 2 kNN tensor pass 1, 3 kNN exact scan, 4 kNN tensor pass 2 (device-conditional)
  * ------------------------------------------------------------------------------------------ */
 long long ac_launch_count(void);
 int ac_profile_enable(int on);

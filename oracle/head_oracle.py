@@ -141,3 +141,65 @@ def init_head(D: int, C: int, seed_reset: bool = True) -> Dict[str, Tensor]:
     p["W2"] = out.weight.detach().clone()
     p["b2"] = torch.zeros(C)
     return p
+
+
+def epoch_permutation(gen: torch.Generator, n: int) -> Tensor:
+    """The order one epoch of DataLoader(TensorDataset, shuffle=True, generator=gen) visits the rows (classifier.py:315-320,
+    :1453-1459): torch's _BaseDataLoaderIter draws an int64 base seed from `gen`, RandomSampler draws randperm(n), and on
+    exhaustion a second randperm(n) whose empty slice is dropped.  Pinned against a real DataLoader and against the
+    reference run's recorded batches (tests/golden/golden_training.npz) in tests/test_oracle_cpu.py."""
+    torch.empty((), dtype=torch.int64).random_(generator=gen)
+    perm = torch.randperm(n, generator=gen)
+    torch.randperm(n, generator=gen)
+    return perm
+
+
+def train_loop(X: Tensor, Y: Tensor, p: Dict[str, Tensor], *, epochs: int, batch_size: int, use_scheduler: bool,
+               loss_kind: str = "ce", batches: Optional[List[List[int]]] = None):
+    """The reference's optimizer loops with dropout as identity: _train_adaptive_head (classifier.py:1453-1520: epochs 10,
+    batch min(32, n), ReduceLROnPlateau(min, factor .5, patience 2, rel threshold 1e-4), early stop patience 3),
+    _train_new_classes (:306-365: epochs 15, batch 32, no scheduler, EWC term == 0) and the multilabel BCE loop
+    (multilabel.py:360-411: no scheduler).  `batches` (a flat list of index lists) overrides the generator-derived order.
+    Updates `p` in place; returns (per-step losses, per-step grad norms, steps per epoch)."""
+    n = X.shape[0]
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v = {k: torch.zeros_like(t) for k, t in p.items()}
+    gen = torch.Generator().manual_seed(42)
+    lr, step = 1e-3, 0
+    best, bad_epochs = float("inf"), 0
+    sched_best, sched_bad = float("inf"), 0
+    losses, gnorms, per_epoch = [], [], []
+    cursor = 0
+    n_batches = (n + batch_size - 1) // batch_size
+    for _epoch in range(epochs):
+        if batches is None:
+            perm = epoch_permutation(gen, n).tolist()
+            todo = [perm[i:i + batch_size] for i in range(0, n, batch_size)]
+        else:
+            todo = batches[cursor:cursor + n_batches]
+            cursor += n_batches
+        total = 0.0
+        for idx in todo:
+            xb, yb = X[idx], Y[idx]
+            loss, g, _ = head_grads(xb, yb, p, None, loss_kind)
+            step += 1
+            gn = clip_and_adamw(p, g, m, v, step, lr=lr)
+            losses.append(float(loss))
+            gnorms.append(float(gn))
+            total += float(loss)
+        per_epoch.append(len(todo))
+        avg = total / len(todo)
+        if use_scheduler:                   # torch ReduceLROnPlateau: is_better = a < best * (1 - 1e-4)
+            if avg < sched_best * (1 - 1e-4):
+                sched_best, sched_bad = avg, 0
+            else:
+                sched_bad += 1
+            if sched_bad > 2:
+                lr, sched_bad = lr * 0.5, 0
+        if avg < best:
+            best, bad_epochs = avg, 0
+        else:
+            bad_epochs += 1
+            if bad_epochs >= 3:
+                break
+    return losses, gnorms, per_epoch

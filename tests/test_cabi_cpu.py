@@ -59,26 +59,34 @@ def test_product_package_never_imports_the_oracle():
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/knn_oracle.c", "").replace("oracle/precision_study.py", "").replace("oracle/deferred_ln_study.py", ""), f   # comments citing the studies
 
 
-def test_options_roundtrip_without_a_gpu(cabi):
-    """ac_set_option / ac_get_option are host-only state: they work without a device; unknown names are rejected"""
-    for name in ("gemm_pair", "knn_pair", "ln_defer", "head_fused", "epi16", "attn_pipe", "pdl", "knn_epi", "cls_attn"):
-        prev = cabi.get_option(name)
-        with cabi.option(name, prev + 2):
-            assert cabi.get_option(name) == prev + 2
-        assert cabi.get_option(name) == prev
-    with pytest.raises(cabi.AdaptiveB200Error):
-        cabi.set_option("not_an_option", 1)
-    with pytest.raises(cabi.AdaptiveB200Error):
-        cabi.get_option("not_an_option")
+def test_no_kernel_selector_switches_in_the_shipped_abi(cabi):
+    """round 2: every kernel variant was either promoted to THE implementation or deleted; the library has no
+    ac_set_option-style selectors and no environment switchboard"""
+    L = cabi.load_library()
+    assert not hasattr(L, "ac_set_option") and not hasattr(L, "ac_get_option")
+    for name in _header_functions():
+        assert "option" not in name and "peer" not in name
 
 
-def test_ac_options_environment_is_applied_on_load():
-    import subprocess, sys
-    code = ("import sys; sys.path.insert(0, %r); from adaptive_classifier_b200 import _cabi; _cabi.load_library(); "
-            "print(_cabi.get_option('ln_defer'), _cabi.get_option('epi16'), _cabi.get_option('gemm_pair'))" % ROOT)
-    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "AC_OPTIONS": "ln_defer=1,epi16=3"},
-                         capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-500:]
-    assert out.stdout.split() == ["1", "3", "0"]
-    bad = subprocess.run([sys.executable, "-c", code], env={**os.environ, "AC_OPTIONS": "bogus=1"}, capture_output=True, text=True, timeout=300)
-    assert bad.returncode != 0 and "bogus" in bad.stderr
+def test_head_training_kernel_on_the_cpu_emulation():
+    """csrc/head_train.cuh (the persistent cooperative training kernel: ownership blocks, streamed chunks, six grid barriers per
+    step) is plain SIMT C++; tests/cpu_shim runs it with every CUDA thread as a fiber and real grid barriers (thread order
+    shuffled between barriers) and compares several optimizer steps / a gradient-only call with a natural-order restatement.
+    This is how the kernel's logic was checked before any GPU time was spent on it."""
+    import subprocess, tempfile
+    shim = os.path.join(ROOT, "tests", "cpu_shim")
+    exe = os.path.join(tempfile.mkdtemp(prefix="ht_emul_"), "head_train_emul")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I/usr/local/cuda/include", os.path.join(shim, "head_train_emul.cpp"),
+                        os.path.join(shim, "cuda_shim.cpp"), "-o", exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    #        D   H0  H1  C    n  batch G loss dropout ewc update seed
+    cases = ["40 40 20 5 50 20 3 0 0.1 0 1 1",          # CE, dropout, last batch partial
+             "40 40 20 5 50 20 2 1 0.1 0 1 2",          # BCE; 2 CTAs -> several ownership blocks per CTA
+             "264 136 68 11 70 32 4 0 0.1 1 1 3",       # K not a multiple of the 128-column chunk; EWC with a grown head
+             "64 64 32 3 45 40 3 0 0.0 1 1 4",          # batch > 32 (two rows per lane), C = 3 (scalar chunk loads)
+             "128 128 64 130 64 32 5 1 0.2 1 1 5",      # C > one chunk: dz streamed in two chunks
+             "264 136 68 11 30 30 4 0 0.0 0 0 6",       # gradient-only mode (Fisher): gradients and accumulators
+             "40 40 20 5 20 20 1 1 0.0 1 0 7"]          # a single CTA owns everything
+    for c in cases:
+        out = subprocess.run([exe] + c.split(), capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "MATCH" in out.stdout, (c, out.stdout[-600:], out.stderr[-300:])

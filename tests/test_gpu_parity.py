@@ -136,6 +136,129 @@ def test_knn_tensor_fp16_shadow_equals_exact_scan(cabi, B, N, C, k):
     assert torch.equal(i1[:, 0].cpu() % C, torch.arange(B) % C)
 
 
+@pytest.mark.parametrize("B,N,D,C,k", [(64, 30_000, 768, 20, 64), (512, 120_000, 768, 1000, 1000), (130, 50_000, 1024, 50, 200),
+                                       (700, 60_000, 768, 100, 100)])
+def test_knn_tensor_large_k_equals_exact_scan(cabi, B, N, D, C, k):
+    """k = num_classes (predict() semantics, classifier.py:424-425) stays on the tensor path: pass 1 bounds the k-th distance,
+    pass 2 collects the provable superset {coarse <= tau + 2 eps}, exact re-rank + (d, id) selection.  B = 700 runs as two
+    query blocks.  Bit-identical to the exact scan (sample of queries) and to the oracle (4 queries)."""
+    P, _ = _synthetic_index(N, D, C, seed=0)
+    Q, _ = _synthetic_index(B, D, C, seed=1)
+    Pg, Qg = P.cuda(), Q.cuda()
+    Ph = cabi.knn_make_shadow(Pg)
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    d1, i1 = cabi.knn_l2_topk(Qg, Pg, k, p_half=Ph, algo=cabi.AC_KNN_TENSOR, stats=stats)
+    sel = torch.arange(0, B, max(1, B // 24))[:24]
+    d0, i0 = cabi.knn_l2_topk(Qg[sel.cuda()].contiguous(), Pg, k, algo=cabi.AC_KNN_EXACT)
+    torch.cuda.synchronize()
+    st = stats.cpu().tolist()
+    assert st[1] == 0 and st[0] == B and k <= st[2] <= 2048, st           # every query took pass 2, nothing overflowed
+    assert torch.equal(i1[sel.cuda()], i0) and torch.equal(d1[sel.cuda()], d0)
+    assert bool((d1[:, 1:] >= d1[:, :-1]).all())
+    d_ref, i_ref = ko.knn_l2(Q[:4].numpy(), P.numpy(), k)
+    assert np.array_equal(i1[:4].cpu().numpy(), i_ref) and np.array_equal(d1[:4].cpu().numpy(), d_ref)
+
+
+def test_knn_tensor_near_duplicate_rows_take_the_second_pass_not_a_full_scan(cabi):
+    """Stress input of VERDICT r1 #14: every query has MANY rows closer to each other than the coarse error bound
+    (gaps < eps ~ 2e-3), so pass-1 certification fails for all of them.  They are resolved by the second tensor pass
+    (device-conditional, no host sync) -- bit-identical to the exact scan, ties by lower row id, and stats say so."""
+    B, N, D, k = 256, 80_000, 768, 5
+    g = torch.Generator().manual_seed(3)
+    base = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1)
+    P = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+    for b in range(B):                      # 48 near-copies of every query's neighbour, 1e-4 apart, scattered over the index:
+        rows = (torch.arange(48) * 1601 + b * 311) % N          # more than the 32 re-ranked candidates -> T - eps < d_k
+        P[rows] = torch.nn.functional.normalize(base[b][None] + 1e-4 * torch.randn(48, D, generator=g), dim=1)
+    P[5] = P[40_005]                        # an exact duplicate: tie -> lower id
+    Q = torch.nn.functional.normalize(base + 1e-3 * torch.randn(B, D, generator=g), dim=1)
+    Pg, Qg = P.cuda().contiguous(), Q.cuda().contiguous()
+    Ph = cabi.knn_make_shadow(Pg)
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    d1, i1 = cabi.knn_l2_topk(Qg, Pg, k, p_half=Ph, algo=cabi.AC_KNN_TENSOR, stats=stats)
+    d0, i0 = cabi.knn_l2_topk(Qg[:64].contiguous(), Pg, k, algo=cabi.AC_KNN_EXACT)
+    torch.cuda.synchronize()
+    st = stats.cpu().tolist()
+    assert st[0] >= B // 2 and st[1] == 0, st          # most queries could not be certified; none overflowed
+    assert torch.equal(i1[:64], i0) and torch.equal(d1[:64], d0)
+    # synchronous mode (no stats pointer) gives the same answer
+    d2, i2 = cabi.knn_l2_topk(Qg, Pg, k, p_half=Ph, algo=cabi.AC_KNN_TENSOR)
+    assert torch.equal(i2, i1) and torch.equal(d2, d1)
+
+
+def test_knn_tensor_overflow_is_reported_and_rescued(cabi):
+    """thousands of identical rows inside the 2-eps band overflow the candidate buffer: with a stats pointer the overflow is
+    reported (stats[1]); without one the call recomputes those queries by the exact scan"""
+    B, N, D, k = 32, 20_000, 768, 5
+    g = torch.Generator().manual_seed(8)
+    P = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+    P[1000:1600] = P[999]                                          # 600 identical rows > cap (256 for k <= 16)
+    Q = torch.nn.functional.normalize(P[999][None] + 0.01 * torch.randn(B, D, generator=g), dim=1)
+    Pg, Qg = P.cuda().contiguous(), Q.cuda().contiguous()
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    cabi.knn_l2_topk(Qg, Pg, k, algo=cabi.AC_KNN_TENSOR, stats=stats)
+    assert stats.cpu().tolist()[1] == B
+    d1, i1 = cabi.knn_l2_topk(Qg, Pg, k, algo=cabi.AC_KNN_TENSOR)          # synchronous mode rescues
+    d0, i0 = cabi.knn_l2_topk(Qg, Pg, k, algo=cabi.AC_KNN_EXACT)
+    assert torch.equal(i1, i0) and torch.equal(d1, d0)
+    assert i1[0].tolist() == [999, 1000, 1001, 1002, 1003]                  # ties -> lower row id
+
+
+@pytest.mark.parametrize("N,D,B", [(1_000_000, 768, 512), (500_000, 1024, 128)])
+def test_knn_tensor_at_the_benched_sizes_equals_oracle(cabi, N, D, B):
+    """BASELINE configs[2] (1 M x 768, 512 queries) and configs[4] (500 k x 1024, 128 queries): the sizes bench.py runs, against
+    the ORACLE on a 32-query sample (bit-exact ids and distances) and the exact scan on the same sample"""
+    from adaptive_classifier_b200 import workload as wl
+    C, k = (1000, 5) if D == 768 else (50, 5)
+    P = wl.synthetic_rows(0, N, D, C, seed=0, device="cuda")
+    Q = wl.synthetic_queries_embeddings(B, D, C, device="cuda")
+    Ph = cabi.knn_make_shadow(P)
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    d1, i1 = cabi.knn_l2_topk(Q, P, k, p_sqnorm=cabi.row_sqnorm(P), p_half=Ph, algo=cabi.AC_KNN_TENSOR, stats=stats)
+    sel = torch.arange(0, B, B // 32)[:32].cuda()
+    d0, i0 = cabi.knn_l2_topk(Q[sel].contiguous(), P, k, algo=cabi.AC_KNN_EXACT)
+    torch.cuda.synchronize()
+    assert stats.cpu().tolist()[1] == 0
+    assert torch.equal(i1[sel], i0) and torch.equal(d1[sel], d0)
+    d_ref, i_ref = ko.knn_l2(Q[sel].cpu().numpy(), P.cpu().numpy(), k)
+    assert np.array_equal(i1[sel].cpu().numpy(), i_ref) and np.array_equal(d1[sel].cpu().numpy(), d_ref)
+
+
+def test_golden_router_prototypes_through_the_cuda_kernels(cabi):
+    """tests/golden/golden_router.npz: the two REAL prototypes of the reference's bundled router (d = 0.001965 apart: the
+    near-tie stress input of SURVEY 8(c)) searched by the reference-side index object -> same (d, id) bits from both CUDA paths"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_router.npz"))
+    P, Q = torch.from_numpy(g["P"]).cuda(), torch.from_numpy(g["Q"]).cuda()
+    d, i = cabi.knn_l2_topk(Q, P, 2, algo=cabi.AC_KNN_EXACT)
+    assert np.array_equal(i.cpu().numpy(), g["i"]) and np.array_equal(d.cpu().numpy(), g["d"])
+    # the tensor path on the same rows embedded in a larger index (the two prototypes stay the nearest rows)
+    filler = torch.nn.functional.normalize(torch.randn(8190, P.shape[1], generator=torch.Generator().manual_seed(1)), dim=1).cuda() * 3.0
+    big = torch.cat([P, filler]).contiguous()
+    Q32 = Q.repeat(3, 1)[:32].contiguous()
+    dt, it = cabi.knn_l2_topk(Q32, big, 2, algo=cabi.AC_KNN_TENSOR)
+    assert np.array_equal(it.cpu().numpy()[:12], g["i"]) and np.array_equal(dt.cpu().numpy()[:12], g["d"])
+
+
+def test_golden_head_through_the_cuda_kernels(cabi):
+    """tests/golden/golden_head.npz: the reference's AdaptiveHead logits and EWC loss values on seeded inputs"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_head.npz"))
+    names = {"W0": "model.0.weight", "b0": "model.0.bias", "W1": "model.3.weight", "b1": "model.3.bias",
+             "W2": "model.6.weight", "b2": "model.6.bias"}
+    pg = {k: torch.from_numpy(g[v]).cuda().contiguous() for k, v in names.items()}
+    X = torch.from_numpy(g["X"]).cuda()
+    logits = cabi.head_forward(X, pg, cabi.AC_ACT_LOGITS).cpu().numpy()
+    assert np.abs(logits - g["logits"]).max() < 1e-5
+    fisher = {k: torch.from_numpy(g["fisher_" + v]).cuda().contiguous() for k, v in names.items()}
+    moved = {k: (v + 0.1).contiguous() for k, v in pg.items()}
+    assert float(cabi.ewc_penalty(pg, fisher, pg, 100.0, None)) == 0.0 == float(g["ewc_loss0"])
+    l1 = float(cabi.ewc_penalty(moved, fisher, pg, 100.0, None))
+    assert abs(l1 - float(g["ewc_loss1"])) <= 1e-4 * float(g["ewc_loss1"])
+    l32 = float(cabi.ewc_penalty(moved, fisher, pg, 100.0, 32))
+    assert abs(l32 - float(g["ewc_loss1_b32"])) <= 1e-4 * float(g["ewc_loss1_b32"])
+
+
 def test_proto_scores_and_merge(cabi):
     rng = np.random.default_rng(3)
     d = np.sort(rng.uniform(0, 4, size=(7, 9)).astype(np.float32), axis=1)
@@ -398,6 +521,84 @@ def test_encoder_cls_matches_oracle(cabi, layers, B, S, pad):
     dd = (((out[:, None, :] - P[None]) ** 2).sum(-1) - ((ref[:, None, :] - P[None]) ** 2).sum(-1)).abs().max()
     assert dd < 1e-3, dd                        # the north_star tolerance itself (distances within 1e-3)
     assert (out.norm(dim=1) - 1).abs().max() < 1e-5
+    enc.close()
+
+
+def _perturb_layernorms(sd, seed=5):
+    """random init has gamma = 1, beta = 0 and row means ~ 0, which would hide the rank-1 corrections of the deferred-LayerNorm
+    epilogues (r (acc - mu c1) + c0 with gamma folded into the weights)"""
+    g = torch.Generator().manual_seed(seed)
+    for k in list(sd.keys()):
+        if k.endswith("LayerNorm.weight"):
+            sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("LayerNorm.bias"):
+            sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("output.dense.bias"):
+            sd[k] = sd[k] + 0.5
+    return sd
+
+
+@pytest.mark.parametrize("layers,B,S,cls_only,pad", [(2, 8, 128, True, False), (3, 5, 96, False, True), (12, 4, 128, True, False),
+                                                      (2, 3, 300, True, True)])
+def test_encoder_with_nontrivial_layernorms_matches_oracle(cabi, layers, B, S, cls_only, pad):
+    """non-unit gamma (up to 1.9), non-zero beta and shifted row means: every term of the deferred LayerNorm is exercised"""
+    sd, cfg, _ = eo.make_bert_state_dict(1234, num_hidden_layers=layers)
+    sd = _perturb_layernorms(sd)
+    ids = eo.synthetic_ids(B, S)
+    mask = torch.ones_like(ids)
+    if pad:
+        for b in range(B):
+            n = S - 1 - 2 * b
+            mask[b, n:] = 0
+            ids[b, n:] = 0
+    ref, ref_hidden = eo.encoder_forward_cls(sd, ids, mask, return_hidden=True)
+    enc = _encoder(cabi, sd, cfg, max_tokens=B * S, cls_only=cls_only)
+    out = enc.forward_cls(ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()).cpu()
+    e = out - ref
+    assert e.abs().max() < 3e-4 and e.norm(dim=1).max() < 1e-3, (e.abs().max(), e.norm(dim=1).max())
+    assert (out.norm(dim=1) - 1).abs().max() < 1e-5
+    if not cls_only:
+        hidden = enc.last_hidden(B, S).cpu()
+        keep = mask.bool()
+        assert (hidden.view(B, S, -1)[keep] - ref_hidden[keep]).abs().max() < 5e-3
+    enc.close()
+
+
+def test_encoder_at_the_benched_batch_matches_oracle_on_sampled_rows(cabi):
+    """BASELINE configs[2]: bert-base, B = 512 x S = 128 (65 536 tokens through every GEMM tile of the step bench.py times);
+    8 sampled sequences against the fp32 CPU oracle"""
+    sd, cfg = _small_bert(12)
+    B, S = 512, 128
+    ids = eo.synthetic_ids(B, S)
+    enc = _encoder(cabi, sd, cfg, max_tokens=B * S)
+    out = enc.forward_cls(ids.to(torch.int32).cuda()).cpu()
+    sel = torch.tensor([0, 1, 63, 127, 128, 300, 510, 511])
+    ref = eo.encoder_forward_cls(sd, ids[sel], None)
+    e = out[sel] - ref
+    assert e.norm(dim=1).max() < 1e-3 and e.abs().max() < 2e-4, (e.norm(dim=1).max(), e.abs().max())
+    assert (out.norm(dim=1) - 1).abs().max() < 1e-5 and bool(torch.isfinite(out).all())
+    enc.close()
+
+
+def test_encoder_roberta_large_shape_with_real_position_ids(cabi):
+    """BASELINE configs[4]: RoBERTa-large (24 layers x 1024, 16 heads, vocab 50265, type_vocab 1, eps 1e-5, pad_idx 1,
+    position ids = cumsum(non-pad) + 1 -- HF models/roberta/modeling_roberta.py:146-159) with padded sequences"""
+    sd, cfg, _ = eo.make_bert_state_dict(1234, arch="roberta", num_hidden_layers=24, hidden_size=1024, num_attention_heads=16,
+                                         intermediate_size=4096, vocab_size=50265, max_position_embeddings=514, type_vocab_size=1,
+                                         layer_norm_eps=1e-5, pad_token_id=1)
+    B, S = 3, 128
+    ids = eo.synthetic_ids(B, S, vocab=50265, arch="roberta")
+    ids[1, 100:] = 1
+    ids[2, 17:] = 1
+    mask = (ids != 1).long()
+    ref = eo.encoder_forward_cls(sd, ids, mask, arch="roberta", num_heads=16, ln_eps=cfg.layer_norm_eps, pad_idx=1)
+    enc = _encoder(cabi, sd, cfg, B * S, arch="roberta")
+    out = enc.forward_cls(ids.to(torch.int32).cuda(), mask.to(torch.int32).cuda()).cpu()
+    e = out - ref
+    assert e.norm(dim=1).max() < 1.5e-3, e.norm(dim=1).max()          # 24 layers of fp16-operand rounding (12 layers: 6e-4)
+    P = torch.nn.functional.normalize(torch.randn(1024, 1024, generator=torch.Generator().manual_seed(0)), dim=1)
+    dd = (((out[:, None, :] - P[None]) ** 2).sum(-1) - ((ref[:, None, :] - P[None]) ** 2).sum(-1)).abs().max()
+    assert dd < 1e-3, dd                                               # the north_star tolerance (distances within 1e-3)
     enc.close()
 
 
