@@ -31,7 +31,7 @@ EXPORTS = [
     "ac_segment_mean",
     "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
-    "ac_proto_class_scores", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
+    "ac_proto_class_scores", "ac_proto_class_scores_n", "ac_blend_dense", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
     "ac_pipeline_create", "ac_pipeline_destroy", "ac_pipeline_predict_device", "ac_pipeline_predict_host",
     "ac_pipeline_encode", "ac_pipeline_embeddings", "ac_pipeline_search_shard", "ac_pipeline_finish_sharded",
     "ac_pipeline_debug_copy", "ac_pipeline_knn_stats", "ac_launch_count", "ac_profile_enable", "ac_profile_read",
@@ -116,6 +116,8 @@ def load_library() -> ctypes.CDLL:
     L.ac_linear_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_void_p]
     L.ac_proto_class_scores.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.ac_proto_class_scores_n.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.ac_blend_dense.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_topk_desc_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
     L.ac_topk_desc.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_blend_topk.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
@@ -510,16 +512,34 @@ class Encoder:
             pass
 
 
-def proto_class_scores(d, idx, row_class=None):
+def proto_class_scores(d, idx, row_class=None, n_classes: Optional[int] = None):
+    """k <= 32: one thread per query; larger k (predict(): k = num_classes): one CTA per query, needs n_classes"""
     L = load_library()
     d = _f32c(d)
     idx = idx.contiguous()
     B, k = d.shape
     cls = torch.empty((B, k), dtype=torch.int32, device=d.device)
     sc = torch.empty((B, k), dtype=torch.float32, device=d.device)
-    check(L.ac_proto_class_scores(d.data_ptr(), idx.data_ptr(), ptr(row_class), B, k, cls.data_ptr(), sc.data_ptr(),
-                                  stream_ptr()), "ac_proto_class_scores")
+    if k <= 32 and n_classes is None:
+        check(L.ac_proto_class_scores(d.data_ptr(), idx.data_ptr(), ptr(row_class), B, k, cls.data_ptr(), sc.data_ptr(),
+                                      stream_ptr()), "ac_proto_class_scores")
+    else:
+        assert n_classes is not None, "k > 32 needs the number of classes"
+        check(L.ac_proto_class_scores_n(d.data_ptr(), idx.data_ptr(), ptr(row_class), B, k, int(n_classes), cls.data_ptr(),
+                                        sc.data_ptr(), stream_ptr()), "ac_proto_class_scores_n")
     return cls, sc
+
+
+def blend_dense(p_cls, p_score, head_probs, w_proto, w_head, kout: int):
+    """predict() blend over all classes (classifier.py:446-480) -> (cls [B,kout] int32, score [B,kout])"""
+    L = load_library()
+    B, kp = p_cls.shape
+    C = w_proto.numel()
+    out_cls = torch.empty((B, kout), dtype=torch.int32, device=p_cls.device)
+    out_sc = torch.empty((B, kout), dtype=torch.float32, device=p_cls.device)
+    check(L.ac_blend_dense(p_cls.data_ptr(), _f32c(p_score).data_ptr(), kp, ptr(head_probs), B, C, _f32c(w_proto).data_ptr(),
+                           ptr(w_head), kout, out_cls.data_ptr(), out_sc.data_ptr(), stream_ptr()), "ac_blend_dense")
+    return out_cls, out_sc
 
 
 def topk_desc(values: torch.Tensor, k: int):

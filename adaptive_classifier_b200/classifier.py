@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import copy
 import logging
+import threading
 from typing import Any, Dict, List, Optional, Set, Tuple, Union
 
 import numpy as np
@@ -87,6 +88,17 @@ class AdaptiveClassifier:
     def strategic_mode(self) -> bool:
         return False
 
+    @property
+    def _device_lock(self):
+        """The encoder handle owns ONE activation workspace and ctypes releases the GIL during every C call: two threads
+        calling predict() / add_examples() on one classifier would interleave kernel launches on the same buffers.  All device
+        work of a classifier is therefore serialised by this re-entrant lock (the reference's PyTorch forward is safe under the
+        same usage; PrototypeMemory has its own lock)."""
+        lk = self.__dict__.get("_dev_lock")
+        if lk is None:
+            lk = self.__dict__.setdefault("_dev_lock", threading.RLock())
+        return lk
+
     # ------------------------------------------------------------------------------------------ E
     def _tokenize(self, texts: List[str]):
         inputs = self.tokenizer(texts, max_length=self.config.max_length, truncation=True, padding=True,
@@ -102,13 +114,14 @@ class AdaptiveClassifier:
         B, S = ids.shape
         per = max(1, self._max_tokens // S)
         outs = []
-        for b0 in range(0, B, per):
-            sl = slice(b0, min(B, b0 + per))
-            i = ids[sl].to(self.device, non_blocking=True).contiguous()
-            m = mask[sl].to(self.device, non_blocking=True).contiguous() if mask is not None else None
-            t = tt[sl].to(self.device, non_blocking=True).contiguous() if tt is not None else None
-            outs.append(self.encoder.forward_cls(i, m, t))
-        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        with self._device_lock, torch.cuda.device(torch.device(self.device)):
+            for b0 in range(0, B, per):
+                sl = slice(b0, min(B, b0 + per))
+                i = ids[sl].to(self.device, non_blocking=True).contiguous()
+                m = mask[sl].to(self.device, non_blocking=True).contiguous() if mask is not None else None
+                t = tt[sl].to(self.device, non_blocking=True).contiguous() if tt is not None else None
+                outs.append(self.encoder.forward_cls(i, m, t))
+            return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def _embed_device(self, texts: List[str]) -> torch.Tensor:
         ids, mask, tt = self._tokenize(texts)
@@ -175,6 +188,10 @@ class AdaptiveClassifier:
         torch.Generator().manual_seed(42) consumed exactly like the reference's DataLoader (dataloader_epoch_permutation), fresh AdamW,
         optional ReduceLROnPlateau(0.5, patience 2), early stopping patience 3."""
         n = X.shape[0]
+        with self._device_lock:
+            return self._run_epochs_locked(X, Y, n, epochs, batch_size, use_scheduler, ewc)
+
+    def _run_epochs_locked(self, X, Y, n, epochs, batch_size, use_scheduler, ewc):
         p, m, v = self._head_blocks()
         gen = torch.Generator().manual_seed(42)
         lr = 0.001
@@ -298,8 +315,9 @@ class AdaptiveClassifier:
     def _head_probs(self, emb: torch.Tensor) -> Optional[torch.Tensor]:
         if self.adaptive_head is None:
             return None
-        self.adaptive_head.eval()
-        return _cabi.head_forward(emb.contiguous(), self.adaptive_head._param_dict(), _cabi.AC_ACT_SOFTMAX)
+        with self._device_lock:
+            self.adaptive_head.eval()
+            return _cabi.head_forward(emb.contiguous(), self.adaptive_head._param_dict(), _cabi.AC_ACT_SOFTMAX)
 
     def _predict_regular(self, text: str, k: int = 5) -> List[Tuple[str, float]]:
         """classifier.py:415-480: prototype scores over ALL classes, head softmax over all classes,
@@ -370,6 +388,10 @@ class AdaptiveClassifier:
     def to(self, device: str) -> "AdaptiveClassifier":
         if not str(device).startswith("cuda"):
             raise _cabi.AdaptiveB200Error("adaptive_classifier_b200 runs on B200 GPUs only")
+        if torch.device(device) != torch.device(self.device) and torch.device(device).index not in (None, torch.device(self.device).index):
+            # the encoder handle and the prototype index live on the device they were built on
+            raise _cabi.AdaptiveB200Error(f"moving a built classifier from {self.device} to {device} is not supported: construct it "
+                                          f"with device={device!r}")
         self.device = device
         if self.adaptive_head is not None:
             self.adaptive_head = self.adaptive_head.to(device)

@@ -47,6 +47,147 @@ __global__ void proto_class_scores_kernel(const float *__restrict__ d, const int
     }
 }
 
+// the same for any k <= 1024 (predict(): k = num_classes, classifier.py:424-425): one CTA per query.  A class keeps its nearest
+// row = the entry of lowest rank among its rows (atomicMin of the rank per class in shared memory); the kept entries stay in
+// rank order (compacted by a block scan), softmax(exp(-d)) over them.  classes: ids < n_classes <= PCS_MAX_CLASSES.
+constexpr int PCS_THREADS = 256;
+constexpr int PCS_MAX_CLASSES = 4096;
+__global__ void __launch_bounds__(PCS_THREADS)
+proto_class_scores_block_kernel(const float *__restrict__ d, const int64_t *__restrict__ idx, const int32_t *__restrict__ row_class,
+                                int k, int n_classes, int32_t *__restrict__ out_cls, float *__restrict__ out_score) {
+    __shared__ int first_rank[PCS_MAX_CLASSES];
+    __shared__ float red[PCS_THREADS];
+    __shared__ int scan[PCS_THREADS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *db = d + static_cast<int64_t>(b) * k;
+    const int64_t *ib = idx + static_cast<int64_t>(b) * k;
+    int32_t *oc = out_cls + static_cast<int64_t>(b) * k;
+    float *os = out_score + static_cast<int64_t>(b) * k;
+    for (int c = tid; c < n_classes; c += PCS_THREADS) first_rank[c] = 0x7fffffff;
+    __syncthreads();
+    constexpr int PER = 4;                                    // k <= 1024 = 256 threads x 4 consecutive ranks
+    int cls[PER];
+    for (int i = 0; i < PER; ++i) {
+        const int j = tid * PER + i;
+        cls[i] = -1;
+        if (j < k) {
+            const int64_t id = ib[j];
+            if (id >= 0) {
+                const int c = row_class ? row_class[id] : static_cast<int>(id);
+                if (c >= 0 && c < n_classes) { cls[i] = c; atomicMin(&first_rank[c], j); }
+            }
+        }
+    }
+    __syncthreads();
+    float e[PER];
+    int keep = 0;
+    float mx = -CUDART_INF_F;
+    for (int i = 0; i < PER; ++i) {
+        const int j = tid * PER + i;
+        const bool kept = cls[i] >= 0 && first_rank[cls[i]] == j;
+        e[i] = kept ? expf(-db[j]) : -CUDART_INF_F;
+        if (!kept) cls[i] = -1;
+        keep += kept ? 1 : 0;
+        mx = fmaxf(mx, e[i]);
+    }
+    red[tid] = mx;
+    scan[tid] = keep;
+    __syncthreads();
+    for (int s2 = PCS_THREADS / 2; s2 > 0; s2 >>= 1) {
+        if (tid < s2) red[tid] = fmaxf(red[tid], red[tid + s2]);
+        __syncthreads();
+    }
+    mx = red[0];
+    __syncthreads();
+    // exclusive scan of the kept counts (rank order) -> output positions
+    for (int off = 1; off < PCS_THREADS; off <<= 1) {
+        const int v = tid >= off ? scan[tid - off] : 0;
+        __syncthreads();
+        scan[tid] += v;
+        __syncthreads();
+    }
+    const int total = scan[PCS_THREADS - 1];
+    int pos = scan[tid] - keep;
+    float sum = 0.f;
+    for (int i = 0; i < PER; ++i)
+        if (cls[i] >= 0) { e[i] = expf(e[i] - mx); sum += e[i]; }
+    red[tid] = sum;
+    __syncthreads();
+    for (int s2 = PCS_THREADS / 2; s2 > 0; s2 >>= 1) {
+        if (tid < s2) red[tid] += red[tid + s2];
+        __syncthreads();
+    }
+    sum = red[0];
+    for (int i = 0; i < PER; ++i)
+        if (cls[i] >= 0) { oc[pos] = cls[i]; os[pos] = e[i] / sum; ++pos; }
+    for (int j = total + tid; j < k; j += PCS_THREADS) { oc[j] = -1; os[j] = 0.f; }
+}
+
+// predict() blend over ALL classes (classifier.py:446-480): combined[c] = proto[c] * wp[c] + head[c] * wh[c] with per-class
+// weights (training_history < 10 -> 0.3 / 0.7, else 0.7 / 0.3), normalised by the sum, top kout by value; ties keep the
+// reference's insertion order (prototype entries by rank, then head-only classes -- by class id here).
+// One CTA per query; the scores of all classes live in shared memory.
+constexpr int BD_THREADS = 256;
+__global__ void __launch_bounds__(BD_THREADS)
+blend_dense_kernel(const int32_t *__restrict__ p_cls, const float *__restrict__ p_score, int kp, const float *__restrict__ probs,
+                   int C, const float *__restrict__ w_proto, const float *__restrict__ w_head, int kout,
+                   int32_t *__restrict__ out_cls, float *__restrict__ out_score) {
+    __shared__ float comb[PCS_MAX_CLASSES];
+    __shared__ int order[PCS_MAX_CLASSES];
+    __shared__ float redv[BD_THREADS];
+    __shared__ int redi[BD_THREADS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < C; c += BD_THREADS) {
+        comb[c] = probs ? probs[static_cast<int64_t>(b) * C + c] * w_head[c] : 0.f;
+        order[c] = kp + c;                                    // head-only classes come after every prototype entry
+    }
+    __syncthreads();
+    for (int j = tid; j < kp; j += BD_THREADS) {
+        const int c = p_cls[static_cast<int64_t>(b) * kp + j];
+        if (c >= 0 && c < C) {                                // a class appears at most once in p_cls
+            comb[c] += p_score[static_cast<int64_t>(b) * kp + j] * w_proto[c];
+            order[c] = j;
+        }
+    }
+    __syncthreads();
+    float tot = 0.f;
+    for (int c = tid; c < C; c += BD_THREADS) tot += comb[c];
+    redv[tid] = tot;
+    __syncthreads();
+    for (int s2 = BD_THREADS / 2; s2 > 0; s2 >>= 1) {
+        if (tid < s2) redv[tid] += redv[tid + s2];
+        __syncthreads();
+    }
+    tot = redv[0];
+    __syncthreads();
+    for (int r = 0; r < kout; ++r) {
+        float bv = -CUDART_INF_F;
+        int bi = -1, bo = 0x7fffffff;
+        for (int c = tid; c < C; c += BD_THREADS) {
+            const float v = comb[c];
+            if (v > bv || (v == bv && order[c] < bo)) { bv = v; bi = c; bo = order[c]; }
+        }
+        redv[tid] = bv; redi[tid] = bi;
+        __syncthreads();
+        for (int s2 = BD_THREADS / 2; s2 > 0; s2 >>= 1) {
+            if (tid < s2) {
+                const float ov = redv[tid + s2];
+                const int oi = redi[tid + s2];
+                const bool better = oi >= 0 && (redi[tid] < 0 || ov > redv[tid] || (ov == redv[tid] && order[oi] < order[redi[tid]]));
+                if (better) { redv[tid] = ov; redi[tid] = oi; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int c = redi[0];
+            out_cls[static_cast<int64_t>(b) * kout + r] = c;
+            out_score[static_cast<int64_t>(b) * kout + r] = c >= 0 ? (tot > 0.f ? redv[0] / tot : redv[0]) : 0.f;
+            if (c >= 0) comb[c] = -CUDART_INF_F;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void negate_kernel(const float *__restrict__ in, int64_t n, float *__restrict__ out) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = -in[i];
@@ -101,10 +242,36 @@ __global__ void blend_topk_kernel(const int32_t *__restrict__ p_cls, const float
 
 using namespace ac;
 
+extern "C" int ac_proto_class_scores_n(const float *d, const int64_t *idx, const int32_t *row_class, int B, int k, int n_classes,
+                                       int32_t *out_cls, float *out_score, ac_stream_t stream) {
+    AC_REQUIRE(d && idx && out_cls && out_score && B >= 0, "ac_proto_class_scores_n: bad arguments");
+    AC_REQUIRE(k >= 1 && k <= 1024 && n_classes >= 1 && n_classes <= PCS_MAX_CLASSES,
+               "ac_proto_class_scores_n: k=%d outside [1,1024] or n_classes=%d outside [1,%d]", k, n_classes, PCS_MAX_CLASSES);
+    if (B == 0) return AC_OK;
+    proto_class_scores_block_kernel<<<B, PCS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(d, idx, row_class, k, n_classes, out_cls,
+                                                                                          out_score);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
+extern "C" int ac_blend_dense(const int32_t *proto_cls, const float *proto_score, int kp, const float *head_probs, int B, int C,
+                              const float *w_proto, const float *w_head, int kout, int32_t *out_cls, float *out_score,
+                              ac_stream_t stream) {
+    AC_REQUIRE(proto_cls && proto_score && w_proto && out_cls && out_score && B >= 0 && kp >= 0, "ac_blend_dense: bad arguments");
+    AC_REQUIRE(C >= 1 && C <= PCS_MAX_CLASSES && kout >= 1 && kout <= C, "ac_blend_dense: C=%d outside [1,%d] or kout=%d", C,
+               PCS_MAX_CLASSES, kout);
+    AC_REQUIRE(!head_probs || w_head, "ac_blend_dense: head weights missing");
+    if (B == 0) return AC_OK;
+    blend_dense_kernel<<<B, BD_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(proto_cls, proto_score, kp, head_probs, C, w_proto, w_head,
+                                                                              kout, out_cls, out_score);
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}
+
 extern "C" int ac_proto_class_scores(const float *d, const int64_t *idx, const int32_t *row_class, int B, int k,
                                      int32_t *out_cls, float *out_score, ac_stream_t stream) {
     AC_REQUIRE(d && idx && out_cls && out_score && B >= 0, "ac_proto_class_scores: bad arguments");
-    AC_REQUIRE(k >= 1 && k <= BLEND_MAX_K, "ac_proto_class_scores: k=%d outside [1,%d]", k, BLEND_MAX_K);
+    AC_REQUIRE(k >= 1 && k <= BLEND_MAX_K, "ac_proto_class_scores: k=%d outside [1,%d] (larger k: ac_proto_class_scores_n)", k, BLEND_MAX_K);
     if (B == 0) return AC_OK;
     proto_class_scores_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d, idx, row_class, B, k,
                                                                                               out_cls, out_score);

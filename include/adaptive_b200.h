@@ -233,6 +233,16 @@ int ac_linear_tc(const void *X, const void *W, const float *bias, const float *r
 int ac_proto_class_scores(const float *d, const int64_t *idx, const int32_t *row_class, int B, int k,
                           int32_t *out_cls, float *out_score, ac_stream_t stream);
 
+/* the same for k up to 1024 (predict(): k = num_classes, classifier.py:424-425); class ids < n_classes <= 4096 */
+int ac_proto_class_scores_n(const float *d, const int64_t *idx, const int32_t *row_class, int B, int k, int n_classes,
+                            int32_t *out_cls, float *out_score, ac_stream_t stream);
+
+/* predict() blend over ALL classes (classifier.py:446-480): combined[c] = proto_score[c] * w_proto[c] + head_probs[b,c] *
+ * w_head[c] (per-class weights from training_history: < 10 examples -> 0.3 / 0.7, else 0.7 / 0.3), normalised by the sum,
+ * top kout.  proto_cls / proto_score [B, kp] as written by ac_proto_class_scores(_n); head_probs [B, C] nullable. */
+int ac_blend_dense(const int32_t *proto_cls, const float *proto_score, int kp, const float *head_probs, int B, int C,
+                   const float *w_proto, const float *w_head, int kout, int32_t *out_cls, float *out_score, ac_stream_t stream);
+
 /* classifier.py:1347-1350 (torch.topk of the head probabilities): out_neg_vals[B,k] holds the k largest values
  * NEGATED (ascending), out_idx[B,k] their column ids; ties -> lower id. */
 int ac_topk_desc_workspace_bytes(int B, int C, int k, size_t *bytes);

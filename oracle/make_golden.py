@@ -416,6 +416,7 @@ def gen_training():
     out["h4_fisher_batches"] = np.array([i for b in fisher_loop[0]["epochs"][0] for i in b], dtype=np.int64)
     out["h4_fisher_batch_sizes"] = np.array([len(b) for b in fisher_loop[0]["epochs"][0]], dtype=np.int64)
     out["h4_fisher_sampled"] = torch.cat([m.reshape(-1) for m in fisher_loop[0]["multinomial"]]).numpy()
+    out["h4_new_texts"] = np.array(texts["cooking"])
     out["h4_memory_order"] = np.array(list(clf.memory.examples.keys()))
     out["h4_label_names"] = np.array([clf.id_to_label[i] for i in range(len(clf.id_to_label))])
     emb_all = torch.stack(clf._get_embeddings(t1 + texts["cooking"])).numpy()
