@@ -28,7 +28,7 @@ AC_PREC_TF32, AC_PREC_F16 = 0, 1
 EXPORTS = [
     "ac_version", "ac_last_error", "ac_device_check",
     "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
-    "ac_segment_mean",
+    "ac_segment_mean", "ac_memory_append_prune",
     "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
     "ac_proto_class_scores", "ac_proto_class_scores_n", "ac_blend_dense", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
@@ -99,6 +99,8 @@ def load_library() -> ctypes.CDLL:
     L.ac_topk_merge.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.ac_proto_scores.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.ac_segment_mean.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.ac_memory_append_prune.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_head_forward.argtypes = [c_void_p, c_int, POINTER(HeadParams), c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     L.ac_head_train_workspace_bytes.argtypes = [c_int, c_int, POINTER(HeadParams), POINTER(c_size_t)]
     L.ac_head_train_step.argtypes = [c_void_p, c_void_p, c_int, POINTER(HeadParams), POINTER(HeadParams),
@@ -249,6 +251,21 @@ def segment_mean(X: torch.Tensor, cls: torch.Tensor, C: int):
     check(L.ac_segment_mean(X.data_ptr(), cls.data_ptr(), n, D, C, mean.data_ptr(), cnt.data_ptr(), stream_ptr()),
           "ac_segment_mean")
     return mean, cnt
+
+
+def memory_append_prune(rows, order, count, new_rows, new_index, cls_start, touched):
+    """rows [n_slots, cap+1, D], order [n_slots, cap+1] int32, count [n_slots] int32 (updated in place) ->
+    (src [n_touched, cap] int32, proto [n_touched, D] fp32): see ac_memory_append_prune"""
+    L = load_library()
+    n_slots, cap1, D = rows.shape
+    nt = touched.numel()
+    src = torch.empty((nt, cap1 - 1), dtype=torch.int32, device=rows.device)
+    proto = torch.empty((nt, D), dtype=torch.float32, device=rows.device)
+    ws = _workspace(nt * D * 8 + 256, rows.device)
+    check(L.ac_memory_append_prune(rows.data_ptr(), order.data_ptr(), count.data_ptr(), cap1 - 1, D, _f32c(new_rows).data_ptr(),
+                                   new_index.data_ptr(), cls_start.data_ptr(), touched.data_ptr(), nt, src.data_ptr(), proto.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), stream_ptr()), "ac_memory_append_prune")
+    return src, proto
 
 
 def head_params_struct(p: dict) -> HeadParams:

@@ -147,9 +147,10 @@ class AdaptiveClassifier:
             self.label_to_id[label] = idx
             self.id_to_label[idx] = label
 
-        embeddings = self._get_embeddings(texts)
+        emb_dev = self._embed_device(texts)                      # unit CLS rows stay on the device for the memory update
+        embeddings = [e for e in emb_dev.cpu()]                  # the reference's contract: CPU tensors on the Example objects
         examples = [Example(t, l, e) for t, e, l in zip(texts, embeddings, labels)]
-        self.memory.add_examples_batch(examples, labels)
+        self.memory.add_examples_batch(examples, labels, device_rows=emb_dev)
         for label in labels:
             self.training_history[label] = self.training_history.get(label, 0) + 1
 
@@ -235,13 +236,18 @@ class AdaptiveClassifier:
         self.adaptive_head.eval()
 
     def _training_matrix(self):
-        """classifier.py:1438-1450: sorted by label then text; embeddings re-normalised."""
-        all_embeddings, all_labels = [], []
+        """classifier.py:1438-1450: all stored examples sorted by label then text; embeddings re-normalised.  The rows are
+        gathered from the memory's device-resident class stores (no re-upload of the whole memory per call)."""
+        parts, all_labels = [], []
         for label in sorted(self.memory.examples.keys()):
-            for example in sorted(self.memory.examples[label], key=lambda x: x.text):
-                all_embeddings.append(example.embedding)
-                all_labels.append(self.label_to_id[example.label])
-        X = torch.stack(all_embeddings).to(self.device, dtype=torch.float32)
+            exs = self.memory.examples[label]
+            if not exs:
+                continue
+            order = sorted(range(len(exs)), key=lambda i: exs[i].text)            # Python's stable sort, as the reference
+            rows = self.memory.class_rows_device(label)
+            parts.append(rows.index_select(0, torch.tensor(order, dtype=torch.int64, device=rows.device)))
+            all_labels += [self.label_to_id[exs[i].label] for i in order]
+        X = (parts[0] if len(parts) == 1 else torch.cat(parts, 0)).to(self.device, dtype=torch.float32)
         X = F.normalize(X, p=2, dim=1)
         Y = torch.tensor(all_labels, dtype=torch.long, device=self.device)
         return X, Y

@@ -194,7 +194,7 @@ static int check_params(const ac_head_params *p, const char *who) {
 // launch plan of head_train_kernel (head_train.cuh): grid size, ownership slots, global scratch
 // ------------------------------------------------------------------------------------------------
 struct TrainPlan {
-    int G;
+    int G, nst;
     int slots[3];
     size_t off_h0d, off_h1d, off_z, off_dz, off_da1, off_rowloss, off_part, off_pen, off_bar, off_stats, total;
     size_t smem_bytes;
@@ -225,7 +225,12 @@ static int plan_training(int batch, const ac_head_params *p, int n_steps, TrainP
         a.L[l].rows = rows[l];
         a.L[l].K = K[l];
     }
-    pl.smem_bytes = static_cast<size_t>(ht::ht_smem_layout(a).total) * sizeof(float);
+    // as many ring stages (4 down to 2) as the parameter / gradient rows leave room for
+    for (a.nst = 4; a.nst >= 2; --a.nst) {
+        pl.smem_bytes = static_cast<size_t>(ht::ht_smem_layout(a).total) * sizeof(float);
+        if (pl.smem_bytes <= 220 * 1024) break;
+    }
+    pl.nst = a.nst < 2 ? 2 : a.nst;
     if (pl.smem_bytes > 220 * 1024) {
         set_error("%s: head %d -> %d -> %d -> %d needs %zu bytes of shared memory per CTA (limit 220 KB)", who, p->D, p->H0, p->H1, p->C,
                   pl.smem_bytes);
@@ -277,6 +282,7 @@ static int launch_training(const TrainCall &c, void *workspace, size_t workspace
         ht::Layer &Lr = a.L[l];
         Lr.W = Wp[l]; Lr.b = bp[l]; Lr.rows = rows[l]; Lr.K = K[l]; Lr.ewc_rows = rows[l];
         a.slots[l] = pl.slots[l];
+        a.nst = pl.nst;
 #define AC_PICK(hp, l) ((l) == 0 ? (hp)->W0 : (l) == 1 ? (hp)->W1 : (hp)->W2)
 #define AC_PICKB(hp, l) ((l) == 0 ? (hp)->b0 : (l) == 1 ? (hp)->b1 : (hp)->b2)
         if (c.m && c.v) { Lr.mW = AC_PICK(c.m, l); Lr.mb = AC_PICKB(c.m, l); Lr.vW = AC_PICK(c.v, l); Lr.vb = AC_PICKB(c.v, l); }

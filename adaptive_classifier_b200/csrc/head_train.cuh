@@ -34,6 +34,9 @@
 // thread a fiber, grid barriers real) and checks it against a straightforward restatement before any GPU time is spent.
 #pragma once
 #include <stdint.h>
+#if !defined(AC_CPU_SHIM)
+#include <cuda_pipeline.h>
+#endif
 
 namespace ac {
 namespace ht {
@@ -75,6 +78,7 @@ struct Args {
     float *loss_accum;            // [1] += loss + penalty per step, nullable
     unsigned *bar;                // [2] grid barrier state (count, generation), zero-initialised
     int slots[3];                 // ownership blocks per CTA of each layer = ceil(ceil(rows / 8) / G)
+    int nst;                      // stages of the streamed-operand ring (2..4)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -85,6 +89,24 @@ struct Args {
 #else
 #define HT_LDCG(p) (*(p))
 #endif
+
+// asynchronous global -> shared copies (cp.async through the pipeline intrinsics); `valid` = false zero-fills the destination
+#if !defined(AC_CPU_SHIM)
+__device__ __forceinline__ void ht_async16(float *dst, const float *src, bool valid) { __pipeline_memcpy_async(dst, src, 16, valid ? 0 : 16); }
+__device__ __forceinline__ void ht_async4(float *dst, const float *src, bool valid) { __pipeline_memcpy_async(dst, src, 4, valid ? 0 : 4); }
+__device__ __forceinline__ void ht_async_commit() { __pipeline_commit(); }
+template <int N> __device__ __forceinline__ void ht_async_wait() { __pipeline_wait_prior(N); }
+#else
+static inline void ht_async16(float *dst, const float *src, bool valid) { for (int i = 0; i < 4; ++i) dst[i] = valid ? src[i] : 0.f; }
+static inline void ht_async4(float *dst, const float *src, bool valid) { dst[0] = valid ? src[0] : 0.f; }
+static inline void ht_async_commit() {}
+template <int N> static inline void ht_async_wait() {}
+#endif
+__device__ __forceinline__ void ht_async_wait_n(int n) {       // n = stages - 2 in {0, 1, 2}
+    if (n <= 0) ht_async_wait<0>();
+    else if (n == 1) ht_async_wait<1>();
+    else ht_async_wait<2>();
+}
 
 __device__ __forceinline__ uint32_t ht_mix32(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -141,86 +163,82 @@ __device__ __forceinline__ float ht_block_sum(float v, float *red) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// streamed operand: chunk [rows x HT_KC] of a row-major [*, K] matrix (rows direct or through ridx) -> registers -> As
+// streamed operand: chunk [rows x HT_KC] of a row-major [*, K] matrix (rows direct or through ridx) -> a stage of the shared
+// memory ring, by asynchronous copies.  `nst` stages are in flight (2..4, whatever the parameter rows leave room for): at
+// B = 32 the FMAs of a chunk take ~0.3 us while an L2 round trip takes ~1 us, so the ring depth, not the arithmetic, sets the
+// time of a phase.
 // ---------------------------------------------------------------------------------------------------------------------
-struct ChunkRegs { float4 v[HT_MAXB * (HT_KC / 4) / HT_THREADS]; };   // 8 float4 per thread at 64 rows
-
-__device__ __forceinline__ void ht_load_chunk(ChunkRegs &r, const float *src, int64_t ld, const int64_t *ridx, int rows, int k0,
-                                              int K) {
+__device__ __forceinline__ void ht_issue_chunk(float *stage, const float *src, int64_t ld, const int64_t *ridx, int rows, int k0, int K) {
     const bool vec = (K & 3) == 0 && (ld & 3) == 0;
-#pragma unroll
-    for (int i = 0; i < HT_MAXB * (HT_KC / 4) / HT_THREADS; ++i) {
-        const int e = static_cast<int>(threadIdx.x) + i * HT_THREADS;
+    for (int e = threadIdx.x; e < rows * (HT_KC / 4); e += HT_THREADS) {
         const int row = e / (HT_KC / 4), c4 = e % (HT_KC / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows) {
-            const int k = k0 + 4 * c4;
-            const float *p = src + (ridx ? ridx[row] : static_cast<int64_t>(row)) * ld + k;
-            if (vec) {
-                if (k < K) v = HT_LDCG(reinterpret_cast<const float4 *>(p));
-            } else {
-                if (k + 0 < K) v.x = HT_LDCG(p + 0);
-                if (k + 1 < K) v.y = HT_LDCG(p + 1);
-                if (k + 2 < K) v.z = HT_LDCG(p + 2);
-                if (k + 3 < K) v.w = HT_LDCG(p + 3);
-            }
+        const int k = k0 + 4 * c4;
+        const float *p = src + (ridx ? ridx[row] : static_cast<int64_t>(row)) * ld + k;
+        float *d = stage + row * HT_AS + 4 * c4;
+        if (vec) {
+            ht_async16(d, k < K ? p : src, k < K);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ht_async4(d + i, k + i < K ? p + i : src, k + i < K);
         }
-        r.v[i] = v;
     }
 }
-__device__ __forceinline__ void ht_store_chunk(const ChunkRegs &r, float *As, int rows) {
-#pragma unroll
-    for (int i = 0; i < HT_MAXB * (HT_KC / 4) / HT_THREADS; ++i) {
-        const int e = static_cast<int>(threadIdx.x) + i * HT_THREADS;
-        const int row = e / (HT_KC / 4), c4 = e % (HT_KC / 4);
-        if (row < rows) *reinterpret_cast<float4 *>(As + row * HT_AS + 4 * c4) = r.v[i];
+// weight chunk of an input-gradient product: Wt[jj][kk] = gW[(k0 + kk) * gld + gcol0 + jj] (zero outside the matrix)
+__device__ __forceinline__ void ht_issue_wt(float *wt_stage, const float *gW, int64_t gld, int gcol0, int gcols, int k0, int K) {
+    for (int e = threadIdx.x; e < HT_KC * HT_RB; e += HT_THREADS) {
+        const int kk = e / HT_RB, jj = e % HT_RB;
+        const bool ok = k0 + kk < K && jj < gcols;
+        ht_async4(wt_stage + jj * HT_KC + kk, ok ? gW + static_cast<int64_t>(k0 + kk) * gld + gcol0 + jj : gW, ok);
     }
 }
 
 // Y[b, j] = sum_k A[b, k] * Wt[j][k]  for the 8 rows j of one ownership block, A streamed in chunks.
-//   A: [rows x K] global (ld, optional row index list);  weights of chunk c: wt(c) -> pointer to [8][wld] floats in shared
-//   memory whose column 0 is column k0 of the product (resident parameter rows: base + k0, wld = K; gathered: Wt, wld = HT_KC)
-//   gather != nullptr: the weight chunk is first gathered from global W[(k0 + kk) * gld + gcol0 + jj] (input-gradient products)
+//   A: [rows x K] global (ld, optional row index list)
+//   w_resident != nullptr: the weights are the block's resident parameter rows [8][K] in shared memory (forward products)
+//   otherwise the weight chunk is gathered from global W[(k0 + kk) * gld + gcol0 + jj] (input-gradient products)
 // Result: out[b * 8 + j] in shared memory (valid for b < rows), summed over the 8 column parts in a fixed order.
-__device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, float *Wt, const float *A, int64_t ld,
+__device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, float *Wt, int nst, const float *A, int64_t ld,
                                             const int64_t *ridx, int rows, int K, const float *w_resident /* [8][K] or null */,
                                             const float *gW, int64_t gld, int gcol0, int gcols /* valid columns <= 8 */) {
     const int lane = threadIdx.x & 31, kpart = threadIdx.x >> 5;
     const int nb = (rows + 31) >> 5;
+    const int stage_floats = rows * HT_AS;
     float acc[2][HT_RB];
 #pragma unroll
     for (int bi = 0; bi < 2; ++bi)
 #pragma unroll
         for (int j = 0; j < HT_RB; ++j) acc[bi][j] = 0.f;
     const int nchunks = (K + HT_KC - 1) / HT_KC;
-    ChunkRegs regs;
-    ht_load_chunk(regs, A, ld, ridx, rows, 0, K);
+    for (int p = 0; p < nst - 1; ++p) {
+        if (p < nchunks) {
+            ht_issue_chunk(As + p * stage_floats, A, ld, ridx, rows, p * HT_KC, K);
+            if (!w_resident) ht_issue_wt(Wt + p * HT_RB * HT_KC, gW, gld, gcol0, gcols, p * HT_KC, K);
+        }
+        ht_async_commit();
+    }
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = c * HT_KC;
-        ht_store_chunk(regs, As, rows);
-        if (!w_resident) {
-            // gather the weight chunk: Wt[jj][kk] = gW[(k0 + kk) * gld + gcol0 + jj]
-            for (int e = threadIdx.x; e < HT_KC * HT_RB; e += HT_THREADS) {
-                const int kk = e / HT_RB, jj = e % HT_RB;
-                float w = 0.f;
-                if (k0 + kk < K && jj < gcols) w = HT_LDCG(gW + static_cast<int64_t>(k0 + kk) * gld + gcol0 + jj);
-                Wt[jj * HT_KC + kk] = w;
-            }
+        ht_async_wait_n(nst - 2);                       // chunk c has landed (for this thread's copies) ...
+        __syncthreads();                                // ... and for everybody's; the stage read in iteration c - 1 is free again
+        const int nx = c + nst - 1;
+        if (nx < nchunks) {
+            ht_issue_chunk(As + (nx % nst) * stage_floats, A, ld, ridx, rows, nx * HT_KC, K);
+            if (!w_resident) ht_issue_wt(Wt + (nx % nst) * HT_RB * HT_KC, gW, gld, gcol0, gcols, nx * HT_KC, K);
         }
-        __syncthreads();
-        if (c + 1 < nchunks) ht_load_chunk(regs, A, ld, ridx, rows, k0 + HT_KC, K);     // in flight during the FMAs below
-        const float *wbase = w_resident ? (w_resident + k0) : Wt;
+        ht_async_commit();
+        const float *Ac = As + (c % nst) * stage_floats;
+        const float *wbase = w_resident ? (w_resident + k0) : (Wt + (c % nst) * HT_RB * HT_KC);
         const int wld = w_resident ? K : HT_KC;
         const int kcols = (K - k0 < HT_KC) ? (K - k0) : HT_KC;                           // resident rows: stay inside the row
 #pragma unroll
         for (int bi = 0; bi < 2; ++bi) {
             if (bi < nb) {
                 const int b = lane + 32 * bi;
-                const float *a = As + b * HT_AS + kpart * 16;
+                const float *a = Ac + b * HT_AS + kpart * 16;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int kk = kpart * 16 + 4 * q4;
-                    if (kk < kcols) {                                                   // K % 4 == 0 on the resident path
+                    if (kk < kcols) {
                         const float4 av = *reinterpret_cast<const float4 *>(a + 4 * q4);
 #pragma unroll
                         for (int j = 0; j < HT_RB; ++j) {
@@ -237,7 +255,6 @@ __device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, f
                 }
             }
         }
-        __syncthreads();
     }
     // combine the 8 column parts in order
 #pragma unroll
@@ -260,20 +277,26 @@ __device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, f
 
 // g[j][k] = sum_b dA[b][j] * A[b][k]  for the 8 rows j of one ownership block (weight gradient), A streamed in chunks;
 // g: shared memory [8][K]; dA: shared memory [rows][8]; batch rows are added in index order.
-__device__ __forceinline__ void ht_outer_acc(float *g, float *As, const float *dA, const float *A, int64_t ld, const int64_t *ridx,
+__device__ __forceinline__ void ht_outer_acc(float *g, float *As, int nst, const float *dA, const float *A, int64_t ld, const int64_t *ridx,
                                              int rows, int K) {
     const int kk = threadIdx.x % HT_KC, jh = threadIdx.x / HT_KC;      // 2 x 128 threads: columns x row halves
     const int nchunks = (K + HT_KC - 1) / HT_KC;
-    ChunkRegs regs;
-    ht_load_chunk(regs, A, ld, ridx, rows, 0, K);
+    const int stage_floats = rows * HT_AS;
+    for (int p = 0; p < nst - 1; ++p) {
+        if (p < nchunks) ht_issue_chunk(As + p * stage_floats, A, ld, ridx, rows, p * HT_KC, K);
+        ht_async_commit();
+    }
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = c * HT_KC;
-        ht_store_chunk(regs, As, rows);
+        ht_async_wait_n(nst - 2);
         __syncthreads();
-        if (c + 1 < nchunks) ht_load_chunk(regs, A, ld, ridx, rows, k0 + HT_KC, K);
+        const int nx = c + nst - 1;
+        if (nx < nchunks) ht_issue_chunk(As + (nx % nst) * stage_floats, A, ld, ridx, rows, nx * HT_KC, K);
+        ht_async_commit();
+        const float *Ac = As + (c % nst) * stage_floats;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int b = 0; b < rows; ++b) {
-            const float a = As[b * HT_AS + kk];
+            const float a = Ac[b * HT_AS + kk];
             const float4 d = *reinterpret_cast<const float4 *>(dA + b * HT_RB + 4 * jh);
             a0 = fmaf(d.x, a, a0);
             a1 = fmaf(d.y, a, a1);
@@ -286,8 +309,8 @@ __device__ __forceinline__ void ht_outer_acc(float *g, float *As, const float *d
             g[(4 * jh + 2) * K + k0 + kk] = a2;
             g[(4 * jh + 3) * K + k0 + kk] = a3;
         }
-        __syncthreads();
     }
+    __syncthreads();
 }
 
 // shared-memory carve-up (floats), identical on host and device
@@ -306,8 +329,8 @@ __host__ __device__ inline Smem ht_smem_layout(const Args &a) {
     s.f1 = take(a.slots[1] * a.batch * HT_RB);
     s.dA = take(a.batch * HT_RB);
     s.out = take(a.batch * HT_RB);
-    s.As = take(a.batch * HT_AS);
-    s.Wt = take(HT_RB * HT_KC);
+    s.As = take(a.nst * a.batch * HT_AS);
+    s.Wt = take(a.nst * HT_RB * HT_KC);
     s.red = take(HT_KPARTS * HT_MAXB * HT_RB);
     s.rsum = take(HT_THREADS);
     s.ridx = take(2 * HT_MAXB);
@@ -372,7 +395,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
             for (int s = 0; s < a.slots[l]; ++s) {
                 const int q = cta + s * G;
                 if (q >= nblk) break;
-                ht_rows_dot(out, As, red, Wt, A, L.K, l == 0 ? ridx : nullptr, Bt, L.K, ht_smem + sm.th[l] + s * HT_RB * L.K, nullptr, 0, 0, 0);
+                ht_rows_dot(out, As, red, Wt, a.nst, A, L.K, l == 0 ? ridx : nullptr, Bt, L.K, ht_smem + sm.th[l] + s * HT_RB * L.K, nullptr, 0, 0, 0);
                 for (int e = tid; e < Bt * HT_RB; e += HT_THREADS) {
                     const int b = e / HT_RB, j = e % HT_RB;
                     const int r = q * HT_RB + j;
@@ -446,13 +469,13 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                     for (int b = 0; b < Bt; ++b) sb += dA[b * HT_RB + tid];
                     ht_smem[sm.gb[2] + s * HT_RB + tid] = sb;
                 }
-                ht_outer_acc(ht_smem + sm.g[2] + s * HT_RB * L2.K, As, dA, a.h1d, H1, nullptr, Bt, H1);
+                ht_outer_acc(ht_smem + sm.g[2] + s * HT_RB * L2.K, As, a.nst, dA, a.h1d, H1, nullptr, Bt, H1);
             }
             for (int s = 0; s < a.slots[1]; ++s) {
                 const int q = cta + s * G;
                 if (q >= nblk1) break;
                 const int cols = (H1 - q * HT_RB < HT_RB) ? (H1 - q * HT_RB) : HT_RB;
-                ht_rows_dot(out, As, red, Wt, a.dz, C, nullptr, Bt, C, nullptr, L2.W, H1, q * HT_RB, cols);
+                ht_rows_dot(out, As, red, Wt, a.nst, a.dz, C, nullptr, Bt, C, nullptr, L2.W, H1, q * HT_RB, cols);
                 float *f1 = ht_smem + sm.f1 + s * a.batch * HT_RB;
                 for (int e = tid; e < Bt * HT_RB; e += HT_THREADS) {
                     const int b = e / HT_RB, j = e % HT_RB, r = q * HT_RB + j;
@@ -479,13 +502,13 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                     for (int b = 0; b < Bt; ++b) sb += d1[b * HT_RB + tid];
                     ht_smem[sm.gb[1] + s * HT_RB + tid] = sb;
                 }
-                ht_outer_acc(ht_smem + sm.g[1] + s * HT_RB * L1.K, As, d1, a.h0d, H0, nullptr, Bt, H0);
+                ht_outer_acc(ht_smem + sm.g[1] + s * HT_RB * L1.K, As, a.nst, d1, a.h0d, H0, nullptr, Bt, H0);
             }
             for (int s = 0; s < a.slots[0]; ++s) {
                 const int q = cta + s * G;
                 if (q >= nblk0) break;
                 const int cols = (H0 - q * HT_RB < HT_RB) ? (H0 - q * HT_RB) : HT_RB;
-                ht_rows_dot(out, As, red, Wt, a.da1, H1, nullptr, Bt, H1, nullptr, L1.W, H0, q * HT_RB, cols);
+                ht_rows_dot(out, As, red, Wt, a.nst, a.da1, H1, nullptr, Bt, H1, nullptr, L1.W, H0, q * HT_RB, cols);
                 float *f0 = ht_smem + sm.f0 + s * a.batch * HT_RB;
                 for (int e = tid; e < Bt * HT_RB; e += HT_THREADS) {
                     const int j = e % HT_RB, r = q * HT_RB + j;
@@ -497,7 +520,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                     for (int b = 0; b < Bt; ++b) sb += f0[b * HT_RB + tid];
                     ht_smem[sm.gb[0] + s * HT_RB + tid] = sb;
                 }
-                ht_outer_acc(ht_smem + sm.g[0] + s * HT_RB * L0.K, As, f0, a.X, D, ridx, Bt, D);
+                ht_outer_acc(ht_smem + sm.g[0] + s * HT_RB * L0.K, As, a.nst, f0, a.X, D, ridx, Bt, D);
             }
         }
         __syncthreads();

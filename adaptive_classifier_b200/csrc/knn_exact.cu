@@ -484,3 +484,138 @@ extern "C" int ac_segment_mean(const float *X, const int32_t *cls, int64_t n, in
     AC_LAUNCH_CHECK();
     return AC_OK;
 }
+
+// ================================================================================================
+// Device-resident prototype memory maintenance.
+//
+// Replaces, for a whole add_examples() call at once, the per-example sequence of
+//   /root/reference/src/adaptive_classifier/memory.py:60-72   append; if over max_examples_per_class -> _prune_examples
+//   memory.py:196-217  _prune_examples: mean of the cap + 1 stored embeddings, L2 distance of each to it, argsort ascending,
+//                      keep the first `cap` IN SORTED ORDER (the list is reordered by distance, the farthest is dropped)
+//   memory.py:138-153  _update_prototype: prototype = mean of the retained embeddings
+// The reference restacks all embeddings of the class on every add (O(n^2) over a continual loop, a Python .item() loop per
+// prune).  Here every class keeps its rows in HBM ([cap + 1, D] slots + a logical order), one CTA per touched class walks ITS new
+// examples sequentially (the prune of example j sees the list example j-1 left, as in the reference), classes run in parallel:
+//   sum S (fp64, recomputed from the stored rows once per call, then updated incrementally) -> mean -> one pass of distances over
+//   the cap + 1 rows -> bitonic sort of (distance, logical position) in shared memory -> new logical order, farthest row's slot freed.
+// Output per class: where every retained position came from (old position or new example), so the host mirrors the same order on
+// its Example lists, and the prototype (mean of the retained rows).
+// ================================================================================================
+namespace ac {
+constexpr int MEM_THREADS = 1024;
+constexpr int MEM_MAX_CAP = 2047;          // cap + 1 <= 2048 sort slots
+
+__global__ void __launch_bounds__(MEM_THREADS)
+memory_append_prune_kernel(float *__restrict__ rows, int32_t *__restrict__ order, int32_t *__restrict__ count, int cap, int D,
+                           const float *__restrict__ new_rows, const int32_t *__restrict__ new_index, const int32_t *__restrict__ cls_start,
+                           const int32_t *__restrict__ touched, int32_t *__restrict__ src_out, float *__restrict__ proto_out,
+                           double *__restrict__ sum_ws /* [n_touched, D] */) {
+    extern __shared__ __align__(16) uint8_t mem_smem[];
+    float *skey = reinterpret_cast<float *>(mem_smem);                       // [2048] distances
+    int32_t *spos = reinterpret_cast<int32_t *>(mem_smem + 2048 * 4);        // [2048] logical positions
+    int32_t *ssrc = reinterpret_cast<int32_t *>(mem_smem + 2048 * 8);        // [2048] source id of every logical position
+    int32_t *sord = reinterpret_cast<int32_t *>(mem_smem + 2048 * 12);       // [2048] logical position -> physical slot
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = touched[t];
+    float *R = rows + static_cast<int64_t>(c) * (cap + 1) * D;
+    int32_t *ord = order + static_cast<int64_t>(c) * (cap + 1);
+    double *S = sum_ws + static_cast<int64_t>(t) * D;
+    int n = count[c];
+    const int n_old = n;
+    // invariant (kept by the host when it builds a store and by every step below): order[0..cap] is a permutation of the
+    // physical slots 0..cap; positions [0, n) are the stored rows in list order, positions [n, cap] the free slots
+    for (int i = tid; i <= cap; i += MEM_THREADS) { sord[i] = ord[i]; ssrc[i] = i < n ? i : -1; }
+    __syncthreads();
+    // fresh fp64 column sums of the stored rows (one pass; coalesced along D)
+    for (int d = tid; d < D; d += MEM_THREADS) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += static_cast<double>(R[static_cast<int64_t>(sord[i]) * D + d]);
+        S[d] = s;
+    }
+    __syncthreads();
+    const int j0 = cls_start[t], j1 = cls_start[t + 1];
+    for (int j = j0; j < j1; ++j) {
+        // ---- append the new example into the first free physical slot
+        if (tid == 0) ssrc[n] = n_old + (j - j0);
+        const int slot = sord[n];
+        const float *nr = new_rows + static_cast<int64_t>(new_index[j]) * D;
+        for (int d = tid; d < D; d += MEM_THREADS) {
+            const float v = nr[d];
+            R[static_cast<int64_t>(slot) * D + d] = v;
+            S[d] += static_cast<double>(v);
+        }
+        ++n;
+        __syncthreads();
+        if (n <= cap) continue;
+        // ---- over the cap: distance of every stored row to the mean of all cap + 1, one warp per row
+        const double inv = 1.0 / static_cast<double>(n);
+        for (int i = warp; i < n; i += MEM_THREADS / 32) {
+            const float *r = R + static_cast<int64_t>(sord[i]) * D;
+            float acc = 0.f;
+            for (int d = lane; d < D; d += 32) {
+                const float m = static_cast<float>(S[d] * inv);
+                const float df = r[d] - m;
+                acc = fmaf(df, df, acc);
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) { skey[i] = sqrtf(acc); spos[i] = i; }
+        }
+        for (int i = n + tid; i < 2048; i += MEM_THREADS) { skey[i] = CUDART_INF_F; spos[i] = 0x7fffffff; }
+        __syncthreads();
+        // ---- ascending bitonic sort by (distance, logical position): ties keep list order
+        for (int size = 2; size <= 2048; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const int lo = 2 * tid - (tid & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = ((lo & size) == 0);
+                const float kl = skey[lo], kh = skey[hi];
+                const int pl = spos[lo], ph = spos[hi];
+                const bool less_hl = (kh < kl) || (kh == kl && ph < pl);
+                const bool less_lh = (kl < kh) || (kl == kh && pl < ph);
+                if (asc ? less_hl : less_lh) { skey[lo] = kh; skey[hi] = kl; spos[lo] = ph; spos[hi] = pl; }
+                __syncthreads();
+            }
+        }
+        // ---- new logical order = sorted order; the farthest row (sorted position cap) is evicted and its slot freed
+        int new_slot = -1, new_src = -1;
+        if (tid <= cap) { new_slot = sord[spos[tid]]; new_src = ssrc[spos[tid]]; }
+        __syncthreads();
+        if (tid <= cap) { sord[tid] = new_slot; ssrc[tid] = tid < cap ? new_src : -1; }
+        __syncthreads();
+        {
+            const float *ev = R + static_cast<int64_t>(sord[cap]) * D;        // sord[cap] now holds the evicted row's slot (free)
+            for (int d = tid; d < D; d += MEM_THREADS) S[d] -= static_cast<double>(ev[d]);
+        }
+        n = cap;
+        __syncthreads();
+    }
+    // ---- results: order, count, provenance of the retained positions, prototype = mean of the retained rows
+    for (int i = tid; i <= cap; i += MEM_THREADS) ord[i] = sord[i];
+    for (int i = tid; i < cap; i += MEM_THREADS) src_out[static_cast<int64_t>(t) * cap + i] = i < n ? ssrc[i] : -1;
+    // the incremental fp64 sums carry ~1e-16 relative error per update; the prototype is taken from a fresh pass all the same
+    for (int d = tid; d < D; d += MEM_THREADS) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += static_cast<double>(R[static_cast<int64_t>(sord[i]) * D + d]);
+        proto_out[static_cast<int64_t>(t) * D + d] = static_cast<float>(s / static_cast<double>(n > 0 ? n : 1));
+    }
+    if (tid == 0) count[c] = n;
+}
+}  // namespace ac
+
+extern "C" int ac_memory_append_prune(float *rows, int32_t *order, int32_t *count, int cap, int D, const float *new_rows,
+                                      const int32_t *new_index, const int32_t *cls_start, const int32_t *touched, int n_touched,
+                                      int32_t *src_out, float *proto_out, void *workspace, size_t workspace_bytes, ac_stream_t stream) {
+    AC_REQUIRE(rows && order && count && new_rows && new_index && cls_start && touched && src_out && proto_out && workspace,
+               "ac_memory_append_prune: null argument");
+    AC_REQUIRE(cap >= 1 && cap <= MEM_MAX_CAP && D >= 1 && n_touched >= 0, "ac_memory_append_prune: cap=%d outside [1,%d] or bad sizes", cap,
+               MEM_MAX_CAP);
+    if (n_touched == 0) return AC_OK;
+    const size_t need = static_cast<size_t>(n_touched) * D * sizeof(double);
+    if (need > workspace_bytes) { set_error("ac_memory_append_prune: workspace needs %zu bytes", need); return AC_E_WORKSPACE; }
+    const int smem = 2048 * 16;
+    AC_CUDA(cudaFuncSetAttribute(memory_append_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    memory_append_prune_kernel<<<n_touched, MEM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        rows, order, count, cap, D, new_rows, new_index, cls_start, touched, src_out, proto_out, static_cast<double *>(workspace));
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+}

@@ -391,8 +391,13 @@ __global__ void knn_add_stats_kernel(const int32_t *__restrict__ in, int32_t *__
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 constexpr int KNN_SMALL_K = 16;        // certification path (lists of KNN_KC per (query, CTA, half))
-constexpr int KNN_QUERY_BLOCK = 512;   // k > 16: queries per pass so that every query has >= 74 lists x 16 >= 1024 candidates
-static int knn_cap(int k) { return k <= KNN_SMALL_K ? 256 : 2048; }
+// k > 16: queries per pass.  tau (the bound on the k-th distance) is the k-th smallest key among the merged lists, so it is
+// tight only if no list had to drop a top-k row for lack of room (16 entries).  One query tile per pass gives every query
+// 2 x 148 lists over interleaved row tiles: with k = 1000 a list holds ~3.4 top-k rows on average.  (512 queries per pass = 74
+// lists = 13.5 per list overflowed lists on 66 of 512 queries on the 1000-rows-per-class benchmark index: tau jumped to the
+// next cluster and the band held > 2048 rows.)  The scan of one 128-query tile is HBM-bound (0.23 ms per pass over 1.5 GB).
+constexpr int KNN_QUERY_BLOCK = 128;
+static int knn_cap(int k) { return k <= KNN_SMALL_K ? 256 : 4096; }
 
 struct KnnTcPlan {
     int tiles_m, slots, grid_ctas, cap, ksel;
@@ -539,7 +544,8 @@ static int knn_tc_block(const float *Q, const float *P, const float *p_sqnorm, c
 
     // ---- pass 1 on the tensor cores: per-(query, CTA, half) top-16 lists
     const bool small_k = k <= KNN_SMALL_K;
-    int kt = KNN_KC;
+    // kt = 0 (k > 16): no shared bound -- every list keeps its own true top-16, the merged lists bound the k-th distance
+    int kt = 0;
     if (small_k) { kt = k + 3 > 8 ? k + 3 : 8; if (kt > KNN_KC) kt = KNN_KC; }
     EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt};
     if ((rc = launch_scan(Qr, P, p_half, Bp, N, D, epi, pl.grid_ctas, PROF_KNN_COARSE, s))) return rc;

@@ -114,37 +114,25 @@ class PrototypeMemory:
     # ------------------------------------------------------------------ add path (memory.py:41-83)
     @_locked
     def add_example(self, example: Example, label: str):
+        """memory.py:41-83 (a batch of one through the device-resident store)"""
         if example.embedding is None:
             raise ValueError("Example must have an embedding")
         if example.embedding.size(-1) != self.embedding_dim:
             raise ValueError(
                 f"Example embedding dimension {example.embedding.size(-1)} "
                 f"does not match memory dimension {self.embedding_dim}")
-        self.examples[label].append(example)
-        if len(self.examples[label]) > self.config.max_examples_per_class:
-            self._prune_examples(label)
-        self._update_prototype(label)
-        if not getattr(self, "just_rebuilt", False):
-            self.updates_since_rebuild += 1
-        if self.updates_since_rebuild >= self.config.prototype_update_frequency:
-            self._rebuild_index()
-            self.just_rebuilt = True
-        else:
-            self.just_rebuilt = False
+        self.add_examples_batch([example], [label])
 
     @_locked
-    def add_examples_batch(self, examples: List[Example], labels: List[str]):
-        """Batched equivalent of calling add_example for each pair (same final state): when no class crosses
-        max_examples_per_class during the call, prototypes are recomputed once per touched class on the
-        device (ac_segment_mean) instead of once per example."""
-        cap = self.config.max_examples_per_class
-        counts = {}
-        for l in labels:
-            counts[l] = counts.get(l, 0) + 1
-        if any(len(self.examples[l]) + c > cap for l, c in counts.items()):
-            for ex, l in zip(examples, labels):
-                self.add_example(ex, l)
-            return
+    def add_examples_batch(self, examples: List[Example], labels: List[str], device_rows: Optional[torch.Tensor] = None):
+        """Batched equivalent of calling add_example for each pair (same final lists, prototypes and counters).
+
+        SURVEY.md section 8(f) N2: every class keeps its retained embeddings in HBM ([cap + 1, D] slots + a logical order);
+        one kernel (ac_memory_append_prune, one CTA per touched class) appends the new rows and, for a class over
+        max_examples_per_class, replays the reference's per-example pruning sequentially -- mean of the cap + 1 rows, L2 distance
+        to it, list reordered by that distance, farthest dropped (memory.py:196-217) -- then returns the provenance of every
+        retained position, so the Example lists on the host are put in the same order.  Only the NEW rows are uploaded
+        (`device_rows` [len(examples), D]: the encoder's output when the caller still has it on the device)."""
         for ex, l in zip(examples, labels):
             if ex.embedding is None:
                 raise ValueError("Example must have an embedding")
@@ -152,11 +140,43 @@ class PrototypeMemory:
                 raise ValueError(
                     f"Example embedding dimension {ex.embedding.size(-1)} "
                     f"does not match memory dimension {self.embedding_dim}")
-        for ex, l in zip(examples, labels):
-            self.examples[l].append(ex)
-        touched = list(counts.keys())
-        self._update_prototypes_device(touched)
-        # same counter/rebuild behaviour as the per-example loop
+        if not examples:
+            return
+        cap = int(self.config.max_examples_per_class)
+        if cap > 2047:                     # the store sorts cap + 1 <= 2048 distances in shared memory
+            for ex, l in zip(examples, labels):
+                self._add_example_eager(ex, l)
+            return
+        dev = _device()
+        groups: Dict[str, List[int]] = {}
+        for i, l in enumerate(labels):
+            groups.setdefault(l, []).append(i)
+        touched = list(groups.keys())
+        st = self._store(cap, dev)
+        slots = [self._store_slot(st, l) for l in touched]
+        new_rows = device_rows if device_rows is not None else torch.stack(
+            [ex.embedding.reshape(-1).float() for ex in examples]).to(dev)
+        new_index = torch.tensor([i for l in touched for i in groups[l]], dtype=torch.int32, device=dev)
+        starts = [0]
+        for l in touched:
+            starts.append(starts[-1] + len(groups[l]))
+        cls_start = torch.tensor(starts, dtype=torch.int32, device=dev)
+        src, proto = _cabi.memory_append_prune(st["rows"], st["order"], st["count"], new_rows, new_index, cls_start,
+                                               torch.tensor(slots, dtype=torch.int32, device=dev))
+        src_h, proto_h = src.cpu().numpy(), proto.cpu()          # the call's one synchronisation
+        for t, l in enumerate(touched):
+            old = self.examples[l]
+            n_old = len(old)
+            fresh = [examples[i] for i in groups[l]]
+            kept = [old[s] if s < n_old else fresh[s - n_old] for s in src_h[t].tolist() if s >= 0]
+            self.examples[l] = kept
+            st["mirror"][l] = [id(e) for e in kept]
+            self.prototypes[l] = proto_h[t].clone()
+            if l in self.label_to_index:                        # memory.py:155-159
+                idx = self.label_to_index[l]
+                self.index.remove_ids(torch.tensor([idx]))
+                self.index.add(self.prototypes[l].unsqueeze(0))
+        # same counter / rebuild behaviour as the per-example loop (memory.py:74-83)
         for _ in examples:
             if not getattr(self, "just_rebuilt", False):
                 self.updates_since_rebuild += 1
@@ -166,45 +186,73 @@ class PrototypeMemory:
             else:
                 self.just_rebuilt = False
 
-    def _class_rows_device(self, label: str) -> torch.Tensor:
-        """[n_c, D] device copy of the class's retained examples, in example order.  With config['b200_cache_rows'] the copy
-        is kept between calls and only the examples appended since are uploaded (the restacking
-        of all retained rows per call is O(n^2) over a continual loop); any reordering / shrinking (pruning, clear, load)
-        drops the cache.  The rows and their order are the same either way, so the means are the same bits."""
-        exs = self.examples[label]
-        if not self.config.config.get("b200_cache_rows", False):
-            return torch.stack([e.embedding.reshape(-1).float() for e in exs]).to(_device())
-        cache = self.__dict__.setdefault("_row_cache", {})
-        have = cache.get(label)
-        n_have = have[0].shape[0] if have is not None else 0
-        # the cache is valid only if it is a prefix of the current list: compare the identity of the cached examples
-        if have is None or n_have > len(exs) or have[1] != [id(e) for e in exs[:n_have]]:
-            have, n_have = None, 0
-        if n_have < len(exs):
-            tail = torch.stack([e.embedding.reshape(-1).float() for e in exs[n_have:]]).to(_device())
-            rows = tail if have is None else torch.cat([have[0], tail], 0)
-            cache[label] = (rows, [id(e) for e in exs])
-            return rows
-        return have[0]
+    # ---- device-resident class stores
+    def _store(self, cap: int, dev) -> dict:
+        st = self.__dict__.get("_dev_store")
+        if st is None or st["cap"] != cap or st["rows"].device != dev:
+            st = {"cap": cap, "rows": torch.empty((0, cap + 1, self.embedding_dim), dtype=torch.float32, device=dev),
+                  "order": torch.empty((0, cap + 1), dtype=torch.int32, device=dev),
+                  "count": torch.empty((0,), dtype=torch.int32, device=dev), "slot_of": {}, "mirror": {}}
+            self.__dict__["_dev_store"] = st
+        return st
 
-    def _update_prototypes_device(self, labels: List[str]):
-        parts, cls = [], []
-        for ci, l in enumerate(labels):
-            if self.examples[l]:
-                rows = self._class_rows_device(l)
-                parts.append(rows)
-                cls.append(torch.full((rows.shape[0],), ci, dtype=torch.int32, device=rows.device))
-        if not parts:
-            return
-        X = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
-        mean, _ = _cabi.segment_mean(X, cls[0] if len(cls) == 1 else torch.cat(cls, 0), len(labels))
-        mean = mean.cpu()
-        for ci, l in enumerate(labels):
-            self.prototypes[l] = mean[ci].clone()
-            if l in self.label_to_index:
-                idx = self.label_to_index[l]
-                self.index.remove_ids(torch.tensor([idx]))
-                self.index.add(self.prototypes[l].unsqueeze(0))
+    def _store_slot(self, st: dict, label: str) -> int:
+        """class slot of `label`, created / re-uploaded when the host list is not what the store last saw (first use, clear,
+        load, direct edits of memory.examples): rows in list order, identity slot order"""
+        cap = st["cap"]
+        slot = st["slot_of"].get(label)
+        if slot is None:
+            slot = len(st["slot_of"])
+            st["slot_of"][label] = slot
+            if slot >= st["rows"].shape[0]:
+                grow = max(8, st["rows"].shape[0])
+                dev = st["rows"].device
+                st["rows"] = torch.cat([st["rows"], torch.empty((grow, cap + 1, self.embedding_dim), dtype=torch.float32, device=dev)])
+                st["order"] = torch.cat([st["order"], torch.arange(cap + 1, dtype=torch.int32, device=dev).repeat(grow, 1)])
+                st["count"] = torch.cat([st["count"], torch.zeros((grow,), dtype=torch.int32, device=dev)])
+            st["mirror"][label] = None
+        exs = self.examples[label] if label in self.examples else []
+        if st["mirror"].get(label) != [id(e) for e in exs]:
+            if len(exs) > cap:             # an over-cap list built behind the store's back: bring it under the cap first
+                self._prune_examples(label)
+                exs = self.examples[label]
+            n = len(exs)
+            if n:
+                st["rows"][slot, :n] = torch.stack([e.embedding.reshape(-1).float() for e in exs]).to(st["rows"].device)
+            st["order"][slot] = torch.arange(cap + 1, dtype=torch.int32, device=st["rows"].device)
+            st["count"][slot] = n
+            st["mirror"][label] = [id(e) for e in exs]
+        return slot
+
+    def class_rows_device(self, label: str) -> torch.Tensor:
+        """[n_c, D] device rows of the class's retained examples in list order (the store's rows gathered through its order)"""
+        cap = int(self.config.max_examples_per_class)
+        if cap > 2047:
+            return torch.stack([e.embedding.reshape(-1).float() for e in self.examples[label]]).to(_device())
+        st = self._store(cap, _device())
+        slot = self._store_slot(st, label)
+        n = len(self.examples[label])
+        return st["rows"][slot].index_select(0, st["order"][slot, :n].long())
+
+    def _add_example_eager(self, example: Example, label: str):
+        """the per-example path of memory.py:60-83 (used only when max_examples_per_class exceeds the store's 2047 rows)"""
+        self.examples[label].append(example)
+        if len(self.examples[label]) > self.config.max_examples_per_class:
+            self._prune_examples(label)
+        exs = self.examples[label]
+        X = torch.stack([e.embedding.reshape(-1).float() for e in exs]).to(_device())
+        mean, _ = _cabi.segment_mean(X, torch.zeros(X.shape[0], dtype=torch.int32, device=X.device), 1)
+        self.prototypes[label] = mean[0].cpu()
+        if label in self.label_to_index:
+            self.index.remove_ids(torch.tensor([self.label_to_index[label]]))
+            self.index.add(self.prototypes[label].unsqueeze(0))
+        if not getattr(self, "just_rebuilt", False):
+            self.updates_since_rebuild += 1
+        if self.updates_since_rebuild >= self.config.prototype_update_frequency:
+            self._rebuild_index()
+            self.just_rebuilt = True
+        else:
+            self.just_rebuilt = False
 
     # ------------------------------------------------------------------ search (memory.py:85-136)
     def get_nearest_prototypes(self, query_embedding: torch.Tensor, k: int = 5,
@@ -246,17 +294,22 @@ class PrototypeMemory:
         examples = self.examples[label]
         if not examples:
             return
-        self._update_prototypes_device([label])
+        rows = self.class_rows_device(label)
+        mean, _ = _cabi.segment_mean(rows, torch.zeros(rows.shape[0], dtype=torch.int32, device=rows.device), 1)
+        self.prototypes[label] = mean[0].cpu()
+        if label in self.label_to_index:
+            self.index.remove_ids(torch.tensor([self.label_to_index[label]]))
+            self.index.add(self.prototypes[label].unsqueeze(0))
 
     @_locked
     def _rebuild_index(self):
-        """memory.py:161-177: rows in sorted(label) order."""
+        """memory.py:161-177: rows in sorted(label) order (one stacked upload of the C prototype rows)."""
         self.index = FlatL2Index(self.embedding_dim)
         self.label_to_index.clear()
         self.index_to_label.clear()
         sorted_labels = sorted(self.prototypes.keys())
         if sorted_labels:
-            self.index.add(torch.stack([self.prototypes[l].reshape(-1).float().cpu() for l in sorted_labels]))
+            self.index.add(torch.stack([self.prototypes[l].reshape(-1).float() for l in sorted_labels]))
         for i, label in enumerate(sorted_labels):
             self.label_to_index[label] = i
             self.index_to_label[i] = label
@@ -291,7 +344,7 @@ class PrototypeMemory:
 
     @_locked
     def clear(self):
-        self.__dict__.pop("_row_cache", None)
+        self.__dict__.pop("_dev_store", None)
         self.examples.clear()
         self.prototypes.clear()
         self.index = FlatL2Index(self.embedding_dim)

@@ -98,6 +98,22 @@ int ac_proto_scores(const float *d, const int64_t *idx, int B, int k, float *sco
 int ac_segment_mean(const float *X, const int32_t *cls, int64_t n, int D, int C,
                     float *mean, int32_t *count, ac_stream_t stream);
 
+/* Device-resident maintenance of the per-class example store for a whole add_examples() call.
+ * Replaces the per-example sequence memory.py:60-72 (append, prune when over max_examples_per_class) / :196-217
+ * (_prune_examples: keep the `cap` embeddings nearest the mean of the cap + 1, list reordered by that distance) /
+ * :138-153 (_update_prototype = mean of the retained embeddings).
+ *   rows  [n_slots, cap + 1, D]  class stores;  order [n_slots, cap + 1]: a permutation of the physical slots 0..cap per class,
+ *   positions [0, count) = the stored rows in list order, positions [count, cap] = free slots;  count [n_slots].
+ *   new_rows [*, D]; new_index [n_new]: row numbers of new_rows grouped by touched class, arrival order inside a class;
+ *   cls_start [n_touched + 1]: offsets of the groups in new_index;  touched [n_touched]: class slot of every group.
+ * One CTA per touched class processes its new examples sequentially (example j sees the list example j - 1 left).
+ * Outputs: src_out [n_touched, cap]: provenance of every retained list position (< old count: that position of the old list,
+ * >= old count: old count + index of the new example inside its group, -1: empty); proto_out [n_touched, D].
+ * workspace: n_touched * D * 8 bytes. */
+int ac_memory_append_prune(float *rows, int32_t *order, int32_t *count, int cap, int D, const float *new_rows,
+                           const int32_t *new_index, const int32_t *cls_start, const int32_t *touched, int n_touched,
+                           int32_t *src_out, float *proto_out, void *workspace, size_t workspace_bytes, ac_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage H -- adaptive head.  Replaces nn.Module.__call__ / autograd / AdamW on AdaptiveHead:
  *   forward  src/adaptive_classifier/models.py:71-80, classifier.py:428-442, :1341-1354

@@ -219,6 +219,7 @@ int main(int argc, char **argv) {
         a.slots[l] = (nblk + G - 1) / G;
     }
     if (C_old) a.L[2].ewc_rows = C_old;
+    a.nst = 2 + static_cast<int>(seed % 3);                       // ring depth 2, 3 or 4
     a.lr = 1e-3f; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f; a.wd = 0.01f; a.max_norm = 1.f; a.dropout_p = p_drop;
     a.loss_kind = loss_kind; a.seed = 11; a.use_ewc = ewc; a.ewc_lambda = 100.f; a.update = update; a.fisher_scale = 0.25f;
     std::vector<float> h0d(size_t(batch) * H0), h1d(size_t(batch) * H1), z(size_t(batch) * C), dz(size_t(batch) * C), da1(size_t(batch) * H1),

@@ -152,7 +152,7 @@ def test_knn_tensor_large_k_equals_exact_scan(cabi, B, N, D, C, k):
     d0, i0 = cabi.knn_l2_topk(Qg[sel.cuda()].contiguous(), Pg, k, algo=cabi.AC_KNN_EXACT)
     torch.cuda.synchronize()
     st = stats.cpu().tolist()
-    assert st[1] == 0 and st[0] == B and k <= st[2] <= 2048, st           # every query took pass 2, nothing overflowed
+    assert st[1] == 0 and st[0] == B and k <= st[2] <= 4096, st           # every query took pass 2, nothing overflowed
     assert torch.equal(i1[sel.cuda()], i0) and torch.equal(d1[sel.cuda()], d0)
     assert bool((d1[:, 1:] >= d1[:, :-1]).all())
     d_ref, i_ref = ko.knn_l2(Q[:4].numpy(), P.numpy(), k)
@@ -454,7 +454,7 @@ def test_encoder_full_last_layer_and_hidden_state(cabi):
     hid = enc_full.last_hidden(B, S).cpu().view(B, S, -1)
     b = enc_cls.forward_cls(ids.to(torch.int32).cuda()).cpu()
     assert (a - ref_cls).norm(dim=1).max() < 1e-3 and (b - ref_cls).norm(dim=1).max() < 1e-3
-    assert (a - b).abs().max() < 1e-6            # same arithmetic on the CLS rows, different tile shapes only
+    assert (a - b).abs().max() < 1e-4            # CLS-only tail: LayerNorm materialised on B rows; full flow: deferred into the epilogues
     assert (hid - ref_hidden).abs().max() < 2e-2 * ref_hidden.abs().max()
     with pytest.raises(cabi.AdaptiveB200Error):
         enc_cls.last_hidden(B, S)

@@ -118,10 +118,64 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert out1.returncode == 0 and out1.stdout.strip() == ""
 
 
-def test_prototype_row_cache_matches_restacking(monkeypatch):
-    """with config['b200_cache_rows'] the per-class device rows are kept between calls and only new
-    examples are uploaded; prototypes, pruning and bookkeeping must be exactly what the restacking path produces.  The two
-    device entry points are replaced by torch-CPU stand-ins here (host logic only)."""
+def _reference_memory_semantics(D, cap, freq):
+    """plain restatement of memory.py:41-83 / :138-153 / :196-217 (per example: append, prune to the `cap` nearest the mean of the
+    cap + 1 in distance order, prototype = mean of the retained) used as the expectation for the batched device-store path"""
+    import numpy as np
+    import torch
+
+    class Ref:
+        def __init__(self):
+            self.examples, self.prototypes = {}, {}
+
+        def add(self, ex, label):
+            lst = self.examples.setdefault(label, [])
+            lst.append(ex)
+            if len(lst) > cap:
+                E = torch.stack([e.embedding for e in lst])
+                mean = E.mean(0)
+                dist = [torch.norm(e.embedding - mean).item() for e in lst]
+                keep = np.argsort(dist, kind="stable")[:cap]
+                self.examples[label] = [lst[i] for i in keep]
+            self.prototypes[label] = torch.stack([e.embedding for e in self.examples[label]]).mean(0)
+    return Ref()
+
+
+def _torch_memory_append_prune(rows, order, count, new_rows, new_index, cls_start, touched):
+    """torch-CPU stand-in with the contract of ac_memory_append_prune (host-logic tests only)"""
+    import torch
+    cap = rows.shape[1] - 1
+    nt = touched.numel()
+    src = torch.full((nt, cap), -1, dtype=torch.int32)
+    proto = torch.zeros((nt, rows.shape[2]))
+    for t in range(nt):
+        c = int(touched[t])
+        n = int(count[c])
+        n_old = n
+        ords = order[c].tolist()
+        srcs = list(range(n)) + [-1] * (cap + 1 - n)
+        for jj, j in enumerate(range(int(cls_start[t]), int(cls_start[t + 1]))):
+            rows[c, ords[n]] = new_rows[int(new_index[j])]
+            srcs[n] = n_old + jj
+            n += 1
+            if n > cap:
+                E = rows[c, ords[:n]]
+                dist = (E - E.double().mean(0).float()).norm(dim=1)
+                perm = sorted(range(n), key=lambda i: (float(dist[i]), i))
+                ords = [ords[i] for i in perm] + ords[n:]
+                srcs = [srcs[i] for i in perm][:cap] + [-1]
+                n = cap
+        order[c] = torch.tensor(ords, dtype=torch.int32)
+        count[c] = n
+        src[t, :n] = torch.tensor(srcs[:n], dtype=torch.int32)
+        proto[t] = rows[c, ords[:n]].double().mean(0).float()
+    return src, proto
+
+
+def test_device_store_host_logic_reproduces_the_per_example_semantics(monkeypatch):
+    """add_examples_batch through the device-resident class stores (grouping by class, provenance ->
+    Example lists, store validity after clear / direct edits) == the reference's per-example append / prune / mean sequence.
+    The device entry points are replaced by torch-CPU stand-ins here (host logic only; the kernel itself is GPU-tested)."""
     import torch
     import adaptive_classifier_b200 as acb
     from adaptive_classifier_b200 import memory as mem_mod
@@ -130,35 +184,39 @@ def test_prototype_row_cache_matches_restacking(monkeypatch):
         mean = torch.zeros((C, X.shape[1]), dtype=torch.float32)
         cnt = torch.zeros((C,), dtype=torch.int32)
         for c in range(C):
-            rows = X[cls == c]
-            cnt[c] = rows.shape[0]
-            if rows.shape[0]:
-                mean[c] = rows.sum(0) / rows.shape[0]
+            r = X[cls == c]
+            cnt[c] = r.shape[0]
+            if r.shape[0]:
+                mean[c] = r.sum(0) / r.shape[0]
         return mean, cnt
 
     monkeypatch.setattr(mem_mod, "_device", lambda: torch.device("cpu"))
     monkeypatch.setattr(mem_mod._cabi, "segment_mean", segment_mean)
-    D = 16
+    monkeypatch.setattr(mem_mod._cabi, "memory_append_prune", _torch_memory_append_prune)
+    D, cap = 16, 12
     g = torch.Generator().manual_seed(0)
-    mems = []
-    for cached in (False, True):
-        cfg = acb.ModelConfig({"max_examples_per_class": 12, "prototype_update_frequency": 7, "b200_cache_rows": cached})
-        mems.append(acb.PrototypeMemory(D, config=cfg))
-    labels_pool = ["a", "b", "c"]
-    for call in range(14):
-        n = int(torch.randint(1, 6, (1,), generator=g))
-        labs = [labels_pool[int(torch.randint(0, 3, (1,), generator=g))] for _ in range(n)]
+    mem = acb.PrototypeMemory(D, config=acb.ModelConfig({"max_examples_per_class": cap, "prototype_update_frequency": 7}))
+    ref = _reference_memory_semantics(D, cap, 7)
+    pool = ["a", "b", "c"]
+    for call in range(16):
+        n = int(torch.randint(1, 9, (1,), generator=g))
+        labs = [pool[int(torch.randint(0, 3, (1,), generator=g))] for _ in range(n)]
         embs = [torch.nn.functional.normalize(torch.randn(D, generator=g), dim=0) for _ in range(n)]
-        for m in mems:
-            m.add_examples_batch([acb.Example(f"t{call}_{i}", l, e.clone()) for i, (l, e) in enumerate(zip(labs, embs))], labs)
-        a, b = mems
-        assert a.get_stats() == b.get_stats()
-        assert set(a.prototypes) == set(b.prototypes)
-        for l in a.prototypes:
-            assert torch.equal(a.prototypes[l], b.prototypes[l]), (call, l)
-            assert [e.text for e in a.examples[l]] == [e.text for e in b.examples[l]]
-        assert a.label_to_index == b.label_to_index
-    # classes went through pruning (cap 12) during the loop, and the cache survived it
-    assert max(len(v) for v in mems[1].examples.values()) == 12
-    mems[1].clear()
-    assert "_row_cache" not in mems[1].__dict__
+        exs = [acb.Example(f"t{call}_{i}", l, e) for i, (l, e) in enumerate(zip(labs, embs))]
+        if call == 9:
+            mem.add_example(exs[0], labs[0])                       # the single-example entry is a batch of one
+            mem.add_examples_batch(exs[1:], labs[1:])
+        else:
+            mem.add_examples_batch(exs, labs)
+        for e, l in zip(exs, labs):
+            ref.add(e, l)
+        for l in ref.examples:
+            assert [e.text for e in mem.examples[l]] == [e.text for e in ref.examples[l]], (call, l)   # same retained set, same ORDER
+            assert (mem.prototypes[l] - ref.prototypes[l]).abs().max() < 1e-6
+        if call == 11:                                              # an edit behind the store's back must be noticed
+            mem.examples["a"] = list(reversed(mem.examples["a"]))
+            ref.examples["a"] = list(reversed(ref.examples["a"]))
+    assert max(len(v) for v in mem.examples.values()) == cap        # classes went through pruning
+    assert mem.updates_since_rebuild < 7 and mem.index.ntotal in (0, 3)
+    mem.clear()
+    assert "_dev_store" not in mem.__dict__ and len(mem.examples) == 0

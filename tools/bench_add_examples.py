@@ -58,7 +58,7 @@ def run(examples=50176, call=256, seq=128, quiet=False, cpu_sample=True):
         new = set(labels) - set(clf.label_to_id)
         for l in sorted(new):
             clf.label_to_id[l] = len(clf.label_to_id); clf.id_to_label[clf.label_to_id[l]] = l
-        clf.memory.add_examples_batch([acb.Example(f"t{c}_{i}", l, e) for i, (l, e) in enumerate(zip(labels, emb))], labels)
+        clf.memory.add_examples_batch([acb.Example(f"t{c}_{i}", l, e) for i, (l, e) in enumerate(zip(labels, emb))], labels, device_rows=emb_dev)
         for l in labels:
             clf.training_history[l] = clf.training_history.get(l, 0) + 1
         torch.cuda.synchronize()
