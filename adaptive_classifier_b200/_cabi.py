@@ -29,7 +29,7 @@ EXPORTS = [
     "ac_version", "ac_last_error", "ac_device_check",
     "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
     "ac_segment_mean", "ac_memory_append_prune",
-    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch", "ac_head_grad", "ac_ewc_penalty",
+    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch", "ac_head_phase_timing", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
     "ac_proto_class_scores", "ac_proto_class_scores_n", "ac_blend_dense", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
     "ac_pipeline_create", "ac_pipeline_destroy", "ac_pipeline_predict_device", "ac_pipeline_predict_host",
@@ -363,6 +363,13 @@ def head_train_epoch(X, targets, perm, p, m, v, *, first_step, batch, loss_kind=
                                 ctypes.byref(hm), ctypes.byref(hv), ctypes.byref(cfg), loss_accum.data_ptr(), ptr(step_stats),
                                 ws.data_ptr(), ws.numel(), stream_ptr()), "ac_head_train_epoch")
     return loss_accum, steps
+
+
+def head_phase_timing(enable: bool = True):
+    """diagnostic: nanoseconds CTA 0 of the training kernel spent per phase / grid barrier since enabled (13 counters)"""
+    out = (ctypes.c_ulonglong * 16)()
+    check(load_library().ac_head_phase_timing(1 if enable else 0, out), "ac_head_phase_timing")
+    return [int(x) for x in out][:13]
 
 
 def head_grad(X, targets, p, *, loss_kind=AC_LOSS_CE, grad_out=None, fisher=None, inv_n_batches=1.0):

@@ -61,23 +61,6 @@ __device__ __forceinline__ float gelu_erf(float y) {
 //       `bias` holding c0 = W beta + b  (see "deferred LayerNorm" below)
 //   COLS:  accumulator columns one epilogue warp drains per tile (128 with 8 epilogue warps, 64 with 16): only the DEFER
 //          variant needs it, to know which chunk is the first of its slice
-// (mu, 1/sqrt(var + eps)) of row `row` from the per-128-column partial (sum, sumsq) the residual epilogue wrote, added in a
-// fixed order (every consumer of a row computes the same bits); a standalone statistics kernel between the GEMMs is not needed
-__device__ __forceinline__ float2 row_stats_from_parts(const float2 *__restrict__ parts, int nparts, int64_t part_stride, float inv_h,
-                                                       float eps, int row, int M) {
-    if (!parts) return make_float2(0.f, 1.f);
-    if (row >= M) return make_float2(0.f, 0.f);
-    float s = 0.f, q = 0.f;
-    for (int p = 0; p < nparts; ++p) {
-        const float2 v = __ldcg(parts + static_cast<int64_t>(p) * part_stride + row);
-        s += v.x;
-        q += v.y;
-    }
-    const float mu = s * inv_h;
-    const float var = fmaxf(q * inv_h - mu * mu, 0.f);
-    return make_float2(mu, 1.f / sqrtf(var + eps));
-}
-
 template <int MODE, bool OUT_HALF, bool VT, bool DEFER = false, int COLS = GEMM_BLOCK_N / 2>
 struct EpiLinear {
     static_assert(!DEFER || (OUT_HALF && MODE != 2), "the deferred-LayerNorm consumer epilogues write fp16 operands");
@@ -89,14 +72,10 @@ struct EpiLinear {
     __half *vT;                           // VT only
     int vt_col0, S, S_pad, H;
     const float *__restrict__ c1;         // DEFER only: [N] row sums of the packed weight
-    // DEFER only: per-128-column (sum, sumsq) partials of the A rows as written by the producing residual epilogue
-    // ([nparts][part_stride]); NULL = the rows are already normalised (layer 0 consumes the embedding LayerNorm's output)
-    const float2 *__restrict__ parts;
-    int nparts;
-    int64_t part_stride;
-    float inv_h, eps;
+    const float2 *__restrict__ row_stats; // DEFER only: [M] (mu, 1/sqrt(var + eps)) of the A rows
 
     static constexpr int kUnrollChunks = 4;   // `buf` must be a compile-time constant (register double buffer)
+    static constexpr int kPrefetchDist = 1;
     struct State {
         // residual (MODE 2) of one 32-column chunk in the layout of the transposed phase: [column half][row pass],
         // double-buffered so chunk c+1 is in flight while chunk c is processed
@@ -120,7 +99,7 @@ struct EpiLinear {
     __device__ __forceinline__ void prefetch(State &st, const GemmTileInfo &ti, int row, int col0, int lane, int buf) const {
         if (DEFER) {
             if (((col0 - ti.n0) & (COLS - 1)) == 0) {                  // first chunk of this warp's column slice
-                const float2 ms = row_stats_from_parts(parts, nparts, part_stride, inv_h, eps, row, M);
+                const float2 ms = (row < M) ? __ldg(row_stats + row) : make_float2(0.f, 0.f);
                 st.mu = ms.x;
                 st.r = ms.y;
             }
@@ -249,17 +228,21 @@ struct EpiResidDefer {
     const float *__restrict__ bias;        // [N]
     float *y;                              // [M, ld] fp32 residual sums: read (old) and written (new) in place
     __half *yh;                            // [M, ld] fp16 copy of the new sums
-    const float2 *__restrict__ parts_prev; // [N / 128][part_stride] partial (sum, sumsq) of the OLD sums (NULL: already normalised)
+    const float2 *__restrict__ stats_prev; // [M] (mu, r) of the old sums
     const float *__restrict__ gamma;       // [N] pending LayerNorm of the old sums
     const float *__restrict__ beta;        // [N]
-    float2 *parts;                         // [N / 128][part_stride] partial (sum, sumsq) of the new sums (a different buffer)
+    float2 *parts;                         // [N / 128][part_stride] partial (sum, sumsq) of the new sums
     int64_t part_stride;
     int M, N, ld;
-    float inv_h, eps;
 
     static constexpr int kUnrollChunks = 4;
+    // The residual epilogues move 327 KB per 128 x 256 tile (fp32 sums read + written, fp16 copy written) against a 3-13 us
+    // mainloop: they are HBM-bound, and with one 4 KB chunk per warp in flight the 8 epilogue warps of an SM sustained only
+    // ~25 GB/s (3.65 TB/s over the chip, out-proj 152 us against an 85 us traffic floor).  Two chunks ahead = three register
+    // buffers doubles the bytes in flight.
+    static constexpr int kPrefetchDist = 2;
     struct State {
-        float4 res[2][8];                  // old sums of one 32-column chunk (transposed-phase layout), double-buffered
+        float4 res[3][8];                  // old sums of 32-column chunks (transposed-phase layout), triple-buffered
         float2 ms[4];                      // (mu, r) of this lane's 4 rows (r8 + 8 i)
         float sum[4], sq[4];               // running partials of the new sums over this warp's 128 columns
     };
@@ -273,7 +256,7 @@ struct EpiResidDefer {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int grow = row_base + r8 + 8 * i;
-                st.ms[i] = row_stats_from_parts(parts_prev, N / (GEMM_BLOCK_N / 2), part_stride, inv_h, eps, grow, M);
+                st.ms[i] = (grow < M) ? __ldg(stats_prev + grow) : make_float2(0.f, 0.f);
                 st.sum[i] = 0.f;
                 st.sq[i] = 0.f;
             }
@@ -350,6 +333,29 @@ struct EpiResidDefer {
     }
 };
 
+// (sum, sumsq) partials of every 128-column part -> (mu, 1/sqrt(var + eps)) per row; parts are added in a fixed order.
+// Kept as a kernel of its own (24 launches of ~3 us per forward): folding these six loads + rsqrt into the consuming epilogues
+// was measured on a B200 and LOST 1 ms per step (35.5 k instead of 37.7 k queries/s, profiles/r02_bench_lnstats_folded.json):
+// the loads sit at the head of every tile's epilogue, which is the critical path of the HBM-bound residual GEMMs.
+__global__ void ln_stats_kernel(const float2 *__restrict__ parts, int nparts, int64_t part_stride, int rows, int H, float eps,
+                                float2 *__restrict__ stats) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float s = 0.f, q = 0.f;
+    for (int p = 0; p < nparts; ++p) {
+        const float2 v = parts[static_cast<int64_t>(p) * part_stride + row];
+        s += v.x;
+        q += v.y;
+    }
+    const float mu = s / static_cast<float>(H);
+    const float var = fmaxf(q / static_cast<float>(H) - mu * mu, 0.f);
+    stats[row] = make_float2(mu, 1.f / sqrtf(var + eps));
+}
+
+__global__ void fill_stats_identity_kernel(float2 *__restrict__ stats, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) stats[i] = make_float2(0.f, 1.f);
+}
 __global__ void fill_value_kernel(float *__restrict__ p, int n, float v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -926,9 +932,8 @@ struct ac_encoder {
     int vt_B = -1, vt_S = -1;
     std::vector<CUtensorMap> p_wqkv_d, p_wo, p_w1_d, p_w2;
     CUtensorMap p_w1_last;
-    // per-128-column (sum, sumsq) partials of the residual sums, ping-pong: a residual epilogue reads the partials of the sums it
-    // consumes from one buffer and writes those of the sums it produces into the other
-    float2 *parts_a = nullptr, *parts_b = nullptr;
+    // row statistics (ping-pong) and the per-128-column partials the residual epilogues write
+    float2 *stats_a = nullptr, *stats_b = nullptr, *stats_id = nullptr, *parts = nullptr;
     float *ones = nullptr, *zeros = nullptr;
     std::vector<void *> allocs;
     int last_B = 0, last_S = 0;
@@ -1058,10 +1063,13 @@ extern "C" int ac_encoder_create(const ac_encoder_config *cfg, const ac_encoder_
         TRY(pack_f16(e, &e->w1_last, w->ff1_w[L - 1], static_cast<size_t>(I) * H));
         TRY(pack_f32(e, &e->b1_last, w->ff1_b[L - 1], I));
     }
-    TRY(dev_alloc(e, &e->parts_a, static_cast<size_t>(H / 128) * T));
-    TRY(dev_alloc(e, &e->parts_b, static_cast<size_t>(H / 128) * T));
+    TRY(dev_alloc(e, &e->stats_a, T));
+    TRY(dev_alloc(e, &e->stats_b, T));
+    TRY(dev_alloc(e, &e->stats_id, T));
+    TRY(dev_alloc(e, &e->parts, static_cast<size_t>(H / 128) * T));
     TRY(dev_alloc(e, &e->ones, H));
     TRY(dev_alloc(e, &e->zeros, H));
+    fill_stats_identity_kernel<<<static_cast<unsigned>((T + 255) / 256), 256>>>(e->stats_id, static_cast<int64_t>(T));
     fill_value_kernel<<<(H + 255) / 256, 256>>>(e->ones, H, 1.f);
     fill_value_kernel<<<(H + 255) / 256, 256>>>(e->zeros, H, 0.f);
     TRY(check_cuda(cudaGetLastError(), "deferred-LayerNorm constants"));
@@ -1158,11 +1166,9 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
                                                     c.type_vocab, e->x, e->xh);
     AC_LAUNCH_CHECK();
     const float *pg = e->ones, *pb = e->zeros;
-    const float2 *parts_in = nullptr;       // partials of the sums in e->x (NULL: identity statistics)
-    const float inv_h = 1.f / static_cast<float>(H);
+    const float2 *st_in = e->stats_id;
     for (int l = 0; l < c.layers; ++l) {
-        EpiQKVDefer eq{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], parts_in, nparts, pstride, inv_h,
-                       c.ln_eps};
+        EpiQKVDefer eq{e->c0qkv[l], nullptr, e->qk, M, 3 * H, 2 * H, 0, e->vT, 2 * H, S, S_pad, H, e->c1qkv[l], st_in};
         if ((rc = launch_linear(e->m_xh, e->p_wqkv_d[l], M, 3 * H, H, eq, s))) return rc;
         if ((rc = launch_attention(e, mask, B, S, s))) return rc;
         if (l == c.layers - 1 && c.cls_only && static_cast<size_t>(B) <= e->Bc) {
@@ -1190,19 +1196,23 @@ extern "C" int ac_encoder_forward_cls(ac_encoder *e, const int32_t *ids, const i
             e->last_cls_only = true;
             return AC_OK;
         }
-        // attention output projection + residual: y <- ctx Wo^T + bo + LN_pending(y); partial statistics of the new sums -> parts_b
-        EpiResidDefer eo{e->bo[l], e->x, e->xh, parts_in, pg, pb, e->parts_b, pstride, M, H, H, inv_h, c.ln_eps};
+        // attention output projection + residual: y <- ctx Wo^T + bo + LN_pending(y); statistics of the new sums
+        EpiResidDefer eo{e->bo[l], e->x, e->xh, st_in, pg, pb, e->parts, pstride, M, H, H};
         if ((rc = launch_linear(e->m_ctx, e->p_wo[l], M, H, H, eo, s))) return rc;
-        EpiGeluDefer16 e1{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->parts_b, nparts, pstride, inv_h, c.ln_eps};
+        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_b);
+        AC_LAUNCH_CHECK();
+        EpiGeluDefer16 e1{e->c0f[l], nullptr, e->ffn, M, I, I, 0, nullptr, 0, 0, 0, 0, e->c1f[l], e->stats_b};
         if ((rc = launch_linear<EpiGeluDefer16, 16>(e->m_xh, e->p_w1_d[l], M, I, H, e1, s))) return rc;
-        // FFN output projection + residual: y <- ffn W2^T + b2 + LN_attention_output(y); partials of the new sums -> parts_a
-        EpiResidDefer e2{e->b2[l], e->x, e->xh, e->parts_b, e->ln1w[l], e->ln1b[l], e->parts_a, pstride, M, H, H, inv_h, c.ln_eps};
+        // FFN output projection + residual: y <- ffn W2^T + b2 + LN_attention_output(y)
+        EpiResidDefer e2{e->b2[l], e->x, e->xh, e->stats_b, e->ln1w[l], e->ln1b[l], e->parts, pstride, M, H, H};
         if ((rc = launch_linear(e->m_ffn, e->p_w2[l], M, H, I, e2, s))) return rc;
+        ln_stats_kernel<<<(M + 255) / 256, 256, 0, s>>>(e->parts, nparts, pstride, M, H, c.ln_eps, e->stats_a);
+        AC_LAUNCH_CHECK();
         pg = e->ln2w[l];
         pb = e->ln2b[l];
-        parts_in = e->parts_a;
+        st_in = e->stats_a;
     }
-    // full hidden state requested (cls_only = 0): materialise the last LayerNorm for every row (two-pass statistics from the sums)
+    // full hidden state requested (cls_only = 0): materialise the last LayerNorm for every row
     layernorm_kernel<<<row_blocks, wpb * 32, 0, s>>>(e->x, pg, pb, c.ln_eps, M, H, e->tmp, nullptr);
     AC_LAUNCH_CHECK();
     if ((rc = launch_cls_normalize(e->tmp, B, S, H, out_unit_cls, s))) return rc;

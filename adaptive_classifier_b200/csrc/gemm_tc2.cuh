@@ -57,7 +57,9 @@ __device__ __forceinline__ void mbar_wait_guarded_cluster(uint64_t *bar, uint32_
 //                 the bias + GELU epilogue issues ~17 instructions per element; two warps per scheduler cannot hide its MUFU /
 //                 dependency latency behind a K = 768 mainloop (FFN1 measured 56 % tensor-pipe active), four can.
 template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kStages = GEMM2_STAGES, int kEpiWarps = GEMM_EPI_WARPS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiWarps, 1)
+// register cap spelled out (65536 / threads, multiple of 8): __launch_bounds__(320, 1) lets ptxas use only 168, which spilled the
+// triple-buffered residual epilogue
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kEpiWarps == 8 ? 200 : 112)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 int M, int N, int K, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
@@ -175,21 +177,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ti.tile_iter = it;
             const int row = ti.m0 + q * 32 + lane;
             const int c_lo = cpart * kColsPerWarp;
-            epi.prefetch(est, ti, row, ti.n0 + c_lo, lane, 0);
+            // operands the epilogue needs from global memory (residual rows) are requested kDist chunks ahead into kDist + 1
+            // register buffers; the first requests go out before the accumulator is even complete
+            constexpr int kDist = Epi::kPrefetchDist, kBufs = kDist + 1, kChunks = kColsPerWarp / 32;
+#pragma unroll
+            for (int d = 0; d < kDist; ++d)
+                if (d < kChunks) epi.prefetch(est, ti, row, ti.n0 + c_lo + 32 * d, lane, d % kBufs);
             mbar_wait_guarded_cluster(&tmem_full[acc], acc_phase, PAIR_SITE_EPI_TMEM_FULL, acc);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BLOCK_N;
 #pragma unroll (Epi::kUnrollChunks)
-            for (int ci = 0; ci < kColsPerWarp / 32; ++ci) {
+            for (int ci = 0; ci < kChunks; ++ci) {
                 const int c = c_lo + 32 * ci;
-                if (ci + 1 < kColsPerWarp / 32) epi.prefetch(est, ti, row, ti.n0 + c + 32, lane, (ci + 1) & 1);
+                if (ci + kDist < kChunks) epi.prefetch(est, ti, row, ti.n0 + c + 32 * kDist, lane, (ci + kDist) % kBufs);
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane, ci & 1, taddr + c);
+                epi.tile(est, ti, row, ti.n0 + c, v, epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES, lane, ci % kBufs, taddr + c);
             }
             tc_fence_before();
             __syncwarp();

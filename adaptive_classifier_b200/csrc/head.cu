@@ -196,7 +196,7 @@ static int check_params(const ac_head_params *p, const char *who) {
 struct TrainPlan {
     int G, nst;
     int slots[3];
-    size_t off_h0d, off_h1d, off_z, off_dz, off_da1, off_rowloss, off_part, off_pen, off_bar, off_stats, total;
+    size_t off_h0d, off_h1d, off_z, off_dz, off_da1, off_rowloss, off_part, off_pen, off_bar, off_stats, off_timing, total;
     size_t smem_bytes;
 };
 
@@ -248,9 +248,12 @@ static int plan_training(int batch, const ac_head_params *p, int n_steps, TrainP
     pl.off_pen = take(sizeof(float) * 256);
     pl.off_bar = take(256);
     pl.off_stats = take(sizeof(float) * 3 * (n_steps > 0 ? n_steps : 1));
+    pl.off_timing = take(16 * sizeof(unsigned long long));
     pl.total = off;
     return AC_OK;
 }
+
+static unsigned long long *g_head_timing_dev = nullptr;
 
 struct TrainCall {
     const float *X; const void *targets; const int64_t *perm; int n, batch, n_steps, first_step;
@@ -315,6 +318,9 @@ static int launch_training(const TrainCall &c, void *workspace, size_t workspace
     a.loss_accum = c.loss_accum;
     if (stats_out) *stats_out = a.stats;
     AC_CUDA(cudaMemsetAsync(a.bar, 0, 256, s));
+    if (g_head_timing_dev) {               // diagnostic: per-phase nanoseconds of CTA 0 (ac_head_phase_timing)
+        a.timing = g_head_timing_dev;
+    }
     static bool attr_set[64] = {};
     int dev = 0;
     AC_CUDA(cudaGetDevice(&dev));
@@ -353,6 +359,24 @@ extern "C" int ac_head_forward(const float *X, int B, const ac_head_params *p, i
         const int wpb = 4;
         softmax_rows_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(out, B, p->C, out, act);
         AC_LAUNCH_CHECK();
+    }
+    return AC_OK;
+}
+
+// diagnostic (tools/head_phase_times.py): enable != 0 starts accumulating, per training launch, the nanoseconds CTA 0 spends in
+// every phase of head_train_kernel and in the grid barriers between them; out16_host (nullable) receives the 13 counters so far
+extern "C" int ac_head_phase_timing(int enable, unsigned long long *out16_host) {
+    if (enable && !g_head_timing_dev) {
+        AC_CUDA(cudaMalloc(reinterpret_cast<void **>(&g_head_timing_dev), 16 * sizeof(unsigned long long)));
+        AC_CUDA(cudaMemset(g_head_timing_dev, 0, 16 * sizeof(unsigned long long)));
+    }
+    if (out16_host && g_head_timing_dev) {
+        AC_CUDA(cudaDeviceSynchronize());
+        AC_CUDA(cudaMemcpy(out16_host, g_head_timing_dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (!enable && g_head_timing_dev) {
+        cudaFree(g_head_timing_dev);
+        g_head_timing_dev = nullptr;
     }
     return AC_OK;
 }

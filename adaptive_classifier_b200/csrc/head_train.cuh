@@ -79,6 +79,7 @@ struct Args {
     unsigned *bar;                // [2] grid barrier state (count, generation), zero-initialised
     int slots[3];                 // ownership blocks per CTA of each layer = ceil(ceil(rows / 8) / G)
     int nst;                      // stages of the streamed-operand ring (2..4)
+    unsigned long long *timing;   // nullable, [16]: nanoseconds CTA 0 spent up to each phase boundary, summed over the steps
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -118,6 +119,26 @@ __device__ __forceinline__ float ht_mask(float p, unsigned long long seed, unsig
     const float u = (r >> 8) * (1.0f / 16777216.0f);
     return (u < p) ? 0.f : 1.f / (1.f - p);
 }
+
+// phase timing (diagnostic, tools/head_phase_times.py): CTA 0 accumulates the global-timer delta since the previous stamp
+#if !defined(AC_CPU_SHIM)
+__device__ __forceinline__ unsigned long long ht_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define HT_STAMP(i)                                                                  \
+    do {                                                                             \
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0) {                       \
+            const unsigned long long now_ = ht_now();                               \
+            a.timing[i] += now_ - t_prev;                                            \
+            t_prev = now_;                                                           \
+        }                                                                            \
+    } while (0)
+#else
+static inline unsigned long long ht_now() { return 0; }
+#define HT_STAMP(i) do { (void)t_prev; } while (0)
+#endif
 
 // grid barrier: all threads of all CTAs.  Cooperative launch guarantees co-residency; a watchdog turns a protocol bug into a
 // launch error instead of a hung GPU.
@@ -376,6 +397,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
     }
     __syncthreads();
 
+    unsigned long long t_prev = ht_now();
     for (int t = 0; t < a.n_steps; ++t) {
         const int step = a.first_step + t;
         const int off = t * a.batch;
@@ -414,7 +436,9 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                 }
                 __syncthreads();
             }
+            HT_STAMP(2 * l);
             ht_grid_sync(a.bar, gen);
+            HT_STAMP(2 * l + 1);
         }
 
         // ================= P3b: loss and dz, one warp per batch row =================
@@ -450,7 +474,9 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                 if (lane == 0) a.rowloss[b] = l / static_cast<float>(C);
             }
         }
+        HT_STAMP(6);
         ht_grid_sync(a.bar, gen);
+        HT_STAMP(7);
 
         // ================= P4: layer-2 weight gradients; da1 of the own layer-1 rows =================
         {
@@ -487,7 +513,9 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
             }
             (void)L1;
         }
+        HT_STAMP(8);
         ht_grid_sync(a.bar, gen);
+        HT_STAMP(9);
 
         // ================= P5: layer-1 weight gradients; da0 of the own layer-0 rows.  P6: layer-0 weight gradients ==========
         {
@@ -569,7 +597,9 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
         ss = ht_block_sum(ss, rsum);
         pen = ht_block_sum(pen, rsum);
         if (tid == 0) { a.part[cta] = ss; a.pen[cta] = pen; }
+        HT_STAMP(10);
         ht_grid_sync(a.bar, gen);
+        HT_STAMP(11);
 
         // ================= P7: global norm, clip, AdamW on the own rows =================
         float tot = 0.f, pt = 0.f;
@@ -605,36 +635,60 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                 if (q >= nblk) break;
                 const float *g = ht_smem + sm.g[l] + s * HT_RB * L.K;
                 float *th = ht_smem + sm.th[l] + s * HT_RB * L.K;
-                for (int e = tid; e < HT_RB * L.K + HT_RB; e += HT_THREADS) {
-                    const bool is_b = e >= HT_RB * L.K;
-                    const int j = is_b ? e - HT_RB * L.K : e / L.K;
-                    const int r = q * HT_RB + j;
-                    if (r >= L.rows) continue;
-                    const int64_t gi = is_b ? r : static_cast<int64_t>(r) * L.K + e % L.K;
-                    const float graw = is_b ? ht_smem[sm.gb[l] + s * HT_RB + j] : g[e];
-                    if (a.update) {
-                        float *pm = is_b ? L.mb : L.mW, *pv = is_b ? L.vb : L.vW, *pp = is_b ? L.b : L.W;
-                        float *ps = is_b ? ht_smem + sm.bs[l] + s * HT_RB + j : th + e;
-                        const float gv = graw * coef;
-                        float p = *ps;
-                        p = p * (1.f - a.lr * a.wd);
-                        const float mi = pm[gi] * a.beta1 + gv * (1.f - a.beta1);
-                        const float vi = pv[gi] * a.beta2 + gv * gv * (1.f - a.beta2);
-                        const float denom = sqrtf(vi) / bc2s + a.eps;
-                        p = p - (a.lr / bc1) * (mi / denom);
-                        *ps = p;
-                        pp[gi] = p;
-                        pm[gi] = mi;
-                        pv[gi] = vi;
-                    } else {
-                        float *og = is_b ? L.gb : L.gW, *oq = is_b ? L.qb : L.qW;
-                        if (og) og[gi] = graw;
-                        if (oq) oq[gi] += graw * graw * a.fisher_scale;
+                const int n_el = HT_RB * L.K + HT_RB;               // the block's weights, then its 8 biases
+                // the moments live in global memory (L2): their loads are issued HT_U at a time before the arithmetic, otherwise
+                // the ~60 elements of a thread pay one L2 round trip each (measured: ~50 us of a 120 us step)
+                constexpr int HT_U = 8;
+                for (int e0 = tid; e0 < n_el; e0 += HT_U * HT_THREADS) {
+                    float mi[HT_U], vi[HT_U];
+                    int64_t gidx[HT_U];
+                    bool ok[HT_U];
+#pragma unroll
+                    for (int u = 0; u < HT_U; ++u) {
+                        const int e = e0 + u * HT_THREADS;
+                        const bool is_b = e >= HT_RB * L.K;
+                        const int j = is_b ? e - HT_RB * L.K : e / L.K;
+                        const int r = q * HT_RB + j;
+                        ok[u] = e < n_el && r < L.rows;
+                        gidx[u] = is_b ? r : static_cast<int64_t>(r) * L.K + e % L.K;
+                        mi[u] = 0.f;
+                        vi[u] = 0.f;
+                        if (ok[u] && a.update) {
+                            mi[u] = (is_b ? L.mb : L.mW)[gidx[u]];
+                            vi[u] = (is_b ? L.vb : L.vW)[gidx[u]];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < HT_U; ++u) {
+                        if (!ok[u]) continue;
+                        const int e = e0 + u * HT_THREADS;
+                        const bool is_b = e >= HT_RB * L.K;
+                        const int j = is_b ? e - HT_RB * L.K : 0;
+                        const float graw = is_b ? ht_smem[sm.gb[l] + s * HT_RB + j] : g[e];
+                        if (a.update) {
+                            float *ps = is_b ? ht_smem + sm.bs[l] + s * HT_RB + j : th + e;
+                            const float gv = graw * coef;
+                            float p = *ps;
+                            p = p * (1.f - a.lr * a.wd);
+                            const float m1 = mi[u] * a.beta1 + gv * (1.f - a.beta1);
+                            const float v1 = vi[u] * a.beta2 + gv * gv * (1.f - a.beta2);
+                            const float denom = sqrtf(v1) / bc2s + a.eps;
+                            p = p - (a.lr / bc1) * (m1 / denom);
+                            *ps = p;
+                            (is_b ? L.b : L.W)[gidx[u]] = p;
+                            (is_b ? L.mb : L.mW)[gidx[u]] = m1;
+                            (is_b ? L.vb : L.vW)[gidx[u]] = v1;
+                        } else {
+                            float *og = is_b ? L.gb : L.gW, *oq = is_b ? L.qb : L.qW;
+                            if (og) og[gidx[u]] = graw;
+                            if (oq) oq[gidx[u]] += graw * graw * a.fisher_scale;
+                        }
                     }
                 }
             }
         }
         __syncthreads();
+        HT_STAMP(12);
     }
 }
 

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Where a head optimizer step spends its time: per-phase / per-barrier microseconds of CTA 0 of head_train_kernel
+(csrc/head_train.cuh), averaged over one epoch of 625 steps at batch 32 (bert-base head, C classes)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from adaptive_classifier_b200 import _cabi
+from adaptive_classifier_b200.models import AdaptiveHead
+
+C = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+head = AdaptiveHead(768, C, hidden_dims=[768, 384]).cuda()
+p = head._param_dict()
+m = {k: torch.zeros_like(v) for k, v in p.items()}
+v = {k: torch.zeros_like(t) for k, t in p.items()}
+n = 20000
+X = torch.nn.functional.normalize(torch.randn(n, 768, device="cuda"), dim=1)
+y = torch.randint(0, C, (n,), device="cuda")
+perm = torch.randperm(n)
+_cabi.head_train_epoch(X, y, perm, p, m, v, first_step=1, batch=32)
+torch.cuda.synchronize()
+_cabi.head_phase_timing(True)
+t0 = time.time()
+_, nb = _cabi.head_train_epoch(X, y, perm, p, m, v, first_step=626, batch=32)
+torch.cuda.synchronize()
+wall = time.time() - t0
+ns = _cabi.head_phase_timing(False)
+names = ["P1 h0", "B1", "P2 h1", "B2", "P3a z", "B3a", "P3b loss/dz", "B3b", "P4 gW2+da1", "B4", "P5/P6 gW1,da0,gW0,norm", "B6", "P7 adamw"]
+print(json.dumps({"classes": C, "steps": nb, "us_per_step_wall": 1e6 * wall / nb,
+                  "us_per_step_by_phase": {nm: round(x / nb / 1e3, 2) for nm, x in zip(names, ns)},
+                  "sum_us": round(sum(ns) / nb / 1e3, 2)}))
