@@ -237,12 +237,16 @@ struct EpiResidDefer {
 
     static constexpr int kUnrollChunks = 4;
     // The residual epilogues move 327 KB per 128 x 256 tile (fp32 sums read + written, fp16 copy written) against a 3-13 us
-    // mainloop: they are HBM-bound, and with one 4 KB chunk per warp in flight the 8 epilogue warps of an SM sustained only
-    // ~25 GB/s (3.65 TB/s over the chip, out-proj 152 us against an 85 us traffic floor).  Two chunks ahead = three register
-    // buffers doubles the bytes in flight.
-    static constexpr int kPrefetchDist = 2;
+    // mainloop: they are HBM-bound, and with one 4 KB chunk per warp in flight the 8 epilogue warps of an SM sustain ~25 GB/s
+    // (3.65 TB/s over the chip; out-proj 152 us against an 85 us traffic floor).  Requesting two chunks ahead needs a third
+    // 32-register buffer: with the 168 registers a 10-warp CTA can have (warps are allocated in fours) it spills, and measured
+    // SLOWER on a B200 (14.5-14.8 ms per step against 13.9-14.1: profiles/r02_variants.md), so the distance stays 1.
+#ifndef AC_RESID_PREFETCH
+#define AC_RESID_PREFETCH 1
+#endif
+    static constexpr int kPrefetchDist = AC_RESID_PREFETCH;
     struct State {
-        float4 res[3][8];                  // old sums of 32-column chunks (transposed-phase layout), triple-buffered
+        float4 res[kPrefetchDist + 1][8];  // old sums of 32-column chunks (transposed-phase layout), one buffer more than the distance
         float2 ms[4];                      // (mu, r) of this lane's 4 rows (r8 + 8 i)
         float sum[4], sq[4];               // running partials of the new sums over this warp's 128 columns
     };

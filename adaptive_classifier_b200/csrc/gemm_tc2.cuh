@@ -57,9 +57,9 @@ __device__ __forceinline__ void mbar_wait_guarded_cluster(uint64_t *bar, uint32_
 //                 the bias + GELU epilogue issues ~17 instructions per element; two warps per scheduler cannot hide its MUFU /
 //                 dependency latency behind a K = 768 mainloop (FFN1 measured 56 % tensor-pipe active), four can.
 template <class Epi, bool kMFastest = false, int kKind = GEMM_KIND_TF32, int kStages = GEMM2_STAGES, int kEpiWarps = GEMM_EPI_WARPS>
-// register cap spelled out (65536 / threads, multiple of 8): __launch_bounds__(320, 1) lets ptxas use only 168, which spilled the
-// triple-buffered residual epilogue
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kEpiWarps == 8 ? 200 : 112)
+// registers: warps are allocated in groups of 4, so the 10 (18) warps of a CTA cost 12 (20) warps of registers: 168 (96) per thread.
+// (__maxnreg__(200) compiled and then failed to launch: 12 x 32 x 200 > 65536.)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 int M, int N, int K, Epi epi) {
     extern __shared__ uint8_t smem_raw[];

@@ -263,13 +263,14 @@ __device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, f
                         const float4 av = *reinterpret_cast<const float4 *>(a + 4 * q4);
 #pragma unroll
                         for (int j = 0; j < HT_RB; ++j) {
-                            const float *w = wbase + j * wld + kk;
-                            // resident rows: K % 4 == 0 (host-checked); gathered chunks are zero-padded to HT_KC
+                            // one 16-byte broadcast load per 4 weights (rows are 16-byte aligned: K, HT_KC and kk are multiples
+                            // of 4); resident rows: K % 4 == 0 (host-checked); gathered chunks are zero-padded to HT_KC
+                            const float4 wv = *reinterpret_cast<const float4 *>(wbase + j * wld + kk);
                             float s = acc[bi][j];
-                            s = fmaf(av.x, w[0], s);
-                            s = fmaf(av.y, w[1], s);
-                            s = fmaf(av.z, w[2], s);
-                            s = fmaf(av.w, w[3], s);
+                            s = fmaf(av.x, wv.x, s);
+                            s = fmaf(av.y, wv.y, s);
+                            s = fmaf(av.z, wv.z, s);
+                            s = fmaf(av.w, wv.w, s);
                             acc[bi][j] = s;
                         }
                     }
@@ -403,6 +404,10 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
         const int off = t * a.batch;
         const int Bt = (a.n - off < a.batch) ? (a.n - off) : a.batch;
         if (tid < Bt) ridx[tid] = a.perm ? a.perm[off + tid] : static_cast<int64_t>(off + tid);
+        if (tid == HT_THREADS - 1) {      // AdamW bias corrections of this step (double precision like Python's 1 - beta ** step), off the critical path
+            scal[1] = static_cast<float>(1.0 - pow(static_cast<double>(a.beta1), static_cast<double>(step)));
+            scal[2] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.beta2), static_cast<double>(step))));
+        }
         __syncthreads();
         const bool drop = a.dropout_p > 0.f;
 
@@ -553,44 +558,46 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
         }
         __syncthreads();
 
-        // ---- EWC gradient on the own rows, partial sum of squares of the own gradients
+        // ---- EWC gradient on the own rows, partial sum of squares of the own gradients (row loops: no integer divisions)
         float ss = 0.f, pen = 0.f;
         const float ewc2 = a.use_ewc ? 2.f * a.ewc_lambda / static_cast<float>(Bt) : 0.f;
         for (int l = 0; l < 3; ++l) {
             const Layer &L = a.L[l];
             const int nblk = (L.rows + HT_RB - 1) / HT_RB;
+            const int K = L.K;
             for (int s = 0; s < a.slots[l]; ++s) {
                 const int q = cta + s * G;
                 if (q >= nblk) break;
-                float *g = ht_smem + sm.g[l] + s * HT_RB * L.K;
-                const float *th = ht_smem + sm.th[l] + s * HT_RB * L.K;
-                for (int e = tid; e < HT_RB * L.K; e += HT_THREADS) {
-                    const int j = e / L.K, k = e % L.K, r = q * HT_RB + j;
-                    if (r >= L.rows) continue;
-                    float gv = g[e];
-                    if (a.use_ewc && r < L.ewc_rows) {
-                        const int64_t gi = static_cast<int64_t>(r) * L.K + k;
-                        const float dlt = th[e] - L.sW[gi];
-                        const float f = L.fW[gi];
-                        gv = fmaf(ewc2 * f, dlt, gv);
-                        pen = fmaf(f * dlt, dlt, pen);
-                        g[e] = gv;
-                    }
-                    ss = fmaf(gv, gv, ss);
-                }
-                if (tid < HT_RB) {
-                    const int r = q * HT_RB + tid;
-                    if (r < L.rows) {
-                        float gv = ht_smem[sm.gb[l] + s * HT_RB + tid];
-                        if (a.use_ewc && r < L.ewc_rows) {
-                            const float dlt = ht_smem[sm.bs[l] + s * HT_RB + tid] - L.sb[r];
-                            const float f = L.fb[r];
+                float *g = ht_smem + sm.g[l] + s * HT_RB * K;
+                const float *th = ht_smem + sm.th[l] + s * HT_RB * K;
+                const int nrow = (L.rows - q * HT_RB < HT_RB) ? (L.rows - q * HT_RB) : HT_RB;
+                for (int j = 0; j < nrow; ++j) {
+                    const int r = q * HT_RB + j;
+                    const bool ew = a.use_ewc && r < L.ewc_rows;
+                    for (int k = tid; k < K; k += HT_THREADS) {
+                        float gv = g[j * K + k];
+                        if (ew) {
+                            const int64_t gi = static_cast<int64_t>(r) * K + k;
+                            const float dlt = th[j * K + k] - L.sW[gi];
+                            const float f = L.fW[gi];
                             gv = fmaf(ewc2 * f, dlt, gv);
                             pen = fmaf(f * dlt, dlt, pen);
-                            ht_smem[sm.gb[l] + s * HT_RB + tid] = gv;
+                            g[j * K + k] = gv;
                         }
                         ss = fmaf(gv, gv, ss);
                     }
+                }
+                if (tid < nrow) {
+                    const int r = q * HT_RB + tid;
+                    float gv = ht_smem[sm.gb[l] + s * HT_RB + tid];
+                    if (a.use_ewc && r < L.ewc_rows) {
+                        const float dlt = ht_smem[sm.bs[l] + s * HT_RB + tid] - L.sb[r];
+                        const float f = L.fb[r];
+                        gv = fmaf(ewc2 * f, dlt, gv);
+                        pen = fmaf(f * dlt, dlt, pen);
+                        ht_smem[sm.gb[l] + s * HT_RB + tid] = gv;
+                    }
+                    ss = fmaf(gv, gv, ss);
                 }
             }
         }
@@ -602,11 +609,16 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
         HT_STAMP(11);
 
         // ================= P7: global norm, clip, AdamW on the own rows =================
-        float tot = 0.f, pt = 0.f;
+        float tot = 0.f, pt = 0.f, ls = 0.f;
         if (warp == 0) {
             // every CTA adds the G partials in the same fixed order: lane-strided sums, then a shuffle tree
             for (int i = lane; i < G; i += 32) { tot += HT_LDCG(a.part + i); pt += HT_LDCG(a.pen + i); }
             for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, o); pt += __shfl_xor_sync(0xffffffffu, pt, o); }
+            if (cta == 0) {                 // batch loss: the row losses are fetched in parallel, added in row order
+                float r0 = lane < Bt ? HT_LDCG(a.rowloss + lane) : 0.f, r1 = lane + 32 < Bt ? HT_LDCG(a.rowloss + lane + 32) : 0.f;
+                for (int b = 0; b < 32; ++b) ls += __shfl_sync(0xffffffffu, r0, b);
+                for (int b = 0; b < 32; ++b) ls += __shfl_sync(0xffffffffu, r1, b);
+            }
         }
         if (tid == 0) {
             const float norm = sqrtf(tot);
@@ -614,11 +626,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
             coef = coef < 1.f ? coef : 1.f;
             if (!(a.max_norm > 0.f)) coef = 1.f;
             scal[0] = coef;
-            scal[1] = static_cast<float>(1.0 - pow(static_cast<double>(a.beta1), static_cast<double>(step)));
-            scal[2] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.beta2), static_cast<double>(step))));
             if (cta == 0) {
-                float ls = 0.f;
-                for (int b = 0; b < Bt; ++b) ls += HT_LDCG(a.rowloss + b);
                 const float loss = ls / static_cast<float>(Bt);
                 const float penalty = a.use_ewc ? a.ewc_lambda / static_cast<float>(Bt) * pt : 0.f;
                 if (a.stats) { a.stats[3 * t + 0] = loss; a.stats[3 * t + 1] = penalty; a.stats[3 * t + 2] = norm; }
@@ -627,62 +635,68 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
         }
         __syncthreads();
         const float coef = scal[0], bc1 = scal[1], bc2s = scal[2];
+        const float decay = 1.f - a.lr * a.wd, lr_c = a.lr / bc1, omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
         for (int l = 0; l < 3; ++l) {
             const Layer &L = a.L[l];
             const int nblk = (L.rows + HT_RB - 1) / HT_RB;
+            const int K = L.K;
             for (int s = 0; s < a.slots[l]; ++s) {
                 const int q = cta + s * G;
                 if (q >= nblk) break;
-                const float *g = ht_smem + sm.g[l] + s * HT_RB * L.K;
-                float *th = ht_smem + sm.th[l] + s * HT_RB * L.K;
-                const int n_el = HT_RB * L.K + HT_RB;               // the block's weights, then its 8 biases
-                // the moments live in global memory (L2): their loads are issued HT_U at a time before the arithmetic, otherwise
-                // the ~60 elements of a thread pay one L2 round trip each (measured: ~50 us of a 120 us step)
-                constexpr int HT_U = 8;
-                for (int e0 = tid; e0 < n_el; e0 += HT_U * HT_THREADS) {
-                    float mi[HT_U], vi[HT_U];
-                    int64_t gidx[HT_U];
-                    bool ok[HT_U];
+                const float *g = ht_smem + sm.g[l] + s * HT_RB * K;
+                float *th = ht_smem + sm.th[l] + s * HT_RB * K;
+                const int nrow = (L.rows - q * HT_RB < HT_RB) ? (L.rows - q * HT_RB) : HT_RB;
+                // thread = column k of the block's 8 rows: the 16 moment loads of a column (global memory, L2) are issued together,
+                // coalesced along k, before any arithmetic
+                for (int k = tid; k < K; k += HT_THREADS) {
+                    float mi[HT_RB], vi[HT_RB];
+                    const int64_t g0 = static_cast<int64_t>(q) * HT_RB * K + k;
+                    if (a.update) {
 #pragma unroll
-                    for (int u = 0; u < HT_U; ++u) {
-                        const int e = e0 + u * HT_THREADS;
-                        const bool is_b = e >= HT_RB * L.K;
-                        const int j = is_b ? e - HT_RB * L.K : e / L.K;
-                        const int r = q * HT_RB + j;
-                        ok[u] = e < n_el && r < L.rows;
-                        gidx[u] = is_b ? r : static_cast<int64_t>(r) * L.K + e % L.K;
-                        mi[u] = 0.f;
-                        vi[u] = 0.f;
-                        if (ok[u] && a.update) {
-                            mi[u] = (is_b ? L.mb : L.mW)[gidx[u]];
-                            vi[u] = (is_b ? L.vb : L.vW)[gidx[u]];
+                        for (int j = 0; j < HT_RB; ++j) {
+                            mi[j] = j < nrow ? L.mW[g0 + static_cast<int64_t>(j) * K] : 0.f;
+                            vi[j] = j < nrow ? L.vW[g0 + static_cast<int64_t>(j) * K] : 0.f;
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < HT_U; ++u) {
-                        if (!ok[u]) continue;
-                        const int e = e0 + u * HT_THREADS;
-                        const bool is_b = e >= HT_RB * L.K;
-                        const int j = is_b ? e - HT_RB * L.K : 0;
-                        const float graw = is_b ? ht_smem[sm.gb[l] + s * HT_RB + j] : g[e];
+                    for (int j = 0; j < HT_RB; ++j) {
+                        if (j >= nrow) continue;
+                        const int64_t gi = g0 + static_cast<int64_t>(j) * K;
+                        const float graw = g[j * K + k];
                         if (a.update) {
-                            float *ps = is_b ? ht_smem + sm.bs[l] + s * HT_RB + j : th + e;
                             const float gv = graw * coef;
-                            float p = *ps;
-                            p = p * (1.f - a.lr * a.wd);
-                            const float m1 = mi[u] * a.beta1 + gv * (1.f - a.beta1);
-                            const float v1 = vi[u] * a.beta2 + gv * gv * (1.f - a.beta2);
+                            float p = th[j * K + k] * decay;
+                            const float m1 = mi[j] * a.beta1 + gv * omb1;
+                            const float v1 = vi[j] * a.beta2 + gv * gv * omb2;
                             const float denom = sqrtf(v1) / bc2s + a.eps;
-                            p = p - (a.lr / bc1) * (m1 / denom);
-                            *ps = p;
-                            (is_b ? L.b : L.W)[gidx[u]] = p;
-                            (is_b ? L.mb : L.mW)[gidx[u]] = m1;
-                            (is_b ? L.vb : L.vW)[gidx[u]] = v1;
+                            p = p - lr_c * (m1 / denom);
+                            th[j * K + k] = p;
+                            L.W[gi] = p;
+                            L.mW[gi] = m1;
+                            L.vW[gi] = v1;
                         } else {
-                            float *og = is_b ? L.gb : L.gW, *oq = is_b ? L.qb : L.qW;
-                            if (og) og[gidx[u]] = graw;
-                            if (oq) oq[gidx[u]] += graw * graw * a.fisher_scale;
+                            if (L.gW) L.gW[gi] = graw;
+                            if (L.qW) L.qW[gi] += graw * graw * a.fisher_scale;
                         }
+                    }
+                }
+                if (tid < nrow) {
+                    const int r = q * HT_RB + tid;
+                    const float graw = ht_smem[sm.gb[l] + s * HT_RB + tid];
+                    if (a.update) {
+                        const float gv = graw * coef;
+                        float p = ht_smem[sm.bs[l] + s * HT_RB + tid] * decay;
+                        const float m1 = L.mb[r] * a.beta1 + gv * omb1;
+                        const float v1 = L.vb[r] * a.beta2 + gv * gv * omb2;
+                        const float denom = sqrtf(v1) / bc2s + a.eps;
+                        p = p - lr_c * (m1 / denom);
+                        ht_smem[sm.bs[l] + s * HT_RB + tid] = p;
+                        L.b[r] = p;
+                        L.mb[r] = m1;
+                        L.vb[r] = v1;
+                    } else {
+                        if (L.gb) L.gb[r] = graw;
+                        if (L.qb) L.qb[r] += graw * graw * a.fisher_scale;
                     }
                 }
             }
