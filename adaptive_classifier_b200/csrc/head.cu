@@ -88,14 +88,89 @@ rowdot_kernel(const float *__restrict__ X, const float *__restrict__ W, float *_
     }
 }
 
+// batched forward (M > 64 rows, the predict step at B = 512): Y[m,n] = epi( sum_k X[m,k] W[n,k] ), both operands K-major.
+// 64 x 64 tile, 256 threads x (4 x 4) outputs, K in slabs of 16 staged transposed in shared memory ([k][row], padded), next slab
+// prefetched into registers.  k is added in ascending order per output.  (rowdot_kernel<4> needed 255 registers -- a whole SM's
+// register file per CTA, so on the side stream it could not share an SM with the prototype scan -- and ran at 2.6 TFLOP/s:
+// 527 us for the three layers at B = 512, profiles/r02_knn_ncu.md; this kernel: see the same file.)
+constexpr int SG_T = 64, SG_K = 16;
+__global__ void __launch_bounds__(256)
+sgemm_nt_kernel(const float *__restrict__ X, const float *__restrict__ W, float *__restrict__ Y, int M, int N, int K, SgemmEpi epi) {
+    __shared__ __align__(16) float sx[2][SG_K][SG_T + 4];
+    __shared__ __align__(16) float sw[2][SG_K][SG_T + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+    const int tx = tid & 15, ty = tid >> 4;                 // outputs: rows m0 + 4 ty .. +3, columns n0 + 4 tx .. +3
+    const int lr = tid >> 2, lk = (tid & 3) * 4;            // loader: row lr of the tile, 4 consecutive k
+    const bool vec = (K & 3) == 0;
+    auto load4 = [&](const float *base, int row, int rows, int k) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows) {
+            const float *p = base + static_cast<int64_t>(row) * K + k;
+            if (vec && k + 4 <= K) v = __ldg(reinterpret_cast<const float4 *>(p));
+            else {
+                if (k + 0 < K) v.x = __ldg(p + 0);
+                if (k + 1 < K) v.y = __ldg(p + 1);
+                if (k + 2 < K) v.z = __ldg(p + 2);
+                if (k + 3 < K) v.w = __ldg(p + 3);
+            }
+        }
+        return v;
+    };
+    auto stage = [&](float (*dst)[SG_T + 4], const float4 &v) {
+        dst[lk + 0][lr] = v.x; dst[lk + 1][lr] = v.y; dst[lk + 2][lr] = v.z; dst[lk + 3][lr] = v.w;
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 rx = load4(X, m0 + lr, M, lk), rw = load4(W, n0 + lr, N, lk);
+    const int nslab = (K + SG_K - 1) / SG_K;
+    for (int sl = 0; sl < nslab; ++sl) {
+        const int buf = sl & 1;
+        stage(sx[buf], rx);
+        stage(sw[buf], rw);
+        __syncthreads();
+        if (sl + 1 < nslab) {
+            rx = load4(X, m0 + lr, M, (sl + 1) * SG_K + lk);
+            rw = load4(W, n0 + lr, N, (sl + 1) * SG_K + lk);
+        }
+#pragma unroll
+        for (int k = 0; k < SG_K; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&sx[buf][k][4 * ty]);
+            const float4 b = *reinterpret_cast<const float4 *>(&sw[buf][k][4 * tx]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        // the buffer written two slabs from now is this one: the barrier at the top of the next iteration orders it
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + 4 * ty + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 4 * tx + j;
+            if (n < N) {
+                const int64_t off = static_cast<int64_t>(m) * N + n;
+                Y[off] = epi_apply(epi, acc[i][j], n, off);
+            }
+        }
+    }
+}
+
 static int rowdot(const float *X, const float *W, float *Y, int M, int N, int K, SgemmEpi epi, cudaStream_t s) {
     if (M <= 0 || N <= 0) return AC_OK;
     if (M <= 64) {
         dim3 grid((N + RD_WARPS - 1) / RD_WARPS, (M + 31) / 32);
         rowdot_kernel<1><<<grid, RD_WARPS * 32, 0, s>>>(X, W, Y, M, N, K, epi);
     } else {
-        dim3 grid((N + 4 * RD_WARPS - 1) / (4 * RD_WARPS), (M + 31) / 32);
-        rowdot_kernel<4><<<grid, RD_WARPS * 32, 0, s>>>(X, W, Y, M, N, K, epi);
+        dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T);
+        sgemm_nt_kernel<<<grid, 256, 0, s>>>(X, W, Y, M, N, K, epi);
     }
     AC_LAUNCH_CHECK();
     return AC_OK;
@@ -196,7 +271,7 @@ static int check_params(const ac_head_params *p, const char *who) {
 struct TrainPlan {
     int G, nst;
     int slots[3];
-    size_t off_h0d, off_h1d, off_z, off_dz, off_da1, off_rowloss, off_part, off_pen, off_bar, off_stats, off_timing, total;
+    size_t off_h0d, off_h1d, off_z, off_dz, off_da1, off_rowloss, off_part, off_pen, off_bar, off_stats, off_timing, off_g[3], total;
     size_t smem_bytes;
 };
 
@@ -226,7 +301,8 @@ static int plan_training(int batch, const ac_head_params *p, int n_steps, TrainP
         a.L[l].K = K[l];
     }
     // as many ring stages (4 down to 2) as the parameter / gradient rows leave room for
-    for (a.nst = 4; a.nst >= 2; --a.nst) {
+    AC_REQUIRE(p->D <= 2048 && p->H0 <= 2048 && p->H1 <= 2048, "%s: layer widths above 2048 are not supported", who);
+    for (a.nst = 8; a.nst >= 2; --a.nst) {
         pl.smem_bytes = static_cast<size_t>(ht::ht_smem_layout(a).total) * sizeof(float);
         if (pl.smem_bytes <= 220 * 1024) break;
     }
@@ -249,6 +325,7 @@ static int plan_training(int batch, const ac_head_params *p, int n_steps, TrainP
     pl.off_bar = take(256);
     pl.off_stats = take(sizeof(float) * 3 * (n_steps > 0 ? n_steps : 1));
     pl.off_timing = take(16 * sizeof(unsigned long long));
+    for (int l = 0; l < 3; ++l) pl.off_g[l] = take(sizeof(float) * static_cast<size_t>(rows[l]) * K[l]);
     pl.total = off;
     return AC_OK;
 }
@@ -284,6 +361,7 @@ static int launch_training(const TrainCall &c, void *workspace, size_t workspace
     for (int l = 0; l < 3; ++l) {
         ht::Layer &Lr = a.L[l];
         Lr.W = Wp[l]; Lr.b = bp[l]; Lr.rows = rows[l]; Lr.K = K[l]; Lr.ewc_rows = rows[l];
+        Lr.xW = reinterpret_cast<float *>(w + pl.off_g[l]);
         a.slots[l] = pl.slots[l];
         a.nst = pl.nst;
 #define AC_PICK(hp, l) ((l) == 0 ? (hp)->W0 : (l) == 1 ? (hp)->W1 : (hp)->W2)

@@ -53,6 +53,7 @@ struct Layer {
     float *W, *b;                 // [rows, K], [rows]   parameters (global; updated in place)
     float *mW, *mb, *vW, *vb;     // AdamW moments (update mode)
     const float *fW, *fb, *sW, *sb;   // EWC Fisher / theta* (nullable)
+    float *xW;                    // [rows, K] gradient scratch in global memory (L2-resident: written and read by the owner CTA only)
     float *gW, *gb;               // gradient outputs (gradient-only mode, nullable)
     float *qW, *qb;               // Fisher accumulators: q += g^2 * fisher_scale (gradient-only mode, nullable)
     int rows, K, ewc_rows;        // ewc_rows: only the first ewc_rows rows carry the EWC term (the head may have grown)
@@ -103,10 +104,16 @@ static inline void ht_async4(float *dst, const float *src, bool valid) { dst[0] 
 static inline void ht_async_commit() {}
 template <int N> static inline void ht_async_wait() {}
 #endif
-__device__ __forceinline__ void ht_async_wait_n(int n) {       // n = stages - 2 in {0, 1, 2}
-    if (n <= 0) ht_async_wait<0>();
-    else if (n == 1) ht_async_wait<1>();
-    else ht_async_wait<2>();
+__device__ __forceinline__ void ht_async_wait_n(int n) {       // n = stages - 2 in [0, 6]
+    switch (n) {
+        case 0: ht_async_wait<0>(); break;
+        case 1: ht_async_wait<1>(); break;
+        case 2: ht_async_wait<2>(); break;
+        case 3: ht_async_wait<3>(); break;
+        case 4: ht_async_wait<4>(); break;
+        case 5: ht_async_wait<5>(); break;
+        default: ht_async_wait<6>(); break;
+    }
 }
 
 __device__ __forceinline__ uint32_t ht_mix32(uint64_t x) {
@@ -297,10 +304,11 @@ __device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, f
     __syncthreads();
 }
 
-// g[j][k] = sum_b dA[b][j] * A[b][k]  for the 8 rows j of one ownership block (weight gradient), A streamed in chunks;
-// g: shared memory [8][K]; dA: shared memory [rows][8]; batch rows are added in index order.
-__device__ __forceinline__ void ht_outer_acc(float *g, float *As, int nst, const float *dA, const float *A, int64_t ld, const int64_t *ridx,
-                                             int rows, int K) {
+// g[j][k] = sum_b dA[b][j] * A[b][k]  for the nrow (<= 8) rows j of one ownership block (weight gradient), A streamed in chunks;
+// g: the block's rows of the gradient scratch in GLOBAL memory ([8][K], owner-private; shared memory is kept for the operand
+// ring); dA: shared memory [rows][8]; batch rows are added in index order.
+__device__ __forceinline__ void ht_outer_acc(float *g, int nrow, float *As, int nst, const float *dA, const float *A, int64_t ld,
+                                             const int64_t *ridx, int rows, int K) {
     const int kk = threadIdx.x % HT_KC, jh = threadIdx.x / HT_KC;      // 2 x 128 threads: columns x row halves
     const int nchunks = (K + HT_KC - 1) / HT_KC;
     const int stage_floats = rows * HT_AS;
@@ -326,10 +334,10 @@ __device__ __forceinline__ void ht_outer_acc(float *g, float *As, int nst, const
             a3 = fmaf(d.w, a, a3);
         }
         if (k0 + kk < K) {
-            g[(4 * jh + 0) * K + k0 + kk] = a0;
-            g[(4 * jh + 1) * K + k0 + kk] = a1;
-            g[(4 * jh + 2) * K + k0 + kk] = a2;
-            g[(4 * jh + 3) * K + k0 + kk] = a3;
+            if (4 * jh + 0 < nrow) g[static_cast<int64_t>(4 * jh + 0) * K + k0 + kk] = a0;
+            if (4 * jh + 1 < nrow) g[static_cast<int64_t>(4 * jh + 1) * K + k0 + kk] = a1;
+            if (4 * jh + 2 < nrow) g[static_cast<int64_t>(4 * jh + 2) * K + k0 + kk] = a2;
+            if (4 * jh + 3 < nrow) g[static_cast<int64_t>(4 * jh + 3) * K + k0 + kk] = a3;
         }
     }
     __syncthreads();
@@ -337,7 +345,7 @@ __device__ __forceinline__ void ht_outer_acc(float *g, float *As, int nst, const
 
 // shared-memory carve-up (floats), identical on host and device
 struct Smem {
-    int th[3], bs[3], g[3], gb[3];     // parameter rows / biases / their gradients per layer: [slots * 8][K], [slots * 8]
+    int th[3], bs[3], gb[3];           // parameter rows / biases / bias gradients per layer: [slots * 8][K], [slots * 8], [slots * 8]
     int f0, f1;                        // relu' * mask factors, later da0 / da1 of the own rows: [slots][batch][8]
     int dA, out, As, Wt, red, rsum, ridx /* int64 */, scal, total;
 };
@@ -346,7 +354,7 @@ __host__ __device__ inline Smem ht_smem_layout(const Args &a) {
     int off = 0;
     auto take = [&](int n) { const int o = off; off += (n + 3) & ~3; return o; };
     for (int l = 0; l < 3; ++l) { s.th[l] = take(a.slots[l] * HT_RB * a.L[l].K); s.bs[l] = take(a.slots[l] * HT_RB); }
-    for (int l = 0; l < 3; ++l) { s.g[l] = take(a.slots[l] * HT_RB * a.L[l].K); s.gb[l] = take(a.slots[l] * HT_RB); }
+    for (int l = 0; l < 3; ++l) s.gb[l] = take(a.slots[l] * HT_RB);
     s.f0 = take(a.slots[0] * a.batch * HT_RB);
     s.f1 = take(a.slots[1] * a.batch * HT_RB);
     s.dA = take(a.batch * HT_RB);
@@ -500,7 +508,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                     for (int b = 0; b < Bt; ++b) sb += dA[b * HT_RB + tid];
                     ht_smem[sm.gb[2] + s * HT_RB + tid] = sb;
                 }
-                ht_outer_acc(ht_smem + sm.g[2] + s * HT_RB * L2.K, As, a.nst, dA, a.h1d, H1, nullptr, Bt, H1);
+                ht_outer_acc(L2.xW + static_cast<int64_t>(q) * HT_RB * L2.K, (C - q * HT_RB < HT_RB) ? (C - q * HT_RB) : HT_RB, As, a.nst, dA, a.h1d, H1, nullptr, Bt, H1);
             }
             for (int s = 0; s < a.slots[1]; ++s) {
                 const int q = cta + s * G;
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                     for (int b = 0; b < Bt; ++b) sb += d1[b * HT_RB + tid];
                     ht_smem[sm.gb[1] + s * HT_RB + tid] = sb;
                 }
-                ht_outer_acc(ht_smem + sm.g[1] + s * HT_RB * L1.K, As, a.nst, d1, a.h0d, H0, nullptr, Bt, H0);
+                ht_outer_acc(L1.xW + static_cast<int64_t>(q) * HT_RB * L1.K, (H1 - q * HT_RB < HT_RB) ? (H1 - q * HT_RB) : HT_RB, As, a.nst, d1, a.h0d, H0, nullptr, Bt, H0);
             }
             for (int s = 0; s < a.slots[0]; ++s) {
                 const int q = cta + s * G;
@@ -553,7 +561,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                     for (int b = 0; b < Bt; ++b) sb += f0[b * HT_RB + tid];
                     ht_smem[sm.gb[0] + s * HT_RB + tid] = sb;
                 }
-                ht_outer_acc(ht_smem + sm.g[0] + s * HT_RB * L0.K, As, a.nst, f0, a.X, D, ridx, Bt, D);
+                ht_outer_acc(L0.xW + static_cast<int64_t>(q) * HT_RB * L0.K, (H0 - q * HT_RB < HT_RB) ? (H0 - q * HT_RB) : HT_RB, As, a.nst, f0, a.X, D, ridx, Bt, D);
             }
         }
         __syncthreads();
@@ -568,14 +576,14 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
             for (int s = 0; s < a.slots[l]; ++s) {
                 const int q = cta + s * G;
                 if (q >= nblk) break;
-                float *g = ht_smem + sm.g[l] + s * HT_RB * K;
+                float *g = L.xW + static_cast<int64_t>(q) * HT_RB * K;         // written by this CTA's ht_outer_acc above
                 const float *th = ht_smem + sm.th[l] + s * HT_RB * K;
                 const int nrow = (L.rows - q * HT_RB < HT_RB) ? (L.rows - q * HT_RB) : HT_RB;
                 for (int j = 0; j < nrow; ++j) {
                     const int r = q * HT_RB + j;
                     const bool ew = a.use_ewc && r < L.ewc_rows;
                     for (int k = tid; k < K; k += HT_THREADS) {
-                        float gv = g[j * K + k];
+                        float gv = HT_LDCG(g + j * K + k);
                         if (ew) {
                             const int64_t gi = static_cast<int64_t>(r) * K + k;
                             const float dlt = th[j * K + k] - L.sW[gi];
@@ -643,40 +651,52 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
             for (int s = 0; s < a.slots[l]; ++s) {
                 const int q = cta + s * G;
                 if (q >= nblk) break;
-                const float *g = ht_smem + sm.g[l] + s * HT_RB * K;
                 float *th = ht_smem + sm.th[l] + s * HT_RB * K;
                 const int nrow = (L.rows - q * HT_RB < HT_RB) ? (L.rows - q * HT_RB) : HT_RB;
-                // thread = column k of the block's 8 rows: the 16 moment loads of a column (global memory, L2) are issued together,
-                // coalesced along k, before any arithmetic
-                for (int k = tid; k < K; k += HT_THREADS) {
-                    float mi[HT_RB], vi[HT_RB];
-                    const int64_t g0 = static_cast<int64_t>(q) * HT_RB * K + k;
-                    if (a.update) {
+                const int64_t g00 = static_cast<int64_t>(q) * HT_RB * K;
+                // thread = column k of the block's 8 rows.  Gradient and moments live in global memory (L2): the 24 loads of a
+                // column are issued together (coalesced along k), and the loads of column k + 256 are in flight while column k
+                // is computed (two register buffers; the loop is fully unrolled so the buffer index is a constant)
+                constexpr int HT_NIT = 8;                             // K <= 8 * 256
+                float gr[2][HT_RB], mi[2][HT_RB], vi[2][HT_RB];
 #pragma unroll
-                        for (int j = 0; j < HT_RB; ++j) {
-                            mi[j] = j < nrow ? L.mW[g0 + static_cast<int64_t>(j) * K] : 0.f;
-                            vi[j] = j < nrow ? L.vW[g0 + static_cast<int64_t>(j) * K] : 0.f;
+                for (int it = 0; it <= HT_NIT; ++it) {
+                    if (it < HT_NIT) {
+                        const int k = tid + it * HT_THREADS;
+                        if (k < K) {
+#pragma unroll
+                            for (int j = 0; j < HT_RB; ++j) {
+                                const int64_t gi = g00 + static_cast<int64_t>(j) * K + k;
+                                gr[it & 1][j] = j < nrow ? HT_LDCG(L.xW + gi) : 0.f;
+                                mi[it & 1][j] = (a.update && j < nrow) ? L.mW[gi] : 0.f;
+                                vi[it & 1][j] = (a.update && j < nrow) ? L.vW[gi] : 0.f;
+                            }
                         }
                     }
+                    if (it >= 1) {
+                        const int k = tid + (it - 1) * HT_THREADS;
+                        if (k < K) {
 #pragma unroll
-                    for (int j = 0; j < HT_RB; ++j) {
-                        if (j >= nrow) continue;
-                        const int64_t gi = g0 + static_cast<int64_t>(j) * K;
-                        const float graw = g[j * K + k];
-                        if (a.update) {
-                            const float gv = graw * coef;
-                            float p = th[j * K + k] * decay;
-                            const float m1 = mi[j] * a.beta1 + gv * omb1;
-                            const float v1 = vi[j] * a.beta2 + gv * gv * omb2;
-                            const float denom = sqrtf(v1) / bc2s + a.eps;
-                            p = p - lr_c * (m1 / denom);
-                            th[j * K + k] = p;
-                            L.W[gi] = p;
-                            L.mW[gi] = m1;
-                            L.vW[gi] = v1;
-                        } else {
-                            if (L.gW) L.gW[gi] = graw;
-                            if (L.qW) L.qW[gi] += graw * graw * a.fisher_scale;
+                            for (int j = 0; j < HT_RB; ++j) {
+                                if (j >= nrow) continue;
+                                const int64_t gi = g00 + static_cast<int64_t>(j) * K + k;
+                                const float graw = gr[(it - 1) & 1][j];
+                                if (a.update) {
+                                    const float gv = graw * coef;
+                                    float p = th[j * K + k] * decay;
+                                    const float m1 = mi[(it - 1) & 1][j] * a.beta1 + gv * omb1;
+                                    const float v1 = vi[(it - 1) & 1][j] * a.beta2 + gv * gv * omb2;
+                                    const float denom = sqrtf(v1) / bc2s + a.eps;
+                                    p = p - lr_c * (m1 / denom);
+                                    th[j * K + k] = p;
+                                    L.W[gi] = p;
+                                    L.mW[gi] = m1;
+                                    L.vW[gi] = v1;
+                                } else {
+                                    if (L.gW) L.gW[gi] = graw;
+                                    if (L.qW) L.qW[gi] += graw * graw * a.fisher_scale;
+                                }
+                            }
                         }
                     }
                 }

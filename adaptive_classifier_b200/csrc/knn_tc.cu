@@ -61,6 +61,8 @@ struct EpiKnn {
     int64_t N;               // rows
     int tiles_m, slots;      // grid = slots/2 * tiles_m CTAs; every CTA owns one query tile and two lists per query
     int kt;                  // a list publishes its kt-th best key (k + 3 <= kt <= KC): see prefetch()
+    float *pmax_out;         // max ||p||^2 over the rows (for the error bound), accumulated here: every row passes through the
+                             // epilogue of some CTA of every query tile anyway (a separate pass over the norms cost 0.11 ms per search)
 
     static constexpr int kUnrollChunks = 1;
     struct State {
@@ -68,6 +70,7 @@ struct EpiKnn {
         int32_t idx[KNN_KC];
         float pn[2];          // ||p||^2 of the 32 rows of a chunk, one per lane, requested one chunk ahead
         float gt;             // global bound for this thread's query, refreshed once per tile
+        float pmax;           // largest ||p||^2 this thread has seen
     };
 
     __device__ __forceinline__ bool skip_kernel() const { return false; }
@@ -76,6 +79,7 @@ struct EpiKnn {
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
         st.pn[0] = st.pn[1] = CUDART_INF_F;
         st.gt = CUDART_INF_F;
+        st.pmax = 0.f;
     }
 
     // Every list (74 per query at B = 512) would on its own perform ~KC ln(n/KC) sorted inserts; sharing a bound
@@ -89,6 +93,7 @@ struct EpiKnn {
         const int64_t n = static_cast<int64_t>(col0) + lane;
         const float x = (n < N) ? __ldg(p_sqnorm + n) : CUDART_INF_F;
         if (buf) st.pn[1] = x; else st.pn[0] = x;
+        if (n < N) st.pmax = fmaxf(st.pmax, x);
         if (buf == 0) {        // first chunk of a tile: publish this list's bound, pick up the others'
             float pub = CUDART_INF_F;
 #pragma unroll
@@ -140,6 +145,10 @@ struct EpiKnn {
     }
 
     __device__ __forceinline__ void end_cta(State &st, int q, int lane) const {
+        if (pmax_out) {
+            const float m = warp_max(st.pmax);                 // non-negative floats order like their bit patterns
+            if (lane == 0) atomicMax(reinterpret_cast<int *>(pmax_out), __float_as_int(m));
+        }
         // two epilogue warps share a query row (one per 128-column half of every tile): each owns a slot
         const int chalf = ((threadIdx.x >> 5) - 2) >> 2;
         const int mt = blockIdx.x % tiles_m;
@@ -225,42 +234,16 @@ __global__ void knn_prep_queries_kernel(const float *__restrict__ Q, int B, int 
     if (lane == 0) qn[row] = s;
 }
 
-// pn[n] = ||P_n||^2 and block maxima of it (for the error bound)
-__global__ void knn_prep_rows_kernel(const float *__restrict__ P, int64_t N, int D, float *__restrict__ pn,
-                                     float *__restrict__ block_max, int have_pn) {
-    __shared__ float smax[8];
+// pn[n] = ||P_n||^2 (only when the caller did not pass the cached norms)
+__global__ void knn_prep_rows_kernel(const float *__restrict__ P, int64_t N, int D, float *__restrict__ pn) {
     const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const float *p = P + row * D;
     float s = 0.f;
-    if (row < N) {
-        if (have_pn) {
-            s = pn[row];
-        } else {
-            const float *p = P + row * D;
-            for (int i = lane; i < D; i += 32) s = fmaf(p[i], p[i], s);
-            s = warp_sum(s);
-            if (lane == 0) pn[row] = s;
-        }
-    }
-    if (lane == 0) smax[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float m = 0.f;
-        for (int i = 0; i < 8; ++i) m = fmaxf(m, smax[i]);
-        block_max[blockIdx.x] = m;
-    }
-}
-__global__ void knn_reduce_max_kernel(const float *__restrict__ v, int64_t n, float *__restrict__ out) {
-    __shared__ float red[256];
-    float m = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += 256) m = fmaxf(m, v[i]);
-    red[threadIdx.x] = m;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[0] = red[0];
+    for (int i = lane; i < D; i += 32) s = fmaf(p[i], p[i], s);
+    s = warp_sum(s);
+    if (lane == 0) pn[row] = s;
 }
 
 // widen the int32 candidate ids of the per-CTA lists for the (key, id) sort
@@ -401,7 +384,7 @@ static int knn_cap(int k) { return k <= KNN_SMALL_K ? 256 : 4096; }
 
 struct KnnTcPlan {
     int tiles_m, slots, grid_ctas, cap, ksel;
-    size_t off_qr, off_qn, off_gthr, off_pn, off_bmax, off_pmax, off_ckey, off_cidx, off_cidx64, off_skey, off_sidx, off_ridx, off_T,
+    size_t off_qr, off_qn, off_gthr, off_pn, off_pmax, off_ckey, off_cidx, off_cidx64, off_skey, off_sidx, off_ridx, off_T,
         off_rd, off_ri, off_thr, off_cnt, off_stats, off_over, off_buf, off_rd2, off_ri2, off_sel, sel_bytes, total;
 };
 
@@ -424,7 +407,6 @@ static KnnTcPlan plan_knn_tc(int B, int64_t N, int D, int k) {
     p.off_qn = take(Bp * 4);
     p.off_gthr = take(Bp * 4);
     p.off_pn = take(static_cast<size_t>(N) * 4);
-    p.off_bmax = take(static_cast<size_t>((N + 7) / 8) * 4);
     p.off_pmax = take(256);
     const size_t nc = static_cast<size_t>(B) * p.slots * KNN_KC;
     p.off_ckey = take(nc * 4);
@@ -498,7 +480,6 @@ static int knn_tc_block(const float *Q, const float *P, const float *p_sqnorm, c
     float *qn = reinterpret_cast<float *>(w + pl.off_qn);
     uint32_t *gthr = reinterpret_cast<uint32_t *>(w + pl.off_gthr);
     float *pn = reinterpret_cast<float *>(w + pl.off_pn);
-    float *bmax = reinterpret_cast<float *>(w + pl.off_bmax);
     float *pmax = reinterpret_cast<float *>(w + pl.off_pmax);
     float *ckey = reinterpret_cast<float *>(w + pl.off_ckey);
     int32_t *cidx = reinterpret_cast<int32_t *>(w + pl.off_cidx);
@@ -531,23 +512,19 @@ static int knn_tc_block(const float *Q, const float *P, const float *p_sqnorm, c
     knn_prep_queries_kernel<<<(B + 3) / 4, 128, 0, s>>>(Q, B, D, Qr, Qh, qn);
     AC_LAUNCH_CHECK();
     const float *pn_use = p_sqnorm;
-    const unsigned rb = static_cast<unsigned>((N + 7) / 8);
-    if (p_sqnorm) {
-        knn_prep_rows_kernel<<<rb, 256, 0, s>>>(P, N, D, const_cast<float *>(p_sqnorm), bmax, 1);
-    } else {
-        knn_prep_rows_kernel<<<rb, 256, 0, s>>>(P, N, D, pn, bmax, 0);
+    if (!p_sqnorm) {
+        knn_prep_rows_kernel<<<static_cast<unsigned>((N + 7) / 8), 256, 0, s>>>(P, N, D, pn);
+        AC_LAUNCH_CHECK();
         pn_use = pn;
     }
-    AC_LAUNCH_CHECK();
-    knn_reduce_max_kernel<<<1, 256, 0, s>>>(bmax, rb, pmax);
-    AC_LAUNCH_CHECK();
+    AC_CUDA(cudaMemsetAsync(pmax, 0, sizeof(float), s));       // max ||p||^2: accumulated by the pass-1 epilogue
 
     // ---- pass 1 on the tensor cores: per-(query, CTA, half) top-16 lists
     const bool small_k = k <= KNN_SMALL_K;
     // kt = 0 (k > 16): no shared bound -- every list keeps its own true top-16, the merged lists bound the k-th distance
     int kt = 0;
     if (small_k) { kt = k + 3 > 8 ? k + 3 : 8; if (kt > KNN_KC) kt = KNN_KC; }
-    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt};
+    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt, pmax};
     if ((rc = launch_scan(Qr, P, p_half, Bp, N, D, epi, pl.grid_ctas, PROF_KNN_COARSE, s))) return rc;
 
     // ---- merge the lists (sorted by (key, id))
