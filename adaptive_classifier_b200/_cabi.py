@@ -366,10 +366,12 @@ def head_train_epoch(X, targets, perm, p, m, v, *, first_step, batch, loss_kind=
 
 
 def head_phase_timing(enable: bool = True):
-    """diagnostic: nanoseconds CTA 0 of the training kernel spent per phase / grid barrier since enabled (13 counters)"""
-    out = (ctypes.c_ulonglong * 16)()
+    """diagnostic: nanoseconds three observed CTAs of the training kernel (holders of a layer-0 / layer-1 / layer-2 block) spent per
+    phase / grid barrier (13 counters) and inside the product routines (7 counters from index 14) since enabled: 3 lists of 24"""
+    out = (ctypes.c_ulonglong * 72)()
     check(load_library().ac_head_phase_timing(1 if enable else 0, out), "ac_head_phase_timing")
-    return [int(x) for x in out][:13]
+    v = [int(x) for x in out]
+    return [v[0:24], v[24:48], v[48:72]]
 
 
 def head_grad(X, targets, p, *, loss_kind=AC_LOSS_CE, grad_out=None, fisher=None, inv_n_batches=1.0):

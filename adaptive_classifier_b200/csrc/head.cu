@@ -269,63 +269,63 @@ static int check_params(const ac_head_params *p, const char *who) {
 // launch plan of head_train_kernel (head_train.cuh): grid size, ownership slots, global scratch
 // ------------------------------------------------------------------------------------------------
 struct TrainPlan {
-    int G, nst;
-    int slots[3];
-    size_t off_h0d, off_h1d, off_z, off_dz, off_da1, off_rowloss, off_part, off_pen, off_bar, off_stats, off_timing, off_g[3], total;
+    int G, nst, res_mv;
+    size_t off_h0d, off_h1d, off_z, off_dz, off_da1, off_rowloss, off_part, off_pen, off_bar, off_stats, total;
     size_t smem_bytes;
 };
 
-static int plan_training(int batch, const ac_head_params *p, int n_steps, TrainPlan &pl, const char *who) {
+static void plan_args(ht::Args &a, int batch, const ac_head_params *p, int G) {
+    const int rows[3] = {p->H0, p->H1, p->C}, K[3] = {p->D, p->H0, p->H1};
+    a.batch = batch;
+    for (int l = 0; l < 3; ++l) { a.L[l].rows = rows[l]; a.L[l].K = K[l]; }
+    ht::ht_assign(a, G);
+}
+
+static int plan_training(int batch, const ac_head_params *p, int n_steps, bool update, TrainPlan &pl, const char *who) {
     AC_REQUIRE(batch >= 1 && batch <= ht::HT_MAXB, "%s: batch=%d outside [1,%d]", who, batch, ht::HT_MAXB);
     AC_REQUIRE(p->D % 4 == 0 && p->H0 % 4 == 0 && p->H1 % 4 == 0, "%s: D, H0, H1 must be multiples of 4 (D=%d H0=%d H1=%d)", who, p->D,
                p->H0, p->H1);
-    // one CTA per SM at most (cooperative launch: all CTAs resident); 128 gives every CTA exactly one 8-row block of each layer
-    // for the reference's head (768 -> 768 -> 384 -> C <= 1024)
-    int G = sm_count();
-    if (G > 128) G = 128;
-    const int rows[3] = {p->H0, p->H1, p->C};
-    int need = 1;
-    for (int l = 0; l < 3; ++l) {
-        const int nblk = (rows[l] + ht::HT_RB - 1) / ht::HT_RB;
-        if (nblk > need) need = nblk;
-    }
-    if (need < G) G = need;                     // tiny heads: no idle CTAs spinning in the barriers
-    pl.G = G;
-    ht::Args a{};
-    a.batch = batch;
-    const int K[3] = {p->D, p->H0, p->H1};
-    for (int l = 0; l < 3; ++l) {
-        const int nblk = (rows[l] + ht::HT_RB - 1) / ht::HT_RB;
-        pl.slots[l] = a.slots[l] = (nblk + G - 1) / G;
-        a.L[l].rows = rows[l];
-        a.L[l].K = K[l];
-    }
-    // as many ring stages (4 down to 2) as the parameter / gradient rows leave room for
     AC_REQUIRE(p->D <= 2048 && p->H0 <= 2048 && p->H1 <= 2048, "%s: layer widths above 2048 are not supported", who);
-    for (a.nst = 8; a.nst >= 2; --a.nst) {
-        pl.smem_bytes = static_cast<size_t>(ht::ht_smem_layout(a).total) * sizeof(float);
-        if (pl.smem_bytes <= 220 * 1024) break;
+    AC_REQUIRE(n_steps <= (1 << 20), "%s: at most 2^20 steps per launch", who);
+    // one CTA per SM at most (cooperative launch: all CTAs resident).  The 8-row blocks of the three layers are dealt round robin:
+    // the reference's head (768 -> 768 -> 384 -> C <= 32) has 96 + 48 + 4 = 148 blocks, one per SM of a B200
+    ht::Args a{};
+    plan_args(a, batch, p, 1);
+    int G = sm_count();
+    if (a.items < G) G = a.items;               // tiny heads: no idle CTAs spinning in the barriers
+    pl.G = G;
+    plan_args(a, batch, p, G);
+    // AdamW moments resident in shared memory if at least three ring stages still fit; then as many stages (<= 8) as there is room for
+    const size_t limit = 220 * 1024;
+    pl.smem_bytes = ~size_t(0);
+    for (int res = update ? 1 : 0; res >= 0; --res) {
+        a.res_mv = res;
+        for (a.nst = 8; a.nst >= (res ? 3 : 2); --a.nst) {
+            const size_t bytes = static_cast<size_t>(ht::ht_smem_layout(a).total) * sizeof(float);
+            if (bytes <= limit) { pl.smem_bytes = bytes; break; }
+        }
+        if (pl.smem_bytes <= limit) break;
     }
-    pl.nst = a.nst < 2 ? 2 : a.nst;
-    if (pl.smem_bytes > 220 * 1024) {
+    if (pl.smem_bytes > limit) {
+        a.res_mv = 0; a.nst = 2;
         set_error("%s: head %d -> %d -> %d -> %d needs %zu bytes of shared memory per CTA (limit 220 KB)", who, p->D, p->H0, p->H1, p->C,
-                  pl.smem_bytes);
+                  static_cast<size_t>(ht::ht_smem_layout(a).total) * sizeof(float));
         return AC_E_UNSUPPORTED;
     }
+    pl.nst = a.nst;
+    pl.res_mv = a.res_mv;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes, 256); return o; };
     pl.off_h0d = take(sizeof(float) * batch * p->H0);
     pl.off_h1d = take(sizeof(float) * batch * p->H1);
     pl.off_z = take(sizeof(float) * batch * p->C);
-    pl.off_dz = take(sizeof(float) * batch * p->C);
+    pl.off_dz = take(sizeof(float) * batch * a.ldz);
     pl.off_da1 = take(sizeof(float) * batch * p->H1);
     pl.off_rowloss = take(sizeof(float) * batch);
     pl.off_part = take(sizeof(float) * 256);
     pl.off_pen = take(sizeof(float) * 256);
     pl.off_bar = take(256);
     pl.off_stats = take(sizeof(float) * 3 * (n_steps > 0 ? n_steps : 1));
-    pl.off_timing = take(16 * sizeof(unsigned long long));
-    for (int l = 0; l < 3; ++l) pl.off_g[l] = take(sizeof(float) * static_cast<size_t>(rows[l]) * K[l]);
     pl.total = off;
     return AC_OK;
 }
@@ -347,7 +347,8 @@ static int launch_training(const TrainCall &c, void *workspace, size_t workspace
     int rc = ac_device_check();
     if (rc) return rc;
     TrainPlan pl;
-    if ((rc = plan_training(c.batch, c.p, c.n_steps, pl, who))) return rc;
+    const bool update = c.m && c.v;
+    if ((rc = plan_training(c.batch, c.p, c.n_steps, update, pl, who))) return rc;
     uint8_t *w = reinterpret_cast<uint8_t *>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
     const size_t slack = w - static_cast<uint8_t *>(workspace);
     if (pl.total + slack > workspace_bytes) { set_error("%s: workspace needs %zu bytes", who, pl.total + 256); return AC_E_WORKSPACE; }
@@ -361,9 +362,6 @@ static int launch_training(const TrainCall &c, void *workspace, size_t workspace
     for (int l = 0; l < 3; ++l) {
         ht::Layer &Lr = a.L[l];
         Lr.W = Wp[l]; Lr.b = bp[l]; Lr.rows = rows[l]; Lr.K = K[l]; Lr.ewc_rows = rows[l];
-        Lr.xW = reinterpret_cast<float *>(w + pl.off_g[l]);
-        a.slots[l] = pl.slots[l];
-        a.nst = pl.nst;
 #define AC_PICK(hp, l) ((l) == 0 ? (hp)->W0 : (l) == 1 ? (hp)->W1 : (hp)->W2)
 #define AC_PICKB(hp, l) ((l) == 0 ? (hp)->b0 : (l) == 1 ? (hp)->b1 : (hp)->b2)
         if (c.m && c.v) { Lr.mW = AC_PICK(c.m, l); Lr.mb = AC_PICKB(c.m, l); Lr.vW = AC_PICK(c.v, l); Lr.vb = AC_PICKB(c.v, l); }
@@ -378,7 +376,19 @@ static int launch_training(const TrainCall &c, void *workspace, size_t workspace
     }
     // the head may have grown since theta* was taken: only the first C_old output rows are penalised (ewc.py:96-115 on the old head)
     if (ewc && cfg->ewc_C_old > 0 && cfg->ewc_C_old < P->C) a.L[2].ewc_rows = cfg->ewc_C_old;
-    a.update = c.m && c.v ? 1 : 0;
+    a.update = update ? 1 : 0;
+    ht::ht_assign(a, pl.G);
+    a.nst = pl.nst;
+    a.res_mv = pl.res_mv;
+    // 16-byte asynchronous copies stream X rows and gather W1 / W2 columns
+    AC_REQUIRE((reinterpret_cast<uintptr_t>(c.X) | reinterpret_cast<uintptr_t>(P->W0) | reinterpret_cast<uintptr_t>(P->W1) |
+                reinterpret_cast<uintptr_t>(P->W2)) % 16 == 0, "%s: X and the weight matrices must be 16-byte aligned", who);
+    if (update) AC_REQUIRE((reinterpret_cast<uintptr_t>(c.m->W0) | reinterpret_cast<uintptr_t>(c.m->W1) | reinterpret_cast<uintptr_t>(c.m->W2) |
+                            reinterpret_cast<uintptr_t>(c.v->W0) | reinterpret_cast<uintptr_t>(c.v->W1) | reinterpret_cast<uintptr_t>(c.v->W2)) % 16 == 0,
+                           "%s: the moment matrices must be 16-byte aligned", who);
+    if (ewc) AC_REQUIRE((reinterpret_cast<uintptr_t>(a.L[0].fW) | reinterpret_cast<uintptr_t>(a.L[1].fW) | reinterpret_cast<uintptr_t>(a.L[2].fW) |
+                         reinterpret_cast<uintptr_t>(a.L[0].sW) | reinterpret_cast<uintptr_t>(a.L[1].sW) | reinterpret_cast<uintptr_t>(a.L[2].sW)) % 16 == 0,
+                        "%s: the EWC matrices must be 16-byte aligned", who);
     if (cfg) {
         a.lr = cfg->lr; a.beta1 = cfg->beta1; a.beta2 = cfg->beta2; a.eps = cfg->eps; a.wd = cfg->weight_decay; a.max_norm = cfg->max_norm;
         a.dropout_p = cfg->dropout_p; a.seed = cfg->seed; a.mask0 = cfg->mask0; a.mask1 = cfg->mask1;
@@ -441,16 +451,17 @@ extern "C" int ac_head_forward(const float *X, int B, const ac_head_params *p, i
     return AC_OK;
 }
 
-// diagnostic (tools/head_phase_times.py): enable != 0 starts accumulating, per training launch, the nanoseconds CTA 0 spends in
-// every phase of head_train_kernel and in the grid barriers between them; out16_host (nullable) receives the 13 counters so far
-extern "C" int ac_head_phase_timing(int enable, unsigned long long *out16_host) {
+// diagnostic (tools/head_phase_times.py): enable != 0 starts accumulating, per training launch, the nanoseconds three observed CTAs
+// (the first holder of a layer-0 block, of a layer-1 block, and the last CTA: layer 2) spend in every phase of head_train_kernel,
+// in the grid barriers between them and inside the two product routines; out72_host (nullable) receives 3 x 24 counters so far
+extern "C" int ac_head_phase_timing(int enable, unsigned long long *out72_host) {
     if (enable && !g_head_timing_dev) {
-        AC_CUDA(cudaMalloc(reinterpret_cast<void **>(&g_head_timing_dev), 16 * sizeof(unsigned long long)));
-        AC_CUDA(cudaMemset(g_head_timing_dev, 0, 16 * sizeof(unsigned long long)));
+        AC_CUDA(cudaMalloc(reinterpret_cast<void **>(&g_head_timing_dev), 3 * ht::HT_TROW * sizeof(unsigned long long)));
+        AC_CUDA(cudaMemset(g_head_timing_dev, 0, 3 * ht::HT_TROW * sizeof(unsigned long long)));
     }
-    if (out16_host && g_head_timing_dev) {
+    if (out72_host && g_head_timing_dev) {
         AC_CUDA(cudaDeviceSynchronize());
-        AC_CUDA(cudaMemcpy(out16_host, g_head_timing_dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        AC_CUDA(cudaMemcpy(out72_host, g_head_timing_dev, 3 * ht::HT_TROW * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
     if (!enable && g_head_timing_dev) {
         cudaFree(g_head_timing_dev);
@@ -462,7 +473,7 @@ extern "C" int ac_head_phase_timing(int enable, unsigned long long *out16_host) 
 extern "C" int ac_head_train_workspace_bytes(int batch, int n_steps, const ac_head_params *p, size_t *bytes) {
     AC_REQUIRE(p && bytes && batch > 0, "ac_head_train_workspace_bytes: bad arguments");
     TrainPlan pl;
-    int rc = plan_training(batch, p, n_steps, pl, "ac_head_train_workspace_bytes");
+    int rc = plan_training(batch, p, n_steps, true, pl, "ac_head_train_workspace_bytes");
     if (rc) return rc;
     *bytes = pl.total + 512;
     return AC_OK;

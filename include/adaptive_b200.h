@@ -172,9 +172,10 @@ int ac_head_train_epoch(const float *X, const void *targets, const int64_t *perm
                         ac_head_params *p, ac_head_params *m, ac_head_params *v, const ac_train_cfg *cfg,
                         float *loss_accum, float *step_stats, void *workspace, size_t workspace_bytes, ac_stream_t stream);
 
-/* diagnostic: per-phase time of the training kernel (nanoseconds CTA 0 spent in each of the 7 phases and 6 grid barriers of a
- * step, summed over all steps since enabled).  enable != 0 starts accumulating; out16_host (nullable) receives 16 counters. */
-int ac_head_phase_timing(int enable, unsigned long long *out16_host);
+/* diagnostic: per-phase time of the training kernel: nanoseconds three observed CTAs (one per layer of the head) spent in each
+ * of the 7 phases and 6 grid barriers of a step (13 counters) and inside the product routines (7 counters from index 14), summed
+ * over all steps since enabled.  enable != 0 starts accumulating; out72_host (nullable) receives 3 x 24 counters. */
+int ac_head_phase_timing(int enable, unsigned long long *out72_host);
 
 /* gradient only (no update) of mean CE/BCE wrt all parameters, eval mode: the building block of
  * EWC._compute_fisher (ewc.py:67-92).  fisher += grad^2 * inv_n_batches when fisher != NULL */

@@ -37,7 +37,7 @@ void run_blocks(const std::vector<dim3> &blocks, dim3 grid, dim3 block, const st
         Block *blk = blks.back().get();
         const size_t slot = blks.size() - 1;
         if (slot == smem_pool.size()) {
-            smem_pool.push_back(static_cast<uint8_t *>(aligned_alloc(1024, 256 * 1024)));
+            smem_pool.push_back(static_cast<uint8_t *>(aligned_alloc(1024, 1024 * 1024)));
             tmem_pool.push_back(reinterpret_cast<float (*)[512]>(aligned_alloc(64, sizeof(float) * 128 * 512)));
         }
         blk->dyn_smem = smem_pool[slot];

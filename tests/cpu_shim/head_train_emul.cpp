@@ -206,7 +206,6 @@ int main(int argc, char **argv) {
         std::fill(K_v.W[l].begin(), K_v.W[l].end(), 0.f); std::fill(K_v.b[l].begin(), K_v.b[l].end(), 0.f);
         std::fill(K_q.W[l].begin(), K_q.W[l].end(), 0.5f); std::fill(K_q.b[l].begin(), K_q.b[l].end(), 0.5f);
     }
-    std::vector<float> scratch[3];
     Args a{};
     a.X = X.data(); a.targets = loss_kind == 0 ? static_cast<const void *>(yi.data()) : static_cast<const void *>(yf.data());
     a.perm = update ? perm.data() : nullptr; a.n = n_use; a.batch = batch; a.n_steps = n_steps; a.first_step = update ? 3 : 1;
@@ -216,22 +215,20 @@ int main(int argc, char **argv) {
         L.mW = K_m.W[l].data(); L.mb = K_m.b[l].data(); L.vW = K_v.W[l].data(); L.vb = K_v.b[l].data();
         L.fW = F.W[l].data(); L.fb = F.b[l].data(); L.sW = St.W[l].data(); L.sb = St.b[l].data();
         L.gW = K_g.W[l].data(); L.gb = K_g.b[l].data(); L.qW = K_q.W[l].data(); L.qb = K_q.b[l].data();
-        scratch[l].assign(size_t(rows[l]) * K[l], -7.f);
-        L.xW = scratch[l].data();
-        const int nblk = (rows[l] + HT_RB - 1) / HT_RB;
-        a.slots[l] = (nblk + G - 1) / G;
     }
+    ht_assign(a, G);
+    a.res_mv = seed % 2;                                          // both homes of the AdamW moments
     if (C_old) a.L[2].ewc_rows = C_old;
     a.nst = 2 + static_cast<int>(seed % 6);                       // ring depth 2 .. 7
     a.lr = 1e-3f; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f; a.wd = 0.01f; a.max_norm = 1.f; a.dropout_p = p_drop;
     a.loss_kind = loss_kind; a.seed = 11; a.use_ewc = ewc; a.ewc_lambda = 100.f; a.update = update; a.fisher_scale = 0.25f;
-    std::vector<float> h0d(size_t(batch) * H0), h1d(size_t(batch) * H1), z(size_t(batch) * C), dz(size_t(batch) * C), da1(size_t(batch) * H1),
+    std::vector<float> h0d(size_t(batch) * H0), h1d(size_t(batch) * H1), z(size_t(batch) * C), dz(size_t(batch) * ((C + 3) & ~3), -7.f), da1(size_t(batch) * H1),
         rowloss(batch), part(256), pen(256), stats(3 * n_steps), accum(1, 0.f);
     std::vector<unsigned> bar(4, 0);
     a.h0d = h0d.data(); a.h1d = h1d.data(); a.z = z.data(); a.dz = dz.data(); a.da1 = da1.data(); a.rowloss = rowloss.data();
     a.part = part.data(); a.pen = pen.data(); a.stats = stats.data(); a.loss_accum = accum.data(); a.bar = bar.data();
     const Smem sm = ht_smem_layout(a);
-    if (size_t(sm.total) * 4 > 256 * 1024) { fprintf(stderr, "shared memory %d floats exceeds the shim's 256 KB\n", sm.total); return 2; }
+    if (size_t(sm.total) * 4 > 1024 * 1024) { fprintf(stderr, "shared memory %d floats exceeds the shim's 1 MB\n", sm.total); return 2; }
     shim::launch_cooperative(dim3(G), dim3(HT_THREADS), [&] { head_train_kernel(a); }, seed);
 
     // ---------------- restatement

@@ -86,7 +86,9 @@ def test_head_training_kernel_on_the_cpu_emulation():
              "64 64 32 3 45 40 3 0 0.0 1 1 4",          # batch > 32 (two rows per lane), C = 3 (scalar chunk loads)
              "128 128 64 130 64 32 5 1 0.2 1 1 5",      # C > one chunk: dz streamed in two chunks
              "264 136 68 11 30 30 4 0 0.0 0 0 6",       # gradient-only mode (Fisher): gradients and accumulators
-             "40 40 20 5 20 20 1 1 0.0 1 0 7"]          # a single CTA owns everything
+             "40 40 20 5 20 20 1 1 0.0 1 0 7",          # a single CTA owns everything
+             "40 40 20 5 50 20 9 0 0.1 1 1 9",
+             "264 136 68 11 70 32 28 0 0.1 1 1 10"]    # one ownership block per CTA (the B200 layout of the reference's head)
     for c in cases:
         out = subprocess.run([exe] + c.split(), capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "MATCH" in out.stdout, (c, out.stdout[-600:], out.stderr[-300:])

@@ -24,7 +24,10 @@ _, nb = _cabi.head_train_epoch(X, y, perm, p, m, v, first_step=626, batch=32)
 torch.cuda.synchronize()
 wall = time.time() - t0
 ns = _cabi.head_phase_timing(False)
-names = ["P1 h0", "B1", "P2 h1", "B2", "P3a z", "B3a", "P3b loss/dz", "B3b", "P4 gW2+da1", "B4", "P5/P6 gW1,da0,gW0,norm", "B6", "P7 adamw"]
-print(json.dumps({"classes": C, "steps": nb, "us_per_step_wall": 1e6 * wall / nb,
-                  "us_per_step_by_phase": {nm: round(x / nb / 1e3, 2) for nm, x in zip(names, ns)},
-                  "sum_us": round(sum(ns) / nb / 1e3, 2)}))
+names = ["P1 h0", "B1", "P2 h1", "B2", "P3a z", "B3a", "P3b loss/dz", "B3b", "P4 gW2|da1", "B4", "P5/P6 gW1|da0,gW0,norm", "B6", "P7 adamw"]
+detail = ["dot wait", "dot issue", "dot multiply", "dot combine", "outer wait", "outer issue", "outer multiply"]
+rows = {}
+for cls, r in zip(("layer0 CTA", "layer1 CTA", "layer2 CTA (last)"), ns):
+    rows[cls] = {"phase_us": {nm: round(x / nb / 1e3, 2) for nm, x in zip(names, r[:13])}, "sum_us": round(sum(r[:13]) / nb / 1e3, 2),
+                 "inside_products_us": {nm: round(x / nb / 1e3, 2) for nm, x in zip(detail, r[14:21])}}
+print(json.dumps({"classes": C, "steps": nb, "us_per_step_wall": 1e6 * wall / nb, "observed": rows}))
