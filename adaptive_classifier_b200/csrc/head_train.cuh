@@ -9,28 +9,34 @@
 //
 // Why one kernel: the head is 0.9 M parameters and a batch is 32 rows -- 171 MFLOP and 25 MB of optimizer traffic per step,
 // i.e. microseconds of work; the round-1 path launched ~21 dependent kernels per step (310 us measured on a B200).  Here the
-// grid stays resident for the whole epoch and a step is seven phases separated by six grid barriers:
+// grid stays resident for the whole epoch and a step is seven phases separated by six grid barriers (47 us per step measured):
 //
-//   ownership   the rows of every weight matrix are dealt to the CTAs in blocks of HT_RB = 8 rows (block q -> CTA q % G).
-//               A CTA keeps ITS rows of W0, W1, W2 (+ biases) in shared memory for the whole launch, computes the
-//               activations / gradients of exactly those rows and applies AdamW to them: parameters never move between
-//               CTAs, gradients never leave shared memory, AdamW of step t needs no barrier before the forward of step t+1.
-//   P1  h0 = dropout(relu(X W0^T + b0))        own rows of layer 0; X rows gathered through the shuffled index list
-//   P2  h1 = dropout(relu(h0 W1^T + b1))       own rows of layer 1
-//   P3a z  = h1 W2^T + b2                      own rows of layer 2
-//   P3b loss, dz per batch row                 one warp per row (softmax-CE or sigmoid-BCE)
-//   P4  gW2, gb2 (own rows of layer 2);  da1 = (dz W2) * relu' * mask   (own columns = own rows of layer 1)
-//   P5  gW1, gb1 (own rows of layer 1);  da0 = (da1 W1) * relu' * mask  (own rows of layer 0)
-//   P6  gW0, gb0;  [EWC: g += 2 lambda / B * F (theta - theta*)];  partial sum of squares of the own gradients
+//   ownership   the rows of every weight matrix are cut into blocks of HT_RB = 8 rows, and the blocks of all three layers form
+//               ONE list of items dealt over the grid (item i -> CTA i % G).  The reference's head (768 -> 768 -> 384 -> C)
+//               has 96 + 48 + ceil(C / 8) items: with C <= 32 that is at most 148, one item per SM of a B200, so every CTA
+//               works for exactly one layer and the weight-gradient work of different layers runs side by side.  A CTA keeps
+//               the rows of ITS item(s) -- parameters, gradient, AdamW moments, biases -- in shared memory for the whole
+//               launch, computes the activations / gradients of exactly those rows and applies AdamW to them: parameters
+//               never move between CTAs, gradients and moments never leave shared memory (moments: when they fit, res_mv),
+//               AdamW of step t needs no barrier before the forward of step t+1.
+//   P1  h0 = dropout(relu(X W0^T + b0))        layer-0 items; X rows gathered through the shuffled index list
+//   P2  h1 = dropout(relu(h0 W1^T + b1))       layer-1 items
+//   P3a z  = h1 W2^T + b2                      layer-2 items
+//   P3b loss, dz per batch row                 one warp per row over the whole grid (softmax-CE or sigmoid-BCE)
+//   P4  gW2, gb2 (layer-2 items)   |   da1 = (dz W2) * relu' * mask of the own rows (layer-1 items)
+//   P5  gW1, gb1 (layer-1 items)   |   P6  da0 = (da1 W1) * relu' * mask, gW0, gb0 (layer-0 items)
+//       [EWC: g += 2 lambda / B * F (theta - theta*)];  partial sum of squares of the own gradients
 //   P7  global grad norm (every CTA adds the G partials in the same order), clip, AdamW on the own rows
-//   Activations cross CTAs through small global (L2-resident) buffers; every product streams its [B x K] operand through shared
-//   memory in chunks of HT_KC columns (register-prefetched), so shared memory holds only the own parameter / gradient rows.
+//   Activations cross CTAs through small global (L2-resident) buffers; every product streams its [B x K] operand through a
+//   ring of shared-memory stages in chunks of HT_KC columns by 16-byte cp.async.cg copies (L2 only: these buffers are rewritten
+//   by other CTAs every step and must never be served from this SM's L1).
+//   The grid barrier is one arrival counter that only grows; the AdamW bias corrections are tabulated 256 steps at a time.
 //
 // All sums have a fixed order: results are deterministic run to run and independent of the grid size up to fp32 rounding of
 // the (grid-size dependent) partial-sum order of the gradient norm.  Parity: the CPU restatement of the optimizer step (tests/test_gpu_parity.py,
 // tests/test_gpu_training_golden.py: the reference's own per-step losses to 1e-5 over 60 steps).
 //
-// This header is plain SIMT C++ (no inline PTX): tests/cpu_shim/head_train_emul.cpp compiles it for the CPU (every CUDA
+// This header is plain SIMT C++ (no inline PTX beyond the timer): tests/cpu_shim/head_train_emul.cpp compiles it for the CPU (every CUDA
 // thread a fiber, grid barriers real) and checks it against a straightforward restatement before any GPU time is spent.
 #pragma once
 #include <stdint.h>
@@ -43,14 +49,19 @@ namespace ht {
 
 constexpr int HT_THREADS = 256;
 constexpr int HT_RB = 8;              // rows per ownership block
-constexpr int HT_KC = 128;            // columns per streamed chunk
+#ifndef HT_KC_COLS
+#define HT_KC_COLS 256
+#endif
+constexpr int HT_KC = HT_KC_COLS;     // columns per streamed chunk (128 or 256)
 constexpr int HT_AS = HT_KC + 4;      // padded row stride of the chunk buffer (floats): conflict-free float4 rows
 constexpr int HT_MAXB = 64;           // rows per batch
-constexpr int HT_KPARTS = HT_THREADS / 32;   // 8 warps split a chunk's columns: 16 each
+constexpr int HT_KPARTS = HT_THREADS / 32;   // 8 warps split a chunk's columns
+constexpr int HT_WC = HT_KC / HT_KPARTS;     // columns of a chunk per warp (16 or 32)
+constexpr int HT_JH = HT_THREADS / HT_KC;    // weight-gradient products: row groups (2 or 1) ...
+constexpr int HT_JR = HT_RB / HT_JH;         // ... of 4 or 8 rows per thread
 constexpr int HT_BCW = 256;           // AdamW bias corrections are tabulated for 256 steps at a time
 constexpr int HT_TROW = 24;           // timing counters per observed CTA
-static_assert(HT_KC == HT_KPARTS * 16, "a warp owns 16 columns of a chunk");
-static_assert(HT_KC * 2 == HT_THREADS, "one 16-byte copy per thread fills a gathered weight chunk");
+static_assert(HT_KC == 128 || HT_KC == 256, "chunk width");
 
 struct Layer {
     float *W, *b;                 // [rows, K], [rows]   parameters (global; updated in place)
@@ -234,9 +245,12 @@ __device__ __forceinline__ void ht_issue_chunk(float *stage, const float *src, i
 // weight chunk of an input-gradient product, as it lies in memory: Wt[kk][0..7] = gW[(k0 + kk) * gld + gcol0 + 0..7] (zero
 // outside the [krows x gld] matrix; gld is a multiple of 4 and gcol0 of 8, so a group of 4 columns is inside or outside)
 __device__ __forceinline__ void ht_issue_wt(float *wt_stage, const float *gW, int64_t gld, int gcol0, int k0, int krows) {
-    const int kk = threadIdx.x >> 1, h4 = 4 * (threadIdx.x & 1);
-    const bool ok = k0 + kk < krows && gcol0 + h4 < gld;
-    ht_async16(wt_stage + kk * HT_RB + h4, ok ? gW + static_cast<int64_t>(k0 + kk) * gld + gcol0 + h4 : gW, ok);
+#pragma unroll
+    for (int e = threadIdx.x; e < 2 * HT_KC; e += HT_THREADS) {
+        const int kk = e >> 1, h4 = 4 * (e & 1);
+        const bool ok = k0 + kk < krows && gcol0 + h4 < gld;
+        ht_async16(wt_stage + kk * HT_RB + h4, ok ? gW + static_cast<int64_t>(k0 + kk) * gld + gcol0 + h4 : gW, ok);
+    }
 }
 
 // Y[b, j] = sum_k A[b, k] * W[j][k]  for the 8 rows j of one ownership block, A streamed in chunks.
@@ -285,10 +299,10 @@ __device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, f
         for (int bi = 0; bi < 2; ++bi) {
             if (bi < nb) {
                 const int b = lane + 32 * bi;
-                const float *ap = Ac + b * HT_AS + kpart * 16;
+                const float *ap = Ac + b * HT_AS + kpart * HT_WC;
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int kk = kpart * 16 + 4 * q4;
+                for (int q4 = 0; q4 < HT_WC / 4; ++q4) {
+                    const int kk = kpart * HT_WC + 4 * q4;
                     if (kk < kcols) {
                         const float4 av = *reinterpret_cast<const float4 *>(ap + 4 * q4);
                         if (GATHER) {
@@ -351,7 +365,7 @@ __device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, f
 // batch rows are added in index order.
 __device__ __forceinline__ void ht_outer_acc(float *g, float *As, int nst, const float *dA, const float *A, int64_t ld,
                                              const int64_t *ridx, int rows, int K, unsigned long long *dt) {
-    const int kk = threadIdx.x % HT_KC, jh = threadIdx.x / HT_KC;      // 2 x 128 threads: columns x row halves
+    const int kk = threadIdx.x % HT_KC, jh = threadIdx.x / HT_KC;      // columns x row groups
     const int nchunks = (K + HT_KC - 1) / HT_KC;
     const int stage_floats = rows * HT_AS;
     unsigned long long d_prev = dt ? ht_now() : 0;
@@ -370,20 +384,23 @@ __device__ __forceinline__ void ht_outer_acc(float *g, float *As, int nst, const
         ht_async_commit();
         HT_DSTAMP(5);
         const float *Ac = As + (c % nst) * stage_floats;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float ac[HT_JR];
+#pragma unroll
+        for (int j = 0; j < HT_JR; ++j) ac[j] = 0.f;
         for (int b = 0; b < rows; ++b) {
             const float av = Ac[b * HT_AS + kk];
-            const float4 d = *reinterpret_cast<const float4 *>(dA + b * HT_RB + 4 * jh);
-            a0 = fmaf(d.x, av, a0);
-            a1 = fmaf(d.y, av, a1);
-            a2 = fmaf(d.z, av, a2);
-            a3 = fmaf(d.w, av, a3);
+#pragma unroll
+            for (int j4 = 0; j4 < HT_JR / 4; ++j4) {
+                const float4 d = *reinterpret_cast<const float4 *>(dA + b * HT_RB + HT_JR * jh + 4 * j4);
+                ac[4 * j4 + 0] = fmaf(d.x, av, ac[4 * j4 + 0]);
+                ac[4 * j4 + 1] = fmaf(d.y, av, ac[4 * j4 + 1]);
+                ac[4 * j4 + 2] = fmaf(d.z, av, ac[4 * j4 + 2]);
+                ac[4 * j4 + 3] = fmaf(d.w, av, ac[4 * j4 + 3]);
+            }
         }
         if (k0 + kk < K) {
-            g[(4 * jh + 0) * K + k0 + kk] = a0;
-            g[(4 * jh + 1) * K + k0 + kk] = a1;
-            g[(4 * jh + 2) * K + k0 + kk] = a2;
-            g[(4 * jh + 3) * K + k0 + kk] = a3;
+#pragma unroll
+            for (int j = 0; j < HT_JR; ++j) g[(HT_JR * jh + j) * K + k0 + kk] = ac[j];
         }
         HT_DSTAMP(6);
     }
@@ -392,9 +409,9 @@ __device__ __forceinline__ void ht_outer_acc(float *g, float *As, int nst, const
 
 // shared-memory carve-up (floats), identical on host and device.  Per slot s: parameter rows th + s * 8 * kmax, gradient rows
 // g + s * 8 * kmax, moments mv + s * 16 * kmax (m then v; only with res_mv), biases bs + 8 s, bias gradients gb + 8 s, relu' * mask
-// factors (later the input gradients of the own rows) fac + s * batch * 8.
+// factors (later the input gradients of the own rows) fac + s * batch * 8, bias moments bm + 16 s (m then v).
 struct Smem {
-    int th, g, mv, bs, gb, fac;
+    int th, g, mv, bs, gb, bm, fac;
     int dA, out, As, Wt, red, rsum, ridx /* int64 */, bc, scal, total;
 };
 __host__ __device__ inline Smem ht_smem_layout(const Args &a) {
@@ -406,6 +423,7 @@ __host__ __device__ inline Smem ht_smem_layout(const Args &a) {
     s.mv = take(a.res_mv ? a.slots * 2 * HT_RB * a.kmax : 0);
     s.bs = take(a.slots * HT_RB);
     s.gb = take(a.slots * HT_RB);
+    s.bm = take(a.slots * 2 * HT_RB);
     s.fac = take(a.slots * a.batch * HT_RB);
     s.dA = take(a.batch * HT_RB);
     s.out = take(a.batch * HT_RB);
@@ -509,7 +527,12 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                 ht_smem[sm.mv + s * 2 * HT_RB * KM + HT_RB * KM + e] = in ? L.vW[g00 + e] : 0.f;
             }
         }
-        if (tid < HT_RB) ht_smem[sm.bs + s * HT_RB + tid] = tid < nrow ? L.b[it.q * HT_RB + tid] : 0.f;
+        if (tid < HT_RB) {
+            const bool in = tid < nrow;
+            ht_smem[sm.bs + s * HT_RB + tid] = in ? L.b[it.q * HT_RB + tid] : 0.f;
+            ht_smem[sm.bm + s * 2 * HT_RB + tid] = (in && a.update) ? L.mb[it.q * HT_RB + tid] : 0.f;
+            ht_smem[sm.bm + s * 2 * HT_RB + HT_RB + tid] = (in && a.update) ? L.vb[it.q * HT_RB + tid] : 0.f;
+        }
     }
     __syncthreads();
 
@@ -572,15 +595,28 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
             float *dr = a.dz + static_cast<int64_t>(b) * ldz;
             if (a.loss_kind == 0) {
                 const int64_t y = static_cast<const int64_t *>(a.targets)[ridx[b]];
-                float mx = -3.402823466e38f;
-                for (int j = lane; j < C; j += 32) mx = fmaxf(mx, HT_LDCG(zr + j));
+                // the first 128 logits of the row are fetched once (one L2 round trip), wider rows re-read the tail
+                float zc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) zc[u] = lane + 32 * u < C ? HT_LDCG(zr + lane + 32 * u) : -3.402823466e38f;
+                const float zy = (y >= 0 && y < C) ? HT_LDCG(zr + y) : 0.f;
+                float mx = fmaxf(fmaxf(zc[0], zc[1]), fmaxf(zc[2], zc[3]));
+                for (int j = lane + 128; j < C; j += 32) mx = fmaxf(mx, HT_LDCG(zr + j));
                 for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 float sum = 0.f;
-                for (int j = lane; j < C; j += 32) sum += expf(HT_LDCG(zr + j) - mx);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (lane + 32 * u < C) sum += expf(zc[u] - mx);
+                for (int j = lane + 128; j < C; j += 32) sum += expf(HT_LDCG(zr + j) - mx);
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 const float lse = mx + logf(sum);
                 const float invB = 1.f / static_cast<float>(Bt);
-                for (int j = lane; j < ldz; j += 32) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = lane + 32 * u;
+                    if (j < C) dr[j] = (expf(zc[u] - mx) / sum - (j == y ? 1.f : 0.f)) * invB;
+                    else if (j < ldz) dr[j] = 0.f;
+                }
+                for (int j = lane + 128; j < ldz; j += 32) {
                     if (j < C) {
                         const float p = expf(HT_LDCG(zr + j) - mx) / sum;
                         dr[j] = (p - (j == y ? 1.f : 0.f)) * invB;
@@ -588,7 +624,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                         dr[j] = 0.f;
                     }
                 }
-                if (lane == 0) a.rowloss[b] = (y >= 0 && y < C) ? (lse - HT_LDCG(zr + y)) : 0.f;
+                if (lane == 0) a.rowloss[b] = (y >= 0 && y < C) ? (lse - zy) : 0.f;
             } else {
                 const float *yr = static_cast<const float *>(a.targets) + ridx[b] * C;
                 const float inv = 1.f / (static_cast<float>(Bt) * static_cast<float>(C));
@@ -779,14 +815,15 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
                 if (a.update) {
                     const float gv = graw * coef;
                     float p = ht_smem[sm.bs + s * HT_RB + tid] * decay;
-                    const float m1 = L.mb[r] * a.beta1 + gv * (1.f - a.beta1);
-                    const float v1 = L.vb[r] * a.beta2 + gv * gv * (1.f - a.beta2);
+                    float *bmom = ht_smem + sm.bm + s * 2 * HT_RB;
+                    const float m1 = bmom[tid] * a.beta1 + gv * (1.f - a.beta1);
+                    const float v1 = bmom[HT_RB + tid] * a.beta2 + gv * gv * (1.f - a.beta2);
                     const float denom = sqrtf(v1) / bc2s + a.eps;
                     p = p - lr_c * (m1 / denom);
                     ht_smem[sm.bs + s * HT_RB + tid] = p;
                     L.b[r] = p;
-                    L.mb[r] = m1;
-                    L.vb[r] = v1;
+                    bmom[tid] = m1;
+                    bmom[HT_RB + tid] = v1;
                 } else {
                     if (L.gb) L.gb[r] = graw;
                     if (L.qb) L.qb[r] += graw * graw * a.fisher_scale;
@@ -810,7 +847,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
     }
 
     // ---- resident moments go back to global memory
-    if (res_mv) {
+    if (a.update) {
         for (int s = 0; s < a.slots; ++s) {
             const int i = cta + s * G;
             if (i >= a.items) break;
@@ -819,9 +856,14 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_train_kernel(const Args a)
             const int K = L.K;
             const int nrow = (L.rows - it.q * HT_RB < HT_RB) ? (L.rows - it.q * HT_RB) : HT_RB;
             const int64_t g00 = static_cast<int64_t>(it.q) * HT_RB * K;
-            for (int e = tid; e < nrow * K; e += HT_THREADS) {
-                L.mW[g00 + e] = ht_smem[sm.mv + s * 2 * HT_RB * KM + e];
-                L.vW[g00 + e] = ht_smem[sm.mv + s * 2 * HT_RB * KM + HT_RB * KM + e];
+            if (res_mv)
+                for (int e = tid; e < nrow * K; e += HT_THREADS) {
+                    L.mW[g00 + e] = ht_smem[sm.mv + s * 2 * HT_RB * KM + e];
+                    L.vW[g00 + e] = ht_smem[sm.mv + s * 2 * HT_RB * KM + HT_RB * KM + e];
+                }
+            if (tid < nrow) {
+                L.mb[it.q * HT_RB + tid] = ht_smem[sm.bm + s * 2 * HT_RB + tid];
+                L.vb[it.q * HT_RB + tid] = ht_smem[sm.bm + s * 2 * HT_RB + HT_RB + tid];
             }
         }
     }

@@ -82,13 +82,15 @@ def test_head_training_kernel_on_the_cpu_emulation():
     #        D   H0  H1  C    n  batch G loss dropout ewc update seed
     cases = ["40 40 20 5 50 20 3 0 0.1 0 1 1",          # CE, dropout, last batch partial
              "40 40 20 5 50 20 2 1 0.1 0 1 2",          # BCE; 2 CTAs -> several ownership blocks per CTA
-             "264 136 68 11 70 32 4 0 0.1 1 1 3",       # K not a multiple of the 128-column chunk; EWC with a grown head
+             "264 136 68 11 70 32 4 0 0.1 1 1 3",       # K not a multiple of the chunk width; EWC with a grown head
              "64 64 32 3 45 40 3 0 0.0 1 1 4",          # batch > 32 (two rows per lane), C = 3 (scalar chunk loads)
              "128 128 64 130 64 32 5 1 0.2 1 1 5",      # C > one chunk: dz streamed in two chunks
              "264 136 68 11 30 30 4 0 0.0 0 0 6",       # gradient-only mode (Fisher): gradients and accumulators
              "40 40 20 5 20 20 1 1 0.0 1 0 7",          # a single CTA owns everything
              "40 40 20 5 50 20 9 0 0.1 1 1 9",
-             "264 136 68 11 70 32 28 0 0.1 1 1 10"]    # one ownership block per CTA (the B200 layout of the reference's head)
+             "264 136 68 11 70 32 28 0 0.1 1 1 10",
+             "520 264 68 11 30 30 4 0 0.0 0 0 6",       # several 256-column chunks per product
+             "128 128 64 130 64 32 5 0 0.2 1 1 11"]     # CE with more than 128 classes (logit tail re-read)    # one ownership block per CTA (the B200 layout of the reference's head)
     for c in cases:
         out = subprocess.run([exe] + c.split(), capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "MATCH" in out.stdout, (c, out.stdout[-600:], out.stderr[-300:])
