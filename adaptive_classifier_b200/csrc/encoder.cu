@@ -241,6 +241,10 @@ struct EpiResidDefer {
     // (3.65 TB/s over the chip; out-proj 152 us against an 85 us traffic floor).  Requesting two chunks ahead needs a third
     // 32-register buffer: with the 168 registers a 10-warp CTA can have (warps are allocated in fours) it spills, and measured
     // SLOWER on a B200 (14.5-14.8 ms per step against 13.9-14.1: profiles/r02_variants.md), so the distance stays 1.
+    // Asking L2 for the next tile's rows one tile ahead (prefetch.global.L2, no registers) was also measured: 14.07 ms (one
+    // request per 128 bytes) and 14.21 ms (per 32-byte sector) against 13.90-13.94 ms without, same box, same run -- the step
+    // runs against the board's power cap (SM clock 1.5-1.7 GHz of 1.965), and extra requests in flight cost more clock than the
+    // shorter load latency returns.
 #ifndef AC_RESID_PREFETCH
 #define AC_RESID_PREFETCH 1
 #endif
