@@ -8,6 +8,7 @@ makes every compute call raise AdaptiveB200Error.
 from __future__ import annotations
 
 import ctypes
+import threading
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 from typing import Optional
@@ -170,15 +171,21 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # thin Python wrappers (tensor in / tensor out) used by the drop-in classes, the tests and bench.py
 # ------------------------------------------------------------------------------------------------
-_ws_cache = {}
+_ws_tls = threading.local()
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Scratch for one C call, cached per (thread, device).  Per THREAD because ctypes releases the GIL: two host threads (e.g. one
+    inside PrototypeMemory's lock running a search, one inside a classifier's device lock running the head) enqueue on the same
+    stream, and a scratch buffer shared between them would be rewritten between two kernels of the other thread's call."""
+    cache = getattr(_ws_tls, "ws", None)
+    if cache is None:
+        cache = _ws_tls.ws = {}
     key = (device.index if device.index is not None else torch.cuda.current_device())
-    ws = _ws_cache.get(key)
+    ws = cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
+        cache[key] = ws
     return ws
 
 

@@ -297,7 +297,7 @@ __device__ __forceinline__ void ht_rows_dot(float *out, float *As, float *red, f
         const int kcols = (K - k0 < HT_KC) ? (K - k0) : HT_KC;                           // resident rows: stay inside the row
 #pragma unroll
         for (int bi = 0; bi < 2; ++bi) {
-            if (bi < nb) {
+            if (lane + 32 * bi < rows) {          // rows past the batch lie in the NEXT stage, which asynchronous copies are filling
                 const int b = lane + 32 * bi;
                 const float *ap = Ac + b * HT_AS + kpart * HT_WC;
 #pragma unroll
