@@ -26,9 +26,12 @@ int check_cuda(cudaError_t e, const char *what) {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launch_n(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
 
 struct ProfSlot { cudaEvent_t a, b; int cls; double flops, bytes; };
 static bool g_prof_on = false;
+bool prof_is_on() { return g_prof_on; }
 static std::vector<ProfSlot> g_prof_slots;
 static size_t g_prof_used = 0;
 static double g_prof_ms[PROF_NUM], g_prof_flops[PROF_NUM], g_prof_bytes[PROF_NUM];

@@ -33,6 +33,9 @@ int check_cuda(cudaError_t e, const char *what);
 
 // every kernel launch of the library passes through here: the counter backs bench.py's `gpu_launches`
 void count_launch();
+void count_launch_n(long long n);      // kernels replayed by a CUDA graph launch
+long long launch_count_now();
+bool prof_is_on();
 #define AC_LAUNCH_CHECK()                                            \
     do {                                                             \
         ::ac::count_launch();                                        \

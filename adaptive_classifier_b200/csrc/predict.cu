@@ -342,6 +342,13 @@ struct ac_pipeline {
     cudaEvent_t ev_emb, ev_head;
     // search statistics accumulated on the device (ac_knn_l2_topk stats): no host synchronisation inside a predict call
     int32_t *knn_stats;
+    // ac_pipeline_predict_host replays the device part of the step as a CUDA graph, one per batch size: at B = 1 the ~110 launches
+    // of a step cost more host time than GPU time.  First call with a batch size: eager; second: captured on `cap`; then replayed.
+    struct GraphSlot { int B, calls; long long launches; cudaGraphExec_t exec; };
+    GraphSlot gslot[8];
+    int n_gslot;
+    bool graph_off;
+    cudaStream_t cap;
 };
 
 extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
@@ -349,6 +356,8 @@ extern "C" int ac_pipeline_destroy(ac_pipeline *pl) {
     void *ptrs[] = {pl->ids_dev, pl->p_cls, pl->out_cls, pl->emb, pl->knn_d, pl->p_score, pl->probs, pl->h_val,
                     pl->out_score, pl->scratch, pl->knn_i, pl->h_idx, pl->ws, pl->ws_topk, pl->knn_stats, pl->loc_d, pl->loc_i};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < pl->n_gslot; ++i) if (pl->gslot[i].exec) cudaGraphExecDestroy(pl->gslot[i].exec);
+    if (pl->cap) cudaStreamDestroy(pl->cap);
     if (pl->side) cudaStreamDestroy(pl->side);
     if (pl->ev_emb) cudaEventDestroy(pl->ev_emb);
     if (pl->ev_head) cudaEventDestroy(pl->ev_head);
@@ -396,6 +405,9 @@ extern "C" int ac_pipeline_create(ac_encoder *enc, const float *P, const float *
     al(reinterpret_cast<void **>(&pl->knn_stats), 4 * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemset(pl->knn_stats, 0, 4 * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->cap, cudaStreamNonBlocking);
+    const char *genv = getenv("AC_PIPELINE_GRAPH");
+    pl->graph_off = genv && genv[0] == '0';
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_emb, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_head, cudaEventDisableTiming);
     if (e != cudaSuccess) { ac_pipeline_destroy(pl); return check_cuda(e, "ac_pipeline_create cudaMalloc"); }
@@ -503,12 +515,55 @@ extern "C" int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_de
 }
 
 // host entry: ids_host[B,S] (pinned) -> H2D -> predict -> D2H of [B,k] class ids + scores, stream-synchronised
+// the device part of a host-boundary step (pl->ids_dev -> pl->out_cls / pl->out_score) on stream s: a CUDA graph replay once the
+// batch size has been seen twice, otherwise the ordinary launches.  The graph is recorded on the pipeline's own stream (the
+// caller's may be the legacy default stream, which cannot capture) and launched into s.  Timed profiling (bench.py's per-kernel
+// events) and AC_PIPELINE_GRAPH=0 keep the step eager; any capture failure turns graphs off for this pipeline.
+static int pipeline_step_host(ac_pipeline *pl, int B, cudaStream_t s) {
+    auto eager = [&]() { return ac_pipeline_predict_device(pl, pl->ids_dev, nullptr, B, pl->out_cls, pl->out_score, s); };
+    if (pl->graph_off || prof_is_on()) return eager();
+    ac_pipeline::GraphSlot *g = nullptr;
+    for (int i = 0; i < pl->n_gslot; ++i) if (pl->gslot[i].B == B) g = &pl->gslot[i];
+    if (!g) {
+        if (pl->n_gslot == 8) return eager();
+        g = &pl->gslot[pl->n_gslot++];
+        g->B = B; g->calls = 0; g->launches = 0; g->exec = nullptr;
+    }
+    g->calls += 1;
+    if (!g->exec) {
+        if (g->calls < 2) return eager();            // one-time function attributes and tensor maps are set by an ordinary call
+        const long long before = launch_count_now();
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(pl->cap, cudaStreamCaptureModeThreadLocal);
+        int rc = AC_OK;
+        if (e == cudaSuccess) {
+            rc = ac_pipeline_predict_device(pl, pl->ids_dev, nullptr, B, pl->out_cls, pl->out_score, pl->cap);
+            e = cudaStreamEndCapture(pl->cap, &graph);
+        }
+        const long long recorded = launch_count_now() - before;
+        count_launch_n(-recorded);                   // recorded, not executed
+        cudaGraphExec_t exec = nullptr;
+        if (rc == AC_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != AC_OK || e != cudaSuccess || !exec) {
+            cudaGetLastError();                      // clear the capture error; this pipeline stays eager from now on
+            pl->graph_off = true;
+            return eager();
+        }
+        g->exec = exec;
+        g->launches = recorded;
+    }
+    AC_CUDA(cudaGraphLaunch(g->exec, s));
+    count_launch_n(g->launches);
+    return AC_OK;
+}
+
 extern "C" int ac_pipeline_predict_host(ac_pipeline *pl, const int32_t *ids_host, int B, int32_t *out_cls_host,
                                         float *out_score_host, ac_stream_t stream) {
     AC_REQUIRE(pl && ids_host && out_cls_host && out_score_host && B > 0 && B <= pl->max_B, "ac_pipeline_predict_host: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     AC_CUDA(cudaMemcpyAsync(pl->ids_dev, ids_host, sizeof(int32_t) * B * pl->S, cudaMemcpyHostToDevice, s));
-    int rc = ac_pipeline_predict_device(pl, pl->ids_dev, nullptr, B, pl->out_cls, pl->out_score, stream);
+    int rc = pipeline_step_host(pl, B, s);
     if (rc) return rc;
     AC_CUDA(cudaMemcpyAsync(out_cls_host, pl->out_cls, sizeof(int32_t) * B * pl->k, cudaMemcpyDeviceToHost, s));
     AC_CUDA(cudaMemcpyAsync(out_score_host, pl->out_score, sizeof(float) * B * pl->k, cudaMemcpyDeviceToHost, s));

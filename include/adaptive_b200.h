@@ -286,7 +286,10 @@ int ac_pipeline_destroy(ac_pipeline *pl);
 /* device buffers at the boundary (bench.py `value`) */
 int ac_pipeline_predict_device(ac_pipeline *pl, const int32_t *ids_dev, const int32_t *mask_dev, int B,
                                int32_t *out_cls_dev, float *out_score_dev, ac_stream_t stream);
-/* HOST buffers at the boundary (bench.py `e2e`): H2D of ids and D2H of the [B,k] result inside the call */
+/* HOST buffers at the boundary (bench.py `e2e`): H2D of ids and D2H of the [B,k] result inside the call.  The device part of the
+ * step is replayed as a CUDA graph from the third call with a batch size on (first: ordinary launches, second: capture) -- at B = 1
+ * the ~110 launches of a step cost more host time than GPU time (0.92 instead of 1.15 ms per query).  Results are identical to the
+ * eager step; AC_PIPELINE_GRAPH=0 in the environment, or enabled per-kernel profiling (ac_profile_enable), keeps the step eager. */
 int ac_pipeline_predict_host(ac_pipeline *pl, const int32_t *ids_host, int B, int32_t *out_cls_host,
                              float *out_score_host, ac_stream_t stream);
 /* The phases of one step, for the row-sharded multi-GPU search: the caller (parallel.py) runs the

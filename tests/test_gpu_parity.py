@@ -644,6 +644,36 @@ def test_pipeline_device_and_host_boundaries(cabi):
     pl.close(); enc.close()
 
 
+def test_pipeline_host_step_replayed_as_a_cuda_graph_equals_the_eager_step(cabi):
+    """ac_pipeline_predict_host: first call with a batch size runs the ordinary launches, the second records the device part of
+    the step as a CUDA graph, later calls replay it.  Every call gets different ids: the replays must read the staging buffer, not
+    data baked in at capture time, must equal the device-boundary (always eager) result bit for bit, and must account for the same
+    number of kernel launches; another batch size gets its own graph."""
+    sd, cfg = _small_bert(2)
+    Bmax, S, N, D, C, k = 8, 32, 3000, 768, 20, 5
+    P, _ = _synthetic_index(N, D, C)
+    Pg = P.cuda()
+    enc = _encoder(cabi, sd, cfg, max_tokens=Bmax * S)
+    p, pg = _head(D, C)
+    row_class = (torch.arange(N) % C).to(torch.int32).cuda()
+    pl = cabi.Pipeline(enc, Pg, Bmax, S, k, head=pg, row_class=row_class)
+    per_call = {}
+    for rep, B in enumerate([3, 3, 3, 3, 8, 8, 8, 3, 1, 1, 1]):
+        ids = eo.synthetic_ids(B, S, seed=100 + rep).to(torch.int32)
+        n0 = cabi.launch_count()
+        oc_h, osc_h = pl.predict_host(ids.pin_memory())
+        oc_h, osc_h = oc_h.clone(), osc_h.clone()
+        n1 = cabi.launch_count()
+        oc, osc = pl.predict_device(ids.cuda())
+        torch.cuda.synchronize()
+        n2 = cabi.launch_count()
+        assert torch.equal(oc.cpu(), oc_h) and torch.equal(osc.cpu(), osc_h), (rep, B)
+        assert n1 - n0 == n2 - n1 > 0, (rep, B, n1 - n0, n2 - n1)      # a replay accounts for the kernels it launches
+        per_call.setdefault(B, []).append(n1 - n0)
+    assert all(len(set(v)) == 1 for v in per_call.values())
+    pl.close(); enc.close()
+
+
 def test_proto_class_scores_reduces_to_reference_form(cabi):
     """one row per class (the reference's usage): ac_proto_class_scores == memory.py:117-134 (ac_proto_scores)"""
     rng = np.random.default_rng(1)
