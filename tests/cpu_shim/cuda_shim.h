@@ -4,7 +4,7 @@
 // flow can: every CUDA thread becomes a fiber (ucontext), __syncthreads / __syncwarp / cooperative grid.sync are fiber
 // barriers, warp shuffles exchange through a per-warp array between two warp barriers, and the scheduler visits the fibers
 // in a shuffled order so that missing barriers show up as wrong results.  Device source is compiled as ordinary C++ with
-// the CUDA keywords defined away (tests/cpu_shim/extract_device_code.py cuts the device code out of the .cu files).
+// the CUDA keywords defined away (head_train.cuh is written to be included as it is: AC_CPU_SHIM selects the few CPU stand-ins).
 #pragma once
 #include <ucontext.h>
 #include <algorithm>
