@@ -375,11 +375,15 @@ __global__ void knn_add_stats_kernel(const int32_t *__restrict__ in, int32_t *__
 // ------------------------------------------------------------------------------------------------
 constexpr int KNN_SMALL_K = 16;        // certification path (lists of KNN_KC per (query, CTA, half))
 // k > 16: queries per pass.  tau (the bound on the k-th distance) is the k-th smallest key among the merged lists, so it is
-// tight only if no list had to drop a top-k row for lack of room (16 entries).  One query tile per pass gives every query
-// 2 x 148 lists over interleaved row tiles: with k = 1000 a list holds ~3.4 top-k rows on average.  (512 queries per pass = 74
-// lists = 13.5 per list overflowed lists on 66 of 512 queries on the 1000-rows-per-class benchmark index: tau jumped to the
-// next cluster and the band held > 2048 rows.)  The scan of one 128-query tile is HBM-bound (0.23 ms per pass over 1.5 GB).
-constexpr int KNN_QUERY_BLOCK = 128;
+// tight only if no list had to drop a top-k row for lack of room (16 entries).  Two query tiles per pass give every query
+// 2 x 74 lists over interleaved row tiles: with k = 1000 a list holds ~6.8 top-k rows on average (P(> 16) ~ 1e-3).  512 queries
+// per pass = 74 lists of 13.5 expected rows overflowed lists on 66 of 512 queries on the 1000-rows-per-class benchmark index
+// (tau jumped to the next cluster and the band held > 2048 rows).  Measured at 512 x 1 M x 768, k = 1000 on a B200: 4.35 ms per
+// search with 128 queries per pass (the scan of one tile is HBM-bound: 0.48 ms per pass over 1.5 GB), 3.03 ms with 256.
+#ifndef AC_KNN_QUERY_BLOCK
+#define AC_KNN_QUERY_BLOCK 256
+#endif
+constexpr int KNN_QUERY_BLOCK = AC_KNN_QUERY_BLOCK;
 static int knn_cap(int k) { return k <= KNN_SMALL_K ? 256 : 4096; }
 
 struct KnnTcPlan {
