@@ -30,7 +30,7 @@ EXPORTS = [
     "ac_version", "ac_last_error", "ac_device_check",
     "ac_knn_workspace_bytes", "ac_knn_l2_topk", "ac_knn_make_shadow", "ac_row_sqnorm", "ac_topk_merge", "ac_proto_scores",
     "ac_segment_mean", "ac_memory_append_prune",
-    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch", "ac_head_phase_timing", "ac_head_grad", "ac_ewc_penalty",
+    "ac_head_forward", "ac_head_train_workspace_bytes", "ac_head_train_step", "ac_head_train_epoch", "ac_head_phase_timing", "ac_head_train_plan", "ac_head_grad", "ac_ewc_penalty",
     "ac_encoder_create", "ac_encoder_destroy", "ac_encoder_forward_cls", "ac_encoder_last_hidden", "ac_linear_tc",
     "ac_proto_class_scores", "ac_proto_class_scores_n", "ac_blend_dense", "ac_topk_desc_workspace_bytes", "ac_topk_desc", "ac_blend_topk",
     "ac_pipeline_create", "ac_pipeline_destroy", "ac_pipeline_predict_device", "ac_pipeline_predict_host",
@@ -379,6 +379,14 @@ def head_phase_timing(enable: bool = True):
     check(load_library().ac_head_phase_timing(1 if enable else 0, out), "ac_head_phase_timing")
     v = [int(x) for x in out]
     return [v[0:24], v[24:48], v[48:72]]
+
+
+def head_train_plan(p, batch: int = 32):
+    """diagnostic: {ctas, stages, moments_resident, smem_bytes} of the training kernel for this head"""
+    hp = head_params_struct(p)
+    out = (ctypes.c_int * 5)()
+    check(load_library().ac_head_train_plan(batch, ctypes.byref(hp), out), "ac_head_train_plan")
+    return dict(zip(("ctas", "stages", "moments_resident", "smem_bytes"), [int(x) for x in out][:4]))
 
 
 def head_grad(X, targets, p, *, loss_kind=AC_LOSS_CE, grad_out=None, fisher=None, inv_n_batches=1.0):

@@ -9,14 +9,14 @@
 //
 // Why one kernel: the head is 0.9 M parameters and a batch is 32 rows -- 171 MFLOP and 25 MB of optimizer traffic per step,
 // i.e. microseconds of work; the round-1 path launched ~21 dependent kernels per step (310 us measured on a B200).  Here the
-// grid stays resident for the whole epoch and a step is seven phases separated by six grid barriers (47 us per step measured):
+// grid stays resident for the whole epoch and a step is seven phases separated by six grid barriers (44 us per step measured):
 //
 //   ownership   the rows of every weight matrix are cut into blocks of HT_RB = 8 rows, and the blocks of all three layers form
 //               ONE list of items dealt over the grid (item i -> CTA i % G).  The reference's head (768 -> 768 -> 384 -> C)
 //               has 96 + 48 + ceil(C / 8) items: with C <= 32 that is at most 148, one item per SM of a B200, so every CTA
 //               works for exactly one layer and the weight-gradient work of different layers runs side by side.  A CTA keeps
-//               the rows of ITS item(s) -- parameters, gradient, AdamW moments, biases -- in shared memory for the whole
-//               launch, computes the activations / gradients of exactly those rows and applies AdamW to them: parameters
+//               the rows of ITS item(s) -- parameters, gradient, biases, and the AdamW moments when they fit (res_mv; for the
+//               reference's head they stay owner-private in L2) -- in shared memory for the whole launch, computes the activations / gradients of exactly those rows and applies AdamW to them: parameters
 //               never move between CTAs, gradients and moments never leave shared memory (moments: when they fit, res_mv),
 //               AdamW of step t needs no barrier before the forward of step t+1.
 //   P1  h0 = dropout(relu(X W0^T + b0))        layer-0 items; X rows gathered through the shuffled index list

@@ -176,6 +176,9 @@ int ac_head_train_epoch(const float *X, const void *targets, const int64_t *perm
  * of the 7 phases and 6 grid barriers of a step (13 counters) and inside the product routines (7 counters from index 14), summed
  * over all steps since enabled.  enable != 0 starts accumulating; out72_host (nullable) receives 3 x 24 counters. */
 int ac_head_phase_timing(int enable, unsigned long long *out72_host);
+/* diagnostic: launch plan of the training kernel: out5 = {CTAs, operand-ring stages, AdamW moments resident in shared memory (0/1),
+ * dynamic shared-memory bytes, reserved} */
+int ac_head_train_plan(int batch, const ac_head_params *p, int *out5);
 
 /* gradient only (no update) of mean CE/BCE wrt all parameters, eval mode: the building block of
  * EWC._compute_fisher (ewc.py:67-92).  fisher += grad^2 * inv_n_batches when fisher != NULL */

@@ -35,4 +35,4 @@ rows = {}
 for cls, r in zip(("layer0 CTA", "layer1 CTA", "layer2 CTA (last)"), ns):
     rows[cls] = {"phase_us": {nm: round(x / nb / 1e3, 2) for nm, x in zip(names, r[:13])}, "sum_us": round(sum(r[:13]) / nb / 1e3, 2),
                  "inside_products_us": {nm: round(x / nb / 1e3, 2) for nm, x in zip(detail, r[14:21])}}
-print(json.dumps({"classes": C, "steps": nb, "us_per_step_untimed": untimed, "us_per_step_wall": 1e6 * wall / nb, "observed": rows}))
+print(json.dumps({"classes": C, "plan": _cabi.head_train_plan(p, 32), "steps": nb, "us_per_step_untimed": untimed, "us_per_step_wall": 1e6 * wall / nb, "observed": rows}))
