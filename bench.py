@@ -468,6 +468,21 @@ def main():
     for _ in range(2):
         step_host()
     ms_e2e, _, _ = timed(step_host, args.steps)
+    # the scan kernel by itself (same queries, same shard, nothing else on the GPU): inside the step it shares the SMs with the head
+    # forward on the side stream, which is what `ms_per_launch` above includes
+    knn_alone_ms = None
+    if rank == 0:
+        q_alone = emb.repeat(G, 1).contiguous() if G > 1 else emb.contiguous()
+        kw = dict(p_sqnorm=p_sqnorm, p_half=p_half)
+        for _ in range(2):
+            _cabi.knn_l2_topk(q_alone, P, K_TOP, **kw)
+        torch.cuda.synchronize()
+        _cabi.profile_enable(True)
+        for _ in range(5):
+            _cabi.knn_l2_topk(q_alone, P, K_TOP, **kw)
+        _cabi.profile_enable(False)
+        pa = _cabi.profile_read(2)
+        knn_alone_ms = pa["ms"] / max(1, pa["launches"])
 
     if rank != 0:
         if G > 1:
@@ -521,6 +536,10 @@ def main():
                          "bound": "tensor" if tfrac >= sfrac else "hbm",
                          "peak_hbm_gbs": pk["hbm_gbs"], "peak_tflops": pk["bf16_tflops_sustained"], "peak_source": pk["source"],
                          "share_of_step": knn["ms"] / ms,
+                         "alone": None if not knn_alone_ms else {
+                             "ms_per_launch": knn_alone_ms, "frac_algorithmic": 4.0 * n_local * D / (knn_alone_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             "tensor_frac": 2.0 * q_scan * n_local * D / (knn_alone_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                             "note": "the same launch timed with nothing else on the GPU (in the step the head forward runs beside it on the side stream)"},
                          "second_pass_ms_per_launch": knn2["ms"] / max(1, knn2["launches"])},
         "knn_uncertified": kstats["second_pass_queries"] / max(1, kstats["searches"]),
         "knn_overflow": kstats["overflow_queries"],
