@@ -61,8 +61,6 @@ struct EpiKnn {
     int64_t N;               // rows
     int tiles_m, slots;      // grid = slots/2 * tiles_m CTAs; every CTA owns one query tile and two lists per query
     int kt;                  // a list publishes its kt-th best key (k + 3 <= kt <= KC): see prefetch()
-    float *pmax_out;         // max ||p||^2 over the rows (for the error bound), accumulated here: every row passes through the
-                             // epilogue of some CTA of every query tile anyway (a separate pass over the norms cost 0.11 ms per search)
 
     static constexpr int kUnrollChunks = 1;
     struct State {
@@ -70,7 +68,6 @@ struct EpiKnn {
         int32_t idx[KNN_KC];
         float pn[2];          // ||p||^2 of the 32 rows of a chunk, one per lane, requested one chunk ahead
         float gt;             // global bound for this thread's query, refreshed once per tile
-        float pmax;           // largest ||p||^2 this thread has seen
     };
 
     __device__ __forceinline__ bool skip_kernel() const { return false; }
@@ -79,7 +76,6 @@ struct EpiKnn {
         for (int i = 0; i < KNN_KC; ++i) { st.key[i] = CUDART_INF_F; st.idx[i] = -1; }
         st.pn[0] = st.pn[1] = CUDART_INF_F;
         st.gt = CUDART_INF_F;
-        st.pmax = 0.f;
     }
 
     // Every list (74 per query at B = 512) would on its own perform ~KC ln(n/KC) sorted inserts; sharing a bound
@@ -93,7 +89,6 @@ struct EpiKnn {
         const int64_t n = static_cast<int64_t>(col0) + lane;
         const float x = (n < N) ? __ldg(p_sqnorm + n) : CUDART_INF_F;
         if (buf) st.pn[1] = x; else st.pn[0] = x;
-        if (n < N) st.pmax = fmaxf(st.pmax, x);
         if (buf == 0) {        // first chunk of a tile: publish this list's bound, pick up the others'
             float pub = CUDART_INF_F;
 #pragma unroll
@@ -145,10 +140,6 @@ struct EpiKnn {
     }
 
     __device__ __forceinline__ void end_cta(State &st, int q, int lane) const {
-        if (pmax_out) {
-            const float m = warp_max(st.pmax);                 // non-negative floats order like their bit patterns
-            if (lane == 0) atomicMax(reinterpret_cast<int *>(pmax_out), __float_as_int(m));
-        }
         // two epilogue warps share a query row (one per 128-column half of every tile): each owns a slot
         const int chalf = ((threadIdx.x >> 5) - 2) >> 2;
         const int mt = blockIdx.x % tiles_m;
@@ -244,6 +235,17 @@ __global__ void knn_prep_rows_kernel(const float *__restrict__ P, int64_t N, int
     for (int i = lane; i < D; i += 32) s = fmaf(p[i], p[i], s);
     s = warp_sum(s);
     if (lane == 0) pn[row] = s;
+}
+
+// max_n ||p_n||^2 (for the error bound) -> out[0] (zeroed by the caller); non-negative floats order like their bit patterns.
+// One grid-stride pass over the 4 MB of norms (~5 us at N = 1 M).  Accumulating the maximum in the scan epilogue instead was
+// measured: it costs the scan 2-4 % (0.02-0.03 ms); the round-1 pass over the norms with one CTA per 8 rows cost 0.11 ms.
+__global__ void knn_max_norm_kernel(const float *__restrict__ pn, int64_t N, float *__restrict__ out) {
+    float m = 0.f;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) m = fmaxf(m, __ldg(pn + i));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));
 }
 
 // widen the int32 candidate ids of the per-CTA lists for the (key, id) sort
@@ -521,14 +523,16 @@ static int knn_tc_block(const float *Q, const float *P, const float *p_sqnorm, c
         AC_LAUNCH_CHECK();
         pn_use = pn;
     }
-    AC_CUDA(cudaMemsetAsync(pmax, 0, sizeof(float), s));       // max ||p||^2: accumulated by the pass-1 epilogue
+    AC_CUDA(cudaMemsetAsync(pmax, 0, sizeof(float), s));
+    knn_max_norm_kernel<<<sm_count() * 2, 256, 0, s>>>(pn_use, N, pmax);
+    AC_LAUNCH_CHECK();
 
     // ---- pass 1 on the tensor cores: per-(query, CTA, half) top-16 lists
     const bool small_k = k <= KNN_SMALL_K;
     // kt = 0 (k > 16): no shared bound -- every list keeps its own true top-16, the merged lists bound the k-th distance
     int kt = 0;
     if (small_k) { kt = k + 3 > 8 ? k + 3 : 8; if (kt > KNN_KC) kt = KNN_KC; }
-    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt, pmax};
+    EpiKnn epi{pn_use, ckey, cidx, gthr, B, N, pl.tiles_m, pl.slots, kt};
     if ((rc = launch_scan(Qr, P, p_half, Bp, N, D, epi, pl.grid_ctas, PROF_KNN_COARSE, s))) return rc;
 
     // ---- merge the lists (sorted by (key, id))
