@@ -298,7 +298,7 @@ static int plan_training(int batch, const ac_head_params *p, int n_steps, bool u
     // AdamW moments resident in shared memory if at least three ring stages still fit; then as many stages (<= 8) as there is room for
     const size_t limit = 220 * 1024;
     pl.smem_bytes = ~size_t(0);
-    static const int res_min_nst = [] { const char *e = getenv("AC_HEAD_RES_MIN_STAGES"); return e ? atoi(e) : 3; }();   // development knob
+    constexpr int res_min_nst = 3;      // measured: moments resident with only two ring stages is slower than L2-resident with three
     for (int res = update ? 1 : 0; res >= 0; --res) {
         a.res_mv = res;
         for (a.nst = 8; a.nst >= (res ? res_min_nst : 2); --a.nst) {
